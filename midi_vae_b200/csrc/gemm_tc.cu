@@ -1,0 +1,393 @@
+// gemm_tc.cu -- bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA into 128B-swizzled shared memory, persistent over output tiles.
+//
+// This is the workhorse for every batchable matrix product of the MIDI-VAE step (input projections of
+// the stacked layers, output Denses, all weight gradients, dX = dG W^T; SURVEY.md section 2 K1,K3,K5,K8),
+// i.e. what the reference leaves to Theano's gemm under Keras Dense/LSTM (vae_definition.py:455-507,533-643).
+//
+//   C[M,N] = act( op(A) op(B) + bias + addend )     or     C += op(A) op(B)   (fp32 red.add, split-K)
+//
+// Layout cases (all row-major in global memory, no transposed copies are ever made):
+//   A "K-major"  : stored [M,K]   (transA = false)     A "MN-major": stored [K,M]   (transA = true, weight grads)
+//   B "K-major"  : stored [N,K]   (transB = true)      B "MN-major": stored [K,N]   (transB = false, plain weights)
+// handled by the UMMA shared-memory descriptors (major-ness bits in the instruction descriptor), with the
+// TMA boxes chosen so that the smem image is the canonical SWIZZLE_128B layout of the respective major-ness.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2..5 epilogue
+// (TMEM -> registers -> global, one output row per thread).  Two TMEM accumulators (2 x BN columns) let
+// the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mvae {
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int kThreads = 192;
+
+struct TcParams {
+  int M, N, K;
+  void* C; int ldc; int c_bf16;
+  const float* bias;
+  const void* addend; int ldadd; int add_bf16;
+  int act; int atomic_acc;
+  int m_tiles, n_tiles, k_splits, kb_total, kb_per_split;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 5;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;   // + alignment slack
+};
+
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int STAGES = L::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_a);
+    ptx::prefetch_tmap(&tma_b);
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1); ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), 2 * BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ks = tile % p.k_splits, mn = tile / p.k_splits;
+        const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+          ptx::mbar_arrive_expect_tx(fb, L::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            ptx::tma_load_2d(sa, &tma_a, fb, k0, m0);                       // box {64 K, 128 M}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) ptx::tma_load_2d(sa + j * 8192, &tma_a, fb, m0 + j * 64, k0);   // box {64 M, 64 K}
+          }
+          if (!B_MN) {
+            ptx::tma_load_2d(sb, &tma_b, fb, k0, n0);                       // box {64 K, BN N}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * 8192, &tma_b, fb, n0 + j * 64, k0);   // box {64 N, 64 K}
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int ks = tile % p.k_splits;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 8-row groups 1024 B apart (SBO), advance 32 B per K=16 slice inside the 128 B swizzle row.
+            // MN-major: 64-element atoms along M/N 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO), 2048 B per K=16 slice.
+            const uint64_t da = A_MN ? ptx::umma_desc_sw128(sa + k * 2048, 8192, 1024) : ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? ptx::umma_desc_sw128(sb + k * 2048, 8192, 1024) : ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
+            ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));     // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(ptx::smem_u32(&tmem_full_bar[acc]));     // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====================
+    const int quad = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int mn = tile / p.k_splits;
+      const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
+      const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
+      ptx::tc_fence_after();
+      const int m = m0 + quad * 32 + lane;
+      const bool row_ok = m < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int nb = n0 + c * 32;
+        if (nb >= p.N) break;                                   // warp-uniform
+        float v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        if (!row_ok) continue;
+        const int nvalid = min(32, p.N - nb);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
+        }
+        if (p.addend) {
+          if (p.add_bf16) {
+            const bf16* ad = (const bf16*)p.addend + (size_t)m * p.ldadd + nb;
+            if (nvalid == 32 && (reinterpret_cast<uintptr_t>(ad) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u = __ldg(reinterpret_cast<const uint4*>(ad) + j);
+                const bf16* e = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[j * 8 + t] += __bfloat162float(e[t]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __bfloat162float(ad[j]);
+            }
+          } else {
+            const float* ad = (const float*)p.addend + (size_t)m * p.ldadd + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += ad[j];
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        }
+        if (p.atomic_acc) {
+          float* cp = (float*)p.C + (size_t)m * p.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < nvalid) atomicAdd(cp + j, v[j]);
+        } else if (p.c_bf16) {
+          bf16* cp = (bf16*)p.C + (size_t)m * p.ldc + nb;
+          if (nvalid == 32 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(v[j * 8 + 2 * t], v[j * 8 + 2 * t + 1]);
+              reinterpret_cast<uint4*>(cp)[j] = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) cp[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          float* cp = (float*)p.C + (size_t)m * p.ldc + nb;
+          if (nvalid == 32 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(cp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) cp[j] = v[j];
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MVAE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    MVAE_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    fn = (EncodeFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major matrix: `inner` contiguous elements per row, `outer` rows, row stride ld elements
+CUtensorMap make_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu box=%ux%u ptr=%p", (int)r, (unsigned long long)inner,
+             (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer, ptr);
+    throw Error(b);
+  }
+  return m;
+}
+
+template <bool A_MN, bool B_MN, int BN>
+void launch(const GemmArgs& g, cudaStream_t st, int sm_count) {
+  using L = SmemLayout<BN>;
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_type == DT_BF16;
+  p.bias = g.bias; p.addend = g.addend; p.ldadd = g.ldadd; p.add_bf16 = g.add_type == DT_BF16; p.act = g.act;
+  p.m_tiles = (g.M + BM - 1) / BM; p.n_tiles = (g.N + BN - 1) / BN; p.kb_total = (g.K + BK - 1) / BK;
+  int splits = 1;
+  if (g.accumulate) {   // split K until the grid fills the chip, keeping >= 8 k-blocks per split
+    const int tiles = p.m_tiles * p.n_tiles;
+    splits = std::max(1, std::min((2 * sm_count + tiles - 1) / tiles, p.kb_total / 8));
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.atomic_acc = g.accumulate ? 1 : 0;
+  const CUtensorMap ma = A_MN ? make_map(g.A, g.M, g.K, g.lda, 64, 64) : make_map(g.A, g.K, g.M, g.lda, 64, BM);
+  const CUtensorMap mb = B_MN ? make_map(g.B, g.N, g.K, g.ldb, 64, 64) : make_map(g.B, g.K, g.N, g.ldb, 64, BN);
+  auto kern = gemm_tc_kernel<A_MN, B_MN, BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const int grid = std::min(tiles, sm_count);
+  kern<<<grid, kThreads, L::TOTAL, st>>>(ma, mb, p);
+  count_launch();
+  MVAE_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmArgs& g) {
+  if (g.in_type != DT_BF16) return false;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
+  if ((g.lda % 8) || (g.ldb % 8)) return false;
+  if (g.accumulate && g.c_type != DT_F32) return false;
+  if (g.accumulate && (g.bias || g.addend || g.act)) return false;
+  return true;
+}
+
+void gemm_tc(const GemmArgs& g, cudaStream_t st, int sm_count) {
+  MVAE_REQUIRE(gemm_tc_supported(g), "shape / alignment not supported by the tcgen05 GEMM");
+  const bool a_mn = g.transA, b_mn = !g.transB;
+  if (!a_mn && !b_mn) launch<false, false, 128>(g, st, sm_count);
+  else if (!a_mn && b_mn) launch<false, true, 128>(g, st, sm_count);
+  else if (a_mn && !b_mn) launch<true, false, 128>(g, st, sm_count);
+  else launch<true, true, 128>(g, st, sm_count);
+}
+
+// ------------------------------------------------------------------------------------------------ self test
+// Random bf16 operands, every layout case, ragged edges, every epilogue; the checker is the SIMT GEMM.
+int gemm_tc_selftest(int device, int verbose) {
+  MVAE_CUDA(cudaSetDevice(device));
+  int sm = 0;
+  MVAE_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+  cudaStream_t st;
+  MVAE_CUDA(cudaStreamCreate(&st));
+  struct Case { int M, N, K; bool ta, tb; int epi; };   // epi: 0 plain f32, 1 bias+tanh bf16 out, 2 addend(bf16) f32 out, 3 accumulate (split-K)
+  std::vector<Case> cases;
+  const int shapes[][3] = {{128, 128, 64}, {128, 128, 256}, {256, 384, 512}, {200, 61, 96}, {77, 130, 72}, {512, 2048, 512}, {61, 256, 4096}, {8, 256, 64}, {300, 16, 128}};
+  for (auto& s : shapes)
+    for (int ta = 0; ta < 2; ++ta)
+      for (int tb = 0; tb < 2; ++tb)
+        for (int epi = 0; epi < 4; ++epi) cases.push_back({s[0], s[1], s[2], ta != 0, tb != 0, epi});
+  int failures = 0;
+  uint32_t seed = 12345u;
+  auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  for (const Case& c : cases) {
+    const int lda = ((c.ta ? c.M : c.K) + 7) / 8 * 8, ldb = ((c.tb ? c.K : c.N) + 7) / 8 * 8, ldc = (c.N + 7) / 8 * 8;
+    const size_t na = (size_t)(c.ta ? c.K : c.M) * lda, nb = (size_t)(c.tb ? c.N : c.K) * ldb, nc = (size_t)c.M * ldc;
+    std::vector<bf16> ha(na), hb(nb), hadd(nc);
+    std::vector<float> hbias(c.N), hc0(nc);
+    for (auto& x : ha) x = __float2bfloat16(rnd());
+    for (auto& x : hb) x = __float2bfloat16(rnd());
+    for (auto& x : hadd) x = __float2bfloat16(rnd());
+    for (auto& x : hbias) x = rnd();
+    for (auto& x : hc0) x = rnd();
+    bf16 *dA, *dB, *dAdd; float *dBias, *dC1, *dC2; bf16 *dCb1, *dCb2;
+    MVAE_CUDA(cudaMalloc(&dA, na * 2)); MVAE_CUDA(cudaMalloc(&dB, nb * 2)); MVAE_CUDA(cudaMalloc(&dAdd, nc * 2));
+    MVAE_CUDA(cudaMalloc(&dBias, c.N * 4)); MVAE_CUDA(cudaMalloc(&dC1, nc * 4)); MVAE_CUDA(cudaMalloc(&dC2, nc * 4));
+    MVAE_CUDA(cudaMalloc(&dCb1, nc * 2)); MVAE_CUDA(cudaMalloc(&dCb2, nc * 2));
+    MVAE_CUDA(cudaMemcpy(dA, ha.data(), na * 2, cudaMemcpyHostToDevice)); MVAE_CUDA(cudaMemcpy(dB, hb.data(), nb * 2, cudaMemcpyHostToDevice));
+    MVAE_CUDA(cudaMemcpy(dAdd, hadd.data(), nc * 2, cudaMemcpyHostToDevice)); MVAE_CUDA(cudaMemcpy(dBias, hbias.data(), c.N * 4, cudaMemcpyHostToDevice));
+    MVAE_CUDA(cudaMemcpy(dC1, hc0.data(), nc * 4, cudaMemcpyHostToDevice)); MVAE_CUDA(cudaMemcpy(dC2, hc0.data(), nc * 4, cudaMemcpyHostToDevice));
+    MVAE_CUDA(cudaMemset(dCb1, 0, nc * 2)); MVAE_CUDA(cudaMemset(dCb2, 0, nc * 2));
+    GemmArgs g; g.M = c.M; g.N = c.N; g.K = c.K; g.A = dA; g.lda = lda; g.transA = c.ta; g.B = dB; g.ldb = ldb; g.transB = c.tb; g.in_type = DT_BF16;
+    g.ldc = ldc;
+    if (c.epi == 1) { g.bias = dBias; g.act = 1; g.c_type = DT_BF16; }
+    if (c.epi == 2) { g.addend = dAdd; g.ldadd = ldc; g.add_type = DT_BF16; }
+    if (c.epi == 3) { g.accumulate = true; }
+    GemmArgs g1 = g, g2 = g;
+    g1.C = c.epi == 1 ? (void*)dCb1 : (void*)dC1;
+    g2.C = c.epi == 1 ? (void*)dCb2 : (void*)dC2;
+    gemm_tc(g1, st, sm);
+    gemm_simt(g2, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { fprintf(stderr, "selftest: kernel failure %s on M%d N%d K%d ta%d tb%d epi%d\n", cudaGetErrorString(e), c.M, c.N, c.K, c.ta, c.tb, c.epi); return 100; }
+    std::vector<float> r1(nc), r2(nc);
+    if (c.epi == 1) {
+      std::vector<bf16> t1(nc), t2(nc);
+      MVAE_CUDA(cudaMemcpy(t1.data(), dCb1, nc * 2, cudaMemcpyDeviceToHost)); MVAE_CUDA(cudaMemcpy(t2.data(), dCb2, nc * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < nc; ++i) { r1[i] = __bfloat162float(t1[i]); r2[i] = __bfloat162float(t2[i]); }
+    } else {
+      MVAE_CUDA(cudaMemcpy(r1.data(), dC1, nc * 4, cudaMemcpyDeviceToHost)); MVAE_CUDA(cudaMemcpy(r2.data(), dC2, nc * 4, cudaMemcpyDeviceToHost));
+    }
+    double max_err = 0, max_ref = 0;
+    for (int m = 0; m < c.M; ++m)
+      for (int n = 0; n < c.N; ++n) {
+        double a = r1[(size_t)m * ldc + n], b = r2[(size_t)m * ldc + n];
+        max_err = std::max(max_err, fabs(a - b)); max_ref = std::max(max_ref, fabs(b));
+      }
+    const double tol = (c.epi == 1 ? 1e-2 : 2e-3) * std::max(1.0, max_ref);
+    const bool ok = max_err <= tol;
+    if (!ok) ++failures;
+    if (verbose || !ok)
+      printf("gemm_tc selftest M=%d N=%d K=%d transA=%d transB=%d epi=%d : max_err=%.3e (ref max %.3e) %s\n", c.M, c.N, c.K, (int)c.ta, (int)c.tb,
+             c.epi, max_err, max_ref, ok ? "ok" : "FAIL");
+    cudaFree(dA); cudaFree(dB); cudaFree(dAdd); cudaFree(dBias); cudaFree(dC1); cudaFree(dC2); cudaFree(dCb1); cudaFree(dCb2);
+  }
+  cudaStreamDestroy(st);
+  printf("gemm_tc selftest: %d cases, %d failures\n", (int)cases.size(), failures);
+  return failures;
+}
+
+}  // namespace mvae

@@ -1,0 +1,555 @@
+// model.cu -- orchestration of the MIDI-VAE hot path on one B200.
+//
+// What the reference runs as one Keras train_function / predict_function (graph built in
+// vae_definition.py:212-441, encoder :443-516, decoder :519-645, style head :730-734; driven from
+// vae_training.py:804-809 and vae_evaluation.py:2180-2181,2474-2483) is laid out here as an explicit,
+// fixed sequence of kernel launches on one CUDA stream:
+//   rolls -> dense padded time-major inputs -> input projections (one GEMM per layer over the whole
+//   sequence) -> recurrences (h U + gate math; step-streamed or persistent) -> latent head -> decoder
+//   initial states (one fused GEMM for all 2*(nd+2) Denses) -> decoder recurrences -> output heads +
+//   Keras losses -> reverse-time sweeps -> batched weight-gradient GEMMs -> [NCCL all-reduce] -> Adam.
+// The hand-derived backward is restated (and checked against autograd) in oracle/manual_bptt.py.
+#include "model.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace mvae {
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+void* Model::alloc(size_t bytes) {
+  void* p = nullptr;
+  bytes = (bytes + 255) / 256 * 256;
+  if (bytes == 0) bytes = 256;
+  MVAE_CUDA(cudaMalloc(&p, bytes));
+  MVAE_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
+  ws_used += bytes;
+  allocs_.push_back(p);
+  return p;
+}
+
+int Model::add_param(const std::string& name, int rows, int cols) {
+  ParamT t;
+  t.name = name; t.rows = rows; t.cols = cols; t.ld = round_up(cols, 8);
+  t.off = arena_n;
+  arena_n += (size_t)round_up(rows * t.ld, 64);
+  ptab.push_back(t);
+  return (int)ptab.size() - 1;
+}
+
+// Internal arena order.  Names match oracle/midivae_oracle.py::param_specs except that the 2*(nd+2)
+// decoder initial-state Denses (vae_definition.py:563-568,599-604,637-642) are stored column-fused as
+// dec_init/kernel (Q, nS*H) so that they are ONE GEMM; midi_vae_b200/weights.py maps both ways.
+void Model::build_params() {
+  auto add_rec = [&](Rec& r, const std::string& nm, int steps, int Din, int ldin, int variant, bool keras) {
+    r.name = nm; r.steps = steps; r.Din = Din; r.ldin = ldin; r.variant = variant;
+    r.iW = add_param(nm + "/kernel", Din, G);
+    if (keras) { r.iU = add_param(nm + "/recurrent_kernel", H, G); r.ib = add_param(nm + "/bias", 1, G); }
+    else { r.ib = add_param(nm + "/bias", 1, G); r.iU = add_param(nm + "/recurrent_kernel", H, G); }
+  };
+  enc_pitch.resize(ne);
+  for (int k = 0; k < ne; ++k) add_rec(enc_pitch[k], "lstm_" + std::to_string(k + 1), T, k == 0 ? Dp : H, k == 0 ? PD : H, MVAE_CELL_STANDARD, true);
+  add_rec(enc_instr, "lstm_meta_instrument", Ti, Di, ID, MVAE_CELL_STANDARD, true);
+  add_rec(enc_vel, "lstm_meta_velocity", T, 1, VD, MVAE_CELL_STANDARD, true);
+  iWa = add_param("extra_instrument_after_concat_layer/kernel", 3 * H, H);
+  iba = add_param("extra_instrument_after_concat_layer/bias", 1, H);
+  if (cfg.extra_layer) { iWe = add_param("extra_layer/kernel", H, H); ibe = add_param("extra_layer/bias", 1, H); }
+  iWmu = add_param("z_mean/kernel", half, L); ibmu = add_param("z_mean/bias", 1, L);
+  iWlv = add_param("z_log_var/kernel", H - half, L); iblv = add_param("z_log_var/bias", 1, L);
+  iWinit = add_param("dec_init/kernel", Q, nS * H); ibinit = add_param("dec_init/bias", 1, nS * H);
+  dec_notes.resize(nd);
+  for (int k = 0; k < nd; ++k)
+    add_rec(dec_notes[k], "notes/cell_" + std::to_string(k + 1), T, k == 0 ? Dp : H, k == 0 ? PD : H, cfg.dec_cell_variant, false);
+  iWy = add_param("notes/out/kernel", H, Dp); iby = add_param("notes/out/bias", 1, Dp);
+  add_rec(dec_instr, "meta_instrument/cell", Ti, Di, ID, cfg.dec_cell_variant, false);
+  iWio = add_param("meta_instrument/out/kernel", H, Di); ibio = add_param("meta_instrument/out/bias", 1, Di);
+  add_rec(dec_vel, "meta_velocity/cell", T, 1, VD, cfg.dec_cell_variant, false);
+  // (H,1) stored as the row vector (1,H): same dense bytes, and the N = 1 head is a row-dot, not a GEMM
+  iWvo = add_param("meta_velocity/out/kernel", 1, H); ibvo = add_param("meta_velocity/out/bias", 1, 1);
+  ld_pn = ptab[iWy].ld; ld_pi = ptab[iWio].ld; ld_pv = 8;
+}
+
+void Model::build_workspace() {
+  const size_t a = asz();
+  const size_t n = NB;
+  auto rec_bufs = [&](Rec& r, bool need_dhext) {
+    r.xw = alloc((size_t)r.steps * n * G * a);
+    r.gates = alloc((size_t)r.steps * n * G * a);
+    r.hseq = alloc((size_t)(r.steps + 1) * n * H * a);
+    r.cseq = alloc((size_t)(r.steps + 1) * n * H * a);
+    if (need_dhext) r.dhext = alloc((size_t)r.steps * n * H * a);
+  };
+  for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
+  rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
+  for (int k = 0; k < nd; ++k) rec_bufs(dec_notes[k], true);
+  rec_bufs(dec_instr, true); rec_bufs(dec_vel, true);
+
+  d_pitch = (uint8_t*)alloc(n * T); d_target = (uint8_t*)alloc(n * T); d_instr = (uint8_t*)alloc(n * Ti);
+  d_style = (uint8_t*)alloc(n); d_song_start = (uint8_t*)alloc(n);
+  d_vel = (float*)alloc(n * T * 4); d_hist = (float*)alloc(n * L * 4); d_eps = (float*)alloc(n * L * 4); d_w = (float*)alloc(n * T * 4);
+  Xp_ext = alloc((size_t)(T + 1) * n * PD * a); Yp_ext = alloc((size_t)(T + 1) * n * PD * a);
+  Xi_ext = alloc((size_t)(Ti + 1) * n * ID * a); Xv_ext = alloc((size_t)(T + 1) * n * VD * a);
+  pre = (float*)alloc(n * G * 4); c_run = (float*)alloc(n * H * 4); dh_run = (float*)alloc(n * H * 4); dc_run = (float*)alloc(n * H * 4);
+  xstep = alloc(n * 64 * a);
+  u = alloc(n * 3 * H * a); a1 = alloc(n * H * a); e = alloc(n * H * a); q = alloc(n * ldq * a);
+  S = alloc(n * nS * H * a); dS = alloc(n * nS * H * a); dSpre = alloc(n * nS * H * a); dq = alloc(n * ldq * a);
+  dmu = alloc(n * ldl * a); dlv = alloc(n * ldl * a); de = alloc(n * H * a); dpre_e = alloc(n * H * a); da1 = alloc(n * H * a);
+  dpre_a = alloc(n * H * a); du = alloc(n * 3 * H * a);
+  mu = (float*)alloc(n * ldl * 4); lv = (float*)alloc(n * ldl * 4); z = (float*)alloc(n * ldl * 4); style_probs = (float*)alloc(n * C * 4);
+  Pn = (float*)alloc((size_t)T * n * ld_pn * 4); Pi = (float*)alloc((size_t)Ti * n * ld_pi * 4); Pv = (float*)alloc((size_t)T * n * ld_pv * 4);
+  dlog_n = alloc((size_t)T * n * ld_pn * a); dlog_i = alloc((size_t)Ti * n * ld_pi * a); dlog_v = alloc((size_t)T * n * ld_pv * a);
+  acc = (double*)alloc(ACC_COUNT * 8); d_metrics = (float*)alloc(MVAE_NUM_METRICS * 4);
+  o_y = (float*)alloc((size_t)n * T * Dp * 4); o_i = (float*)alloc((size_t)n * Ti * Di * 4); o_v = (float*)alloc((size_t)n * T * 4);
+  o_z = (float*)alloc((size_t)n * L * 4 * 3); o_pitch = (uint8_t*)alloc(n * T); o_instr = (uint8_t*)alloc(n * Ti);
+  // pinned staging: inputs + the largest output set
+  pin_bytes = n * T * 2 + n * Ti + n * 2 + (size_t)n * T * 4 * 2 + (size_t)n * L * 4 * 3 + (size_t)n * T * Dp * 4 + (size_t)n * Ti * Di * 4 +
+              (size_t)n * T * 4 + (size_t)n * C * 4 + 4096;
+  MVAE_CUDA(cudaMallocHost((void**)&pin, pin_bytes));
+}
+
+Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
+  MVAE_REQUIRE(c.input_length > 0 && c.lstm_size > 0 && c.latent_rep_size > 0, "input_length, lstm_size, latent_rep_size must be > 0 (vae_definition.py:179-182)");
+  MVAE_REQUIRE(c.num_layers_encoder > 0 && c.num_layers_decoder > 0, "num_layers must be > 0 (vae_definition.py:177-178)");
+  MVAE_REQUIRE(c.beta > 0, "beta must be > 0 (vae_definition.py:183)");
+  MVAE_REQUIRE(c.max_batch > 0, "max_batch must be > 0");
+  MVAE_REQUIRE(c.input_dim > 0 && c.input_dim <= 64, "input_dim must be in 1..64");
+  MVAE_REQUIRE(c.meta_instrument_dim > 0 && c.meta_instrument_dim <= 64, "meta_instrument_dim must be in 1..64");
+  MVAE_REQUIRE(c.num_composers >= 1 && c.num_composers <= c.latent_rep_size, "num_composers must be in 1..latent_rep_size");
+  MVAE_REQUIRE(c.split_lstm_vector == 1, "only split_lstm_vector=True (settings.py:139) is implemented");
+  MVAE_REQUIRE(c.precision == MVAE_PREC_FP32 || c.precision == MVAE_PREC_BF16, "precision");
+  MVAE_REQUIRE(c.decoder_feedback >= 0 && c.decoder_feedback <= 2, "decoder_feedback");
+  if (c.precision == MVAE_PREC_BF16) MVAE_REQUIRE(c.lstm_size % 16 == 0, "bf16 precision needs lstm_size % 16 == 0");
+  MVAE_CUDA(cudaSetDevice(dev));
+  int major = 0;
+  MVAE_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  MVAE_REQUIRE(major == 10, "libmidivae.so is built for sm_100a (B200) only");
+  MVAE_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  MVAE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  act = c.precision == MVAE_PREC_FP32 ? DT_F32 : DT_BF16;
+  T = c.input_length; H = c.lstm_size; L = c.latent_rep_size; Dp = c.input_dim; Di = c.meta_instrument_dim; Ti = c.meta_instrument_length;
+  C = c.num_composers; ne = c.num_layers_encoder; nd = c.num_layers_decoder; G = 4 * H; NB = c.max_batch;
+  PD = round_up(Dp, 8); ID = round_up(Di, 8); VD = 8;
+  ldl = round_up(L, 8); Q = c.history ? 2 * L : L; ldq = round_up(Q, 8); nS = 2 * (nd + 2); half = H / 2;
+  build_params();
+  P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
+  if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
+  build_workspace();
+  MVAE_CUDA(cudaStreamSynchronize(stream));
+}
+
+Model::~Model() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  for (auto& ev : evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  if (nccl_comm) nccl_comm_destroy(nccl_comm);
+  for (void* p : allocs_) cudaFree(p);
+  if (pin) cudaFreeHost(pin);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void Model::commit_params() {
+  if (Pb) k_f32_to_bf16((long)arena_n, P, Pb, st);
+}
+
+// --------------------------------------------------------------------------------------------- profiling
+void Model::prof_begin(int cls) {
+  if (!profiling) return;
+  Ev ev; ev.cls = cls;
+  MVAE_CUDA(cudaEventCreate(&ev.a)); MVAE_CUDA(cudaEventCreate(&ev.b));
+  MVAE_CUDA(cudaEventRecord(ev.a, st));
+  evs.push_back(ev);
+}
+void Model::prof_end() {
+  if (!profiling) return;
+  MVAE_CUDA(cudaEventRecord(evs.back().b, st));
+}
+void Model::prof_collect() {
+  for (int i = 0; i < PC_COUNT; ++i) { prof_ms[i] = 0; prof_n[i] = 0; }
+  for (auto& ev : evs) {
+    MVAE_CUDA(cudaEventSynchronize(ev.b));
+    float ms = 0;
+    MVAE_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    prof_ms[ev.cls] += ms; prof_n[ev.cls] += 1;
+    cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+  }
+  evs.clear();
+}
+
+// --------------------------------------------------------------------------------------------- GEMM routing
+void Model::gemm(GemmArgs g) {
+  g.in_type = act;
+  if (act == DT_BF16 && gemm_tc_supported(g)) gemm_tc(g, st, sm_count);
+  else gemm_simt(g, st);
+}
+
+// --------------------------------------------------------------------------------------------- batch plumbing
+void Model::check_batch(const mvae_batch& b, bool need_style) const {
+  MVAE_REQUIRE(b.n >= 1 && b.n <= NB, "mini-batch size must be in 1..max_batch");
+  MVAE_REQUIRE(b.pitch && b.instr && b.velocity, "pitch, instr and velocity rolls are required");
+  if (need_style) MVAE_REQUIRE(b.style != nullptr, "style classes are required for train/evaluate");
+}
+
+// host batch -> pinned staging -> device input buffers; returns the device-pointer view
+mvae_batch Model::upload(const mvae_batch& hb, const uint8_t* song_start) {
+  mvae_batch d{}; d.n = hb.n;
+  const size_t n = hb.n;
+  char* p = pin;
+  auto stage = [&](const void* src, void* dst, size_t bytes) -> const void* {
+    if (!src) return nullptr;
+    memcpy(p, src, bytes);
+    MVAE_CUDA(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, st));
+    p += (bytes + 15) / 16 * 16;
+    h2d_bytes += bytes;
+    return dst;
+  };
+  d.pitch = (const uint8_t*)stage(hb.pitch, d_pitch, n * T);
+  d.target = (const uint8_t*)stage(hb.target, d_target, n * T);
+  d.instr = (const uint8_t*)stage(hb.instr, d_instr, n * Ti);
+  d.velocity = (const float*)stage(hb.velocity, d_vel, n * T * 4);
+  d.style = (const uint8_t*)stage(hb.style, d_style, n);
+  d.history = (const float*)stage(hb.history, d_hist, n * L * 4);
+  d.eps = (const float*)stage(hb.eps, d_eps, n * L * 4);
+  d.w_notes = (const float*)stage(hb.w_notes, d_w, n * T * 4);
+  if (song_start) stage(song_start, d_song_start, n);
+  return d;
+}
+
+void Model::prepare_inputs(const mvae_batch& b, bool need_target) {
+  prof_begin(PC_POINTWISE);
+  const bool distinct_target = need_target && b.target && b.target != b.pitch;
+  k_expand_inputs(act, b.n, T, Ti, PD, ID, VD, b.pitch, b.target, b.instr, b.velocity, Xp_ext, distinct_target ? Yp_ext : nullptr, Xi_ext, Xv_ext, st);
+  Y_ext_cur = distinct_target ? Yp_ext : Xp_ext;
+  prof_end();
+}
+
+// --------------------------------------------------------------------------------------------- one recurrence, forward
+// kind: IN_DENSE  X = (steps, n, ldin) act rows;  IN_RANK1  X = per-row scalar (stride VD);  IN_NONE  x == 0 (as_wired decoder)
+void Model::rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, const void* c0, int ld0) {
+  const long rows = (long)r.steps * n;
+  prof_begin(PC_GEMM);
+  if (kind == IN_DENSE) {
+    GemmArgs g; g.M = (int)rows; g.N = G; g.K = r.Din; g.A = X; g.lda = r.ldin; g.B = W(r.iW); g.ldb = ld(r.iW);
+    g.C = r.xw; g.ldc = G; g.c_type = act; g.bias = Wf(r.ib);
+    gemm(g);
+  } else if (kind == IN_RANK1) {
+    k_rank1_rows(act, r.xw, rows, G, X, VD, Wf(r.iW), Wf(r.ib), st);
+  } else {
+    k_fill_rows(act, r.xw, rows, G, Wf(r.ib), st);
+  }
+  prof_end();
+  prof_begin(PC_REC_FWD);
+  if (h0) {
+    k_copy2d(act, act, n, H, h0, ld0, r.hseq, H, st);
+    k_copy2d(act, act, n, H, c0, ld0, r.cseq, H, st);
+    k_copy2d(act, DT_F32, n, H, c0, ld0, c_run, H, st);
+  } else {
+    MVAE_CUDA(cudaMemsetAsync(r.hseq, 0, (size_t)n * H * asz(), st));
+    MVAE_CUDA(cudaMemsetAsync(r.cseq, 0, (size_t)n * H * asz(), st));
+    MVAE_CUDA(cudaMemsetAsync(c_run, 0, (size_t)n * H * 4, st));
+  }
+  rec_steps_forward(r, n, 0, r.steps);
+  prof_end();
+}
+
+// steps [t0, t1): pre = h_{t-1} U + xw_t ; gate math  (step-streamed form)
+void Model::rec_steps_forward(Rec& r, int n, int t0, int t1) {
+  for (int t = t0; t < t1; ++t) {
+    GemmArgs g; g.M = n; g.N = G; g.K = H; g.A = slab(r.hseq, t, (long)n * H); g.lda = H; g.B = W(r.iU); g.ldb = ld(r.iU);
+    g.C = pre; g.ldc = G; g.c_type = DT_F32; g.addend = slab(r.xw, t, (long)n * G); g.ldadd = G; g.add_type = act;
+    gemm(g);
+    k_cell_fwd(act, cc(r.variant), n, H, pre, c_run, slab(r.gates, t, (long)n * G), slab(r.cseq, t + 1, (long)n * H),
+               slab(r.hseq, t + 1, (long)n * H), st);
+  }
+}
+
+// --------------------------------------------------------------------------------------------- one recurrence, backward
+void Model::rec_backward(Rec& r, int n, int kind, const void* X, bool use_dhext, const void* dh_last, int ld_last, bool need_dx, void* dx_out,
+                         void* dS_h, void* dS_c, int ldS) {
+  const long rows = (long)r.steps * n;
+  void* dG = r.xw;  // the pre-activation buffer is dead after the forward sweep
+  prof_begin(PC_REC_BWD);
+  MVAE_CUDA(cudaMemsetAsync(dh_run, 0, (size_t)n * H * 4, st));
+  MVAE_CUDA(cudaMemsetAsync(dc_run, 0, (size_t)n * H * 4, st));
+  for (int t = r.steps - 1; t >= 0; --t) {
+    k_cell_bwd(act, cc(r.variant), n, H, dh_run, use_dhext ? slab(r.dhext, t, (long)n * H) : nullptr, t == r.steps - 1 ? dh_last : nullptr,
+               ld_last, act, dc_run, slab(r.gates, t, (long)n * G), slab(r.cseq, t, (long)n * H), slab(r.cseq, t + 1, (long)n * H),
+               slab(dG, t, (long)n * G), st);
+    GemmArgs g; g.M = n; g.N = H; g.K = G; g.A = slab(dG, t, (long)n * G); g.lda = G; g.B = W(r.iU); g.ldb = ld(r.iU); g.transB = true;
+    g.C = dh_run; g.ldc = H; g.c_type = DT_F32;
+    gemm(g);
+  }
+  if (dS_h) {
+    k_copy2d(DT_F32, act, n, H, dh_run, H, dS_h, ldS, st);
+    k_copy2d(DT_F32, act, n, H, dc_run, H, dS_c, ldS, st);
+  }
+  prof_end();
+  prof_begin(PC_GEMM);
+  {  // dU += Hprev^T dG
+    GemmArgs g; g.M = H; g.N = G; g.K = (int)rows; g.A = r.hseq; g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
+    g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
+    gemm(g);
+  }
+  if (kind == IN_DENSE) {  // dW += X^T dG
+    GemmArgs g; g.M = r.Din; g.N = G; g.K = (int)rows; g.A = X; g.lda = r.ldin; g.transA = true; g.B = dG; g.ldb = G;
+    g.C = Gp(r.iW); g.ldc = ld(r.iW); g.c_type = DT_F32; g.accumulate = true;
+    gemm(g);
+  } else if (kind == IN_RANK1) {
+    k_colsum(act, rows, G, G, dG, X, VD, Gp(r.iW), st);
+  }
+  k_colsum(act, rows, G, G, dG, nullptr, 0, Gp(r.ib), st);
+  if (need_dx) {  // dx = dG W^T
+    GemmArgs g; g.M = (int)rows; g.N = r.Din; g.K = G; g.A = dG; g.lda = G; g.B = W(r.iW); g.ldb = ld(r.iW); g.transB = true;
+    g.C = dx_out; g.ldc = H; g.c_type = act;
+    gemm(g);
+  }
+  prof_end();
+}
+
+// --------------------------------------------------------------------------------------------- encoder (vae_definition.py:443-516)
+void Model::encoder_forward(int n) {
+  for (int k = 0; k < ne; ++k) {
+    const void* X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
+    rec_forward(enc_pitch[k], n, IN_DENSE, X, nullptr, nullptr, 0);
+  }
+  rec_forward(enc_instr, n, IN_DENSE, slab(Xi_ext, 1, (long)n * ID), nullptr, nullptr, 0);
+  rec_forward(enc_vel, n, IN_RANK1, slab(Xv_ext, 1, (long)n * VD), nullptr, nullptr, 0);
+}
+
+// concat -> Dense(tanh) -> Dense(tanh) -> split -> z_mean / z_log_var -> KL -> z (vae_definition.py:468-515, 29-37)
+void Model::head_forward(const mvae_batch& b, bool with_style_loss) {
+  const int n = b.n;
+  prof_begin(PC_POINTWISE);
+  k_concat3(act, n, H, slab(enc_pitch[ne - 1].hseq, T, (long)n * H), slab(enc_instr.hseq, Ti, (long)n * H), slab(enc_vel.hseq, T, (long)n * H), u, st);
+  prof_end();
+  prof_begin(PC_GEMM);
+  { GemmArgs g; g.M = n; g.N = H; g.K = 3 * H; g.A = u; g.lda = 3 * H; g.B = W(iWa); g.ldb = ld(iWa); g.C = a1; g.ldc = H; g.c_type = act;
+    g.bias = Wf(iba); g.act = 1; gemm(g); }
+  void* ecur = a1;
+  if (cfg.extra_layer) {
+    GemmArgs g; g.M = n; g.N = H; g.K = H; g.A = a1; g.lda = H; g.B = W(iWe); g.ldb = ld(iWe); g.C = e; g.ldc = H; g.c_type = act;
+    g.bias = Wf(ibe); g.act = 1; gemm(g);
+    ecur = e;
+  }
+  e_cur = ecur;
+  { GemmArgs g; g.M = n; g.N = L; g.K = half; g.A = ecur; g.lda = H; g.B = W(iWmu); g.ldb = ld(iWmu); g.C = mu; g.ldc = ldl; g.c_type = DT_F32;
+    g.bias = Wf(ibmu); gemm(g); }
+  { GemmArgs g; g.M = n; g.N = L; g.K = H - half; g.A = (const char*)ecur + (size_t)half * asz(); g.lda = H; g.B = W(iWlv); g.ldb = ld(iWlv);
+    g.C = lv; g.ldc = ldl; g.c_type = DT_F32; g.bias = Wf(iblv); gemm(g); }
+  prof_end();
+  prof_begin(PC_POINTWISE);
+  k_latent_fwd(act, n, L, ldl, mu, lv, b.eps, b.history, cfg.history, z, q, ldq, cfg.beta, cfg.prior_mean, cfg.prior_std, acc, st);
+  k_style_head(n, C, z, ldl, with_style_loss ? b.style : nullptr, style_probs, acc, st);
+  prof_end();
+}
+
+// decoder (vae_definition.py:519-645): q = [z | history] must already be in this->q
+void Model::decoder_forward(const mvae_batch& b, int feedback) {
+  const int n = b.n;
+  prof_begin(PC_GEMM);
+  { GemmArgs g; g.M = n; g.N = nS * H; g.K = Q; g.A = q; g.lda = ldq; g.B = W(iWinit); g.ldb = ld(iWinit); g.C = S; g.ldc = nS * H; g.c_type = act;
+    g.bias = Wf(ibinit); g.act = 1; gemm(g); }
+  prof_end();
+  if (feedback == MVAE_FB_FREE_RUNNING) { decoder_stepwise(n); return; }
+  const bool tf = feedback == MVAE_FB_TEACHER_FORCED;
+  auto st1 = [&](int r) { return (const char*)S + (size_t)(2 * r) * H * asz(); };
+  auto st2 = [&](int r) { return (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
+  for (int k = 0; k < nd; ++k) {
+    if (k == 0) rec_forward(dec_notes[0], n, tf ? IN_DENSE : IN_NONE, tf ? Y_ext_cur : nullptr, st1(0), st2(0), nS * H);
+    else rec_forward(dec_notes[k], n, IN_DENSE, slab(dec_notes[k - 1].hseq, 1, (long)n * H), st1(k), st2(k), nS * H);
+  }
+  rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
+  rec_forward(dec_vel, n, tf ? IN_RANK1 : IN_NONE, tf ? Xv_ext : nullptr, st1(nd + 1), st2(nd + 1), nS * H);
+  prof_begin(PC_GEMM);
+  { GemmArgs g; g.M = T * n; g.N = Dp; g.K = H; g.A = slab(dec_notes[nd - 1].hseq, 1, (long)n * H); g.lda = H; g.B = W(iWy); g.ldb = ld(iWy);
+    g.C = Pn; g.ldc = ld_pn; g.c_type = DT_F32; g.bias = Wf(iby); gemm(g); }
+  { GemmArgs g; g.M = Ti * n; g.N = Di; g.K = H; g.A = slab(dec_instr.hseq, 1, (long)n * H); g.lda = H; g.B = W(iWio); g.ldb = ld(iWio);
+    g.C = Pi; g.ldc = ld_pi; g.c_type = DT_F32; g.bias = Wf(ibio); gemm(g); }
+  k_rowdot(act, (long)T * n, H, slab(dec_vel.hseq, 1, (long)n * H), Wf(iWvo), Wf(ibvo), Pv, ld_pv, st);
+  prof_end();
+}
+
+// free-running decode (inference only): x_t = previous prediction, one step at a time
+void Model::decoder_stepwise(int n) {
+  auto st1 = [&](int r) { return (const char*)S + (size_t)(2 * r) * H * asz(); };
+  auto st2 = [&](int r) { return (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
+  auto init = [&](Rec& r, int sidx) {
+    k_copy2d(act, act, n, H, st1(sidx), nS * H, r.hseq, H, st);
+    k_copy2d(act, act, n, H, st2(sidx), nS * H, r.cseq, H, st);
+  };
+  auto step = [&](Rec& r, int t, int kind, const void* x, int ldx) {  // one cell step with input x (n rows) or none (t == 0 start vector = 0)
+    void* xw_t = slab(r.xw, t, (long)n * G);
+    if (kind == IN_DENSE) {
+      GemmArgs g; g.M = n; g.N = G; g.K = r.Din; g.A = x; g.lda = ldx; g.B = W(r.iW); g.ldb = ld(r.iW); g.C = xw_t; g.ldc = G; g.c_type = act;
+      g.bias = Wf(r.ib); gemm(g);
+    } else if (kind == IN_RANK1) {
+      k_rank1_rows(act, xw_t, n, G, x, ldx, Wf(r.iW), Wf(r.ib), st);
+    } else {
+      k_fill_rows(act, xw_t, n, G, Wf(r.ib), st);
+    }
+    k_copy2d(act, DT_F32, n, H, slab(r.cseq, t, (long)n * H), H, c_run, H, st);
+    rec_steps_forward(r, n, t, t + 1);
+  };
+  prof_begin(PC_REC_FWD);
+  // notes
+  for (int k = 0; k < nd; ++k) init(dec_notes[k], k);
+  for (int t = 0; t < T; ++t) {
+    if (t == 0) step(dec_notes[0], 0, IN_NONE, nullptr, 0);
+    else {
+      k_copy2d(DT_F32, act, n, PD, Pn + (size_t)(t - 1) * n * ld_pn, ld_pn, xstep, PD, st);
+      step(dec_notes[0], t, IN_DENSE, xstep, PD);
+    }
+    for (int k = 1; k < nd; ++k) step(dec_notes[k], t, IN_DENSE, slab(dec_notes[k - 1].hseq, t + 1, (long)n * H), H);
+    float* Pt = Pn + (size_t)t * n * ld_pn;
+    GemmArgs g; g.M = n; g.N = Dp; g.K = H; g.A = slab(dec_notes[nd - 1].hseq, t + 1, (long)n * H); g.lda = H; g.B = W(iWy); g.ldb = ld(iWy);
+    g.C = Pt; g.ldc = ld_pn; g.c_type = DT_F32; g.bias = Wf(iby); gemm(g);
+    k_softmax_ce(act, 1, n, Dp, Pt, ld_pn, nullptr, nullptr, nullptr, 0.f, nullptr, ld_pn, acc, ACC_CE_NOTES, ACC_ACC_NOTES, st);
+  }
+  // instrument
+  init(dec_instr, nd);
+  for (int t = 0; t < Ti; ++t) {
+    if (t == 0) step(dec_instr, 0, IN_NONE, nullptr, 0);
+    else {
+      k_copy2d(DT_F32, act, n, ID, Pi + (size_t)(t - 1) * n * ld_pi, ld_pi, xstep, ID, st);
+      step(dec_instr, t, IN_DENSE, xstep, ID);
+    }
+    float* Pt = Pi + (size_t)t * n * ld_pi;
+    GemmArgs g; g.M = n; g.N = Di; g.K = H; g.A = slab(dec_instr.hseq, t + 1, (long)n * H); g.lda = H; g.B = W(iWio); g.ldb = ld(iWio);
+    g.C = Pt; g.ldc = ld_pi; g.c_type = DT_F32; g.bias = Wf(ibio); gemm(g);
+    k_softmax_ce(act, 1, n, Di, Pt, ld_pi, nullptr, nullptr, nullptr, 0.f, nullptr, ld_pi, acc, ACC_CE_INSTR, ACC_ACC_INSTR, st);
+  }
+  // velocity
+  init(dec_vel, nd + 1);
+  for (int t = 0; t < T; ++t) {
+    if (t == 0) step(dec_vel, 0, IN_NONE, nullptr, 0);
+    else {
+      k_copy2d(DT_F32, act, n, 1, Pv + (size_t)(t - 1) * n * ld_pv, ld_pv, xstep, VD, st);
+      step(dec_vel, t, IN_RANK1, xstep, VD);
+    }
+    float* Pt = Pv + (size_t)t * n * ld_pv;
+    k_rowdot(act, n, H, slab(dec_vel.hseq, t + 1, (long)n * H), Wf(iWvo), Wf(ibvo), Pt, ld_pv, st);
+    k_sigmoid_mse(act, 1, n, Pt, ld_pv, nullptr, 0.f, nullptr, ld_pv, acc, st);
+  }
+  prof_end();
+  stepwise_done = true;
+}
+
+// softmax / sigmoid heads + Keras losses; train => also the gradients wrt the logits
+void Model::losses(const mvae_batch& b, bool train) {
+  const int n = b.n;
+  prof_begin(PC_POINTWISE);
+  k_count_nonzero(b.w_notes, (long)n * T, acc, st);
+  const uint8_t* tgt = b.target ? b.target : b.pitch;
+  k_softmax_ce(act, T, n, Dp, Pn, ld_pn, tgt, b.w_notes, acc + ACC_WNZ, cfg.notes_weight, train ? dlog_n : nullptr, ld_pn, acc, ACC_CE_NOTES,
+               ACC_ACC_NOTES, st);
+  k_softmax_ce(act, Ti, n, Di, Pi, ld_pi, b.instr, nullptr, nullptr, cfg.meta_instrument_weight, train ? dlog_i : nullptr, ld_pi, acc, ACC_CE_INSTR,
+               ACC_ACC_INSTR, st);
+  k_sigmoid_mse(act, T, n, Pv, ld_pv, b.velocity, cfg.meta_velocity_weight, train ? dlog_v : nullptr, ld_pv, acc, st);
+  k_finalize_metrics(acc, n, T, Ti, cfg.notes_weight, cfg.meta_instrument_weight, cfg.meta_velocity_weight, cfg.composer_weight, d_metrics, st);
+  prof_end();
+}
+
+// --------------------------------------------------------------------------------------------- backward
+void Model::backward(const mvae_batch& b) {
+  const int n = b.n;
+  const bool tf = cfg.decoder_feedback == MVAE_FB_TEACHER_FORCED;
+  MVAE_CUDA(cudaMemsetAsync(Gr, 0, arena_n * 4, st));
+  // ---- output heads
+  prof_begin(PC_GEMM);
+  Rec& top = dec_notes[nd - 1];
+  { GemmArgs g; g.M = H; g.N = Dp; g.K = T * n; g.A = slab(top.hseq, 1, (long)n * H); g.lda = H; g.transA = true; g.B = dlog_n; g.ldb = ld_pn;
+    g.C = Gp(iWy); g.ldc = ld(iWy); g.c_type = DT_F32; g.accumulate = true; gemm(g); }
+  k_colsum(act, (long)T * n, Dp, ld_pn, dlog_n, nullptr, 0, Gp(iby), st);
+  { GemmArgs g; g.M = T * n; g.N = H; g.K = Dp; g.A = dlog_n; g.lda = ld_pn; g.B = W(iWy); g.ldb = ld(iWy); g.transB = true;
+    g.C = top.dhext; g.ldc = H; g.c_type = act; gemm(g); }
+  { GemmArgs g; g.M = H; g.N = Di; g.K = Ti * n; g.A = slab(dec_instr.hseq, 1, (long)n * H); g.lda = H; g.transA = true; g.B = dlog_i; g.ldb = ld_pi;
+    g.C = Gp(iWio); g.ldc = ld(iWio); g.c_type = DT_F32; g.accumulate = true; gemm(g); }
+  k_colsum(act, (long)Ti * n, Di, ld_pi, dlog_i, nullptr, 0, Gp(ibio), st);
+  { GemmArgs g; g.M = Ti * n; g.N = H; g.K = Di; g.A = dlog_i; g.lda = ld_pi; g.B = W(iWio); g.ldb = ld(iWio); g.transB = true;
+    g.C = dec_instr.dhext; g.ldc = H; g.c_type = act; gemm(g); }
+  prof_end();
+  // velocity head (N = 1): rank-1 forms instead of GEMMs
+  prof_begin(PC_POINTWISE);
+  k_colsum(act, (long)T * n, H, H, slab(dec_vel.hseq, 1, (long)n * H), dlog_v, ld_pv, Gp(iWvo), st);   // dWv[j] = sum_r dlog[r] h[r,j]
+  k_colsum(act, (long)T * n, 1, ld_pv, dlog_v, nullptr, 0, Gp(ibvo), st);
+  k_rank1_rows(act, dec_vel.dhext, (long)T * n, H, dlog_v, ld_pv, Wf(iWvo), nullptr, st);              // dh[r,:] = dlog[r] * Wv
+  prof_end();
+  // ---- decoder recurrences (top layer first)
+  auto dS1 = [&](int r) { return (char*)dS + (size_t)(2 * r) * H * asz(); };
+  auto dS2 = [&](int r) { return (char*)dS + (size_t)(2 * r + 1) * H * asz(); };
+  for (int k = nd - 1; k >= 0; --k) {
+    const void* X = k == 0 ? (tf ? Y_ext_cur : nullptr) : slab(dec_notes[k - 1].hseq, 1, (long)n * H);
+    int kind = k == 0 ? (tf ? IN_DENSE : IN_NONE) : IN_DENSE;
+    rec_backward(dec_notes[k], n, kind, X, true, nullptr, 0, k > 0, k > 0 ? dec_notes[k - 1].dhext : nullptr, dS1(k), dS2(k), nS * H);
+  }
+  rec_backward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, true, nullptr, 0, false, nullptr, dS1(nd), dS2(nd), nS * H);
+  rec_backward(dec_vel, n, tf ? IN_RANK1 : IN_NONE, tf ? Xv_ext : nullptr, true, nullptr, 0, false, nullptr, dS1(nd + 1), dS2(nd + 1), nS * H);
+  // ---- initial-state Denses -> dq
+  prof_begin(PC_POINTWISE);
+  k_tanh_bwd(act, (long)n * nS * H, dS, S, dSpre, st);
+  prof_end();
+  prof_begin(PC_GEMM);
+  { GemmArgs g; g.M = Q; g.N = nS * H; g.K = n; g.A = q; g.lda = ldq; g.transA = true; g.B = dSpre; g.ldb = nS * H;
+    g.C = Gp(iWinit); g.ldc = ld(iWinit); g.c_type = DT_F32; g.accumulate = true; gemm(g); }
+  k_colsum(act, n, nS * H, nS * H, dSpre, nullptr, 0, Gp(ibinit), st);
+  { GemmArgs g; g.M = n; g.N = Q; g.K = nS * H; g.A = dSpre; g.lda = nS * H; g.B = W(iWinit); g.ldb = ld(iWinit); g.transB = true;
+    g.C = dq; g.ldc = ldq; g.c_type = act; gemm(g); }
+  prof_end();
+  // ---- style head + reparameterisation + KL
+  prof_begin(PC_POINTWISE);
+  k_latent_bwd(act, n, L, ldl, C, dq, ldq, mu, lv, b.eps, style_probs, b.style, cfg.beta, cfg.prior_mean, cfg.prior_std, cfg.composer_weight, dmu,
+               dlv, st);
+  prof_end();
+  // ---- latent head Denses
+  prof_begin(PC_GEMM);
+  const void* e1 = e_cur;
+  const void* e2 = (const char*)e_cur + (size_t)half * asz();
+  { GemmArgs g; g.M = half; g.N = L; g.K = n; g.A = e1; g.lda = H; g.transA = true; g.B = dmu; g.ldb = ldl; g.C = Gp(iWmu); g.ldc = ld(iWmu);
+    g.c_type = DT_F32; g.accumulate = true; gemm(g); }
+  k_colsum(act, n, L, ldl, dmu, nullptr, 0, Gp(ibmu), st);
+  { GemmArgs g; g.M = H - half; g.N = L; g.K = n; g.A = e2; g.lda = H; g.transA = true; g.B = dlv; g.ldb = ldl; g.C = Gp(iWlv); g.ldc = ld(iWlv);
+    g.c_type = DT_F32; g.accumulate = true; gemm(g); }
+  k_colsum(act, n, L, ldl, dlv, nullptr, 0, Gp(iblv), st);
+  { GemmArgs g; g.M = n; g.N = half; g.K = L; g.A = dmu; g.lda = ldl; g.B = W(iWmu); g.ldb = ld(iWmu); g.transB = true; g.C = de; g.ldc = H;
+    g.c_type = act; gemm(g); }
+  { GemmArgs g; g.M = n; g.N = H - half; g.K = L; g.A = dlv; g.lda = ldl; g.B = W(iWlv); g.ldb = ld(iWlv); g.transB = true;
+    g.C = (char*)de + (size_t)half * asz(); g.ldc = H; g.c_type = act; gemm(g); }
+  prof_end();
+  const void* d_a1 = de;
+  if (cfg.extra_layer) {
+    prof_begin(PC_POINTWISE);
+    k_tanh_bwd(act, (long)n * H, de, e, dpre_e, st);
+    prof_end();
+    prof_begin(PC_GEMM);
+    { GemmArgs g; g.M = H; g.N = H; g.K = n; g.A = a1; g.lda = H; g.transA = true; g.B = dpre_e; g.ldb = H; g.C = Gp(iWe); g.ldc = ld(iWe);
+      g.c_type = DT_F32; g.accumulate = true; gemm(g); }
+    k_colsum(act, n, H, H, dpre_e, nullptr, 0, Gp(ibe), st);
+    { GemmArgs g; g.M = n; g.N = H; g.K = H; g.A = dpre_e; g.lda = H; g.B = W(iWe); g.ldb = ld(iWe); g.transB = true; g.C = da1; g.ldc = H;
+      g.c_type = act; gemm(g); }
+    prof_end();
+    d_a1 = da1;
+  }
+  prof_begin(PC_POINTWISE);
+  k_tanh_bwd(act, (long)n * H, d_a1, a1, dpre_a, st);
+  prof_end();
+  prof_begin(PC_GEMM);
+  { GemmArgs g; g.M = 3 * H; g.N = H; g.K = n; g.A = u; g.lda = 3 * H; g.transA = true; g.B = dpre_a; g.ldb = H; g.C = Gp(iWa); g.ldc = ld(iWa);
+    g.c_type = DT_F32; g.accumulate = true; gemm(g); }
+  k_colsum(act, n, H, H, dpre_a, nullptr, 0, Gp(iba), st);
+  { GemmArgs g; g.M = n; g.N = 3 * H; g.K = H; g.A = dpre_a; g.lda = H; g.B = W(iWa); g.ldb = ld(iWa); g.transB = true; g.C = du; g.ldc = 3 * H;
+    g.c_type = act; gemm(g); }
+  prof_end();
+  // ---- encoder recurrences: only the last step of each top recurrence receives a gradient
+  for (int k = ne - 1; k >= 0; --k) {
+    const void* X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
+    const bool is_top = k == ne - 1;
+    rec_backward(enc_pitch[k], n, IN_DENSE, X, !is_top, is_top ? du : nullptr, 3 * H, k > 0, k > 0 ? enc_pitch[k - 1].dhext : nullptr, nullptr,
+                 nullptr, 0);
+  }
+  rec_backward(enc_instr, n, IN_DENSE, slab(Xi_ext, 1, (long)n * ID), false, (const char*)du + (size_t)H * asz(), 3 * H, false, nullptr, nullptr,
+               nullptr, 0);
+  rec_backward(enc_vel, n, IN_RANK1, slab(Xv_ext, 1, (long)n * VD), false, (const char*)du + (size_t)2 * H * asz(), 3 * H, false, nullptr, nullptr,
+               nullptr, 0);
+}
+
+}  // namespace mvae

@@ -1,0 +1,155 @@
+// model.cuh -- the MIDI-VAE model handle: parameter arena, workspace, and the orchestration of one
+// train / eval / predict / style-transfer call as a fixed sequence of kernel launches on one stream.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/midivae.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace mvae {
+
+struct ParamT {
+  std::string name;
+  size_t off;
+  int rows, cols, ld;
+};
+
+enum InKind { IN_NONE = 0, IN_DENSE = 1, IN_RANK1 = 2 };
+
+// One LSTM recurrence (an encoder layer or a decoder cell) with its sequence buffers, all time-major.
+struct Rec {
+  std::string name;
+  int steps = 0;
+  int Din = 0;     // real input width (K of the input projection)
+  int ldin = 0;    // padded width of the dense input rows
+  int iW = -1, iU = -1, ib = -1;
+  int variant = 0;
+  void* xw = nullptr;     // (steps, n, 4H) act : pre-activations x W + b; reused as dG in the backward sweep
+  void* hseq = nullptr;   // (steps+1, n, H) act : slot 0 = initial state
+  void* cseq = nullptr;   // (steps+1, n, H) act
+  void* gates = nullptr;  // (steps, n, 4H) act : post-activation gates
+  void* dhext = nullptr;  // (steps, n, H) act : gradient arriving from the layer / head above
+};
+
+enum ProfClass { PC_REC_FWD = 0, PC_REC_BWD, PC_GEMM, PC_POINTWISE, PC_ADAM, PC_ALLREDUCE, PC_COUNT };
+
+struct Model {
+  mvae_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+  DT act = DT_F32;
+  // dimensions
+  int T = 0, H = 0, L = 0, Dp = 0, Di = 0, Ti = 0, C = 0, ne = 0, nd = 0, G = 0, NB = 0;
+  int PD = 64, ID = 16, VD = 8;        // padded widths of the dense pitch / instrument / velocity rows
+  int ldl = 0, Q = 0, ldq = 0, nS = 0, half = 0;
+  int ld_pn = 64, ld_pi = 16, ld_pv = 8;
+  // parameters
+  std::vector<ParamT> ptab;
+  size_t arena_n = 0;
+  float *P = nullptr, *Gr = nullptr, *M1 = nullptr, *V2 = nullptr;
+  __nv_bfloat16* Pb = nullptr;
+  long long iterations = 0;
+  int iWa = -1, iba = -1, iWe = -1, ibe = -1, iWmu = -1, ibmu = -1, iWlv = -1, iblv = -1, iWinit = -1, ibinit = -1;
+  int iWy = -1, iby = -1, iWio = -1, ibio = -1, iWvo = -1, ibvo = -1;
+  // recurrences
+  std::vector<Rec> enc_pitch, dec_notes;
+  Rec enc_instr, enc_vel, dec_instr, dec_vel;
+  // workspace
+  char* ws = nullptr;
+  size_t ws_bytes = 0, ws_used = 0;
+  // device copies of one mini-batch (host API) + expanded rolls
+  uint8_t *d_pitch = nullptr, *d_target = nullptr, *d_instr = nullptr, *d_style = nullptr, *d_song_start = nullptr;
+  float *d_vel = nullptr, *d_hist = nullptr, *d_eps = nullptr, *d_w = nullptr;
+  void *Xp_ext = nullptr, *Yp_ext = nullptr, *Xi_ext = nullptr, *Xv_ext = nullptr;
+  // per-step scratch
+  float *pre = nullptr, *c_run = nullptr, *dh_run = nullptr, *dc_run = nullptr;
+  void* xstep = nullptr;  // (n, 64) act : free-running decoder input
+  // head
+  void *u = nullptr, *a1 = nullptr, *e = nullptr, *q = nullptr, *S = nullptr, *dS = nullptr, *dSpre = nullptr, *dq = nullptr;
+  void *dmu = nullptr, *dlv = nullptr, *de = nullptr, *dpre_e = nullptr, *da1 = nullptr, *dpre_a = nullptr, *du = nullptr;
+  float *mu = nullptr, *lv = nullptr, *z = nullptr, *style_probs = nullptr;
+  // output heads
+  float *Pn = nullptr, *Pi = nullptr, *Pv = nullptr;
+  void *dlog_n = nullptr, *dlog_i = nullptr, *dlog_v = nullptr;
+  // metrics
+  double* acc = nullptr;
+  float* d_metrics = nullptr;
+  // staging for the host API
+  char* pin = nullptr;
+  size_t pin_bytes = 0;
+  float *o_y = nullptr, *o_i = nullptr, *o_v = nullptr, *o_z = nullptr;
+  uint8_t *o_pitch = nullptr, *o_instr = nullptr;
+  // data parallel
+  void* nccl_comm = nullptr;
+  int world = 1, rank = 0;
+  // profiling
+  bool profiling = false;
+  struct Ev { int cls; cudaEvent_t a, b; };
+  std::vector<Ev> evs;
+  float prof_ms[PC_COUNT] = {0};
+  long long prof_n[PC_COUNT] = {0};
+  long long launches = 0;
+  size_t h2d_bytes = 0, d2h_bytes = 0;
+  cudaStream_t st = nullptr;          // stream of the call in flight
+  const void* Y_ext_cur = nullptr;   // teacher-forcing source: Yp_ext or (target == pitch) Xp_ext
+  const void* e_cur = nullptr;       // output of the last tanh Dense before the split
+  bool stepwise_done = false;
+  std::vector<void*> allocs_;
+
+  explicit Model(const mvae_config& c, int dev);
+  ~Model();
+
+  // helpers
+  const void* W(int idx) const { return act == DT_F32 ? (const void*)(P + ptab[idx].off) : (const void*)(Pb + ptab[idx].off); }
+  const float* Wf(int idx) const { return P + ptab[idx].off; }
+  float* Gp(int idx) const { return Gr + ptab[idx].off; }
+  int ld(int idx) const { return ptab[idx].ld; }
+  size_t asz() const { return dt_size(act); }
+  void* slab(void* base, long idx, long elems_per_slab) const { return (char*)base + (size_t)idx * elems_per_slab * asz(); }
+  CellCfg cc(int variant) const { return CellCfg{cfg.gate_act, variant}; }
+
+  void* alloc(size_t bytes);
+  int add_param(const std::string& name, int rows, int cols);
+  void build_params();
+  void build_workspace();
+  void commit_params();
+  void gemm(GemmArgs g);
+  void prof_begin(int cls);
+  void prof_end();
+  void prof_collect();
+
+  // batch plumbing
+  mvae_batch upload(const mvae_batch& hb, const uint8_t* song_start = nullptr);
+  void check_batch(const mvae_batch& b, bool need_style) const;
+
+  // graph pieces
+  void prepare_inputs(const mvae_batch& b, bool need_target);
+  void rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, const void* c0, int ld0);
+  void rec_steps_forward(Rec& r, int n, int t0, int t1);
+  void rec_backward(Rec& r, int n, int kind, const void* X, bool use_dhext, const void* dh_last, int ld_last, bool need_dx, void* dx_out,
+                    void* dS_h, void* dS_c, int ldS);
+  void encoder_forward(int n);
+  void head_forward(const mvae_batch& b, bool with_style_loss);
+  void decoder_forward(const mvae_batch& b, int feedback);
+  void decoder_stepwise(int n);
+  void losses(const mvae_batch& b, bool train);
+  void backward(const mvae_batch& b);
+  void forward_backward(const mvae_batch& b, float* dev_metrics, cudaStream_t st);
+  void allreduce_grads();
+  void apply_update(float grad_scale, cudaStream_t st);
+  void eval_step(const mvae_batch& b, float* dev_metrics, cudaStream_t st);
+  void style_transfer(const mvae_batch& b, const uint8_t* song_start, int c_from, int c_to, int feedback, uint8_t* pitch_out,
+                      uint8_t* instr_out, float* vel_out, cudaStream_t st);
+};
+
+// NCCL through dlopen (libnccl.so.2); no link-time dependency
+int nccl_get_unique_id(void* out128);
+void* nccl_comm_init(const void* id128, int world, int rank);
+void nccl_comm_destroy(void* comm);
+void nccl_allreduce_sum_f32(void* comm, float* buf, size_t count, cudaStream_t st);
+
+}  // namespace mvae

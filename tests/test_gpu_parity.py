@@ -1,0 +1,232 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libmidivae.so) against the CPU oracle on the same
+seeded inputs.  Tolerances: fp32 precision 1e-4 relative (north_star), bf16 precision stated per test.
+Integer outputs (argmax pitch / instrument indices) are bit-exact wherever the oracle's top-2 margin exceeds the
+stated tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from midi_vae_b200 import Engine, METRIC_KEYS, synth
+from oracle import midivae_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-4
+
+
+def _engine(ecfg, w):
+    eng = Engine(ecfg, 0)
+    eng.set_weights(w)
+    return eng
+
+
+def _compare_step(ecfg, ocfg, n, weights=False, tol=TOL32, grad_tol=None, seed=7):
+    w = util.make_weights(ecfg)
+    eng = _engine(ecfg, w)
+    r, hist, eps, sw = util.make_batch(ecfg, n, seed=seed, weights=weights)
+    p = util.to_torch(w)
+    X, I, V, C, th, te, tsw = util.oracle_inputs(ocfg, r, hist, eps, sw)
+    m_ref, g_ref, _ = O.loss_and_grads(ocfg, p, X, I, V, C, th, te, sample_weight=tsw)
+    m = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)
+    for k in METRIC_KEYS:
+        assert abs(m[k] - m_ref[k]) <= tol * max(1.0, abs(m_ref[k])), (k, m[k], m_ref[k])
+    g = eng.get_grads()
+    gt = grad_tol or tol
+    worst = max(g_ref, key=lambda k: util.rel_err(g[k], g_ref[k].numpy()))
+    for k in g_ref:
+        ref = g_ref[k].numpy()
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(g[k] - ref).max() <= gt * scale + 1e-9, (k, float(np.abs(g[k] - ref).max()), float(scale), "worst", worst)
+    # one Keras-Adam step on the same gradients
+    opt = O.KerasAdam(p, lr=ocfg.learning_rate)
+    opt.step(p, g_ref)
+    w_new = eng.get_weights()
+    for k in p:
+        # the first Adam step moves every weight by ~lr*sign(g); compare the UPDATE, not the weight
+        d_ref = p[k].numpy() - w[k]
+        d = w_new[k] - w[k]
+        live = np.abs(g_ref[k].numpy()) > 1e-4   # |g| >> eps/sqrt(1-beta_2): the update is ~lr*sign(g)
+        if live.any():
+            assert np.abs(d - d_ref)[live].max() <= 0.05 * ocfg.learning_rate, k
+    eng.close()
+    return m, m_ref
+
+
+@pytest.mark.parametrize("feedback", ["as_wired", "teacher_forced"])
+@pytest.mark.parametrize("gate", ["hard_sigmoid", "sigmoid"])
+def test_train_step_fp32_matches_oracle(feedback, gate):
+    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, feedback=feedback, gate=gate, max_batch=8)   # cfg1 (BASELINE.json configs[0])
+    _compare_step(ecfg, ocfg, 8, weights=True)
+
+
+def test_train_step_fp32_recalled_cell_and_layers():
+    ecfg, ocfg = util.make_cfgs(T=8, H=32, L=12, ne=1, nd=3, feedback="teacher_forced", variant="recurrentshop_recalled", max_batch=6)
+    _compare_step(ecfg, ocfg, 5)
+
+
+@pytest.mark.parametrize("n", [1, 3, 8])
+def test_ragged_batch_sizes(n):
+    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, feedback="teacher_forced", max_batch=8)
+    _compare_step(ecfg, ocfg, n)
+
+
+def test_trajectory_fp32_ten_steps():
+    """10 consecutive train steps (history fed from the previous batch's z as in SURVEY 8(d)) track the oracle."""
+    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, feedback="teacher_forced", max_batch=8, lr=2e-3)
+    w = util.make_weights(ecfg)
+    eng = _engine(ecfg, w)
+    p = util.to_torch(w)
+    opt = O.KerasAdam(p, lr=ocfg.learning_rate)
+    for step in range(10):
+        r, hist, eps, _ = util.make_batch(ecfg, 8, seed=100 + step)
+        X, I, V, C, th, te, _ = util.oracle_inputs(ocfg, r, hist, eps, None)
+        m_ref, _ = O.train_on_batch(ocfg, p, opt, X, I, V, C, th, te)
+        m = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps)
+        assert abs(m["loss"] - m_ref["loss"]) <= 5e-4 * abs(m_ref["loss"]), (step, m["loss"], m_ref["loss"])
+    w_new = eng.get_weights()
+    for k in p:
+        assert np.abs(w_new[k] - p[k].numpy()).max() <= 2e-4, k
+    assert eng.iterations == 10
+    eng.close()
+
+
+def test_evaluate_and_predict_fp32():
+    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, feedback="teacher_forced", max_batch=8)
+    w = util.make_weights(ecfg)
+    eng = _engine(ecfg, w)
+    p = util.to_torch(w)
+    r, hist, eps, sw = util.make_batch(ecfg, 8, weights=True)
+    X, I, V, C, th, te, tsw = util.oracle_inputs(ocfg, r, hist, eps, sw)
+    m_ref, outs, aux = O.evaluate_batch(ocfg, p, X, I, V, C, th, te, sample_weight=tsw)
+    m = eng.evaluate_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)
+    for k in METRIC_KEYS:
+        assert abs(m[k] - m_ref[k]) <= TOL32 * max(1.0, abs(m_ref[k])), k
+    z, mu, lv = eng.encode(r.pitch, r.instr, r.velocity, eps)
+    assert util.rel_err(z, aux[0].numpy()) <= TOL32 and util.rel_err(mu, aux[1].numpy()) <= TOL32 and util.rel_err(lv, aux[2].numpy()) <= TOL32
+    Y, Ih, Vh, S, z2 = eng.autoencode(r.pitch, r.instr, r.velocity, hist, eps)
+    assert util.rel_err(Y, outs[0].numpy()) <= TOL32
+    assert util.rel_err(Ih, outs[1].numpy()) <= TOL32
+    assert util.rel_err(Vh, outs[2].numpy()[..., 0]) <= TOL32
+    assert util.rel_err(S, outs[3].numpy()) <= TOL32
+    # decoder.predict on a given z, all three feedback modes
+    for fb in ("as_wired", "teacher_forced", "free_running"):
+        Yr, Ir, Vr = O.decode(ocfg, p, aux[0], th, X, I, V, fb)
+        Yd, Id, Vd = eng.decode(z, hist, fb, r.pitch, r.instr, r.velocity)
+        assert util.rel_err(Yd, Yr.numpy()) <= 2 * TOL32, fb
+        assert util.rel_err(Id, Ir.numpy()) <= 2 * TOL32, fb
+        assert util.rel_err(Vd, Vr.numpy()[..., 0]) <= 2 * TOL32, fb
+    eng.close()
+
+
+@pytest.mark.parametrize("feedback", ["as_wired", "free_running"])
+def test_style_transfer_argmax_exact(feedback):
+    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, max_batch=40)
+    w = util.make_weights(ecfg, jitter=0.2)
+    eng = _engine(ecfg, w)
+    p = util.to_torch(w)
+    songs = synth.make_songs(3, 16, seed=5, min_chunks=8, max_chunks=14)
+    r = synth.concat(songs)
+    X, I, V, C = [torch.tensor(a) for a in r.dense(np.float64)]
+    ref = O.style_transfer(ocfg, p, X, I, V, 0, 1, r.song_start, feedback)
+    P, Ii, Vv = eng.style_transfer(r.pitch, r.instr, r.velocity, 0, 1, r.song_start, feedback)
+    tol = 1e-4
+    safe_p = O.top2_margin(ref["Yh"]).numpy() > tol
+    safe_i = O.top2_margin(ref["Ih"]).numpy() > tol
+    assert safe_p.mean() > 0.9
+    assert np.array_equal(P[safe_p], ref["pitch"].numpy()[safe_p])
+    assert np.array_equal(Ii[safe_i], ref["instr"].numpy()[safe_i])
+    assert util.rel_err(Vv, ref["Vh"].numpy()[..., 0]) <= 2e-4
+    eng.close()
+
+
+def test_golden_fixture_cfg1():
+    """Committed oracle-derived golden vectors (tests/golden/make_golden.py) for BASELINE config[0] shapes."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_step.npz"))
+    ecfg, _ = util.make_cfgs(T=16, H=64, L=16, feedback=str(g["feedback"]), max_batch=8)
+    w = {k[2:]: g[k] for k in g.files if k.startswith("w/")}
+    eng = _engine(ecfg, w)
+    P, Ii, Vv = eng.style_transfer(g["pitch"], g["instr"], g["velocity"], 0, 1, None, "as_wired")   # before the weights move
+    m = eng.train_on_batch(g["pitch"], g["instr"], g["velocity"], g["style"], g["hist"], g["eps"])
+    for i, k in enumerate(METRIC_KEYS):
+        assert abs(m[k] - g["metrics"][i]) <= TOL32 * max(1.0, abs(g["metrics"][i])), k
+    gr = eng.get_grads()
+    for k in gr:
+        ref = g["g/" + k]
+        assert np.abs(gr[k] - ref).max() <= TOL32 * max(np.abs(ref).max(), 1e-6) + 1e-9, k
+    safe = g["st_margin"] > 1e-4
+    assert np.array_equal(P[safe], g["st_pitch"][safe])
+    eng.close()
+
+
+def test_gemm_tc_selftest():
+    """tcgen05 GEMM (all four major-ness cases, ragged edges, all epilogues) against the SIMT GEMM."""
+    from midi_vae_b200 import _lib
+    assert _lib.load().mvae_selftest_gemm(0, 0) == 0
+
+
+@pytest.mark.parametrize("feedback", ["as_wired", "teacher_forced"])
+def test_train_step_bf16_tolerance(feedback):
+    """bf16 tensor-core precision: operands rounded to bf16, fp32 accumulation and fp32 cell state.
+    Stated tolerance: metrics 2e-2 relative, gradients 6e-2 of each tensor's max (T=64 recurrent steps)."""
+    ecfg, ocfg = util.make_cfgs(T=64, H=256, L=100, feedback=feedback, precision="bf16", max_batch=16)   # cfg2 shapes, small batch
+    _compare_step(ecfg, ocfg, 16, tol=2e-2, grad_tol=6e-2)
+
+
+def test_bf16_tracks_fp32_full_cfg2():
+    """BASELINE cfg2 (T64,H256,L100,B128) at full size: size-independent properties instead of the slow oracle:
+    the bf16 path agrees with the fp32 CUDA path (itself oracle-checked above) and the loss decreases."""
+    ecfg32, _ = util.make_cfgs(T=64, H=256, L=100, feedback="teacher_forced", precision="fp32", max_batch=128, lr=1e-3)
+    ecfg16, _ = util.make_cfgs(T=64, H=256, L=100, feedback="teacher_forced", precision="bf16", max_batch=128, lr=1e-3)
+    w = util.make_weights(ecfg32)
+    e32, e16 = _engine(ecfg32, w), _engine(ecfg16, w)
+    r, hist, eps, _ = util.make_batch(ecfg32, 128, seed=3)
+    l32, l16 = [], []
+    for _ in range(8):
+        l32.append(e32.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps)["loss"])
+        l16.append(e16.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps)["loss"])
+    assert l32[-1] < l32[0] and l16[-1] < l16[0]
+    for a, b in zip(l32, l16):
+        assert abs(a - b) <= 2e-2 * abs(a), (l32, l16)
+    e32.close(); e16.close()
+
+
+def test_keras_facade_fit_evaluate_predict():
+    """The reference-shaped surface: VAE.create(**kwargs) -> autoencoder.fit / evaluate / predict with the
+    reference's positional input lists (vae_definition.py:880-1045)."""
+    from midi_vae_b200 import VAE, marshal
+    T, H, L = 16, 64, 16
+    vae = VAE().create(input_dim=61, output_dim=61, input_length=T, output_length=T, latent_rep_size=L, lstm_size=H, activation='softmax',
+                       include_composer_decoder=True, num_composers=2, composer_weight=0.1, num_layers_encoder=2, num_layers_decoder=2,
+                       learning_rate=2e-4, beta=0.1, extra_layer=True, meta_instrument=True, meta_instrument_dim=16, meta_instrument_length=4,
+                       meta_instrument_activation='softmax', meta_instrument_weight=0.1, meta_velocity=True, meta_velocity_length=T,
+                       meta_velocity_weight=1.0, epsilon_std=0.01, max_batch=8)
+    song = synth.make_song(np.random.default_rng(0), 20, T, style=1)
+    X, I, V, C = song.dense(np.float64)
+    H0 = np.zeros((len(song), L))
+    inputs, targets, sw = marshal.prepare_autoencoder_input_and_output_list(X, X, 1, I[0], V[..., 0], H0, return_sample_weight=True)
+    names = vae.autoencoder.metrics_names
+    assert names[0] == "loss" and names.count("decoder_loss") == 3
+    hist = vae.autoencoder.fit(inputs, targets, epochs=1, batch_size=8, shuffle=False, sample_weight=sw, verbose=False)
+    assert set(["loss", "decoder_loss_1", "decoder_acc_3", "composer_decoder_acc"]).issubset(hist.history.keys())
+    ev = vae.autoencoder.evaluate(inputs, targets, batch_size=8, verbose=False)
+    assert len(ev) == len(names) and np.isfinite(ev).all()
+    z = vae.encoder.predict(marshal.prepare_encoder_input_list(X, I[0], V[..., 0]), batch_size=8)
+    assert z.shape == (20, L)
+    Y, Ih, Vh = vae.decoder.predict(marshal.prepare_decoder_input(z), batch_size=8)
+    assert Y.shape == (20, T, 61) and Ih.shape == (20, 4, 16) and Vh.shape == (20, T, 1)
+    assert np.allclose(Y.sum(-1), 1, atol=1e-4)
+    outs = vae.autoencoder.predict(inputs, batch_size=8)
+    assert [o.shape for o in outs] == [(20, T, 61), (20, 4, 16), (20, T, 1), (20, 2)]
+    # weights round trip
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "autoencoderEpoch0.pickle")
+        vae.autoencoder.save_weights(path)
+        before = vae.autoencoder.get_weights()
+        vae.autoencoder.fit(inputs, targets, epochs=1, batch_size=8, sample_weight=sw)
+        vae.autoencoder.load_weights(path, by_name=False)
+        after = vae.autoencoder.get_weights()
+        assert all(np.array_equal(a, b) for a, b in zip(before, after))
+    vae.engine.close()
