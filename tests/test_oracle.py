@@ -1,0 +1,123 @@
+"""CPU tests of the oracle itself: finite-difference gradient checks (fp64), the hand-derived BPTT blueprint the
+kernels follow against autograd, Keras-semantics identities, and the committed golden vectors."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from midi_vae_b200 import METRIC_KEYS, synth
+from oracle import manual_bptt as M
+from oracle import midivae_oracle as O
+from tests import util
+
+
+def _setup(feedback="teacher_forced", gate="hard_sigmoid", variant="standard", T=8, H=16, L=8, n=4, ne=2, nd=2):
+    ecfg, ocfg = util.make_cfgs(T=T, H=H, L=L, ne=ne, nd=nd, feedback=feedback, gate=gate, variant=variant, max_batch=n)
+    w = util.make_weights(ecfg, jitter=0.05)
+    p = util.to_torch(w)
+    r, hist, eps, sw = util.make_batch(ecfg, n, weights=True)
+    return ocfg, p, r, util.oracle_inputs(ocfg, r, hist, eps, sw)
+
+
+@pytest.mark.parametrize("feedback", ["as_wired", "teacher_forced", "free_running"])
+@pytest.mark.parametrize("gate", ["hard_sigmoid", "sigmoid"])
+def test_autograd_matches_finite_differences(feedback, gate):
+    ocfg, p, r, (X, I, V, C, hist, eps, sw) = _setup(feedback, gate)
+    _, g, _ = O.loss_and_grads(ocfg, p, X, I, V, C, hist, eps, sample_weight=sw)
+    rng = np.random.default_rng(0)
+    for name in ["lstm_1/kernel", "lstm_2/recurrent_kernel", "lstm_meta_velocity/kernel", "z_log_var/kernel", "notes/cell_2/recurrent_kernel",
+                 "meta_velocity/out/kernel", "dec_init/instr_s2/kernel", "extra_layer/bias"]:
+        wt = p[name]
+        for _ in range(2):
+            idx = tuple(int(rng.integers(0, s)) for s in wt.shape)
+            old = wt[idx].item(); h = 1e-6
+            wt[idx] = old + h; lp = O.evaluate_batch(ocfg, p, X, I, V, C, hist, eps, sample_weight=sw)[0]["loss"]
+            wt[idx] = old - h; lm = O.evaluate_batch(ocfg, p, X, I, V, C, hist, eps, sample_weight=sw)[0]["loss"]
+            wt[idx] = old
+            assert abs((lp - lm) / (2 * h) - g[name][idx].item()) < 1e-7, name
+
+
+@pytest.mark.parametrize("feedback", ["as_wired", "teacher_forced"])
+@pytest.mark.parametrize("gate", ["hard_sigmoid", "sigmoid"])
+@pytest.mark.parametrize("variant", ["standard", "recurrentshop_recalled"])
+def test_manual_bptt_matches_autograd(feedback, gate, variant):
+    """The derivation the CUDA kernels transcribe (time-major buffers, padded one-hots, stashed gates)."""
+    ocfg, p, r, (X, I, V, C, hist, eps, sw) = _setup(feedback, gate, variant, n=5)
+    m, g, _ = O.loss_and_grads(ocfg, p, X, I, V, C, hist, eps, sample_weight=sw)
+    m2, g2 = M.train_step_manual(ocfg, p, r.pitch, r.instr, r.velocity, r.style, hist, eps, w_notes=sw[0])
+    for k in METRIC_KEYS:
+        assert abs(m[k] - m2[k]) < 1e-12, k
+    for k in g:
+        assert (g[k] - g2[k]).abs().max().item() <= 1e-12 * max(1.0, g[k].abs().max().item()), k
+
+
+def test_single_layer_and_three_layer_stacks():
+    for ne, nd in ((1, 1), (3, 1), (1, 3)):
+        ocfg, p, r, (X, I, V, C, hist, eps, sw) = _setup(ne=ne, nd=nd)
+        m, g, _ = O.loss_and_grads(ocfg, p, X, I, V, C, hist, eps)
+        m2, g2 = M.train_step_manual(ocfg, p, r.pitch, r.instr, r.velocity, r.style, hist, eps)
+        assert abs(m["loss"] - m2["loss"]) < 1e-12
+        assert max((g[k] - g2[k]).abs().max().item() for k in g) < 1e-12
+
+
+def test_keras_loss_identities():
+    ocfg, p, r, (X, I, V, C, hist, eps, sw) = _setup()
+    m, outs, (z, mu, lv) = O.evaluate_batch(ocfg, p, X, I, V, C, hist, eps)
+    # total = sum w_i * loss_i + KL, and the script's KL recovery (vae_training.py:946-957)
+    s = 1.0 * m["decoder_loss_1"] + 0.1 * m["decoder_loss_2"] + 1.0 * m["decoder_loss_3"] + 0.1 * m["composer_decoder_loss"]
+    assert abs(m["loss"] - s - m["kl"]) < 1e-12
+    # KL closed form for a standard-normal prior
+    kl = 0.1 * (-0.5 * (1 + lv - mu ** 2 - lv.exp()).sum(1)).mean()
+    assert abs(float(kl) - m["kl"]) < 1e-12
+    # softmax outputs are normalised; CE of a one-hot target is -log p_target
+    Yh = outs[0]
+    assert torch.allclose(Yh.sum(-1), torch.ones_like(Yh.sum(-1)))
+    ce = -(X * Yh.clamp(1e-7, 1 - 1e-7).log()).sum(-1).mean()
+    assert abs(float(ce) - m["decoder_loss_1"]) < 1e-9
+    # temporal sample weights: zero weights drop out of numerator AND normaliser
+    w = torch.ones(X.shape[0], X.shape[1], dtype=X.dtype); w[:, ::2] = 0
+    mw, _, _ = O.evaluate_batch(ocfg, p, X, I, V, C, hist, eps, sample_weight=(w, None, None, None))
+    ce_kept = -(X * Yh.clamp(1e-7, 1 - 1e-7).log()).sum(-1)[:, 1::2].mean()
+    assert abs(float(ce_kept) - mw["decoder_loss_1"]) < 1e-9
+
+
+def test_keras_adam_first_steps():
+    p = {"w": torch.tensor([1.0, -2.0, 3.0], dtype=torch.float64)}
+    opt = O.KerasAdam(p, lr=1e-3)
+    g = {"w": torch.tensor([0.5, -0.25, 0.0], dtype=torch.float64)}
+    opt.step(p, g)
+    lr_t = 1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    exp = torch.tensor([1.0, -2.0, 3.0], dtype=torch.float64) - lr_t * (0.1 * g["w"]) / ((0.001 * g["w"] ** 2).sqrt() + 1e-8)
+    assert torch.allclose(p["w"], exp, atol=1e-15)
+
+
+def test_param_inventory_matches_survey():
+    """14.144 M parameters at cfg3, 3.510 M at cfg2, 0.245 M at cfg1."""
+    for (T, H, L), n in (((256, 512, 256), 14.144e6), ((64, 256, 100), 3.510e6), ((16, 64, 16), 0.245e6)):
+        c = O.OracleConfig(input_length=T, lstm_size=H, latent_rep_size=L)
+        assert abs(O.param_count(c) - n) / n < 2e-3, (O.param_count(c), n)
+
+
+def test_history_shift_and_style_swap():
+    ocfg, p, r, (X, I, V, C, hist, eps, sw) = _setup(n=6)
+    ss = np.array([1, 0, 0, 1, 0, 0], bool)
+    out = O.style_transfer(ocfg, p, X, I, V, 0, 1, ss)
+    assert torch.equal(out["z_sw"][:, 0], out["z"][:, 1]) and torch.equal(out["z_sw"][:, 1], out["z"][:, 0])
+    assert torch.equal(out["z_sw"][:, 2:], out["z"][:, 2:])
+    assert float(out["H_sw"][0].abs().sum()) == 0 and float(out["H_sw"][3].abs().sum()) == 0
+    assert torch.equal(out["H_sw"][1], out["z_sw"][0]) and torch.equal(out["H_sw"][5], out["z_sw"][4])
+
+
+def test_golden_vectors_reproduce():
+    """tests/golden/cfg1_step.npz is what tests/golden/make_golden.py writes (oracle-derived, fp64)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_step.npz"))
+    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, feedback=str(g["feedback"]), max_batch=8)
+    p = {k[2:]: torch.tensor(g[k], dtype=torch.float64) for k in g.files if k.startswith("w/")}
+    r = synth.Rolls(g["pitch"], g["instr"], g["velocity"], g["style"])
+    X, I, V, C, th, te, _ = util.oracle_inputs(ocfg, r, g["hist"], g["eps"], None)
+    m, gr, _ = O.loss_and_grads(ocfg, p, X, I, V, C, th, te)
+    assert np.allclose([m[k] for k in METRIC_KEYS], g["metrics"], rtol=0, atol=1e-12)
+    for k, v in gr.items():
+        assert np.abs(v.numpy() - g["g/" + k]).max() <= 1e-6 * max(1.0, float(v.abs().max())), k
