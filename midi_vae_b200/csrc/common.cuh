@@ -22,6 +22,7 @@ struct Error : std::runtime_error {
     if (_e != cudaSuccess) {                                                                    \
       char _b[512];                                                                             \
       snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      (void)cudaGetLastError(); /* clear the sticky last-error so that later launch checks do not re-report it */ \
       throw mvae::Error(_b);                                                                    \
     }                                                                                           \
   } while (0)

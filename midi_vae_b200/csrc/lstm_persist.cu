@@ -1,4 +1,473 @@
-// lstm_persist.cu -- persistent LSTM recurrence kernels (placeholder until the tcgen05 version lands).
+// lstm_persist.cu -- persistent-RNN kernels for the LSTM recurrences (bf16 tensor-core precision).
+//
+// One launch runs ALL timesteps of one recurrence (an encoder layer or a decoder cell of
+// vae_definition.py:455-474,533-632).  The reference runs this loop as a Theano scan / K.rnn with one
+// small gemm + elementwise ops per step; the step-streamed form in model.cu does the same with one
+// tcgen05 GEMM + one pointwise launch per step.  Here the loop lives inside the kernel:
+//
+//   * batch rows are independent, so the batch is cut into GROUPS of 128 rows (one UMMA M tile);
+//   * within a group, CTA j owns HS hidden units (all four gates of each): its slice of the recurrent
+//     weights stays RESIDENT in shared memory for the whole sequence (<= 128 KB), as the B operand;
+//   * per step each CTA TMA-loads the group's h_{t-1} (forward) or dG_{t+1} (backward) rows from L2 as the
+//     A operand, runs the K loop with tcgen05.mma into TMEM, and its four epilogue warps (one batch row per
+//     thread) apply the gate math with the cell state c (forward) / dc (backward) living in REGISTERS for
+//     the whole sequence, write the stash (gates, c, h / dG) with 16-byte stores, and publish the step with
+//     a release-increment of a per-(group, step) counter that the TMA-producer warps of the group's CTAs
+//     acquire before loading the next step's operand.  No grid-wide barrier, no host round trip.
+//
+// Forward:  pre = xw_t + h_{t-1} U ;  i,f,o = gate(pre) ; g = tanh(pre) ; c' = f c + i g ; h' = o tanh(c')
+// Backward: dh_t = dh_ext_t + dG_{t+1} U^T ;  dG_t = pointwise(dh_t, dc, stash_t) ; dc <- ds f      (oracle/manual_bptt.py)
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "../../include/midivae.h"
 #include "common.cuh"
+#include "ptx.cuh"
+#include "rec_persist.cuh"
+
 namespace mvae {
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr int BM = 128, BK = 64, UMMA_K = 16, A_STAGES = 4, A_STAGE_BYTES = BM * BK * 2;
+constexpr int kThreads = 192;
+
+struct RecKP {
+  int n, H, G, steps, cpg, HS, group0;
+  int gate_act, variant;
+  unsigned* flags;   // [groups][steps + 2]
+  int flag_stride;
+  // forward
+  const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates;
+  // backward
+  const bf16* dhext; const bf16* dh_last; int ld_last; bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void wait_flag(const unsigned* p, unsigned target) {
+  long long t0 = clock64();
+  while (ld_acquire(p) < target) {
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug must trap, not hang the GPU
+      printf("rec_persist: flag wait timeout block %d (have %u want %u)\n", (int)blockIdx.x, ld_acquire(p), target);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gate_fwd(int gate_act, float x) {
+  return gate_act == MVAE_GATE_HARD_SIGMOID ? fminf(fmaxf(0.2f * x + 0.5f, 0.f), 1.f) : 0.5f * tanh_fast(0.5f * x) + 0.5f;
+}
+__device__ __forceinline__ float gate_bwd(int gate_act, float s) {
+  return gate_act == MVAE_GATE_HARD_SIGMOID ? ((s > 0.f && s < 1.f) ? 0.2f : 0.f) : s * (1.f - s);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// FWD: A = h_{t-1} rows of the group (K = H), B = packed U slice [4*HS gate columns][H] resident, D = [128 rows][4*HS]
+//      packed column n = ublock*32 + gate*8 + u8  <->  unit j*HS + ublock*8 + u8, semantic gate (i,f,g,o)
+// BWD: A = dG_{t+1} rows of the group (K = 4H), B = U rows of the CTA's HS units [HS][4H] resident, D = [128 rows][HS]
+template <bool FWD, int HS>
+__global__ void __launch_bounds__(kThreads, 1)
+rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const RecKP p) {
+  constexpr int BN = FWD ? 4 * HS : HS;              // UMMA N
+  constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;      // the epilogue reads 32-column chunks
+  constexpr int TM_COLS = 2 * ACC_STRIDE;
+  constexpr int B_KB_BYTES = BN * BK * 2;            // bytes of one resident K-block of B
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[A_STAGES], empty_bar[A_STAGES], tmem_full_bar[2], tmem_empty_bar[2], b_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int K = FWD ? p.H : p.G;
+  const int kblocks = K / BK;
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_b = smem_base;                                   // resident weights: kblocks * B_KB_BYTES
+  const uint32_t smem_a = smem_base + (uint32_t)kblocks * B_KB_BYTES;   // A ring
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = p.group0 + blockIdx.x / p.cpg, j = blockIdx.x % p.cpg;
+  const int row0 = g * BM;
+  unsigned* flags = p.flags + (size_t)g * p.flag_stride;
+  const int T = p.steps;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_a);
+    ptx::prefetch_tmap(&tma_b);
+    for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1); ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), 4); }
+    ptx::mbar_init(ptx::smem_u32(&b_full_bar), 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), TM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // number of MMA rounds: forward T (one per step); backward T (dG_{t+1} U^T for t = T-2..0 and the final dh0)
+  const int rounds = T;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // resident weights, once
+      const uint32_t bb = ptx::smem_u32(&b_full_bar);
+      ptx::mbar_arrive_expect_tx(bb, (uint32_t)kblocks * B_KB_BYTES);
+      for (int kb = 0; kb < kblocks; ++kb) ptx::tma_load_2d(smem_b + kb * B_KB_BYTES, &tma_b, bb, kb * BK, j * BN);
+      int stage = 0; uint32_t phase = 0;
+      for (int r = 0; r < rounds; ++r) {
+        // forward round r consumes h_{r-1} = hseq slab r (slab 0 = initial state, written before the launch);
+        // backward round r consumes dG slab (T-1-r), published by the epilogues of round r (r = 0 has no MMA input)
+        const int slab = FWD ? r : (T - 1 - r);
+        if (!FWD || r > 0) {
+          wait_flag(flags + slab, (unsigned)p.cpg);
+          fence_proxy_async_global();
+        }
+        const int arow = slab * p.n + row0;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+          ptx::mbar_arrive_expect_tx(fb, A_STAGE_BYTES);
+          ptx::tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, fb, kb * BK, arow);
+          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, false, false);
+      ptx::mbar_wait(ptx::smem_u32(&b_full_bar), 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int r = 0; r < rounds; ++r) {
+        const int acc = r & 1; const uint32_t acc_phase = (r >> 1) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_a + stage * A_STAGE_BYTES, sb = smem_b + kb * B_KB_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(sa + k * 32, 16, 1024), ptx::umma_desc_sw128(sb + k * 32, 16, 1024), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
+          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(ptx::smem_u32(&tmem_full_bar[acc]));
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..5: one batch row per thread =====================
+    const int quad = warp & 3;
+    const int m = row0 + quad * 32 + lane;
+    const bool row_ok = m < p.n;
+    const int H = p.H, G = p.G;
+    const int bi = p.variant == MVAE_CELL_STANDARD ? 0 : 1, bfk = p.variant == MVAE_CELL_STANDARD ? 1 : 0;   // column block of i and f
+    const int blk[4] = {bi, bfk, 2, 3};
+    const int u0 = j * HS;
+    float cst[HS];   // forward: cell state c ; backward: dc
+#pragma unroll
+    for (int u = 0; u < HS; ++u) cst[u] = 0.f;
+
+    if (FWD) {
+      if (row_ok) {
+#pragma unroll
+        for (int ub = 0; ub < HS / 8; ++ub) {
+          uint4 cv = *reinterpret_cast<const uint4*>(p.cseq + (size_t)m * H + u0 + ub * 8);   // slab 0 = c0
+          unpack8(cv, &cst[ub * 8]);
+        }
+      }
+      for (int t = 0; t < T; ++t) {
+        const int acc = t & 1; const uint32_t acc_phase = (t >> 1) & 1;
+        const size_t rowG = ((size_t)t * p.n + m) * G, rowH1 = ((size_t)(t + 1) * p.n + m) * H;
+        // the input projection of this step does not depend on the recurrence: fetch it while the MMAs run
+        uint4 xq[HS / 8][4];
+        if (row_ok) {
+#pragma unroll
+          for (int ub = 0; ub < HS / 8; ++ub)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xq[ub][q] = __ldg(reinterpret_cast<const uint4*>(p.xw + rowG + blk[q] * H + u0 + ub * 8));
+        }
+        ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ub = 0; ub < HS / 8; ++ub) {
+          float v[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + ub * 32), v);
+          if (row_ok) {
+            float xi[8], xf[8], xg[8], xo[8], gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
+            unpack8(xq[ub][0], xi); unpack8(xq[ub][1], xf); unpack8(xq[ub][2], xg); unpack8(xq[ub][3], xo);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              gi[u] = gate_fwd(p.gate_act, v[u] + xi[u]);
+              gf[u] = gate_fwd(p.gate_act, v[8 + u] + xf[u]);
+              gg[u] = tanh_fast(v[16 + u] + xg[u]);
+              go[u] = gate_fwd(p.gate_act, v[24 + u] + xo[u]);
+              const float s = gf[u] * cst[ub * 8 + u] + gi[u] * gg[u];
+              if (p.variant == MVAE_CELL_STANDARD) { cn[u] = s; hn[u] = go[u] * tanh_fast(s); }
+              else { cn[u] = tanh_fast(s); hn[u] = go[u] * cn[u]; }
+              cst[ub * 8 + u] = cn[u];
+            }
+            bf16* gt = p.gates + rowG + u0 + ub * 8;
+            *reinterpret_cast<uint4*>(gt + blk[0] * H) = pack8(gi);
+            *reinterpret_cast<uint4*>(gt + blk[1] * H) = pack8(gf);
+            *reinterpret_cast<uint4*>(gt + 2 * H) = pack8(gg);
+            *reinterpret_cast<uint4*>(gt + 3 * H) = pack8(go);
+            *reinterpret_cast<uint4*>(p.cseq + rowH1 + u0 + ub * 8) = pack8(cn);
+            *reinterpret_cast<uint4*>(p.hseq + rowH1 + u0 + ub * 8) = pack8(hn);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
+        // publish h_t: every thread's stores -> device scope -> (async proxy) -> one release-increment per CTA
+        __threadfence();
+        fence_proxy_async_global();
+        epi_barrier();
+        if (warp == 2 && lane == 0) red_release_add(flags + (t + 1), 1u);
+      }
+    } else {
+      // backward: iteration it = 0..T: t = T-1-it is the step whose dG is produced; it == T produces dh0 / dc0 only
+      for (int it = 0; it <= T; ++it) {
+        const int t = T - 1 - it;
+        float dh[HS];
+#pragma unroll
+        for (int u = 0; u < HS; ++u) dh[u] = 0.f;
+        // stash loads for step t do not depend on the recurrence
+        uint4 sg[HS / 8][4], sc0[HS / 8], sc1[HS / 8], se[HS / 8];
+        if (t >= 0 && row_ok) {
+          const size_t rowG = ((size_t)t * p.n + m) * G, rowH0 = ((size_t)t * p.n + m) * H, rowH1 = ((size_t)(t + 1) * p.n + m) * H;
+#pragma unroll
+          for (int ub = 0; ub < HS / 8; ++ub) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sg[ub][q] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + blk[q] * H + u0 + ub * 8));
+            sc0[ub] = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH0 + u0 + ub * 8));
+            sc1[ub] = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH1 + u0 + ub * 8));
+            if (p.dhext) se[ub] = __ldg(reinterpret_cast<const uint4*>(p.dhext + rowH0 + u0 + ub * 8));
+          }
+        }
+        if (it > 0) {
+          const int r = it - 1;
+          const int acc = r & 1; const uint32_t acc_phase = (r >> 1) & 1;
+          ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
+          ptx::tc_fence_after();
+          if (HS == 32) {
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE), dh);
+          } else {
+            float v[32];
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE), v);   // columns >= BN are never used
+#pragma unroll
+            for (int u = 0; u < HS; ++u) dh[u] = v[u];
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
+        }
+        if (t >= 0) {
+          if (row_ok) {
+            const size_t rowG = ((size_t)t * p.n + m) * G;
+#pragma unroll
+            for (int ub = 0; ub < HS / 8; ++ub) {
+              float gi[8], gf[8], gg[8], go[8], c0[8], c1[8], ex[8], di[8], df[8], dg[8], dob[8];
+              unpack8(sg[ub][0], gi); unpack8(sg[ub][1], gf); unpack8(sg[ub][2], gg); unpack8(sg[ub][3], go);
+              unpack8(sc0[ub], c0); unpack8(sc1[ub], c1);
+              if (p.dhext) unpack8(se[ub], ex);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                float d = dh[ub * 8 + u];
+                if (p.dhext) d += ex[u];
+                if (it == 0 && p.dh_last) d += __bfloat162float(p.dh_last[(size_t)m * p.ld_last + u0 + ub * 8 + u]);
+                float d_o, ds;
+                if (p.variant == MVAE_CELL_STANDARD) {
+                  const float tc = tanh_fast(c1[u]);
+                  d_o = d * tc;
+                  ds = cst[ub * 8 + u] + d * go[u] * (1.f - tc * tc);
+                } else {
+                  d_o = d * c1[u];
+                  ds = (cst[ub * 8 + u] + d * go[u]) * (1.f - c1[u] * c1[u]);
+                }
+                di[u] = ds * gg[u] * gate_bwd(p.gate_act, gi[u]);
+                df[u] = ds * c0[u] * gate_bwd(p.gate_act, gf[u]);
+                dg[u] = ds * gi[u] * (1.f - gg[u] * gg[u]);
+                dob[u] = d_o * gate_bwd(p.gate_act, go[u]);
+                cst[ub * 8 + u] = ds * gf[u];
+              }
+              bf16* dgp = p.dG + rowG + u0 + ub * 8;
+              *reinterpret_cast<uint4*>(dgp + blk[0] * H) = pack8(di);
+              *reinterpret_cast<uint4*>(dgp + blk[1] * H) = pack8(df);
+              *reinterpret_cast<uint4*>(dgp + 2 * H) = pack8(dg);
+              *reinterpret_cast<uint4*>(dgp + 3 * H) = pack8(dob);
+            }
+          }
+          __threadfence();
+          fence_proxy_async_global();
+          epi_barrier();
+          if (warp == 2 && lane == 0) red_release_add(flags + t, 1u);
+        } else if (row_ok && p.dS_h) {
+          // gradients wrt the initial states (h0, c0) of a decoder cell
+#pragma unroll
+          for (int ub = 0; ub < HS / 8; ++ub) {
+            *reinterpret_cast<uint4*>(p.dS_h + (size_t)m * p.ldS + u0 + ub * 8) = pack8(&dh[ub * 8]);
+            *reinterpret_cast<uint4*>(p.dS_c + (size_t)m * p.ldS + u0 + ub * 8) = pack8(&cst[ub * 8]);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TM_COLS);
+}
+
+// U (H, 4H) fp32 master, natural Keras column blocks -> per-CTA packed bf16 [cpg][4*HS][H], K-major:
+// row n = ublock*32 + gate*8 + u8 of CTA j holds column blk(gate)*H + j*HS + ublock*8 + u8 of U.
+__global__ void pack_u_kernel(const float* __restrict__ U, int ldu, bf16* __restrict__ out, int H, int HS, int variant) {
+  const int BN = 4 * HS;
+  const long total = (long)H * 4 * H;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % H);
+    const long rn = e / H;            // j*BN + n
+    const int n = (int)(rn % BN), j = (int)(rn / BN);
+    const int ub = n / 32, gate = (n % 32) / 8, u8 = n % 8;
+    int blk = gate;
+    if (variant != MVAE_CELL_STANDARD && gate < 2) blk = 1 - gate;
+    const int col = blk * H + j * HS + ub * 8 + u8;
+    out[e] = __float2bfloat16_rn(U[(long)k * ldu + col]);
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MVAE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    MVAE_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = (EncodeFn)p;
+  }
+  return fn;
+}
+CUtensorMap make_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (rec_persist)");
+  return m;
+}
+
+template <bool FWD, int HS>
+void launch(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
+  constexpr int BN = FWD ? 4 * HS : HS;
+  const int H = a.H, G = 4 * H, K = FWD ? H : G, kblocks = K / BK;
+  const int cpg = H / HS;
+  const int groups = (a.n + BM - 1) / BM;
+  const size_t smem = (size_t)kblocks * BN * BK * 2 + (size_t)A_STAGES * A_STAGE_BYTES + 1024;
+  auto kern = rec_persist_kernel<FWD, HS>;
+  MVAE_REQUIRE(smem <= smem_max_bytes(), "recurrent weight slice does not fit in shared memory");
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) { MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+  MVAE_REQUIRE(cpg <= sm_count, "hidden size too large for a co-resident group");
+  RecKP p{};
+  p.n = a.n; p.H = H; p.G = G; p.steps = a.steps; p.cpg = cpg; p.HS = HS; p.gate_act = a.gate_act; p.variant = a.variant;
+  p.flags = a.flags; p.flag_stride = a.steps + 2;
+  p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates;
+  p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last; p.dG = (bf16*)a.dG;
+  p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  MVAE_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)groups * p.flag_stride * sizeof(unsigned), st));
+  // A: forward  = hseq  as a 2-D matrix [(steps+1)*n, H]  ; backward = dG as [steps*n, 4H]
+  const CUtensorMap ma = FWD ? make_map(a.hseq, H, (uint64_t)(a.steps + 1) * a.n, H, 64, BM) : make_map(a.dG, G, (uint64_t)a.steps * a.n, G, 64, BM);
+  // B: forward  = packed U [cpg*4HS, H] ; backward = U shadow [H, 4H] (rows = this CTA's units)
+  const CUtensorMap mb = FWD ? make_map(a.upack, H, (uint64_t)cpg * BN, H, 64, BN) : make_map(a.u_shadow, G, H, a.ldu, 64, BN);
+  const int gmax = std::max(1, sm_count / cpg);   // groups that can be co-resident
+  for (int g0 = 0; g0 < groups; g0 += gmax) {
+    const int ng = std::min(gmax, groups - g0);
+    p.group0 = g0;
+    kern<<<ng * cpg, kThreads, smem, st>>>(ma, mb, p);
+    count_launch();
+    MVAE_CUDA(cudaGetLastError());
+  }
+}
+
+}  // namespace
+
+size_t smem_max_bytes() { return 227 * 1024 - 1024; }   // 227 KB opt-in limit minus the kernels' static shared memory (barriers)
+
+int rec_persist_hs(int H) {
+  if (H % 64 != 0) return 0;
+  for (int hs : {32, 16}) {
+    if (H % hs) continue;
+    const size_t fwd = (size_t)(H / 64) * (4 * hs) * 64 * 2, bwd = (size_t)(4 * H / 64) * hs * 64 * 2;
+    if (std::max(fwd, bwd) + A_STAGES * A_STAGE_BYTES + 1024 <= smem_max_bytes()) return hs;
+  }
+  return 0;
+}
+
+bool rec_persist_supported(int H, int sm_count) {
+  const int hs = rec_persist_hs(H);
+  return hs > 0 && H / hs <= sm_count;
+}
+
+size_t rec_persist_flag_count(int n, int steps) { return (size_t)((n + BM - 1) / BM) * (steps + 2); }
+
+void rec_persist_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st) {
+  const int hs = rec_persist_hs(H);
+  MVAE_REQUIRE(hs > 0, "persistent recurrence unsupported for this hidden size");
+  pack_u_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack, H, hs, variant);
+  count_launch();
+  MVAE_CUDA(cudaGetLastError());
+}
+
+void rec_persist_forward(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
+  switch (rec_persist_hs(a.H)) {
+    case 32: launch<true, 32>(a, st, sm_count); break;
+    case 16: launch<true, 16>(a, st, sm_count); break;
+    default: throw Error("persistent recurrence unsupported for this hidden size");
+  }
+}
+
+void rec_persist_backward(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
+  switch (rec_persist_hs(a.H)) {
+    case 32: launch<false, 32>(a, st, sm_count); break;
+    case 16: launch<false, 16>(a, st, sm_count); break;
+    default: throw Error("persistent recurrence unsupported for this hidden size");
+  }
+}
+
+}  // namespace mvae

@@ -14,6 +14,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
+
 namespace mvae {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -79,7 +81,9 @@ void Model::build_workspace() {
     r.hseq = alloc((size_t)(r.steps + 1) * n * H * a);
     r.cseq = alloc((size_t)(r.steps + 1) * n * H * a);
     if (need_dhext) r.dhext = alloc((size_t)r.steps * n * H * a);
+    if (use_persist) r.upack = alloc((size_t)G * H * 2);
   };
+  if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
   for (int k = 0; k < nd; ++k) rec_bufs(dec_notes[k], true);
@@ -131,6 +135,9 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   C = c.num_composers; ne = c.num_layers_encoder; nd = c.num_layers_decoder; G = 4 * H; NB = c.max_batch;
   PD = round_up(Dp, 8); ID = round_up(Di, 8); VD = 8;
   ldl = round_up(L, 8); Q = c.history ? 2 * L : L; ldq = round_up(Q, 8); nS = 2 * (nd + 2); half = H / 2;
+  use_persist = act == DT_BF16 && cfg.rnn_mode != MVAE_RNN_STREAMED && rec_persist_supported(H, sm_count);
+  if (cfg.rnn_mode == MVAE_RNN_PERSISTENT)
+    MVAE_REQUIRE(use_persist, "rnn_mode=persistent needs bf16 precision and lstm_size % 64 == 0 with a weight slice that fits in shared memory");
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
@@ -248,7 +255,15 @@ void Model::rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, 
     MVAE_CUDA(cudaMemsetAsync(r.cseq, 0, (size_t)n * H * asz(), st));
     MVAE_CUDA(cudaMemsetAsync(c_run, 0, (size_t)n * H * 4, st));
   }
-  rec_steps_forward(r, n, 0, r.steps);
+  if (use_persist) {
+    rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, r.variant, st);
+    RecPersistArgs a;
+    a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = rec_flags;
+    a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates;
+    rec_persist_forward(a, st, sm_count);
+  } else {
+    rec_steps_forward(r, n, 0, r.steps);
+  }
   prof_end();
 }
 
@@ -269,6 +284,14 @@ void Model::rec_backward(Rec& r, int n, int kind, const void* X, bool use_dhext,
   const long rows = (long)r.steps * n;
   void* dG = r.xw;  // the pre-activation buffer is dead after the forward sweep
   prof_begin(PC_REC_BWD);
+  if (use_persist) {
+    RecPersistArgs a;
+    a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = rec_flags;
+    a.gates = r.gates; a.cseq = r.cseq; a.u_shadow = W(r.iU); a.ldu = ld(r.iU);
+    a.dhext = use_dhext ? r.dhext : nullptr; a.dh_last = dh_last; a.ld_last = ld_last; a.dG = dG;
+    a.dS_h = dS_h; a.dS_c = dS_c; a.ldS = ldS;
+    rec_persist_backward(a, st, sm_count);
+  } else {
   MVAE_CUDA(cudaMemsetAsync(dh_run, 0, (size_t)n * H * 4, st));
   MVAE_CUDA(cudaMemsetAsync(dc_run, 0, (size_t)n * H * 4, st));
   for (int t = r.steps - 1; t >= 0; --t) {
@@ -282,6 +305,7 @@ void Model::rec_backward(Rec& r, int n, int kind, const void* X, bool use_dhext,
   if (dS_h) {
     k_copy2d(DT_F32, act, n, H, dh_run, H, dS_h, ldS, st);
     k_copy2d(DT_F32, act, n, H, dc_run, H, dS_c, ldS, st);
+  }
   }
   prof_end();
   prof_begin(PC_GEMM);

@@ -7,6 +7,7 @@
 #include "../../include/midivae.h"
 #include "common.cuh"
 #include "kernels.cuh"
+#include "rec_persist.cuh"
 
 namespace mvae {
 
@@ -31,6 +32,7 @@ struct Rec {
   void* cseq = nullptr;   // (steps+1, n, H) act
   void* gates = nullptr;  // (steps, n, 4H) act : post-activation gates
   void* dhext = nullptr;  // (steps, n, H) act : gradient arriving from the layer / head above
+  void* upack = nullptr;  // (4H, H) bf16 : recurrent weights packed per CTA for the persistent forward kernel
 };
 
 enum ProfClass { PC_REC_FWD = 0, PC_REC_BWD, PC_GEMM, PC_POINTWISE, PC_ADAM, PC_ALLREDUCE, PC_COUNT };
@@ -98,6 +100,8 @@ struct Model {
   const void* Y_ext_cur = nullptr;   // teacher-forcing source: Yp_ext or (target == pitch) Xp_ext
   const void* e_cur = nullptr;       // output of the last tanh Dense before the split
   bool stepwise_done = false;
+  bool use_persist = false;          // persistent-RNN kernels (bf16 precision, supported hidden size)
+  unsigned* rec_flags = nullptr;     // per-(group, step) publication counters of the persistent kernels
   std::vector<void*> allocs_;
 
   explicit Model(const mvae_config& c, int dev);

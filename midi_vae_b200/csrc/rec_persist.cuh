@@ -1,0 +1,38 @@
+// rec_persist.cuh -- host interface of the persistent LSTM recurrence kernels (lstm_persist.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace mvae {
+
+struct RecPersistArgs {
+  int n = 0, H = 0, steps = 0;
+  int gate_act = 0, variant = 0;
+  unsigned* flags = nullptr;          // rec_persist_flag_count(n, steps) counters (zeroed by the launcher)
+  // forward
+  const void* upack = nullptr;        // packed recurrent weights, rec_persist_pack_u
+  const void* xw = nullptr;           // (steps, n, 4H) bf16 pre-activations x W + b
+  void* hseq = nullptr;               // (steps+1, n, H) bf16, slab 0 = h0 (read), slabs 1.. written
+  void* cseq = nullptr;               // (steps+1, n, H) bf16, slab 0 = c0 (read), slabs 1.. written
+  void* gates = nullptr;              // (steps, n, 4H) bf16 post-activation gates (written forward, read backward)
+  // backward
+  const void* u_shadow = nullptr;     // (H, 4H) bf16 recurrent weights, natural layout
+  int ldu = 0;
+  const void* dhext = nullptr;        // (steps, n, H) bf16 or null
+  const void* dh_last = nullptr;      // (n, ld_last) bf16 or null: extra gradient into the last step's h
+  int ld_last = 0;
+  void* dG = nullptr;                 // (steps, n, 4H) bf16 written
+  void* dS_h = nullptr;               // (n, ldS) bf16 gradient wrt h0 / c0 (or null)
+  void* dS_c = nullptr;
+  int ldS = 0;
+};
+
+size_t smem_max_bytes();
+int rec_persist_hs(int H);                           // hidden units per CTA (0 = unsupported)
+bool rec_persist_supported(int H, int sm_count);
+size_t rec_persist_flag_count(int n, int steps);
+void rec_persist_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st);
+void rec_persist_forward(const RecPersistArgs& a, cudaStream_t st, int sm_count);
+void rec_persist_backward(const RecPersistArgs& a, cudaStream_t st, int sm_count);
+
+}  // namespace mvae
