@@ -19,6 +19,8 @@
 // Backward: dh_t = dh_ext_t + dG_{t+1} U^T ;  dG_t = pointwise(dh_t, dc, stash_t) ; dc <- ds f      (oracle/manual_bptt.py)
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "../../include/midivae.h"
@@ -30,11 +32,12 @@ namespace mvae {
 namespace {
 
 using bf16 = __nv_bfloat16;
-constexpr int BM = 128, BK = 64, UMMA_K = 16, A_STAGES = 4, A_STAGE_BYTES = BM * BK * 2;
-constexpr int kThreads = 192;
+constexpr int BM = 128, BK = 64, UMMA_K = 16, MAX_STAGES = 12, A_STAGE_BYTES = BM * BK * 2;
+constexpr int EPI_WARPS = 8, PROD_LANES = 8;
+constexpr int kThreads = 32 * (2 + EPI_WARPS);
 
 struct RecKP {
-  int n, H, G, steps, cpg, HS, group0;
+  int n, H, G, steps, cpg, HS, group0, stages, kb_rot, prod_lanes;
   int gate_act, variant;
   unsigned* flags;   // [groups][steps + 2]
   int flag_stride;
@@ -42,7 +45,13 @@ struct RecKP {
   const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates;
   // backward
   const bf16* dhext; const bf16* dh_last; int ld_last; bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
+  long long* trace;   // optional per-phase clock64 stamps of CTA 0 (debug / profiling)
 };
+
+#define REC_TRACE(step, point)                                                                  \
+  do {                                                                                          \
+    if (p.trace && blockIdx.x == 0 && (step) >= 16 && (step) < 24) p.trace[((step) - 16) * 16 + (point)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -53,7 +62,10 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void red_relaxed_add(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned target) {
   long long t0 = clock64();
@@ -93,6 +105,11 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // FWD: A = h_{t-1} rows of the group (K = H), B = packed U slice [4*HS gate columns][H] resident, D = [128 rows][4*HS]
 //      packed column n = ublock*32 + gate*8 + u8  <->  unit j*HS + ublock*8 + u8, semantic gate (i,f,g,o)
 // BWD: A = dG_{t+1} rows of the group (K = 4H), B = U rows of the CTA's HS units [HS][4H] resident, D = [128 rows][HS]
+//
+// Warp roles (10 warps): 0 = TMA producer (PROD_LANES lanes issue K-blocks concurrently: one lane's issue costs ~350
+// cycles, so a single issuer would pace the whole gather), 1 = MMA issuer + TMEM owner, 2..9 = epilogue: warp w works on
+// TMEM lane quadrant w%4 (one batch row per lane) and on the 8-unit chunks ub with ub % 2 == (w-2)/4, so that every
+// SM sub-partition has two epilogue warps to hide each other's latencies.
 template <bool FWD, int HS>
 __global__ void __launch_bounds__(kThreads, 1)
 rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const RecKP p) {
@@ -100,9 +117,12 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;      // the epilogue reads 32-column chunks
   constexpr int TM_COLS = 2 * ACC_STRIDE;
   constexpr int B_KB_BYTES = BN * BK * 2;            // bytes of one resident K-block of B
+  constexpr int NCH = HS / 8;                        // 8-unit chunks per CTA
+  constexpr int MYCH = NCH / 2;                      // chunks per epilogue thread
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[A_STAGES], empty_bar[A_STAGES], tmem_full_bar[2], tmem_empty_bar[2], b_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2], b_full_bar;
   __shared__ uint32_t tmem_base_slot;
+  const int A_STAGES = p.stages;
 
   const int K = FWD ? p.H : p.G;
   const int kblocks = K / BK;
@@ -119,7 +139,7 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
     for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1); ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), 4); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), EPI_WARPS); }
     ptx::mbar_init(ptx::smem_u32(&b_full_bar), 1);
     ptx::fence_barrier_init();
   }
@@ -136,29 +156,37 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   const int rounds = T;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      // resident weights, once
+    // ===================== TMA producer: PROD_LANES lanes, K-block sequence number q -> lane q % PROD_LANES =====================
+    if (lane == 0) {   // resident weights, once
       const uint32_t bb = ptx::smem_u32(&b_full_bar);
       ptx::mbar_arrive_expect_tx(bb, (uint32_t)kblocks * B_KB_BYTES);
       for (int kb = 0; kb < kblocks; ++kb) ptx::tma_load_2d(smem_b + kb * B_KB_BYTES, &tma_b, bb, kb * BK, j * BN);
-      int stage = 0; uint32_t phase = 0;
-      for (int r = 0; r < rounds; ++r) {
+    }
+    if (lane < p.prod_lanes) {
+      const int NL = p.prod_lanes;
+      const long total = (long)rounds * kblocks;
+      int waited_round = -1;
+      for (long q = lane; q < total; q += NL) {
+        const int r = (int)(q / kblocks), kb = (int)(q % kblocks);
         // forward round r consumes h_{r-1} = hseq slab r (slab 0 = initial state, written before the launch);
-        // backward round r consumes dG slab (T-1-r), published by the epilogues of round r (r = 0 has no MMA input)
+        // backward round r consumes dG slab (T-1-r), published by the epilogue of iteration r
         const int slab = FWD ? r : (T - 1 - r);
-        if (!FWD || r > 0) {
+        if ((!FWD || r > 0) && waited_round != r) {
+          if (lane == 0) REC_TRACE(r, 0);
           wait_flag(flags + slab, (unsigned)p.cpg);
           fence_proxy_async_global();
+          waited_round = r;
+          if (lane == 0) REC_TRACE(r, 1);
         }
-        const int arow = slab * p.n + row0;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
-          ptx::mbar_arrive_expect_tx(fb, A_STAGE_BYTES);
-          ptx::tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, fb, kb * BK, arow);
-          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
-        }
+        const int stage = (int)(q % A_STAGES);
+        const uint32_t phase = (uint32_t)((q / A_STAGES) & 1);
+        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+        ptx::mbar_arrive_expect_tx(fb, A_STAGE_BYTES);
+        // CTAs of a group read the SAME rows: start each at a different K-block so they do not sweep the same L2 lines in lockstep
+        const int kbr = (kb + j * p.kb_rot) % kblocks;
+        ptx::tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, fb, kbr * BK, slab * p.n + row0);
+        if (kb == kblocks - 1) REC_TRACE(r, 2);
       }
     }
   } else if (warp == 1) {
@@ -175,7 +203,9 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
           ptx::tc_fence_after();
-          const uint32_t sa = smem_a + stage * A_STAGE_BYTES, sb = smem_b + kb * B_KB_BYTES;
+          if (kb == 0) REC_TRACE(r, 3);
+          if (kb == kblocks - 1) REC_TRACE(r, 4);
+          const uint32_t sa = smem_a + stage * A_STAGE_BYTES, sb = smem_b + ((kb + j * p.kb_rot) % kblocks) * B_KB_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(sa + k * 32, 16, 1024), ptx::umma_desc_sw128(sb + k * 32, 16, 1024), idesc,
@@ -187,108 +217,125 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue warps 2..5: one batch row per thread =====================
-    const int quad = warp & 3;
+    // ===================== epilogue warps 2..9 =====================
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int m = row0 + quad * 32 + lane;
     const bool row_ok = m < p.n;
+    const bool tracer = (threadIdx.x == 64);
     const int H = p.H, G = p.G;
-    const int bi = p.variant == MVAE_CELL_STANDARD ? 0 : 1, bfk = p.variant == MVAE_CELL_STANDARD ? 1 : 0;   // column block of i and f
-    const int blk[4] = {bi, bfk, 2, 3};
+    const int bi = p.variant == MVAE_CELL_STANDARD ? 0 : 1, bfk = 1 - bi;   // column block of the i and f gates
     const int u0 = j * HS;
-    float cst[HS];   // forward: cell state c ; backward: dc
+    float cst[MYCH * 8];   // forward: cell state c ; backward: dc   (this thread's units, for the whole sequence)
 #pragma unroll
-    for (int u = 0; u < HS; ++u) cst[u] = 0.f;
+    for (int u = 0; u < MYCH * 8; ++u) cst[u] = 0.f;
 
     if (FWD) {
       if (row_ok) {
 #pragma unroll
-        for (int ub = 0; ub < HS / 8; ++ub) {
+        for (int c = 0; c < MYCH; ++c) {
+          const int ub = 2 * c + half;
           uint4 cv = *reinterpret_cast<const uint4*>(p.cseq + (size_t)m * H + u0 + ub * 8);   // slab 0 = c0
-          unpack8(cv, &cst[ub * 8]);
+          unpack8(cv, &cst[c * 8]);
         }
       }
       for (int t = 0; t < T; ++t) {
         const int acc = t & 1; const uint32_t acc_phase = (t >> 1) & 1;
         const size_t rowG = ((size_t)t * p.n + m) * G, rowH1 = ((size_t)(t + 1) * p.n + m) * H;
         // the input projection of this step does not depend on the recurrence: fetch it while the MMAs run
-        uint4 xq[HS / 8][4];
+        uint4 xq[MYCH][4];
         if (row_ok) {
 #pragma unroll
-          for (int ub = 0; ub < HS / 8; ++ub)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) xq[ub][q] = __ldg(reinterpret_cast<const uint4*>(p.xw + rowG + blk[q] * H + u0 + ub * 8));
+          for (int c = 0; c < MYCH; ++c) {
+            const int ub = 2 * c + half;
+            xq[c][0] = __ldg(reinterpret_cast<const uint4*>(p.xw + rowG + bi * H + u0 + ub * 8));
+            xq[c][1] = __ldg(reinterpret_cast<const uint4*>(p.xw + rowG + bfk * H + u0 + ub * 8));
+            xq[c][2] = __ldg(reinterpret_cast<const uint4*>(p.xw + rowG + 2 * H + u0 + ub * 8));
+            xq[c][3] = __ldg(reinterpret_cast<const uint4*>(p.xw + rowG + 3 * H + u0 + ub * 8));
+          }
         }
+        if (tracer) REC_TRACE(t, 5);
         ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
         ptx::tc_fence_after();
+        if (tracer) REC_TRACE(t, 6);
 #pragma unroll
-        for (int ub = 0; ub < HS / 8; ++ub) {
+        for (int c = 0; c < MYCH; ++c) {
+          const int ub = 2 * c + half;
           float v[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + ub * 32), v);
+          if (tracer && c == 0) REC_TRACE(t, 12);
           if (row_ok) {
             float xi[8], xf[8], xg[8], xo[8], gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
-            unpack8(xq[ub][0], xi); unpack8(xq[ub][1], xf); unpack8(xq[ub][2], xg); unpack8(xq[ub][3], xo);
+            unpack8(xq[c][0], xi); unpack8(xq[c][1], xf); unpack8(xq[c][2], xg); unpack8(xq[c][3], xo);
+            if (tracer && c == 0) { if (xi[0] == 12345.f) REC_TRACE(t, 15); REC_TRACE(t, 13); }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               gi[u] = gate_fwd(p.gate_act, v[u] + xi[u]);
               gf[u] = gate_fwd(p.gate_act, v[8 + u] + xf[u]);
               gg[u] = tanh_fast(v[16 + u] + xg[u]);
               go[u] = gate_fwd(p.gate_act, v[24 + u] + xo[u]);
-              const float s = gf[u] * cst[ub * 8 + u] + gi[u] * gg[u];
+              const float s = gf[u] * cst[c * 8 + u] + gi[u] * gg[u];
               if (p.variant == MVAE_CELL_STANDARD) { cn[u] = s; hn[u] = go[u] * tanh_fast(s); }
               else { cn[u] = tanh_fast(s); hn[u] = go[u] * cn[u]; }
-              cst[ub * 8 + u] = cn[u];
+              cst[c * 8 + u] = cn[u];
             }
+            // h first: it is what the other CTAs are waiting for
+            if (tracer && c == 0) { if (hn[0] == 12345.f) REC_TRACE(t, 15); REC_TRACE(t, 14); }
+            *reinterpret_cast<uint4*>(p.hseq + rowH1 + u0 + ub * 8) = pack8(hn);
+            *reinterpret_cast<uint4*>(p.cseq + rowH1 + u0 + ub * 8) = pack8(cn);
             bf16* gt = p.gates + rowG + u0 + ub * 8;
-            *reinterpret_cast<uint4*>(gt + blk[0] * H) = pack8(gi);
-            *reinterpret_cast<uint4*>(gt + blk[1] * H) = pack8(gf);
+            *reinterpret_cast<uint4*>(gt + bi * H) = pack8(gi);
+            *reinterpret_cast<uint4*>(gt + bfk * H) = pack8(gf);
             *reinterpret_cast<uint4*>(gt + 2 * H) = pack8(gg);
             *reinterpret_cast<uint4*>(gt + 3 * H) = pack8(go);
-            *reinterpret_cast<uint4*>(p.cseq + rowH1 + u0 + ub * 8) = pack8(cn);
-            *reinterpret_cast<uint4*>(p.hseq + rowH1 + u0 + ub * 8) = pack8(hn);
           }
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
-        // publish h_t: every thread's stores -> device scope -> (async proxy) -> one release-increment per CTA
-        __threadfence();
+        // publish h_t: the CTA barrier orders every thread's stores before thread 64, whose gpu-scope fence is cumulative
+        if (tracer) REC_TRACE(t, 7);
         fence_proxy_async_global();
+        if (tracer) REC_TRACE(t, 8);
         epi_barrier();
-        if (warp == 2 && lane == 0) red_release_add(flags + (t + 1), 1u);
+        if (tracer) {
+          REC_TRACE(t, 9);
+          __threadfence();
+          REC_TRACE(t, 10);
+          red_relaxed_add(flags + (t + 1), 1u);
+          REC_TRACE(t, 11);
+        }
       }
     } else {
       // backward: iteration it = 0..T: t = T-1-it is the step whose dG is produced; it == T produces dh0 / dc0 only
       for (int it = 0; it <= T; ++it) {
         const int t = T - 1 - it;
-        float dh[HS];
-#pragma unroll
-        for (int u = 0; u < HS; ++u) dh[u] = 0.f;
         // stash loads for step t do not depend on the recurrence
-        uint4 sg[HS / 8][4], sc0[HS / 8], sc1[HS / 8], se[HS / 8];
+        uint4 sg[MYCH][4], sc0[MYCH], sc1[MYCH], se[MYCH];
         if (t >= 0 && row_ok) {
           const size_t rowG = ((size_t)t * p.n + m) * G, rowH0 = ((size_t)t * p.n + m) * H, rowH1 = ((size_t)(t + 1) * p.n + m) * H;
 #pragma unroll
-          for (int ub = 0; ub < HS / 8; ++ub) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) sg[ub][q] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + blk[q] * H + u0 + ub * 8));
-            sc0[ub] = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH0 + u0 + ub * 8));
-            sc1[ub] = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH1 + u0 + ub * 8));
-            if (p.dhext) se[ub] = __ldg(reinterpret_cast<const uint4*>(p.dhext + rowH0 + u0 + ub * 8));
+          for (int c = 0; c < MYCH; ++c) {
+            const int ub = 2 * c + half;
+            sg[c][0] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + bi * H + u0 + ub * 8));
+            sg[c][1] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + bfk * H + u0 + ub * 8));
+            sg[c][2] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + 2 * H + u0 + ub * 8));
+            sg[c][3] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + 3 * H + u0 + ub * 8));
+            sc0[c] = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH0 + u0 + ub * 8));
+            sc1[c] = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH1 + u0 + ub * 8));
+            if (p.dhext) se[c] = __ldg(reinterpret_cast<const uint4*>(p.dhext + rowH0 + u0 + ub * 8));
           }
         }
+        float v[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = 0.f;
         if (it > 0) {
           const int r = it - 1;
           const int acc = r & 1; const uint32_t acc_phase = (r >> 1) & 1;
+          if (tracer) REC_TRACE(r, 5);
           ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
           ptx::tc_fence_after();
-          if (HS == 32) {
-            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE), dh);
-          } else {
-            float v[32];
-            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE), v);   // columns >= BN are never used
-#pragma unroll
-            for (int u = 0; u < HS; ++u) dh[u] = v[u];
-          }
+          if (tracer) REC_TRACE(r, 6);
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE), v);   // columns >= HS are never used
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
@@ -297,48 +344,60 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           if (row_ok) {
             const size_t rowG = ((size_t)t * p.n + m) * G;
 #pragma unroll
-            for (int ub = 0; ub < HS / 8; ++ub) {
+            for (int c = 0; c < MYCH; ++c) {
+              const int ub = 2 * c + half;
               float gi[8], gf[8], gg[8], go[8], c0[8], c1[8], ex[8], di[8], df[8], dg[8], dob[8];
-              unpack8(sg[ub][0], gi); unpack8(sg[ub][1], gf); unpack8(sg[ub][2], gg); unpack8(sg[ub][3], go);
-              unpack8(sc0[ub], c0); unpack8(sc1[ub], c1);
-              if (p.dhext) unpack8(se[ub], ex);
+              unpack8(sg[c][0], gi); unpack8(sg[c][1], gf); unpack8(sg[c][2], gg); unpack8(sg[c][3], go);
+              unpack8(sc0[c], c0); unpack8(sc1[c], c1);
+              if (p.dhext) unpack8(se[c], ex);
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                float d = dh[ub * 8 + u];
+                float d = half ? v[((2 * c + 1) * 8 + u) & 31] : v[(2 * c * 8 + u) & 31];
                 if (p.dhext) d += ex[u];
                 if (it == 0 && p.dh_last) d += __bfloat162float(p.dh_last[(size_t)m * p.ld_last + u0 + ub * 8 + u]);
                 float d_o, ds;
                 if (p.variant == MVAE_CELL_STANDARD) {
                   const float tc = tanh_fast(c1[u]);
                   d_o = d * tc;
-                  ds = cst[ub * 8 + u] + d * go[u] * (1.f - tc * tc);
+                  ds = cst[c * 8 + u] + d * go[u] * (1.f - tc * tc);
                 } else {
                   d_o = d * c1[u];
-                  ds = (cst[ub * 8 + u] + d * go[u]) * (1.f - c1[u] * c1[u]);
+                  ds = (cst[c * 8 + u] + d * go[u]) * (1.f - c1[u] * c1[u]);
                 }
                 di[u] = ds * gg[u] * gate_bwd(p.gate_act, gi[u]);
                 df[u] = ds * c0[u] * gate_bwd(p.gate_act, gf[u]);
                 dg[u] = ds * gi[u] * (1.f - gg[u] * gg[u]);
                 dob[u] = d_o * gate_bwd(p.gate_act, go[u]);
-                cst[ub * 8 + u] = ds * gf[u];
+                cst[c * 8 + u] = ds * gf[u];
               }
               bf16* dgp = p.dG + rowG + u0 + ub * 8;
-              *reinterpret_cast<uint4*>(dgp + blk[0] * H) = pack8(di);
-              *reinterpret_cast<uint4*>(dgp + blk[1] * H) = pack8(df);
+              *reinterpret_cast<uint4*>(dgp + bi * H) = pack8(di);
+              *reinterpret_cast<uint4*>(dgp + bfk * H) = pack8(df);
               *reinterpret_cast<uint4*>(dgp + 2 * H) = pack8(dg);
               *reinterpret_cast<uint4*>(dgp + 3 * H) = pack8(dob);
             }
           }
-          __threadfence();
+          if (tracer) REC_TRACE(it, 7);
           fence_proxy_async_global();
+          if (tracer) REC_TRACE(it, 8);
           epi_barrier();
-          if (warp == 2 && lane == 0) red_release_add(flags + t, 1u);
+          if (tracer) {
+            REC_TRACE(it, 9);
+            __threadfence();
+            REC_TRACE(it, 10);
+            red_relaxed_add(flags + t, 1u);
+            REC_TRACE(it, 11);
+          }
         } else if (row_ok && p.dS_h) {
           // gradients wrt the initial states (h0, c0) of a decoder cell
 #pragma unroll
-          for (int ub = 0; ub < HS / 8; ++ub) {
-            *reinterpret_cast<uint4*>(p.dS_h + (size_t)m * p.ldS + u0 + ub * 8) = pack8(&dh[ub * 8]);
-            *reinterpret_cast<uint4*>(p.dS_c + (size_t)m * p.ldS + u0 + ub * 8) = pack8(&cst[ub * 8]);
+          for (int c = 0; c < MYCH; ++c) {
+            const int ub = 2 * c + half;
+            float d8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d8[u] = half ? v[((2 * c + 1) * 8 + u) & 31] : v[(2 * c * 8 + u) & 31];
+            *reinterpret_cast<uint4*>(p.dS_h + (size_t)m * p.ldS + u0 + ub * 8) = pack8(d8);
+            *reinterpret_cast<uint4*>(p.dS_c + (size_t)m * p.ldS + u0 + ub * 8) = pack8(&cst[c * 8]);
           }
         }
       }
@@ -398,18 +457,27 @@ void launch(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
   const int H = a.H, G = 4 * H, K = FWD ? H : G, kblocks = K / BK;
   const int cpg = H / HS;
   const int groups = (a.n + BM - 1) / BM;
-  const size_t smem = (size_t)kblocks * BN * BK * 2 + (size_t)A_STAGES * A_STAGE_BYTES + 1024;
+  const size_t b_bytes = (size_t)kblocks * BN * BK * 2;
+  int stages = (int)std::min<size_t>(MAX_STAGES, (smem_max_bytes() - 1024 - b_bytes) / A_STAGE_BYTES);
+  MVAE_REQUIRE(stages >= 2, "recurrent weight slice leaves no room for the operand ring");
+  // every ring slot must always be refilled by the SAME producer lane (parity waits cannot tell phase k from k+2),
+  // i.e. the slot count is a multiple of the lane count
+  if (stages >= PROD_LANES) stages = stages / PROD_LANES * PROD_LANES;
+  const int prod_lanes = stages >= PROD_LANES ? PROD_LANES : stages;
+  const size_t smem = b_bytes + (size_t)stages * A_STAGE_BYTES + 1024;
   auto kern = rec_persist_kernel<FWD, HS>;
   MVAE_REQUIRE(smem <= smem_max_bytes(), "recurrent weight slice does not fit in shared memory");
   static size_t attr_smem = 0;
   if (smem > attr_smem) { MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
   MVAE_REQUIRE(cpg <= sm_count, "hidden size too large for a co-resident group");
   RecKP p{};
-  p.n = a.n; p.H = H; p.G = G; p.steps = a.steps; p.cpg = cpg; p.HS = HS; p.gate_act = a.gate_act; p.variant = a.variant;
+  p.n = a.n; p.H = H; p.G = G; p.steps = a.steps; p.cpg = cpg; p.HS = HS; p.stages = stages; p.prod_lanes = prod_lanes;
+  { static int rot = -1; if (rot < 0) { const char* e = getenv("MVAE_REC_ROT"); rot = e ? atoi(e) : 1; } p.kb_rot = rot; } p.gate_act = a.gate_act; p.variant = a.variant;
   p.flags = a.flags; p.flag_stride = a.steps + 2;
   p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates;
   p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last; p.dG = (bf16*)a.dG;
   p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  p.trace = (long long*)a.trace;
   MVAE_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)groups * p.flag_stride * sizeof(unsigned), st));
   // A: forward  = hseq  as a 2-D matrix [(steps+1)*n, H]  ; backward = dG as [steps*n, 4H]
   const CUtensorMap ma = FWD ? make_map(a.hseq, H, (uint64_t)(a.steps + 1) * a.n, H, 64, BM) : make_map(a.dG, G, (uint64_t)a.steps * a.n, G, 64, BM);
@@ -429,12 +497,17 @@ void launch(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
 
 size_t smem_max_bytes() { return 227 * 1024 - 1024; }   // 227 KB opt-in limit minus the kernels' static shared memory (barriers)
 
+// Hidden units per CTA.  Smaller slices leave more shared memory for the operand ring (the per-step gather of
+// h / dG from L2 is latency-bound: bytes in flight per SM set its rate) and spread a group over more SMs.
 int rec_persist_hs(int H) {
   if (H % 64 != 0) return 0;
-  for (int hs : {32, 16}) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MVAE_REC_HS"); forced = e ? atoi(e) : 0; }
+  for (int hs : {16, 32}) {
+    if (forced && hs != forced) continue;
     if (H % hs) continue;
     const size_t fwd = (size_t)(H / 64) * (4 * hs) * 64 * 2, bwd = (size_t)(4 * H / 64) * hs * 64 * 2;
-    if (std::max(fwd, bwd) + A_STAGES * A_STAGE_BYTES + 1024 <= smem_max_bytes()) return hs;
+    if (std::max(fwd, bwd) + 4 * A_STAGE_BYTES + 1024 <= smem_max_bytes()) return hs;
   }
   return 0;
 }

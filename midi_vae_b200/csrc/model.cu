@@ -12,6 +12,7 @@
 #include "model.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -142,6 +143,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
   build_workspace();
+  if (getenv("MVAE_REC_TRACE")) trace_buf = (long long*)alloc(128 * sizeof(long long));
   MVAE_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -181,6 +183,26 @@ void Model::prof_collect() {
     cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
   }
   evs.clear();
+}
+
+// MVAE_REC_TRACE=1: print the per-phase clock64 stamps CTA 0 of a persistent recurrence recorded for 8 steps
+void Model::dump_trace(const char* dir, const Rec& r) {
+  if (!trace_buf || r.steps < 32) return;
+  if (trace_dumps >= 16) return;
+  ++trace_dumps;
+  MVAE_CUDA(cudaStreamSynchronize(st));
+  long long hbuf[128];
+  MVAE_CUDA(cudaMemcpy(hbuf, trace_buf, sizeof(hbuf), cudaMemcpyDeviceToHost));
+  MVAE_CUDA(cudaMemset(trace_buf, 0, sizeof(hbuf)));
+  fprintf(stderr, "rec trace %s %s: cycles relative to the step's first stamp; points: 0 poll-start 1 flag-seen 2 tma-issued 3 first-kblock-landed "
+                  "4 last-kblock-landed 5 epi-wait 6 epi-wake 7 stores-done 8 proxy-fence 9 barrier 10 threadfence 11 flag-published\n", dir, r.name.c_str());
+  for (int sidx = 0; sidx < 8; ++sidx) {
+    long long base = 0;
+    for (int k = 0; k < 16; ++k) if (hbuf[sidx * 16 + k] && (!base || hbuf[sidx * 16 + k] < base)) base = hbuf[sidx * 16 + k];
+    fprintf(stderr, "  step %2d:", 16 + sidx);
+    for (int k = 0; k < 16; ++k) fprintf(stderr, " %d:%lld", k, hbuf[sidx * 16 + k] ? hbuf[sidx * 16 + k] - base : -1);
+    fprintf(stderr, "  | abs0 %lld\n", base);
+  }
 }
 
 // --------------------------------------------------------------------------------------------- GEMM routing
@@ -260,7 +282,9 @@ void Model::rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, 
     RecPersistArgs a;
     a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = rec_flags;
     a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates;
+    a.trace = trace_buf;
     rec_persist_forward(a, st, sm_count);
+    dump_trace("fwd", r);
   } else {
     rec_steps_forward(r, n, 0, r.steps);
   }
@@ -290,7 +314,9 @@ void Model::rec_backward(Rec& r, int n, int kind, const void* X, bool use_dhext,
     a.gates = r.gates; a.cseq = r.cseq; a.u_shadow = W(r.iU); a.ldu = ld(r.iU);
     a.dhext = use_dhext ? r.dhext : nullptr; a.dh_last = dh_last; a.ld_last = ld_last; a.dG = dG;
     a.dS_h = dS_h; a.dS_c = dS_c; a.ldS = ldS;
+    a.trace = trace_buf;
     rec_persist_backward(a, st, sm_count);
+    dump_trace("bwd", r);
   } else {
   MVAE_CUDA(cudaMemsetAsync(dh_run, 0, (size_t)n * H * 4, st));
   MVAE_CUDA(cudaMemsetAsync(dc_run, 0, (size_t)n * H * 4, st));

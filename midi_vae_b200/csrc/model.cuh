@@ -101,6 +101,8 @@ struct Model {
   const void* e_cur = nullptr;       // output of the last tanh Dense before the split
   bool stepwise_done = false;
   bool use_persist = false;          // persistent-RNN kernels (bf16 precision, supported hidden size)
+  long long* trace_buf = nullptr;    // MVAE_REC_TRACE=1 debugging aid
+  int trace_dumps = 0;
   unsigned* rec_flags = nullptr;     // per-(group, step) publication counters of the persistent kernels
   std::vector<void*> allocs_;
 
@@ -125,6 +127,7 @@ struct Model {
   void prof_begin(int cls);
   void prof_end();
   void prof_collect();
+  void dump_trace(const char* dir, const Rec& r);
 
   // batch plumbing
   mvae_batch upload(const mvae_batch& hb, const uint8_t* song_start = nullptr);

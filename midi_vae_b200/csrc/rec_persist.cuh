@@ -25,6 +25,7 @@ struct RecPersistArgs {
   void* dS_h = nullptr;               // (n, ldS) bf16 gradient wrt h0 / c0 (or null)
   void* dS_c = nullptr;
   int ldS = 0;
+  void* trace = nullptr;              // optional: 8 steps x 16 clock64 stamps of CTA 0 (profiling aid)
 };
 
 size_t smem_max_bytes();
