@@ -333,35 +333,67 @@ __global__ void tanh_bwd_kernel(long count, const AT* dout, const AT* out, AT* d
   }
 }
 
-// column sums of a tall matrix: grid (ceil(cols/32), row chunks); block (32, 8)
+// column sums of a tall matrix (bias gradients, rank-1 weight gradients): each thread owns 8 consecutive columns
+// (one 16-byte load per row for bf16), a block covers 256 columns x 8 row lanes; grid (ceil(cols/256), row chunks)
 template <typename AT>
-__global__ void colsum_kernel(long rows, int cols, int ld, const AT* src, const AT* weight, int ldw, float* dst) {
-  __shared__ float sh[8][33];
-  int c = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (c < cols) {
-    if (weight)
-      for (long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long)gridDim.y * 8) s += ldf<AT>(weight + r * ldw) * ldf<AT>(src + r * ld + c);
-    else
-      for (long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long)gridDim.y * 8) s += ldf<AT>(src + r * ld + c);
+__global__ void colsum_kernel(long rows, int cols, int ld, const AT* __restrict__ src, const AT* __restrict__ weight, int ldw, float* dst) {
+  __shared__ float sh[8][256 + 8];
+  const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  const bool vec = (c0 + 8 <= cols) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && sizeof(AT) == 2;
+  if (c0 < cols) {
+    for (long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long)gridDim.y * 8) {
+      const float wgt = weight ? ldf<AT>(weight + r * ldw) : 1.f;
+      if (vec) {
+        uint4 u = *reinterpret_cast<const uint4*>(src + r * ld + c0);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h2[i]); s[2 * i] += wgt * f.x; s[2 * i + 1] += wgt * f.y; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c0 + i < cols) s[i] += wgt * ldf<AT>(src + r * ld + c0 + i);
+      }
+    }
   }
-  sh[threadIdx.y][threadIdx.x] = s;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[threadIdx.y][threadIdx.x * 8 + i] = s[i];
   __syncthreads();
-  if (threadIdx.y == 0 && c < cols) {
+  const int t = threadIdx.y * 32 + threadIdx.x;   // 0..255: one column each
+  const int c = blockIdx.x * 256 + t;
+  if (c < cols) {
     float tsum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tsum += sh[i][threadIdx.x];
+    for (int i = 0; i < 8; ++i) tsum += sh[i][t];
     atomicAdd(dst + c, tsum);
   }
 }
 
+// out[r, c] = x[r] * w[c] + bias[c]: grid-stride over rows, each thread writes 8 consecutive columns per row
 template <typename AT>
-__global__ void rank1_rows_kernel(AT* out, long rows, int cols, const AT* x, int ldx, const float* w, const float* bias) {
-  long total = rows * cols;
-  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    int c = (int)(e % cols);
-    long r = e / cols;
-    stf<AT>(out + e, ldf<AT>(x + r * ldx) * w[c] + (bias ? bias[c] : 0.f));
+__global__ void rank1_rows_kernel(AT* __restrict__ out, long rows, int cols, const AT* __restrict__ x, int ldx, const float* __restrict__ w,
+                                  const float* __restrict__ bias) {
+  const int cthreads = (cols + 7) / 8;                 // threads along the columns
+  const int tcol = threadIdx.x % cthreads, trow = threadIdx.x / cthreads, rpb = blockDim.x / cthreads;
+  const int c0 = tcol * 8;
+  if (trow >= rpb) return;
+  float wv[8], bv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { wv[i] = (c0 + i < cols) ? w[c0 + i] : 0.f; bv[i] = (bias && c0 + i < cols) ? bias[c0 + i] : 0.f; }
+  const bool vec = (c0 + 8 <= cols) && (cols % 8 == 0) && sizeof(AT) == 2 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (long r = (long)blockIdx.x * rpb + trow; r < rows; r += (long)gridDim.x * rpb) {
+    const float xv = ldf<AT>(x + r * ldx);
+    if (vec) {
+      uint4 u;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h2[i] = __floats2bfloat162_rn(xv * wv[2 * i] + bv[2 * i], xv * wv[2 * i + 1] + bv[2 * i + 1]);
+      *reinterpret_cast<uint4*>(out + r * cols + c0) = u;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (c0 + i < cols) stf<AT>(out + r * cols + c0 + i, xv * wv[i] + bv[i]);
+    }
   }
 }
 
@@ -566,7 +598,13 @@ void k_tanh_bwd(DT act, long count, const void* dout, const void* out, void* dpr
 }
 
 void k_rank1_rows(DT act, void* out, long rows, int cols, const void* x, int ldx, const float* w, const float* bias, cudaStream_t st) {
-  DISPATCH_ACT(act, { rank1_rows_kernel<AT><<<nblk(rows * cols), TPB, 0, st>>>((AT*)out, rows, cols, (const AT*)x, ldx, w, bias); LAUNCH_CHECK(); });
+  MVAE_REQUIRE((cols + 7) / 8 <= 1024, "rank-1 row kernel: too many columns");
+  const int cthreads = (cols + 7) / 8;
+  const int threads = cthreads >= 256 ? cthreads : (256 / cthreads) * cthreads;   // whole rows per block
+  const int rpb = threads / cthreads;
+  long blocks = (rows + rpb - 1) / rpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  DISPATCH_ACT(act, { rank1_rows_kernel<AT><<<(int)(blocks < 1 ? 1 : blocks), threads, 0, st>>>((AT*)out, rows, cols, (const AT*)x, ldx, w, bias); LAUNCH_CHECK(); });
 }
 
 void k_rowdot(DT act, long rows, int H, const void* h, const float* w, const float* b, float* out, int ldo, cudaStream_t st) {
@@ -574,8 +612,10 @@ void k_rowdot(DT act, long rows, int H, const void* h, const float* w, const flo
 }
 
 void k_colsum(DT act, long rows, int cols, int ld, const void* src, const void* weight, int ldw, float* dst, cudaStream_t st) {
-  long chunks = (rows + 255) / 256;
-  dim3 grid((cols + 31) / 32, (unsigned)(chunks < 1 ? 1 : (chunks > 512 ? 512 : chunks)));
+  long chunks = (rows + 127) / 128;
+  const unsigned gx = (cols + 255) / 256;
+  const long cap = (148 * 8 + gx - 1) / gx;
+  dim3 grid(gx, (unsigned)(chunks < 1 ? 1 : (chunks > cap ? cap : chunks)));
   dim3 block(32, 8);
   DISPATCH_ACT(act, { colsum_kernel<AT><<<grid, block, 0, st>>>(rows, cols, ld, (const AT*)src, (const AT*)weight, ldw, dst); LAUNCH_CHECK(); });
 }

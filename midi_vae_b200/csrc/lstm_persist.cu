@@ -257,42 +257,32 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
         ptx::tc_fence_after();
         if (tracer) REC_TRACE(t, 6);
+        uint4 st_g[MYCH][4], st_c[MYCH];
 #pragma unroll
         for (int c = 0; c < MYCH; ++c) {
           const int ub = 2 * c + half;
           float v[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE + ub * 32), v);
-          if (tracer && c == 0) REC_TRACE(t, 12);
-          if (row_ok) {
-            float xi[8], xf[8], xg[8], xo[8], gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
-            unpack8(xq[c][0], xi); unpack8(xq[c][1], xf); unpack8(xq[c][2], xg); unpack8(xq[c][3], xo);
-            if (tracer && c == 0) { if (xi[0] == 12345.f) REC_TRACE(t, 15); REC_TRACE(t, 13); }
+          float xi[8], xf[8], xg[8], xo[8], gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
+          unpack8(xq[c][0], xi); unpack8(xq[c][1], xf); unpack8(xq[c][2], xg); unpack8(xq[c][3], xo);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              gi[u] = gate_fwd(p.gate_act, v[u] + xi[u]);
-              gf[u] = gate_fwd(p.gate_act, v[8 + u] + xf[u]);
-              gg[u] = tanh_fast(v[16 + u] + xg[u]);
-              go[u] = gate_fwd(p.gate_act, v[24 + u] + xo[u]);
-              const float s = gf[u] * cst[c * 8 + u] + gi[u] * gg[u];
-              if (p.variant == MVAE_CELL_STANDARD) { cn[u] = s; hn[u] = go[u] * tanh_fast(s); }
-              else { cn[u] = tanh_fast(s); hn[u] = go[u] * cn[u]; }
-              cst[c * 8 + u] = cn[u];
-            }
-            // h first: it is what the other CTAs are waiting for
-            if (tracer && c == 0) { if (hn[0] == 12345.f) REC_TRACE(t, 15); REC_TRACE(t, 14); }
-            *reinterpret_cast<uint4*>(p.hseq + rowH1 + u0 + ub * 8) = pack8(hn);
-            *reinterpret_cast<uint4*>(p.cseq + rowH1 + u0 + ub * 8) = pack8(cn);
-            bf16* gt = p.gates + rowG + u0 + ub * 8;
-            *reinterpret_cast<uint4*>(gt + bi * H) = pack8(gi);
-            *reinterpret_cast<uint4*>(gt + bfk * H) = pack8(gf);
-            *reinterpret_cast<uint4*>(gt + 2 * H) = pack8(gg);
-            *reinterpret_cast<uint4*>(gt + 3 * H) = pack8(go);
+          for (int u = 0; u < 8; ++u) {
+            gi[u] = gate_fwd(p.gate_act, v[u] + xi[u]);
+            gf[u] = gate_fwd(p.gate_act, v[8 + u] + xf[u]);
+            gg[u] = tanh_fast(v[16 + u] + xg[u]);
+            go[u] = gate_fwd(p.gate_act, v[24 + u] + xo[u]);
+            const float s = gf[u] * cst[c * 8 + u] + gi[u] * gg[u];
+            if (p.variant == MVAE_CELL_STANDARD) { cn[u] = s; hn[u] = go[u] * tanh_fast(s); }
+            else { cn[u] = tanh_fast(s); hn[u] = go[u] * cn[u]; }
+            cst[c * 8 + u] = cn[u];
           }
+          if (row_ok) *reinterpret_cast<uint4*>(p.hseq + rowH1 + u0 + ub * 8) = pack8(hn);   // what the other CTAs wait for
+          st_g[c][0] = pack8(gi); st_g[c][1] = pack8(gf); st_g[c][2] = pack8(gg); st_g[c][3] = pack8(go); st_c[c] = pack8(cn);
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
-        // publish h_t: the CTA barrier orders every thread's stores before thread 64, whose gpu-scope fence is cumulative
+        // publish h_t: the CTA barrier orders every thread's h stores before thread 64, whose gpu-scope fence is cumulative
         if (tracer) REC_TRACE(t, 7);
         fence_proxy_async_global();
         if (tracer) REC_TRACE(t, 8);
@@ -303,6 +293,19 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           REC_TRACE(t, 10);
           red_relaxed_add(flags + (t + 1), 1u);
           REC_TRACE(t, 11);
+        }
+        // the rest of the stash (read only by the backward pass) is written after the release: off the critical path
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < MYCH; ++c) {
+            const int ub = 2 * c + half;
+            *reinterpret_cast<uint4*>(p.cseq + rowH1 + u0 + ub * 8) = st_c[c];
+            bf16* gt = p.gates + rowG + u0 + ub * 8;
+            *reinterpret_cast<uint4*>(gt + bi * H) = st_g[c][0];
+            *reinterpret_cast<uint4*>(gt + bfk * H) = st_g[c][1];
+            *reinterpret_cast<uint4*>(gt + 2 * H) = st_g[c][2];
+            *reinterpret_cast<uint4*>(gt + 3 * H) = st_g[c][3];
+          }
         }
       }
     } else {
