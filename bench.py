@@ -250,13 +250,14 @@ def main():
                "ms_per_step": ms_e2e, "api": "Engine.train_on_batch (mvae_train_step_host), host numpy rolls"}
 
     # ---- per-kernel-class CUDA-event timing of one more step (rank 0), for the roofline of the dominant kernel
+    # (every rank runs the step -- it contains the all-reduce -- rank 0 reports)
     roof = None
+    eng.set_profiling(True)
+    eng.train_step_device(dev[0][1], metrics_dev.data_ptr())
+    eng.sync()
+    kms = eng.kernel_ms()
+    eng.set_profiling(False)
     if rank == 0:
-        eng.set_profiling(True)
-        eng.train_step_device(dev[0][1], metrics_dev.data_ptr())
-        eng.sync()
-        kms = eng.kernel_ms()
-        eng.set_profiling(False)
         pk = peaks()
         fwd, rec_fwd = flops_per_seq(T, H, L, args.feedback)
         train = 3 * fwd

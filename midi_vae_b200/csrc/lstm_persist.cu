@@ -33,7 +33,7 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 constexpr int BM = 128, BK = 64, UMMA_K = 16, MAX_STAGES = 12, A_STAGE_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 8, PROD_LANES = 8;
+constexpr int EPI_WARPS = 8, PROD_LANES = 8, ROW_THREADS = 32 * EPI_WARPS;
 constexpr int kThreads = 32 * (2 + EPI_WARPS);
 
 struct RecKP {
@@ -46,6 +46,8 @@ struct RecKP {
   // backward
   const bf16* dhext; const bf16* dh_last; int ld_last; bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
   long long* trace;   // optional per-phase clock64 stamps of CTA 0 (debug / profiling)
+  void* partial;      // K-split backward: bf16 exchange buffer [2][groups_total][cpg][128][H]
+  int groups_total;
 };
 
 #define REC_TRACE(step, point)                                                                  \
@@ -63,6 +65,9 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void st_shared16(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void red_relaxed_add(unsigned* p, unsigned v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -412,6 +417,233 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   if (warp == 1) ptx::tmem_dealloc(tmem_base, TM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward recurrence, K-split form (H <= 512).
+//
+// dh_{t-1} = dG_t U^T needs, per output unit, ALL 4H columns of dG_t.  The N-split kernel above therefore gathers the
+// group's whole dG_t (128 rows x 4H = 512 KB at H=512) into every CTA each step -- 4x the forward exchange, and the
+// gather is what its step time is made of.  Here each CTA instead multiplies only the 64 gate columns it PRODUCES itself
+// (operand A written straight from registers into the swizzled smem tile, no gather at all) with the matching 64 rows
+// of U^T (resident, [H units][64] K-major), giving a partial dh for ALL H units in TMEM (H fp32 columns); the partials
+// are exchanged as bf16 through L2 (128 KB written + 128 KB read per CTA per step, the forward's volume) and summed in
+// fp32 by the CTA that owns the units.
+//   iteration it (t = T-1-it):  [reduce partials of t+1 -> dh_t] -> gate-gradient math -> dG_t (smem A tile + global)
+//                               -> 8 UMMAs (M128 x N256 x K16) -> TMEM -> bf16 partial -> global -> publish flags[t]
+template <int HS>
+__global__ void __launch_bounds__(kThreads, 1)
+rec_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tma_b, const RecKP p) {
+  static_assert(HS == 16, "one 64-column K block per CTA");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t b_full_bar, a_full_bar, tmem_full_bar, tmem_empty_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int H = p.H, G = p.G, T = p.steps;
+  const int NH = H <= 256 ? 1 : H / 256, NB = H / NH;              // MMA N chunks
+  const uint32_t tm_cols = H <= 32 ? 32 : (H <= 64 ? 64 : (H <= 128 ? 128 : (H <= 256 ? 256 : 512)));
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_b = smem_base;                                // [H][64] bf16 K-major, H*128 bytes
+  const uint32_t smem_a = smem_base + (uint32_t)H * 128;            // [128][64] bf16 K-major, 16 KB
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = p.group0 + blockIdx.x / p.cpg, j = blockIdx.x % p.cpg;
+  const int row0 = g * BM;
+  unsigned* flags = p.flags + (size_t)g * p.flag_stride;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_b);
+    ptx::mbar_init(ptx::smem_u32(&b_full_bar), 1);
+    ptx::mbar_init(ptx::smem_u32(&a_full_bar), ROW_THREADS);
+    ptx::mbar_init(ptx::smem_u32(&tmem_full_bar), 1);
+    ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar), EPI_WARPS);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), tm_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bb = ptx::smem_u32(&b_full_bar);
+      ptx::mbar_arrive_expect_tx(bb, (uint32_t)H * 128);
+      for (int nh = 0; nh < NH; ++nh) ptx::tma_load_2d(smem_b + nh * NB * 128, &tma_b, bb, 0, j * H + nh * NB);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(BM, NB, false, false);
+      ptx::mbar_wait(ptx::smem_u32(&b_full_bar), 0);
+      for (int it = 0; it < T; ++it) {
+        ptx::mbar_wait(ptx::smem_u32(&a_full_bar), it & 1);                 // dG_t tile written by the row warps
+        ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar), (it & 1) ^ 1);       // previous partial drained
+        ptx::tc_fence_after();
+        for (int nh = 0; nh < NH; ++nh)
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            ptx::umma_bf16(tmem_base + nh * NB, ptx::umma_desc_sw128(smem_a + k * 32, 16, 1024),
+                           ptx::umma_desc_sw128(smem_b + nh * NB * 128 + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+        ptx::umma_commit(ptx::smem_u32(&tmem_full_bar));
+      }
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    const int r = quad * 32 + lane, m = row0 + r;
+    const bool row_ok = m < p.n;
+    const bool tracer = (etid == 0);
+    const int bi = p.variant == MVAE_CELL_STANDARD ? 0 : 1, bfk = 1 - bi;
+    const int u0 = j * HS + half * 8;                                   // this thread's 8 units
+    bf16* part = (bf16*)p.partial;                                      // [2][groups_total][cpg][128][H]
+    const size_t part_cta = (size_t)BM * H, part_grp = part_cta * p.cpg, part_buf = part_grp * p.groups_total;
+    float dc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dc[u] = 0.f;
+
+    for (int it = 0; it <= T; ++it) {
+      const int t = T - 1 - it;
+      uint4 sg[4], sc0, sc1, se;
+      if (t >= 0 && row_ok) {
+        const size_t rowG = ((size_t)t * p.n + m) * G, rowH0 = ((size_t)t * p.n + m) * H, rowH1 = ((size_t)(t + 1) * p.n + m) * H;
+        sg[0] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + bi * H + u0));
+        sg[1] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + bfk * H + u0));
+        sg[2] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + 2 * H + u0));
+        sg[3] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + 3 * H + u0));
+        sc0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH0 + u0));
+        sc1 = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH1 + u0));
+        if (p.dhext) se = __ldg(reinterpret_cast<const uint4*>(p.dhext + rowH0 + u0));
+      }
+      // ---- dh_t = sum over the group's CTAs of their partial dG_{t+1} U^T, for this thread's 8 units
+      float dh[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dh[u] = 0.f;
+      if (it > 0) {
+        if (tracer) { REC_TRACE(it, 0); wait_flag(flags + (t + 1), (unsigned)p.cpg); REC_TRACE(it, 1); }
+        epi_barrier();
+        // exchange layout [cta][H/8 granules][128 rows][8]: a warp's 32 rows read 512 contiguous bytes per instruction
+        const bf16* src = part + (size_t)((it - 1) & 1) * part_buf + (size_t)g * part_grp + ((size_t)(u0 >> 3) * BM + r) * 8;
+        for (int j0 = 0; j0 < p.cpg; j0 += 16) {
+          uint4 q[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj)
+            if (j0 + jj < p.cpg) q[jj] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(j0 + jj) * part_cta));   // L2 only: written by other SMs
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj)
+            if (j0 + jj < p.cpg) {
+              float f[8];
+              unpack8(q[jj], f);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) dh[u] += f[u];
+            }
+        }
+        if (tracer) REC_TRACE(it, 2);
+      }
+      if (t < 0) {
+        if (row_ok && p.dS_h) {
+          *reinterpret_cast<uint4*>(p.dS_h + (size_t)m * p.ldS + u0) = pack8(dh);
+          *reinterpret_cast<uint4*>(p.dS_c + (size_t)m * p.ldS + u0) = pack8(dc);
+        }
+        break;
+      }
+      // ---- gate-gradient math for step t
+      float di[8], df[8], dg[8], dob[8];
+      {
+        float gi[8], gf[8], gg[8], go[8], c0[8], c1[8], ex[8];
+        unpack8(sg[0], gi); unpack8(sg[1], gf); unpack8(sg[2], gg); unpack8(sg[3], go); unpack8(sc0, c0); unpack8(sc1, c1);
+        if (p.dhext) unpack8(se, ex);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float d = dh[u];
+          if (p.dhext) d += ex[u];
+          if (it == 0 && p.dh_last) d += row_ok ? __bfloat162float(p.dh_last[(size_t)m * p.ld_last + u0 + u]) : 0.f;
+          float d_o, ds;
+          if (p.variant == MVAE_CELL_STANDARD) {
+            const float tc = tanh_fast(c1[u]);
+            d_o = d * tc;
+            ds = dc[u] + d * go[u] * (1.f - tc * tc);
+          } else {
+            d_o = d * c1[u];
+            ds = (dc[u] + d * go[u]) * (1.f - c1[u] * c1[u]);
+          }
+          di[u] = ds * gg[u] * gate_bwd(p.gate_act, gi[u]);
+          df[u] = ds * c0[u] * gate_bwd(p.gate_act, gf[u]);
+          dg[u] = ds * gi[u] * (1.f - gg[u] * gg[u]);
+          dob[u] = d_o * gate_bwd(p.gate_act, go[u]);
+          dc[u] = ds * gf[u];
+          if (!row_ok) { di[u] = 0.f; df[u] = 0.f; dg[u] = 0.f; dob[u] = 0.f; dc[u] = 0.f; }
+        }
+      }
+      const uint4 pi_ = pack8(di), pf_ = pack8(df), pg_ = pack8(dg), po_ = pack8(dob);
+      // operand A: row r = [di(16) | df(16) | dg(16) | do(16)], 16-byte chunk (gate*2 + half), SWIZZLE_128B image
+      {
+        const uint32_t rowa = smem_a + r * 128;
+        const int sw = r & 7;
+        st_shared16(rowa + (((0 * 2 + half) ^ sw) << 4), pi_);
+        st_shared16(rowa + (((1 * 2 + half) ^ sw) << 4), pf_);
+        st_shared16(rowa + (((2 * 2 + half) ^ sw) << 4), pg_);
+        st_shared16(rowa + (((3 * 2 + half) ^ sw) << 4), po_);
+      }
+      ptx::fence_proxy_async();                                     // generic-proxy smem writes -> tensor core (async proxy)
+      ptx::mbar_arrive(ptx::smem_u32(&a_full_bar));
+      if (row_ok) {                                                  // dG_t for the batched weight-gradient GEMMs
+        bf16* dgp = p.dG + ((size_t)t * p.n + m) * G + u0;
+        *reinterpret_cast<uint4*>(dgp + bi * H) = pi_;
+        *reinterpret_cast<uint4*>(dgp + bfk * H) = pf_;
+        *reinterpret_cast<uint4*>(dgp + 2 * H) = pg_;
+        *reinterpret_cast<uint4*>(dgp + 3 * H) = po_;
+      }
+      // ---- partial dh_{t-1} for all H units: TMEM -> bf16 -> this CTA's slot of the exchange buffer
+      if (tracer) REC_TRACE(it, 5);
+      ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar), it & 1);
+      ptx::tc_fence_after();
+      if (tracer) REC_TRACE(it, 6);
+      {
+        bf16* dst = part + (size_t)(it & 1) * part_buf + (size_t)g * part_grp + (size_t)j * part_cta;
+        const int nch = H / 64;                                      // 32-column chunks in this thread's half
+        for (int c = 0; c < nch; ++c) {
+          float v[32];
+          const int col0 = half * (H / 2) + c * 32;
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, v);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + ((size_t)((col0 >> 3) + q4) * BM + r) * 8) = pack8(&v[q4 * 8]);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar));
+      if (tracer) REC_TRACE(it, 7);
+      epi_barrier();
+      if (tracer) {
+        REC_TRACE(it, 9);
+        __threadfence();
+        REC_TRACE(it, 10);
+        red_relaxed_add(flags + t, 1u);
+        REC_TRACE(it, 11);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, tm_cols);
+}
+
+// U (H, 4H) fp32 -> per-CTA packed bf16 [cpg][H units][64] K-major for the K-split backward:
+// column kk = gate*16 + uu of CTA j's block holds U[k, blk(gate)*H + j*16 + uu]
+__global__ void pack_u_bwd_kernel(const float* __restrict__ U, int ldu, bf16* __restrict__ out, int H, int variant) {
+  const long total = (long)H * 4 * H;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int kk = (int)(e % 64);
+    const long rk = e / 64;               // j*H + k
+    const int k = (int)(rk % H), j = (int)(rk / H);
+    const int gate = kk / 16, uu = kk % 16;
+    int blk = gate;
+    if (variant != MVAE_CELL_STANDARD && gate < 2) blk = 1 - gate;
+    out[e] = __float2bfloat16_rn(U[(long)k * ldu + blk * H + j * 16 + uu]);
+  }
+}
+
 // U (H, 4H) fp32 master, natural Keras column blocks -> per-CTA packed bf16 [cpg][4*HS][H], K-major:
 // row n = ublock*32 + gate*8 + u8 of CTA j holds column blk(gate)*H + j*HS + ublock*8 + u8 of U.
 __global__ void pack_u_kernel(const float* __restrict__ U, int ldu, bf16* __restrict__ out, int H, int HS, int variant) {
@@ -538,7 +770,56 @@ void rec_persist_forward(const RecPersistArgs& a, cudaStream_t st, int sm_count)
   }
 }
 
+bool rec_persist_ksplit_ok(int H) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("MVAE_REC_KSPLIT"); enabled = e ? atoi(e) : 1; }
+  if (!enabled || rec_persist_hs(H) != 16 || H > 512) return false;
+  const int NH = H <= 256 ? 1 : H / 256;
+  return (H <= 256 || H % 256 == 0) && (H / NH) % 16 == 0;
+}
+
+size_t rec_persist_partial_bytes(int n, int H) {
+  if (!rec_persist_ksplit_ok(H)) return 0;
+  const size_t groups = (n + BM - 1) / BM;
+  return 2 * groups * (size_t)(H / 16) * BM * H * 2;
+}
+
+void rec_persist_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int variant, cudaStream_t st) {
+  pack_u_bwd_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack_bwd, H, variant);
+  count_launch();
+  MVAE_CUDA(cudaGetLastError());
+}
+
+static void launch_bwd_ksplit(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
+  const int H = a.H, G = 4 * H, HS = 16, cpg = H / HS;
+  const int groups = (a.n + BM - 1) / BM;
+  const int NH = H <= 256 ? 1 : H / 256, NB = H / NH;
+  const size_t smem = (size_t)H * 128 + 16384 + 1024;
+  auto kern = rec_bwd_ksplit_kernel<16>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) { MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+  MVAE_REQUIRE(a.upack_bwd && a.partial, "K-split backward needs the packed weights and the exchange buffer");
+  RecKP p{};
+  p.n = a.n; p.H = H; p.G = G; p.steps = a.steps; p.cpg = cpg; p.HS = HS; p.gate_act = a.gate_act; p.variant = a.variant;
+  p.flags = a.flags; p.flag_stride = a.steps + 2;
+  p.gates = (bf16*)a.gates; p.cseq = (bf16*)a.cseq;
+  p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last; p.dG = (bf16*)a.dG;
+  p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  p.trace = (long long*)a.trace; p.partial = a.partial; p.groups_total = groups;
+  MVAE_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)groups * p.flag_stride * sizeof(unsigned), st));
+  const CUtensorMap mb = make_map(a.upack_bwd, 64, (uint64_t)cpg * H, 64, 64, NB);
+  const int gmax = std::max(1, sm_count / cpg);
+  for (int g0 = 0; g0 < groups; g0 += gmax) {
+    const int ng = std::min(gmax, groups - g0);
+    p.group0 = g0;
+    kern<<<ng * cpg, kThreads, smem, st>>>(mb, p);
+    count_launch();
+    MVAE_CUDA(cudaGetLastError());
+  }
+}
+
 void rec_persist_backward(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
+  if (rec_persist_ksplit_ok(a.H) && a.upack_bwd && a.partial) { launch_bwd_ksplit(a, st, sm_count); return; }
   switch (rec_persist_hs(a.H)) {
     case 32: launch<false, 32>(a, st, sm_count); break;
     case 16: launch<false, 16>(a, st, sm_count); break;

@@ -83,7 +83,9 @@ void Model::build_workspace() {
     r.cseq = alloc((size_t)(r.steps + 1) * n * H * a);
     if (need_dhext) r.dhext = alloc((size_t)r.steps * n * H * a);
     if (use_persist) r.upack = alloc((size_t)G * H * 2);
+    if (use_persist && rec_persist_ksplit_ok(H)) r.upack_b = alloc((size_t)G * H * 2);
   };
+  if (use_persist && rec_persist_ksplit_ok(H)) rec_partial = alloc(rec_persist_partial_bytes(NB, H));
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
@@ -314,6 +316,7 @@ void Model::rec_backward(Rec& r, int n, int kind, const void* X, bool use_dhext,
     a.gates = r.gates; a.cseq = r.cseq; a.u_shadow = W(r.iU); a.ldu = ld(r.iU);
     a.dhext = use_dhext ? r.dhext : nullptr; a.dh_last = dh_last; a.ld_last = ld_last; a.dG = dG;
     a.dS_h = dS_h; a.dS_c = dS_c; a.ldS = ldS;
+    if (r.upack_b) { rec_persist_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, r.variant, st); a.upack_bwd = r.upack_b; a.partial = rec_partial; }
     a.trace = trace_buf;
     rec_persist_backward(a, st, sm_count);
     dump_trace("bwd", r);

@@ -32,6 +32,7 @@ struct Rec {
   void* cseq = nullptr;   // (steps+1, n, H) act
   void* gates = nullptr;  // (steps, n, 4H) act : post-activation gates
   void* dhext = nullptr;  // (steps, n, H) act : gradient arriving from the layer / head above
+  void* upack_b = nullptr;  // (cpg, H, 64) bf16 : recurrent weights packed for the K-split persistent backward kernel
   void* upack = nullptr;  // (4H, H) bf16 : recurrent weights packed per CTA for the persistent forward kernel
 };
 
@@ -103,6 +104,7 @@ struct Model {
   bool use_persist = false;          // persistent-RNN kernels (bf16 precision, supported hidden size)
   long long* trace_buf = nullptr;    // MVAE_REC_TRACE=1 debugging aid
   int trace_dumps = 0;
+  void* rec_partial = nullptr;       // bf16 partial-dh exchange buffer of the K-split backward kernel
   unsigned* rec_flags = nullptr;     // per-(group, step) publication counters of the persistent kernels
   std::vector<void*> allocs_;
 
