@@ -42,7 +42,7 @@ struct RecKP {
   unsigned* flags;   // [groups][steps + 2]
   int flag_stride;
   // forward
-  const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates;
+  const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates; const bf16* c0; int ldc0;
   // backward
   const bf16* dhext; const bf16* dh_last; int ld_last; bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
   long long* trace;   // optional per-phase clock64 stamps of CTA 0 (debug / profiling)
@@ -65,6 +65,11 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// stash layout of the persistent kernels (private to them): [slab][column/8 granules][n rows][8] -- the 32 lanes of a warp
+// are 32 consecutive rows, so one 16-byte access per lane is 512 contiguous bytes per warp instruction
+__device__ __forceinline__ size_t gran_off(int slab, int ngran, int gran, int n, int m) {
+  return (((size_t)slab * ngran + gran) * n + m) * 8;
+}
 __device__ __forceinline__ void st_shared16(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -239,8 +244,10 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 #pragma unroll
         for (int c = 0; c < MYCH; ++c) {
           const int ub = 2 * c + half;
-          uint4 cv = *reinterpret_cast<const uint4*>(p.cseq + (size_t)m * H + u0 + ub * 8);   // slab 0 = c0
+          uint4 cv = make_uint4(0u, 0u, 0u, 0u);
+          if (p.c0) cv = *reinterpret_cast<const uint4*>(p.c0 + (size_t)m * p.ldc0 + u0 + ub * 8);
           unpack8(cv, &cst[c * 8]);
+          *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, (u0 >> 3) + ub, p.n, m)) = cv;   // stash slab 0 = c0
         }
       }
       for (int t = 0; t < T; ++t) {
@@ -304,12 +311,12 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 #pragma unroll
           for (int c = 0; c < MYCH; ++c) {
             const int ub = 2 * c + half;
-            *reinterpret_cast<uint4*>(p.cseq + rowH1 + u0 + ub * 8) = st_c[c];
-            bf16* gt = p.gates + rowG + u0 + ub * 8;
-            *reinterpret_cast<uint4*>(gt + bi * H) = st_g[c][0];
-            *reinterpret_cast<uint4*>(gt + bfk * H) = st_g[c][1];
-            *reinterpret_cast<uint4*>(gt + 2 * H) = st_g[c][2];
-            *reinterpret_cast<uint4*>(gt + 3 * H) = st_g[c][3];
+            const int gu = (u0 >> 3) + ub;
+            *reinterpret_cast<uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, p.n, m)) = st_c[c];
+            *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, p.n, m)) = st_g[c][0];
+            *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, p.n, m)) = st_g[c][1];
+            *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, p.n, m)) = st_g[c][2];
+            *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, p.n, m)) = st_g[c][3];
           }
         }
       }
@@ -324,12 +331,13 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 #pragma unroll
           for (int c = 0; c < MYCH; ++c) {
             const int ub = 2 * c + half;
-            sg[c][0] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + bi * H + u0 + ub * 8));
-            sg[c][1] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + bfk * H + u0 + ub * 8));
-            sg[c][2] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + 2 * H + u0 + ub * 8));
-            sg[c][3] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + 3 * H + u0 + ub * 8));
-            sc0[c] = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH0 + u0 + ub * 8));
-            sc1[c] = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH1 + u0 + ub * 8));
+            const int gu = (u0 >> 3) + ub;
+            sg[c][0] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, p.n, m)));
+            sg[c][1] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, p.n, m)));
+            sg[c][2] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, p.n, m)));
+            sg[c][3] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, p.n, m)));
+            sc0[c] = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t, H / 8, gu, p.n, m)));
+            sc1[c] = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, p.n, m)));
             if (p.dhext) se[c] = __ldg(reinterpret_cast<const uint4*>(p.dhext + rowH0 + u0 + ub * 8));
           }
         }
@@ -506,12 +514,13 @@ rec_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tma_b, const RecKP p) 
       uint4 sg[4], sc0, sc1, se;
       if (t >= 0 && row_ok) {
         const size_t rowG = ((size_t)t * p.n + m) * G, rowH0 = ((size_t)t * p.n + m) * H, rowH1 = ((size_t)(t + 1) * p.n + m) * H;
-        sg[0] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + bi * H + u0));
-        sg[1] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + bfk * H + u0));
-        sg[2] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + 2 * H + u0));
-        sg[3] = __ldg(reinterpret_cast<const uint4*>(p.gates + rowG + 3 * H + u0));
-        sc0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH0 + u0));
-        sc1 = __ldg(reinterpret_cast<const uint4*>(p.cseq + rowH1 + u0));
+        const int gu = u0 >> 3;
+        sg[0] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, p.n, m)));
+        sg[1] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, p.n, m)));
+        sg[2] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, p.n, m)));
+        sg[3] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, p.n, m)));
+        sc0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t, H / 8, gu, p.n, m)));
+        sc1 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, p.n, m)));
         if (p.dhext) se = __ldg(reinterpret_cast<const uint4*>(p.dhext + rowH0 + u0));
       }
       // ---- dh_t = sum over the group's CTAs of their partial dG_{t+1} U^T, for this thread's 8 units
@@ -586,13 +595,6 @@ rec_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tma_b, const RecKP p) 
       }
       ptx::fence_proxy_async();                                     // generic-proxy smem writes -> tensor core (async proxy)
       ptx::mbar_arrive(ptx::smem_u32(&a_full_bar));
-      if (row_ok) {                                                  // dG_t for the batched weight-gradient GEMMs
-        bf16* dgp = p.dG + ((size_t)t * p.n + m) * G + u0;
-        *reinterpret_cast<uint4*>(dgp + bi * H) = pi_;
-        *reinterpret_cast<uint4*>(dgp + bfk * H) = pf_;
-        *reinterpret_cast<uint4*>(dgp + 2 * H) = pg_;
-        *reinterpret_cast<uint4*>(dgp + 3 * H) = po_;
-      }
       // ---- partial dh_{t-1} for all H units: TMEM -> bf16 -> this CTA's slot of the exchange buffer
       if (tracer) REC_TRACE(it, 5);
       ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar), it & 1);
@@ -620,6 +622,13 @@ rec_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tma_b, const RecKP p) 
         REC_TRACE(it, 10);
         red_relaxed_add(flags + t, 1u);
         REC_TRACE(it, 11);
+      }
+      if (row_ok) {   // dG_t for the batched weight-gradient GEMMs: row-major (16-byte pieces), off the critical path
+        bf16* dgp = p.dG + ((size_t)t * p.n + m) * G + u0;
+        *reinterpret_cast<uint4*>(dgp + bi * H) = pi_;
+        *reinterpret_cast<uint4*>(dgp + bfk * H) = pf_;
+        *reinterpret_cast<uint4*>(dgp + 2 * H) = pg_;
+        *reinterpret_cast<uint4*>(dgp + 3 * H) = po_;
       }
     }
   }
@@ -709,7 +718,7 @@ void launch(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
   p.n = a.n; p.H = H; p.G = G; p.steps = a.steps; p.cpg = cpg; p.HS = HS; p.stages = stages; p.prod_lanes = prod_lanes;
   { static int rot = -1; if (rot < 0) { const char* e = getenv("MVAE_REC_ROT"); rot = e ? atoi(e) : 1; } p.kb_rot = rot; } p.gate_act = a.gate_act; p.variant = a.variant;
   p.flags = a.flags; p.flag_stride = a.steps + 2;
-  p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates;
+  p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates; p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0;
   p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last; p.dG = (bf16*)a.dG;
   p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
   p.trace = (long long*)a.trace;

@@ -283,7 +283,7 @@ void Model::rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, 
     rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, r.variant, st);
     RecPersistArgs a;
     a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = rec_flags;
-    a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates;
+    a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates; a.c0 = c0; a.ldc0 = ld0;
     a.trace = trace_buf;
     rec_persist_forward(a, st, sm_count);
     dump_trace("fwd", r);

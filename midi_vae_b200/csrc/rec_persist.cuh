@@ -13,8 +13,10 @@ struct RecPersistArgs {
   const void* upack = nullptr;        // packed recurrent weights, rec_persist_pack_u
   const void* xw = nullptr;           // (steps, n, 4H) bf16 pre-activations x W + b
   void* hseq = nullptr;               // (steps+1, n, H) bf16, slab 0 = h0 (read), slabs 1.. written
-  void* cseq = nullptr;               // (steps+1, n, H) bf16, slab 0 = c0 (read), slabs 1.. written
-  void* gates = nullptr;              // (steps, n, 4H) bf16 post-activation gates (written forward, read backward)
+  void* cseq = nullptr;               // cell-state stash, (steps+1) slabs in the kernels' private granule layout, all written
+  const void* c0 = nullptr;           // (n, ldc0) bf16 initial cell state, row-major (null = zeros)
+  int ldc0 = 0;
+  void* gates = nullptr;              // post-activation gates stash, granule layout (written forward, read backward)
   // backward
   const void* u_shadow = nullptr;     // (H, 4H) bf16 recurrent weights, natural layout
   int ldu = 0;
