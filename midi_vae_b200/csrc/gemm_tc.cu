@@ -18,6 +18,8 @@
 // the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -309,6 +311,17 @@ bool gemm_tc_supported(const GemmArgs& g) {
 void gemm_tc(const GemmArgs& g, cudaStream_t st, int sm_count) {
   MVAE_REQUIRE(gemm_tc_supported(g), "shape / alignment not supported by the tcgen05 GEMM");
   const bool a_mn = g.transA, b_mn = !g.transB;
+  // 128x256 tiles (87 FLOP per operand byte instead of 64) when N is wide enough to fill them
+  static int wide = -1;
+  if (wide < 0) { const char* e = getenv("MVAE_GEMM_BN256"); wide = e ? atoi(e) : 1; }
+  const bool bn256 = wide && g.N >= 256 && (g.N % 256 == 0 || g.N >= 1024);
+  if (bn256) {
+    if (!a_mn && !b_mn) launch<false, false, 256>(g, st, sm_count);
+    else if (!a_mn && b_mn) launch<false, true, 256>(g, st, sm_count);
+    else if (a_mn && !b_mn) launch<true, false, 256>(g, st, sm_count);
+    else launch<true, true, 256>(g, st, sm_count);
+    return;
+  }
   if (!a_mn && !b_mn) launch<false, false, 128>(g, st, sm_count);
   else if (!a_mn && b_mn) launch<false, true, 128>(g, st, sm_count);
   else if (a_mn && !b_mn) launch<true, false, 128>(g, st, sm_count);
