@@ -6,6 +6,6 @@ compute path: importing ``Engine``/``VAE`` works without a GPU, constructing the
 """
 from .engine import Engine, EngineConfig, METRIC_KEYS, reference_param_specs, nccl_unique_id  # noqa: F401
 from .vae import VAE, History, initial_weights  # noqa: F401
-from . import synth, marshal  # noqa: F401
+from . import synth, marshal, postprocess, training  # noqa: F401
 
 __version__ = "0.1.0"

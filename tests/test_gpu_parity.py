@@ -256,3 +256,40 @@ def test_keras_facade_fit_evaluate_predict():
         after = vae.autoencoder.get_weights()
         assert all(np.array_equal(a, b) for a, b in zip(before, after))
     vae.engine.close()
+
+
+def test_per_song_training_driver_cfg1():
+    """BASELINE config[0]: 2 styles x 10 synthetic songs, seq_len=16, hidden=64, latent=16, batch=8, driven through the
+    per-song loop of vae_training.py:728-864 (history from the encoder after epoch 0).  Epoch 0 is checked against the
+    oracle running the same loop; later epochs must keep improving."""
+    from midi_vae_b200 import VAE, training
+    T, H, L = 16, 64, 16
+    vae = VAE().create(input_dim=61, output_dim=61, input_length=T, output_length=T, latent_rep_size=L, lstm_size=H, activation='softmax',
+                       include_composer_decoder=True, num_composers=2, composer_weight=0.1, num_layers_encoder=2, num_layers_decoder=2,
+                       learning_rate=2e-3, beta=0.1, extra_layer=True, meta_instrument=True, meta_instrument_dim=16, meta_instrument_length=4,
+                       meta_instrument_activation='softmax', meta_instrument_weight=0.1, meta_velocity=True, meta_velocity_length=T,
+                       meta_velocity_weight=1.0, epsilon_std=0.0, max_batch=8, decoder_feedback="teacher_forced")
+    songs = synth.make_songs(20, T, seed=1235, min_chunks=8, max_chunks=20)
+    # oracle, epoch 0 (history = zeros, eps = 0)
+    ecfg = vae.engine.cfg
+    _, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="teacher_forced", max_batch=8, lr=2e-3)
+    p = util.to_torch(vae.engine.get_weights())
+    opt = O.KerasAdam(p, lr=2e-3)
+    per_song = []
+    for s in songs[:4]:
+        X, I, V, C = [torch.tensor(a) for a in s.dense(np.float64)]
+        tot = 0.0
+        for a in range(0, len(s), 8):
+            b = min(len(s), a + 8)
+            z0 = torch.zeros(b - a, L, dtype=torch.float64)
+            m, _ = O.train_on_batch(ocfg, p, opt, X[a:b], I[a:b], V[a:b], C[a:b], z0, z0)
+            tot += m["loss"] * (b - a)
+        per_song.append(tot / len(s))
+    m0 = training.train_epoch(vae, songs[:4], epoch=0, batch_size=8)
+    assert abs(m0["loss"] - np.mean(per_song)) <= 2e-3 * np.mean(per_song), (m0["loss"], np.mean(per_song))
+    assert abs(m0["kl_loss"] * 0.1 - (m0["loss"] - m0["decoder_loss_1"] - 0.1 * m0["decoder_loss_2"] - m0["decoder_loss_3"] - 0.1 * m0["composer_decoder_loss"])) < 1e-6
+    losses = [training.train_epoch(vae, songs, epoch=e, batch_size=8)["loss"] for e in range(1, 4)]
+    assert losses[-1] < losses[0] < m0["loss"] * 1.05, (m0["loss"], losses)
+    ev = training.evaluate_songs(vae, songs[:5], batch_size=8)
+    assert np.isfinite(list(ev.values())).all()
+    vae.engine.close()

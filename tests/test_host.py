@@ -114,3 +114,44 @@ def test_work_model_matches_baseline_md():
         assert 0 < rec < f
     f_aw, _ = bench.flops_per_seq(256, 512, 256, "as_wired")
     assert abs(3 * f_aw - 13.1997e9) / 13.1997e9 < 2e-3
+
+
+def _reference_postprocess_loop(pitch, vel, thr=0.5, mv=4):
+    """Literal transcription of vae_definition.py:1143-1221 (argmax sampling already applied)."""
+    p = pitch.reshape(-1); V = vel.astype(np.float64).reshape(-1).copy()
+    Y = np.zeros((len(p), 60))
+    for i, c in enumerate(p):
+        if c != 60:
+            Y[i, c] = 1
+    for s in range(len(V)):
+        if Y[s].sum() == 0:
+            V[s] = 0
+    for voice in range(mv):
+        previous_pitch = -1; previous_velocity = 0.0
+        for i, (nv, velocity) in enumerate(zip(Y[voice::mv], V[voice::mv])):
+            pitch_is_silent = nv.sum() == 0
+            pitch_ = -1 if pitch_is_silent else int(np.argmax(nv))
+            velocity_is_silent = velocity < thr
+            if velocity_is_silent:
+                if (not pitch_is_silent) and previous_pitch > 0 and previous_pitch != pitch_:
+                    V[i * mv + voice] = previous_velocity
+            elif pitch_is_silent:
+                V[i * mv + voice] = 0
+            previous_pitch = pitch_
+            if not velocity_is_silent:
+                previous_velocity = velocity
+    D = np.ones(len(V)); D[V > thr] = 0
+    return Y, V, D
+
+
+def test_postprocess_matches_the_reference_loop():
+    from midi_vae_b200 import postprocess
+    rng = np.random.default_rng(0)
+    for trial in range(10):
+        r = synth.make_batch(3, 32, seed=trial)
+        vel = np.where(rng.random(r.velocity.shape) < 0.3, rng.random(r.velocity.shape), r.velocity).astype(np.float32)
+        pit = np.where(rng.random(r.pitch.shape) < 0.2, 60, r.pitch).astype(np.uint8)
+        Y, I, V, D = postprocess.process_decoder_outputs(pit, r.instr, vel)
+        Y2, V2, D2 = _reference_postprocess_loop(pit, vel)
+        assert np.array_equal(Y, Y2) and np.allclose(V, V2) and np.array_equal(D, D2)
+        assert I.shape == (3, 4, 16) and np.all(I.sum(-1) == 1)
