@@ -47,6 +47,7 @@ struct RecKP {
   const bf16* dhext; const bf16* dh_last; int ld_last; bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
   long long* trace;   // optional per-phase clock64 stamps of CTA 0 (debug / profiling)
   void* partial;      // K-split backward: bf16 exchange buffer [2][groups_total][cpg][128][H]
+  bf16* hx;           // forward: h exchange buffer [2][groups_total][H/8 granules][128 rows][8]
   int groups_total;
 };
 
@@ -181,7 +182,7 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         // forward round r consumes h_{r-1} = hseq slab r (slab 0 = initial state, written before the launch);
         // backward round r consumes dG slab (T-1-r), published by the epilogue of iteration r
         const int slab = FWD ? r : (T - 1 - r);
-        if ((!FWD || r > 0) && waited_round != r) {
+        if (waited_round != r) {
           if (lane == 0) REC_TRACE(r, 0);
           wait_flag(flags + slab, (unsigned)p.cpg);
           fence_proxy_async_global();
@@ -195,7 +196,14 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         ptx::mbar_arrive_expect_tx(fb, A_STAGE_BYTES);
         // CTAs of a group read the SAME rows: start each at a different K-block so they do not sweep the same L2 lines in lockstep
         const int kbr = (kb + j * p.kb_rot) % kblocks;
-        ptx::tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, fb, kbr * BK, slab * p.n + row0);
+        if (FWD) {
+          // h_{r-1} of the whole group is one contiguous 128*H*2-byte block [H/8 granules][128 rows][8] of the exchange buffer;
+          // K-block kbr = granules 8*kbr .. 8*kbr+7 = 16 KB contiguous -> one bulk copy, landing as the no-swizzle K-major image
+          const bf16* src = p.hx + ((size_t)(r & 1) * p.groups_total + g) * ((size_t)BM * p.H) + (size_t)kbr * 8 * BM * 8;
+          ptx::bulk_load(smem_a + stage * A_STAGE_BYTES, src, A_STAGE_BYTES, fb);
+        } else {
+          ptx::tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, fb, kbr * BK, slab * p.n + row0);
+        }
         if (kb == kblocks - 1) REC_TRACE(r, 2);
       }
     }
@@ -217,9 +225,11 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           if (kb == kblocks - 1) REC_TRACE(r, 4);
           const uint32_t sa = smem_a + stage * A_STAGE_BYTES, sb = smem_b + ((kb + j * p.kb_rot) % kblocks) * B_KB_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(sa + k * 32, 16, 1024), ptx::umma_desc_sw128(sb + k * 32, 16, 1024), idesc,
-                           (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // forward: A tile is [8 granules][128 rows][16 B] (no swizzle): core matrices 128 B apart along M (SBO), 2 KB apart along K (LBO)
+            const uint64_t da = FWD ? ptx::umma_desc_noswz(sa + k * 4096, 2048, 128) : ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
+            ptx::umma_bf16(d_tmem, da, ptx::umma_desc_sw128(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
           ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -250,6 +260,18 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, (u0 >> 3) + ub, p.n, m)) = cv;   // stash slab 0 = c0
         }
       }
+      {   // h0 (hseq slab 0, row-major) -> exchange buffer 0, published like any other step
+        bf16* hx0 = p.hx + ((size_t)0 * p.groups_total + g) * ((size_t)BM * H);
+#pragma unroll
+        for (int c = 0; c < MYCH; ++c) {
+          const int ub = 2 * c + half;
+          uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+          if (row_ok) hv = *reinterpret_cast<const uint4*>(p.hseq + (size_t)m * H + u0 + ub * 8);
+          *reinterpret_cast<uint4*>(hx0 + ((size_t)((u0 >> 3) + ub) * BM + (quad * 32 + lane)) * 8) = hv;
+        }
+        epi_barrier();
+        if (warp == 2 && lane == 0) { __threadfence(); fence_proxy_async_global(); red_relaxed_add(flags + 0, 1u); }
+      }
       for (int t = 0; t < T; ++t) {
         const int acc = t & 1; const uint32_t acc_phase = (t >> 1) & 1;
         const size_t rowG = ((size_t)t * p.n + m) * G, rowH1 = ((size_t)(t + 1) * p.n + m) * H;
@@ -269,7 +291,8 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
         ptx::tc_fence_after();
         if (tracer) REC_TRACE(t, 6);
-        uint4 st_g[MYCH][4], st_c[MYCH];
+        uint4 st_g[MYCH][4], st_c[MYCH], st_h[MYCH];
+        bf16* hx1 = p.hx + ((size_t)((t + 1) & 1) * p.groups_total + g) * ((size_t)BM * H);
 #pragma unroll
         for (int c = 0; c < MYCH; ++c) {
           const int ub = 2 * c + half;
@@ -288,7 +311,10 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             else { cn[u] = tanh_fast(s); hn[u] = go[u] * cn[u]; }
             cst[c * 8 + u] = cn[u];
           }
-          if (row_ok) *reinterpret_cast<uint4*>(p.hseq + rowH1 + u0 + ub * 8) = pack8(hn);   // what the other CTAs wait for
+          st_h[c] = pack8(hn);
+          if (!row_ok) st_h[c] = make_uint4(0u, 0u, 0u, 0u);
+          // what the other CTAs wait for: coalesced 16-byte granules of the exchange buffer
+          *reinterpret_cast<uint4*>(hx1 + ((size_t)((u0 >> 3) + ub) * BM + (quad * 32 + lane)) * 8) = st_h[c];
           st_g[c][0] = pack8(gi); st_g[c][1] = pack8(gf); st_g[c][2] = pack8(gg); st_g[c][3] = pack8(go); st_c[c] = pack8(cn);
         }
         ptx::tc_fence_before();
@@ -312,6 +338,7 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           for (int c = 0; c < MYCH; ++c) {
             const int ub = 2 * c + half;
             const int gu = (u0 >> 3) + ub;
+            *reinterpret_cast<uint4*>(p.hseq + rowH1 + u0 + ub * 8) = st_h[c];      // row-major copy for the batched GEMMs
             *reinterpret_cast<uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, p.n, m)) = st_c[c];
             *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, p.n, m)) = st_g[c][0];
             *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, p.n, m)) = st_g[c][1];
@@ -532,16 +559,28 @@ rec_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tma_b, const RecKP p) 
         epi_barrier();
         // exchange layout [cta][H/8 granules][128 rows][8]: a warp's 32 rows read 512 contiguous bytes per instruction
         const bf16* src = part + (size_t)((it - 1) & 1) * part_buf + (size_t)g * part_grp + ((size_t)(u0 >> 3) * BM + r) * 8;
+        // software-pipelined: batch b+1 is in flight while batch b is summed (the loop is one L2 latency long, not cpg/8)
+        uint4 qa[8], qb[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) if (jj < p.cpg) qa[jj] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)jj * part_cta));
         for (int j0 = 0; j0 < p.cpg; j0 += 16) {
-          uint4 q[16];
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj)
-            if (j0 + jj < p.cpg) q[jj] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(j0 + jj) * part_cta));   // L2 only: written by other SMs
+          for (int jj = 0; jj < 8; ++jj) if (j0 + 8 + jj < p.cpg) qb[jj] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(j0 + 8 + jj) * part_cta));
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj)
+          for (int jj = 0; jj < 8; ++jj)
             if (j0 + jj < p.cpg) {
               float f[8];
-              unpack8(q[jj], f);
+              unpack8(qa[jj], f);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) dh[u] += f[u];
+            }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) if (j0 + 16 + jj < p.cpg) qa[jj] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(j0 + 16 + jj) * part_cta));
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            if (j0 + 8 + jj < p.cpg) {
+              float f[8];
+              unpack8(qb[jj], f);
 #pragma unroll
               for (int u = 0; u < 8; ++u) dh[u] += f[u];
             }
@@ -722,6 +761,8 @@ void launch(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
   p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last; p.dG = (bf16*)a.dG;
   p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
   p.trace = (long long*)a.trace;
+  p.hx = (bf16*)a.hx; p.groups_total = groups;
+  if (FWD) MVAE_REQUIRE(a.hx != nullptr, "persistent forward needs the h exchange buffer");
   MVAE_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)groups * p.flag_stride * sizeof(unsigned), st));
   // A: forward  = hseq  as a 2-D matrix [(steps+1)*n, H]  ; backward = dG as [steps*n, 4H]
   const CUtensorMap ma = FWD ? make_map(a.hseq, H, (uint64_t)(a.steps + 1) * a.n, H, 64, BM) : make_map(a.dG, G, (uint64_t)a.steps * a.n, G, 64, BM);
@@ -760,6 +801,8 @@ bool rec_persist_supported(int H, int sm_count) {
   const int hs = rec_persist_hs(H);
   return hs > 0 && H / hs <= sm_count;
 }
+
+size_t rec_persist_hx_bytes(int n, int H) { return 2 * (size_t)((n + BM - 1) / BM) * BM * H * 2; }
 
 size_t rec_persist_flag_count(int n, int steps) { return (size_t)((n + BM - 1) / BM) * (steps + 2); }
 

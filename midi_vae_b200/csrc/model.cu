@@ -86,6 +86,7 @@ void Model::build_workspace() {
     if (use_persist && rec_persist_ksplit_ok(H)) r.upack_b = alloc((size_t)G * H * 2);
   };
   if (use_persist && rec_persist_ksplit_ok(H)) rec_partial = alloc(rec_persist_partial_bytes(NB, H));
+  if (use_persist) rec_hx = alloc(rec_persist_hx_bytes(NB, H));
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
@@ -283,7 +284,7 @@ void Model::rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, 
     rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, r.variant, st);
     RecPersistArgs a;
     a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = rec_flags;
-    a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates; a.c0 = c0; a.ldc0 = ld0;
+    a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates; a.c0 = c0; a.ldc0 = ld0; a.hx = rec_hx;
     a.trace = trace_buf;
     rec_persist_forward(a, st, sm_count);
     dump_trace("fwd", r);

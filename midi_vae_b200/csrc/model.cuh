@@ -104,6 +104,7 @@ struct Model {
   bool use_persist = false;          // persistent-RNN kernels (bf16 precision, supported hidden size)
   long long* trace_buf = nullptr;    // MVAE_REC_TRACE=1 debugging aid
   int trace_dumps = 0;
+  void* rec_hx = nullptr;            // h exchange buffer of the persistent forward kernel
   void* rec_partial = nullptr;       // bf16 partial-dh exchange buffer of the K-split backward kernel
   unsigned* rec_flags = nullptr;     // per-(group, step) publication counters of the persistent kernels
   std::vector<void*> allocs_;

@@ -27,6 +27,7 @@ struct RecPersistArgs {
   void* dS_h = nullptr;               // (n, ldS) bf16 gradient wrt h0 / c0 (or null)
   void* dS_c = nullptr;
   int ldS = 0;
+  void* hx = nullptr;                 // forward: h exchange buffer, rec_persist_hx_bytes
   const void* upack_bwd = nullptr;    // K-split backward: packed weights, rec_persist_pack_u_bwd
   void* partial = nullptr;            // K-split backward: exchange buffer, rec_persist_partial_bytes
   void* trace = nullptr;              // optional: 8 steps x 16 clock64 stamps of CTA 0 (profiling aid)
@@ -36,6 +37,7 @@ size_t smem_max_bytes();
 int rec_persist_hs(int H);                           // hidden units per CTA (0 = unsupported)
 bool rec_persist_supported(int H, int sm_count);
 size_t rec_persist_flag_count(int n, int steps);
+size_t rec_persist_hx_bytes(int n, int H);
 void rec_persist_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st);
 bool rec_persist_ksplit_ok(int H);
 size_t rec_persist_partial_bytes(int n, int H);

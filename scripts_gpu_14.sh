@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --maxfail=40 -p no:cacheprovider -k "persistent or bf16" 2>&1 | tail -4
+echo "=== bench bf16 cfg3"; timeout 900 python bench.py --workload cfg3 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b14.log 2>&1; tail -1 gpurun_out/b14.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['class_ms'])"
+MVAE_REC_TRACE=1 timeout 300 python scripts_one_step.py persistent 1 > gpurun_out/trace14.log 2>&1
+grep -A2 "rec trace" gpurun_out/trace14.log | grep -A2 -E "rec trace (fwd lstm_1|bwd lstm_1)" | cut -c1-330

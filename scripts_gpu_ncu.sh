@@ -1,25 +1,9 @@
 #!/bin/bash
-# ncu: launch list of one cfg3 step + full captures of the persistent recurrence kernels and the GEMM
+# ncu: launch list of one cfg3 step (persistent) + full captures of the dominant kernels
 mkdir -p gpurun_out
-cat > /tmp/one_step.py <<'PY'
-import sys, os
-sys.path.insert(0, '.')
-import numpy as np
-from midi_vae_b200 import Engine, EngineConfig, initial_weights, synth
-wl = dict(T=256, H=512, L=256, B=512)
-mode = sys.argv[1] if len(sys.argv) > 1 else "persistent"
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-cfg = EngineConfig(input_length=wl["T"], lstm_size=wl["H"], latent_rep_size=wl["L"], decoder_feedback="teacher_forced", precision="bf16", rnn_mode=mode, max_batch=wl["B"])
-eng = Engine(cfg, 0); eng.set_weights(initial_weights(cfg, 42))
-r = synth.make_batch(wl["B"], wl["T"], seed=1); eps = synth.make_eps(wl["B"], wl["L"], 1)
-for i in range(steps):
-    m = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, None, eps)
-print(m["loss"])
-PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_cfg3_persistent.csv python /tmp/one_step.py persistent 2 > gpurun_out/ncu_list.log 2>&1
-tail -2 gpurun_out/ncu_list.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:rec_persist_kernel -s 8 -c 4 -o gpurun_out/prof_rec_persist python /tmp/one_step.py persistent 2 > gpurun_out/ncu_rec.log 2>&1
-tail -2 gpurun_out/ncu_rec.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 30 -c 6 -o gpurun_out/prof_gemm_tc python /tmp/one_step.py persistent 2 > gpurun_out/ncu_gemm.log 2>&1
-tail -2 gpurun_out/ncu_gemm.log
-ls -la gpurun_out/
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_cfg3.csv python scripts_one_step.py persistent 2 > gpurun_out/ncu_list.log 2>&1
+tail -1 gpurun_out/ncu_list.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rec_persist_kernel|rec_bwd_ksplit" -s 8 -c 6 -o gpurun_out/prof_rec python scripts_one_step.py persistent 2 > gpurun_out/ncu_rec.log 2>&1
+tail -1 gpurun_out/ncu_rec.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 100 -c 40 -o gpurun_out/prof_gemm python scripts_one_step.py persistent 2 > gpurun_out/ncu_gemm.log 2>&1
+tail -1 gpurun_out/ncu_gemm.log
