@@ -261,17 +261,29 @@ def main():
         pk = peaks()
         fwd, rec_fwd = flops_per_seq(T, H, L, args.feedback)
         train = 3 * fwd
-        rec_train = 2 * rec_fwd                      # h U forward + dG U^T backward (the sequential chain)
-        gemm_train = train - rec_train               # everything batchable
-        rec_ms = kms["rec_fwd"][0] + kms["rec_bwd"][0]
-        gemm_ms = kms["gemm"][0]
-        dom = "recurrence (h*U / dG*U^T per step + gate math)" if rec_ms >= gemm_ms else "batched GEMMs (input projections, heads, weight gradients)"
-        dom_flops = (rec_train if rec_ms >= gemm_ms else gemm_train) * B
-        dom_ms = max(rec_ms, gemm_ms)
+        # kernel classes and their algorithmic FLOPs per step (B sequences): the forward recurrences do h*U, the backward
+        # recurrences dG*U^T (same count), everything else (input projections, heads, all weight gradients) is batched GEMM
+        classes = {
+            "rec_bwd": ("persistent backward recurrence (dG*U^T per step + gate-gradient math)" if args.rnn_mode != "streamed" and args.precision == "bf16"
+                        else "step-streamed backward recurrence", rec_fwd * B),
+            "rec_fwd": ("persistent forward recurrence (h*U per step + gate math)" if args.rnn_mode != "streamed" and args.precision == "bf16"
+                        else "step-streamed forward recurrence", rec_fwd * B),
+            "gemm": ("batched tcgen05 GEMMs (input projections, heads, weight gradients)", (train - 2 * rec_fwd) * B),
+        }
+        dom = max(classes, key=lambda k: kms[k][0])
+        dom_ms = kms[dom][0]
         peak = pk["bf16_sustained"]
-        achieved = dom_flops / (dom_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+        achieved = classes[dom][1] / (dom_ms / 1e3) / 1e12
+        traffic = None
+        ncu_file = os.path.join(ROOT, "profiles", "r1", "ncu_rec_bwd_ksplit_cfg3.json")
+        if dom == "rec_bwd" and args.workload == "cfg3" and os.path.exists(ncu_file):
+            ks = [k for k in json.load(open(ncu_file))["kernels"] if k["gpu__time_duration.sum"] > 1.0]   # the T=256 launches
+            if ks:
+                traffic = {"dram_bytes_per_launch": sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in ks) / len(ks) * 1e6,
+                           "launches_per_step": 6, "source": "profiles/r1/ncu_rec_bwd_ksplit_cfg3.json (ncu --set full)"}
+        roof = {"bound": "tensor", "kernel": classes[dom][0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "kernel_ms_per_step": dom_ms, "kernel_flops_per_step": classes[dom][1],
                 "step": {"achieved": value / world * train / 1e12, "frac": value / world * train / 1e12 / peak,
                          "frac_of_burst": value / world * train / 1e12 / pk["bf16_burst"], "train_flops_per_seq": train},
                 "class_ms": {k: round(v[0], 4) for k, v in kms.items()}, "class_launch_groups": {k: v[1] for k, v in kms.items()}}

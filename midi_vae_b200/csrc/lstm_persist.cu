@@ -677,6 +677,268 @@ rec_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tma_b, const RecKP p) 
   if (warp == 1) ptx::tmem_dealloc(tmem_base, tm_cols);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K-split backward, general form: HS = 16 or 32 hidden units per CTA (K = 4*HS = 64 or 128 gate columns) and ONE or TWO
+// independent recurrences per launch.  Every phase of a step is an L2 round trip, so a recurrence on its own leaves the
+// SMs idle ~90 % of the time; two recurrences that do not depend on each other (e.g. the top notes cell and the velocity
+// cell of the decoder) therefore share one launch: CTAs [0, ctas0) run recurrence 0, the rest recurrence 1, each with its
+// own flags / exchange buffer / weights, and with HS = 32 each needs only 16 CTAs per 128-row group.
+struct KsplitPair {
+  RecKP p[2];
+  int ctas0;     // CTAs of recurrence 0 (the launch has ctas0 + ctas1)
+};
+
+template <int HS>
+__global__ void __launch_bounds__(kThreads, 1)
+rec_bwd_ksplit2_kernel(const __grid_constant__ CUtensorMap tma_b0, const __grid_constant__ CUtensorMap tma_b1, const __grid_constant__ KsplitPair pp) {
+  constexpr int KC = 4 * HS;               // gate columns (MMA K) owned by this CTA
+  constexpr int KB = KC / BK;              // K blocks of 64
+  constexpr int MYCH = HS / 16;            // 8-unit chunks per row thread
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t b_full_bar, a_full_bar, tmem_full_bar, tmem_empty_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int which = (int)blockIdx.x >= pp.ctas0 ? 1 : 0;
+  const RecKP& p = pp.p[which];
+  const CUtensorMap* tma_b = which ? &tma_b1 : &tma_b0;
+  const int bid = (int)blockIdx.x - (which ? pp.ctas0 : 0);
+
+  const int H = p.H, G = p.G, T = p.steps;
+  const int NH = H <= 256 ? 1 : H / 256, NB = H / NH;              // MMA N chunks
+  const uint32_t tm_cols = H <= 32 ? 32 : (H <= 64 ? 64 : (H <= 128 ? 128 : (H <= 256 ? 256 : 512)));
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_b = smem_base;                                // KB x [H][64] bf16 K-major
+  const uint32_t smem_a = smem_base + (uint32_t)KB * H * 128;       // KB x [128][64] bf16 K-major
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = p.group0 + bid / p.cpg, j = bid % p.cpg;
+  const int row0 = g * BM;
+  unsigned* flags = p.flags + (size_t)g * p.flag_stride;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(tma_b);
+    ptx::mbar_init(ptx::smem_u32(&b_full_bar), 1);
+    ptx::mbar_init(ptx::smem_u32(&a_full_bar), ROW_THREADS);
+    ptx::mbar_init(ptx::smem_u32(&tmem_full_bar), 1);
+    ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar), EPI_WARPS);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), tm_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // resident weights [cpg][KB][H][64]
+      const uint32_t bb = ptx::smem_u32(&b_full_bar);
+      ptx::mbar_arrive_expect_tx(bb, (uint32_t)KB * H * 128);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int nh = 0; nh < NH; ++nh) ptx::tma_load_2d(smem_b + (kb * H + nh * NB) * 128, tma_b, bb, 0, (j * KB + kb) * H + nh * NB);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(BM, NB, false, false);
+      ptx::mbar_wait(ptx::smem_u32(&b_full_bar), 0);
+      for (int it = 0; it < T; ++it) {
+        ptx::mbar_wait(ptx::smem_u32(&a_full_bar), it & 1);                 // dG_t tile written by the row warps
+        ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar), (it & 1) ^ 1);       // previous partial drained
+        ptx::tc_fence_after();
+        for (int nh = 0; nh < NH; ++nh)
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              ptx::umma_bf16(tmem_base + nh * NB, ptx::umma_desc_sw128(smem_a + kb * 16384 + k * 32, 16, 1024),
+                             ptx::umma_desc_sw128(smem_b + (kb * H + nh * NB) * 128 + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        ptx::umma_commit(ptx::smem_u32(&tmem_full_bar));
+      }
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    const int r = quad * 32 + lane, m = row0 + r;
+    const bool row_ok = m < p.n;
+    const bool tracer = (etid == 0);
+    const int bi = p.variant == MVAE_CELL_STANDARD ? 0 : 1, bfk = 1 - bi;
+    bf16* part = (bf16*)p.partial;                                      // [2][groups_total][cpg][H/8 granules][128 rows][8]
+    const size_t part_cta = (size_t)BM * H, part_grp = part_cta * p.cpg, part_buf = part_grp * p.groups_total;
+    float dc[MYCH * 8];
+#pragma unroll
+    for (int u = 0; u < MYCH * 8; ++u) dc[u] = 0.f;
+
+    for (int it = 0; it <= T; ++it) {
+      const int t = T - 1 - it;
+      uint4 sg[MYCH][4], sc0[MYCH], sc1[MYCH], se[MYCH];
+      if (t >= 0 && row_ok) {
+#pragma unroll
+        for (int c = 0; c < MYCH; ++c) {
+          const int u0 = j * HS + (2 * c + half) * 8, gu = u0 >> 3;
+          sg[c][0] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, p.n, m)));
+          sg[c][1] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, p.n, m)));
+          sg[c][2] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, p.n, m)));
+          sg[c][3] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, p.n, m)));
+          sc0[c] = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t, H / 8, gu, p.n, m)));
+          sc1[c] = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, p.n, m)));
+          if (p.dhext) se[c] = __ldg(reinterpret_cast<const uint4*>(p.dhext + ((size_t)t * p.n + m) * H + u0));
+        }
+      }
+      // ---- dh_t = sum over the group's CTAs of their partial dG_{t+1} U^T, for this thread's units
+      float dh[MYCH * 8];
+#pragma unroll
+      for (int u = 0; u < MYCH * 8; ++u) dh[u] = 0.f;
+      if (it > 0) {
+        if (tracer) { REC_TRACE(it, 0); wait_flag(flags + (t + 1), (unsigned)p.cpg); REC_TRACE(it, 1); }
+        epi_barrier();
+#pragma unroll
+        for (int c = 0; c < MYCH; ++c) {
+          const int u0 = j * HS + (2 * c + half) * 8;
+          const bf16* src = part + (size_t)((it - 1) & 1) * part_buf + (size_t)g * part_grp + ((size_t)(u0 >> 3) * BM + r) * 8;
+          uint4 qa[8], qb[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) if (jj < p.cpg) qa[jj] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)jj * part_cta));
+          for (int j0 = 0; j0 < p.cpg; j0 += 16) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) if (j0 + 8 + jj < p.cpg) qb[jj] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(j0 + 8 + jj) * part_cta));
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              if (j0 + jj < p.cpg) {
+                float f[8];
+                unpack8(qa[jj], f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dh[c * 8 + u] += f[u];
+              }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) if (j0 + 16 + jj < p.cpg) qa[jj] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)(j0 + 16 + jj) * part_cta));
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              if (j0 + 8 + jj < p.cpg) {
+                float f[8];
+                unpack8(qb[jj], f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dh[c * 8 + u] += f[u];
+              }
+          }
+        }
+        if (tracer) REC_TRACE(it, 2);
+      }
+      if (t < 0) {
+        if (row_ok && p.dS_h) {
+#pragma unroll
+          for (int c = 0; c < MYCH; ++c) {
+            const int u0 = j * HS + (2 * c + half) * 8;
+            *reinterpret_cast<uint4*>(p.dS_h + (size_t)m * p.ldS + u0) = pack8(&dh[c * 8]);
+            *reinterpret_cast<uint4*>(p.dS_c + (size_t)m * p.ldS + u0) = pack8(&dc[c * 8]);
+          }
+        }
+        break;
+      }
+      // ---- gate-gradient math for step t; operand A row r = [di(HS) | df(HS) | dg(HS) | do(HS)] in 16-byte chunks
+      uint4 pk[MYCH][4];
+#pragma unroll
+      for (int c = 0; c < MYCH; ++c) {
+        const int u0 = j * HS + (2 * c + half) * 8;
+        float gi[8], gf[8], gg[8], go[8], c0[8], c1[8], ex[8], di[8], df[8], dg[8], dob[8];
+        unpack8(sg[c][0], gi); unpack8(sg[c][1], gf); unpack8(sg[c][2], gg); unpack8(sg[c][3], go); unpack8(sc0[c], c0); unpack8(sc1[c], c1);
+        if (p.dhext) unpack8(se[c], ex);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float d = dh[c * 8 + u];
+          if (p.dhext) d += ex[u];
+          if (it == 0 && p.dh_last) d += row_ok ? __bfloat162float(p.dh_last[(size_t)m * p.ld_last + u0 + u]) : 0.f;
+          float d_o, ds;
+          if (p.variant == MVAE_CELL_STANDARD) {
+            const float tc = tanh_fast(c1[u]);
+            d_o = d * tc;
+            ds = dc[c * 8 + u] + d * go[u] * (1.f - tc * tc);
+          } else {
+            d_o = d * c1[u];
+            ds = (dc[c * 8 + u] + d * go[u]) * (1.f - c1[u] * c1[u]);
+          }
+          di[u] = ds * gg[u] * gate_bwd(p.gate_act, gi[u]);
+          df[u] = ds * c0[u] * gate_bwd(p.gate_act, gf[u]);
+          dg[u] = ds * gi[u] * (1.f - gg[u] * gg[u]);
+          dob[u] = d_o * gate_bwd(p.gate_act, go[u]);
+          dc[c * 8 + u] = ds * gf[u];
+          if (!row_ok) { di[u] = 0.f; df[u] = 0.f; dg[u] = 0.f; dob[u] = 0.f; dc[c * 8 + u] = 0.f; }
+        }
+        pk[c][0] = pack8(di); pk[c][1] = pack8(df); pk[c][2] = pack8(dg); pk[c][3] = pack8(dob);
+        const int sw = r & 7;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = q * (HS / 8) + (2 * c + half);            // 16-byte chunk index along K (0 .. KC/8-1)
+          st_shared16(smem_a + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ sw) << 4), pk[c][q]);
+        }
+      }
+      ptx::fence_proxy_async();                                     // generic-proxy smem writes -> tensor core (async proxy)
+      ptx::mbar_arrive(ptx::smem_u32(&a_full_bar));
+      // ---- partial dh_{t-1} for all H units: TMEM -> bf16 -> this CTA's slot of the exchange buffer
+      if (tracer) REC_TRACE(it, 5);
+      ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar), it & 1);
+      ptx::tc_fence_after();
+      if (tracer) REC_TRACE(it, 6);
+      {
+        bf16* dst = part + (size_t)(it & 1) * part_buf + (size_t)g * part_grp + (size_t)j * part_cta;
+        const int nch = H / 64;                                      // 32-column chunks in this thread's half
+        for (int c = 0; c < nch; ++c) {
+          float v[32];
+          const int col0 = half * (H / 2) + c * 32;
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, v);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + ((size_t)((col0 >> 3) + q4) * BM + r) * 8) = pack8(&v[q4 * 8]);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar));
+      if (tracer) REC_TRACE(it, 7);
+      epi_barrier();
+      if (tracer) {
+        REC_TRACE(it, 9);
+        __threadfence();
+        REC_TRACE(it, 10);
+        red_relaxed_add(flags + t, 1u);
+        REC_TRACE(it, 11);
+      }
+      if (row_ok) {   // dG_t for the batched weight-gradient GEMMs: row-major (16-byte pieces), off the critical path
+#pragma unroll
+        for (int c = 0; c < MYCH; ++c) {
+          bf16* dgp = p.dG + ((size_t)t * p.n + m) * G + j * HS + (2 * c + half) * 8;
+          *reinterpret_cast<uint4*>(dgp + bi * H) = pk[c][0];
+          *reinterpret_cast<uint4*>(dgp + bfk * H) = pk[c][1];
+          *reinterpret_cast<uint4*>(dgp + 2 * H) = pk[c][2];
+          *reinterpret_cast<uint4*>(dgp + 3 * H) = pk[c][3];
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, tm_cols);
+}
+
+// U (H, 4H) fp32 -> packed bf16 [cpg][KB][H units][64] K-major for the general K-split backward:
+// K index kk = gate*HS + uu of CTA j (K block kk/64, column kk%64) holds U[k, blk(gate)*H + j*HS + uu]
+__global__ void pack_u_bwd2_kernel(const float* __restrict__ U, int ldu, bf16* __restrict__ out, int H, int HS, int variant) {
+  const long total = (long)H * 4 * H;
+  const int KC = 4 * HS, KB = KC / 64;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int col = (int)(e % 64);
+    long rest = e / 64;
+    const int k = (int)(rest % H); rest /= H;
+    const int kb = (int)(rest % KB);
+    const int j = (int)(rest / KB);
+    const int kk = kb * 64 + col;
+    const int gate = kk / HS, uu = kk % HS;
+    int blk = gate;
+    if (variant != MVAE_CELL_STANDARD && gate < 2) blk = 1 - gate;
+    out[e] = __float2bfloat16_rn(U[(long)k * ldu + blk * H + j * HS + uu]);
+  }
+}
+
 // U (H, 4H) fp32 -> per-CTA packed bf16 [cpg][H units][64] K-major for the K-split backward:
 // column kk = gate*16 + uu of CTA j's block holds U[k, blk(gate)*H + j*16 + uu]
 __global__ void pack_u_bwd_kernel(const float* __restrict__ U, int ldu, bf16* __restrict__ out, int H, int variant) {
@@ -836,42 +1098,81 @@ size_t rec_persist_partial_bytes(int n, int H) {
   return 2 * groups * (size_t)(H / 16) * BM * H * 2;
 }
 
-void rec_persist_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int variant, cudaStream_t st) {
-  pack_u_bwd_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack_bwd, H, variant);
+void rec_persist_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int HS, int variant, cudaStream_t st) {
+  MVAE_REQUIRE(HS == 16 || HS == 32, "K-split backward: 16 or 32 units per CTA");
+  pack_u_bwd2_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack_bwd, H, HS, variant);
   count_launch();
   MVAE_CUDA(cudaGetLastError());
 }
 
-static void launch_bwd_ksplit(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
-  const int H = a.H, G = 4 * H, HS = 16, cpg = H / HS;
-  const int groups = (a.n + BM - 1) / BM;
-  const int NH = H <= 256 ? 1 : H / 256, NB = H / NH;
-  const size_t smem = (size_t)H * 128 + 16384 + 1024;
-  auto kern = rec_bwd_ksplit_kernel<16>;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) { MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
-  MVAE_REQUIRE(a.upack_bwd && a.partial, "K-split backward needs the packed weights and the exchange buffer");
+static size_t ksplit_smem(int H, int HS) { return (size_t)(4 * HS / 64) * ((size_t)H * 128 + 16384) + 1024; }
+
+// units per CTA with which TWO recurrences of batch n fit into one co-resident launch (0 = they do not)
+int rec_persist_pair_hs(int H, int n, int sm_count) {
+  if (!rec_persist_ksplit_ok(H)) return 0;
+  const int groups = (n + BM - 1) / BM;
+  for (int hs : {16, 32}) {
+    if (H % hs) continue;
+    if (ksplit_smem(H, hs) > smem_max_bytes()) continue;
+    if (2 * groups * (H / hs) <= sm_count) return hs;
+  }
+  return 0;
+}
+
+static RecKP ksplit_params(const RecPersistArgs& a, int HS, int groups) {
   RecKP p{};
-  p.n = a.n; p.H = H; p.G = G; p.steps = a.steps; p.cpg = cpg; p.HS = HS; p.gate_act = a.gate_act; p.variant = a.variant;
+  p.n = a.n; p.H = a.H; p.G = 4 * a.H; p.steps = a.steps; p.cpg = a.H / HS; p.HS = HS; p.gate_act = a.gate_act; p.variant = a.variant;
   p.flags = a.flags; p.flag_stride = a.steps + 2;
   p.gates = (bf16*)a.gates; p.cseq = (bf16*)a.cseq;
   p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last; p.dG = (bf16*)a.dG;
   p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
   p.trace = (long long*)a.trace; p.partial = a.partial; p.groups_total = groups;
-  MVAE_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)groups * p.flag_stride * sizeof(unsigned), st));
-  const CUtensorMap mb = make_map(a.upack_bwd, 64, (uint64_t)cpg * H, 64, 64, NB);
+  return p;
+}
+
+template <int HS>
+static void launch_bwd_ksplit2(const RecPersistArgs& a, const RecPersistArgs* b, cudaStream_t st, int sm_count) {
+  const int H = a.H, cpg = H / HS, KB = 4 * HS / 64;
+  const int NH = H <= 256 ? 1 : H / 256, NB = H / NH;
+  const size_t smem = ksplit_smem(H, HS);
+  MVAE_REQUIRE(smem <= smem_max_bytes(), "K-split backward: weight slice does not fit in shared memory");
+  auto kern = rec_bwd_ksplit2_kernel<HS>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) { MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+  MVAE_REQUIRE(a.upack_bwd && a.partial && (!b || (b->upack_bwd && b->partial && b->H == H)), "K-split backward needs packed weights and exchange buffers");
+  const int ga = (a.n + BM - 1) / BM, gb = b ? (b->n + BM - 1) / BM : 0;
+  KsplitPair pp{};
+  pp.p[0] = ksplit_params(a, HS, ga);
+  MVAE_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)ga * pp.p[0].flag_stride * sizeof(unsigned), st));
+  const CUtensorMap ma = make_map(a.upack_bwd, 64, (uint64_t)cpg * KB * H, 64, 64, NB);
+  if (b) {
+    pp.p[1] = ksplit_params(*b, HS, gb);
+    MVAE_CUDA(cudaMemsetAsync(b->flags, 0, (size_t)gb * pp.p[1].flag_stride * sizeof(unsigned), st));
+    const CUtensorMap mbm = make_map(b->upack_bwd, 64, (uint64_t)cpg * KB * H, 64, 64, NB);
+    MVAE_REQUIRE((ga + gb) * cpg <= sm_count, "paired recurrences must be co-resident");
+    pp.p[0].group0 = 0; pp.p[1].group0 = 0; pp.ctas0 = ga * cpg;
+    kern<<<(ga + gb) * cpg, kThreads, smem, st>>>(ma, mbm, pp);
+    count_launch();
+    MVAE_CUDA(cudaGetLastError());
+    return;
+  }
   const int gmax = std::max(1, sm_count / cpg);
-  for (int g0 = 0; g0 < groups; g0 += gmax) {
-    const int ng = std::min(gmax, groups - g0);
-    p.group0 = g0;
-    kern<<<ng * cpg, kThreads, smem, st>>>(mb, p);
+  for (int g0 = 0; g0 < ga; g0 += gmax) {
+    const int ng = std::min(gmax, ga - g0);
+    pp.p[0].group0 = g0; pp.ctas0 = ng * cpg;
+    kern<<<ng * cpg, kThreads, smem, st>>>(ma, ma, pp);
     count_launch();
     MVAE_CUDA(cudaGetLastError());
   }
 }
 
+void rec_persist_backward_pair(const RecPersistArgs& a, const RecPersistArgs* b, int HS, cudaStream_t st, int sm_count) {
+  if (HS == 32) launch_bwd_ksplit2<32>(a, b, st, sm_count);
+  else launch_bwd_ksplit2<16>(a, b, st, sm_count);
+}
+
 void rec_persist_backward(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
-  if (rec_persist_ksplit_ok(a.H) && a.upack_bwd && a.partial) { launch_bwd_ksplit(a, st, sm_count); return; }
+  if (rec_persist_ksplit_ok(a.H) && a.upack_bwd && a.partial) { rec_persist_backward_pair(a, nullptr, 16, st, sm_count); return; }
   switch (rec_persist_hs(a.H)) {
     case 32: launch<false, 32>(a, st, sm_count); break;
     case 16: launch<false, 16>(a, st, sm_count); break;

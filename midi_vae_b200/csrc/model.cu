@@ -85,7 +85,8 @@ void Model::build_workspace() {
     if (use_persist) r.upack = alloc((size_t)G * H * 2);
     if (use_persist && rec_persist_ksplit_ok(H)) r.upack_b = alloc((size_t)G * H * 2);
   };
-  if (use_persist && rec_persist_ksplit_ok(H)) rec_partial = alloc(rec_persist_partial_bytes(NB, H));
+  if (use_persist && rec_persist_ksplit_ok(H)) { rec_partial = alloc(rec_persist_partial_bytes(NB, H)); rec_partial2 = alloc(rec_persist_partial_bytes(NB, H)); }
+  if (use_persist) rec_flags2 = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   if (use_persist) rec_hx = alloc(rec_persist_hx_bytes(NB, H));
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
@@ -146,6 +147,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
   build_workspace();
+  { const char* e = getenv("MVAE_REC_PAIR"); pair_recs = e ? atoi(e) != 0 : true; }
   if (getenv("MVAE_REC_TRACE")) trace_buf = (long long*)alloc(128 * sizeof(long long));
   MVAE_CUDA(cudaStreamSynchronize(stream));
 }
@@ -306,58 +308,109 @@ void Model::rec_steps_forward(Rec& r, int n, int t0, int t1) {
 }
 
 // --------------------------------------------------------------------------------------------- one recurrence, backward
-void Model::rec_backward(Rec& r, int n, int kind, const void* X, bool use_dhext, const void* dh_last, int ld_last, bool need_dx, void* dx_out,
-                         void* dS_h, void* dS_c, int ldS) {
-  const long rows = (long)r.steps * n;
-  void* dG = r.xw;  // the pre-activation buffer is dead after the forward sweep
+RecPersistArgs Model::bwd_args(const BwdJob& j, int n, int slot, int hs) {
+  Rec& r = *j.r;
+  RecPersistArgs a;
+  a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant;
+  a.flags = slot ? rec_flags2 : rec_flags;
+  a.gates = r.gates; a.cseq = r.cseq; a.u_shadow = W(r.iU); a.ldu = ld(r.iU);
+  a.dhext = j.use_dhext ? r.dhext : nullptr; a.dh_last = j.dh_last; a.ld_last = j.ld_last; a.dG = r.xw;
+  a.dS_h = j.dS_h; a.dS_c = j.dS_c; a.ldS = j.ldS;
+  if (r.upack_b && hs) {
+    rec_persist_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, hs, r.variant, st);
+    a.upack_bwd = r.upack_b; a.partial = slot ? rec_partial2 : rec_partial;
+  }
+  a.trace = slot ? nullptr : trace_buf;
+  return a;
+}
+
+// reverse-time sweep(s): dh_ext -> dG (into r.xw) and the gradients wrt the initial states.  Two independent recurrences
+// share one persistent launch when the K-split kernel can pair them (each step is a chain of L2 round trips; the second
+// recurrence fills the idle time of the first).
+void Model::rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n) {
   prof_begin(PC_REC_BWD);
   if (use_persist) {
-    RecPersistArgs a;
-    a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = rec_flags;
-    a.gates = r.gates; a.cseq = r.cseq; a.u_shadow = W(r.iU); a.ldu = ld(r.iU);
-    a.dhext = use_dhext ? r.dhext : nullptr; a.dh_last = dh_last; a.ld_last = ld_last; a.dG = dG;
-    a.dS_h = dS_h; a.dS_c = dS_c; a.ldS = ldS;
-    if (r.upack_b) { rec_persist_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, r.variant, st); a.upack_bwd = r.upack_b; a.partial = rec_partial; }
-    a.trace = trace_buf;
-    rec_persist_backward(a, st, sm_count);
-    dump_trace("bwd", r);
+    // pairing pays only when both recurrences run the same number of steps (a 4-step instrument cell cannot fill the gaps of a T-step one)
+    const int hs_pair = (jb && pair_recs && ja->r->steps == jb->r->steps) ? rec_persist_pair_hs(H, n, sm_count) : 0;
+    if (hs_pair) {
+      RecPersistArgs a = bwd_args(*ja, n, 0, hs_pair), b = bwd_args(*jb, n, 1, hs_pair);
+      rec_persist_backward_pair(a, &b, hs_pair, st, sm_count);
+      dump_trace("bwd", *ja->r);
+    } else {
+      for (const BwdJob* j : {ja, jb}) {
+        if (!j) continue;
+        RecPersistArgs a = bwd_args(*j, n, 0, rec_persist_ksplit_ok(H) ? 16 : 0);
+        if (a.upack_bwd) rec_persist_backward_pair(a, nullptr, 16, st, sm_count);
+        else rec_persist_backward(a, st, sm_count);
+        dump_trace("bwd", *j->r);
+      }
+    }
   } else {
-  MVAE_CUDA(cudaMemsetAsync(dh_run, 0, (size_t)n * H * 4, st));
-  MVAE_CUDA(cudaMemsetAsync(dc_run, 0, (size_t)n * H * 4, st));
-  for (int t = r.steps - 1; t >= 0; --t) {
-    k_cell_bwd(act, cc(r.variant), n, H, dh_run, use_dhext ? slab(r.dhext, t, (long)n * H) : nullptr, t == r.steps - 1 ? dh_last : nullptr,
-               ld_last, act, dc_run, slab(r.gates, t, (long)n * G), slab(r.cseq, t, (long)n * H), slab(r.cseq, t + 1, (long)n * H),
-               slab(dG, t, (long)n * G), st);
-    GemmArgs g; g.M = n; g.N = H; g.K = G; g.A = slab(dG, t, (long)n * G); g.lda = G; g.B = W(r.iU); g.ldb = ld(r.iU); g.transB = true;
-    g.C = dh_run; g.ldc = H; g.c_type = DT_F32;
-    gemm(g);
-  }
-  if (dS_h) {
-    k_copy2d(DT_F32, act, n, H, dh_run, H, dS_h, ldS, st);
-    k_copy2d(DT_F32, act, n, H, dc_run, H, dS_c, ldS, st);
-  }
+    for (const BwdJob* j : {ja, jb}) {
+      if (!j) continue;
+      Rec& r = *j->r;
+      void* dG = r.xw;
+      MVAE_CUDA(cudaMemsetAsync(dh_run, 0, (size_t)n * H * 4, st));
+      MVAE_CUDA(cudaMemsetAsync(dc_run, 0, (size_t)n * H * 4, st));
+      for (int t = r.steps - 1; t >= 0; --t) {
+        k_cell_bwd(act, cc(r.variant), n, H, dh_run, j->use_dhext ? slab(r.dhext, t, (long)n * H) : nullptr, t == r.steps - 1 ? j->dh_last : nullptr,
+                   j->ld_last, act, dc_run, slab(r.gates, t, (long)n * G), slab(r.cseq, t, (long)n * H), slab(r.cseq, t + 1, (long)n * H),
+                   slab(dG, t, (long)n * G), st);
+        GemmArgs g; g.M = n; g.N = H; g.K = G; g.A = slab(dG, t, (long)n * G); g.lda = G; g.B = W(r.iU); g.ldb = ld(r.iU); g.transB = true;
+        g.C = dh_run; g.ldc = H; g.c_type = DT_F32;
+        gemm(g);
+      }
+      if (j->dS_h) {
+        k_copy2d(DT_F32, act, n, H, dh_run, H, j->dS_h, j->ldS, st);
+        k_copy2d(DT_F32, act, n, H, dc_run, H, j->dS_c, j->ldS, st);
+      }
+    }
   }
   prof_end();
+}
+
+// batched weight gradients of one recurrence (dU = Hprev^T dG, dW = X^T dG, db = colsum dG) and dx = dG W^T for the layer below
+void Model::rec_backward_gemms(const BwdJob& j, int n) {
+  Rec& r = *j.r;
+  const long rows = (long)r.steps * n;
+  void* dG = r.xw;  // the pre-activation buffer is dead after the forward sweep
   prof_begin(PC_GEMM);
+  if (j.need_dx) {  // dx = dG W^T first: the layer below is waiting for it
+    GemmArgs g; g.M = (int)rows; g.N = r.Din; g.K = G; g.A = dG; g.lda = G; g.B = W(r.iW); g.ldb = ld(r.iW); g.transB = true;
+    g.C = j.dx_out; g.ldc = H; g.c_type = act;
+    gemm(g);
+  }
   {  // dU += Hprev^T dG
     GemmArgs g; g.M = H; g.N = G; g.K = (int)rows; g.A = r.hseq; g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
     gemm(g);
   }
-  if (kind == IN_DENSE) {  // dW += X^T dG
-    GemmArgs g; g.M = r.Din; g.N = G; g.K = (int)rows; g.A = X; g.lda = r.ldin; g.transA = true; g.B = dG; g.ldb = G;
+  if (j.kind == IN_DENSE) {  // dW += X^T dG
+    GemmArgs g; g.M = r.Din; g.N = G; g.K = (int)rows; g.A = j.X; g.lda = r.ldin; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iW); g.ldc = ld(r.iW); g.c_type = DT_F32; g.accumulate = true;
     gemm(g);
-  } else if (kind == IN_RANK1) {
-    k_colsum(act, rows, G, G, dG, X, VD, Gp(r.iW), st);
+  } else if (j.kind == IN_RANK1) {
+    k_colsum(act, rows, G, G, dG, j.X, VD, Gp(r.iW), st);
   }
   k_colsum(act, rows, G, G, dG, nullptr, 0, Gp(r.ib), st);
-  if (need_dx) {  // dx = dG W^T
-    GemmArgs g; g.M = (int)rows; g.N = r.Din; g.K = G; g.A = dG; g.lda = G; g.B = W(r.iW); g.ldb = ld(r.iW); g.transB = true;
-    g.C = dx_out; g.ldc = H; g.c_type = act;
-    gemm(g);
-  }
   prof_end();
+}
+
+// a stack of layers (top first) plus independent side recurrences: pair the i-th stack layer with the i-th side recurrence
+void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n) {
+  size_t si = 0;
+  for (size_t k = 0; k < stack.size(); ++k) {
+    const BwdJob* partner = si < side.size() ? &side[si] : nullptr;
+    rec_backward_sweep(&stack[k], partner, n);
+    rec_backward_gemms(stack[k], n);          // produces dhext of stack[k+1]
+    if (partner) { rec_backward_gemms(*partner, n); ++si; }
+  }
+  for (; si < side.size(); si += 2) {
+    const BwdJob* partner = si + 1 < side.size() ? &side[si + 1] : nullptr;
+    rec_backward_sweep(&side[si], partner, n);
+    rec_backward_gemms(side[si], n);
+    if (partner) rec_backward_gemms(*partner, n);
+  }
 }
 
 // --------------------------------------------------------------------------------------------- encoder (vae_definition.py:443-516)
@@ -531,13 +584,22 @@ void Model::backward(const mvae_batch& b) {
   // ---- decoder recurrences (top layer first)
   auto dS1 = [&](int r) { return (char*)dS + (size_t)(2 * r) * H * asz(); };
   auto dS2 = [&](int r) { return (char*)dS + (size_t)(2 * r + 1) * H * asz(); };
-  for (int k = nd - 1; k >= 0; --k) {
-    const void* X = k == 0 ? (tf ? Y_ext_cur : nullptr) : slab(dec_notes[k - 1].hseq, 1, (long)n * H);
-    int kind = k == 0 ? (tf ? IN_DENSE : IN_NONE) : IN_DENSE;
-    rec_backward(dec_notes[k], n, kind, X, true, nullptr, 0, k > 0, k > 0 ? dec_notes[k - 1].dhext : nullptr, dS1(k), dS2(k), nS * H);
+  {
+    std::vector<BwdJob> stack, side;
+    for (int k = nd - 1; k >= 0; --k) {
+      BwdJob j; j.r = &dec_notes[k];
+      j.X = k == 0 ? (tf ? Y_ext_cur : nullptr) : slab(dec_notes[k - 1].hseq, 1, (long)n * H);
+      j.kind = k == 0 ? (tf ? IN_DENSE : IN_NONE) : IN_DENSE;
+      j.use_dhext = true; j.need_dx = k > 0; j.dx_out = k > 0 ? dec_notes[k - 1].dhext : nullptr;
+      j.dS_h = dS1(k); j.dS_c = dS2(k); j.ldS = nS * H;
+      stack.push_back(j);
+    }
+    { BwdJob j; j.r = &dec_vel; j.kind = tf ? IN_RANK1 : IN_NONE; j.X = tf ? Xv_ext : nullptr; j.use_dhext = true;
+      j.dS_h = dS1(nd + 1); j.dS_c = dS2(nd + 1); j.ldS = nS * H; side.push_back(j); }
+    { BwdJob j; j.r = &dec_instr; j.kind = tf ? IN_DENSE : IN_NONE; j.X = tf ? Xi_ext : nullptr; j.use_dhext = true;
+      j.dS_h = dS1(nd); j.dS_c = dS2(nd); j.ldS = nS * H; side.push_back(j); }
+    rec_backward_group(stack, side, n);
   }
-  rec_backward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, true, nullptr, 0, false, nullptr, dS1(nd), dS2(nd), nS * H);
-  rec_backward(dec_vel, n, tf ? IN_RANK1 : IN_NONE, tf ? Xv_ext : nullptr, true, nullptr, 0, false, nullptr, dS1(nd + 1), dS2(nd + 1), nS * H);
   // ---- initial-state Denses -> dq
   prof_begin(PC_POINTWISE);
   k_tanh_bwd(act, (long)n * nS * H, dS, S, dSpre, st);
@@ -594,16 +656,22 @@ void Model::backward(const mvae_batch& b) {
     g.c_type = act; gemm(g); }
   prof_end();
   // ---- encoder recurrences: only the last step of each top recurrence receives a gradient
-  for (int k = ne - 1; k >= 0; --k) {
-    const void* X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
-    const bool is_top = k == ne - 1;
-    rec_backward(enc_pitch[k], n, IN_DENSE, X, !is_top, is_top ? du : nullptr, 3 * H, k > 0, k > 0 ? enc_pitch[k - 1].dhext : nullptr, nullptr,
-                 nullptr, 0);
+  {
+    std::vector<BwdJob> stack, side;
+    for (int k = ne - 1; k >= 0; --k) {
+      const bool is_top = k == ne - 1;
+      BwdJob j; j.r = &enc_pitch[k]; j.kind = IN_DENSE;
+      j.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
+      j.use_dhext = !is_top; j.dh_last = is_top ? du : nullptr; j.ld_last = 3 * H;
+      j.need_dx = k > 0; j.dx_out = k > 0 ? enc_pitch[k - 1].dhext : nullptr;
+      stack.push_back(j);
+    }
+    { BwdJob j; j.r = &enc_vel; j.kind = IN_RANK1; j.X = slab(Xv_ext, 1, (long)n * VD); j.dh_last = (const char*)du + (size_t)2 * H * asz(); j.ld_last = 3 * H;
+      side.push_back(j); }
+    { BwdJob j; j.r = &enc_instr; j.kind = IN_DENSE; j.X = slab(Xi_ext, 1, (long)n * ID); j.dh_last = (const char*)du + (size_t)H * asz(); j.ld_last = 3 * H;
+      side.push_back(j); }
+    rec_backward_group(stack, side, n);
   }
-  rec_backward(enc_instr, n, IN_DENSE, slab(Xi_ext, 1, (long)n * ID), false, (const char*)du + (size_t)H * asz(), 3 * H, false, nullptr, nullptr,
-               nullptr, 0);
-  rec_backward(enc_vel, n, IN_RANK1, slab(Xv_ext, 1, (long)n * VD), false, (const char*)du + (size_t)2 * H * asz(), 3 * H, false, nullptr, nullptr,
-               nullptr, 0);
 }
 
 }  // namespace mvae

@@ -36,6 +36,21 @@ struct Rec {
   void* upack = nullptr;  // (4H, H) bf16 : recurrent weights packed per CTA for the persistent forward kernel
 };
 
+// one backward recurrence: where its inputs / external gradients come from and where its outputs go
+struct BwdJob {
+  Rec* r = nullptr;
+  int kind = IN_NONE;
+  const void* X = nullptr;
+  bool use_dhext = false;
+  const void* dh_last = nullptr;
+  int ld_last = 0;
+  bool need_dx = false;
+  void* dx_out = nullptr;
+  void* dS_h = nullptr;
+  void* dS_c = nullptr;
+  int ldS = 0;
+};
+
 enum ProfClass { PC_REC_FWD = 0, PC_REC_BWD, PC_GEMM, PC_POINTWISE, PC_ADAM, PC_ALLREDUCE, PC_COUNT };
 
 struct Model {
@@ -106,7 +121,10 @@ struct Model {
   int trace_dumps = 0;
   void* rec_hx = nullptr;            // h exchange buffer of the persistent forward kernel
   void* rec_partial = nullptr;       // bf16 partial-dh exchange buffer of the K-split backward kernel
-  unsigned* rec_flags = nullptr;     // per-(group, step) publication counters of the persistent kernels
+  unsigned* rec_flags = nullptr;
+  unsigned* rec_flags2 = nullptr;    // second recurrence of a paired launch
+  void* rec_partial2 = nullptr;
+  bool pair_recs = true;             // MVAE_REC_PAIR=0 disables pairing two recurrences per launch     // per-(group, step) publication counters of the persistent kernels
   std::vector<void*> allocs_;
 
   explicit Model(const mvae_config& c, int dev);
@@ -140,8 +158,10 @@ struct Model {
   void prepare_inputs(const mvae_batch& b, bool need_target);
   void rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, const void* c0, int ld0);
   void rec_steps_forward(Rec& r, int n, int t0, int t1);
-  void rec_backward(Rec& r, int n, int kind, const void* X, bool use_dhext, const void* dh_last, int ld_last, bool need_dx, void* dx_out,
-                    void* dS_h, void* dS_c, int ldS);
+  RecPersistArgs bwd_args(const BwdJob& j, int n, int slot, int hs);
+  void rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n);
+  void rec_backward_gemms(const BwdJob& j, int n);
+  void rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n);
   void encoder_forward(int n);
   void head_forward(const mvae_batch& b, bool with_style_loss);
   void decoder_forward(const mvae_batch& b, int feedback);

@@ -41,7 +41,9 @@ size_t rec_persist_hx_bytes(int n, int H);
 void rec_persist_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st);
 bool rec_persist_ksplit_ok(int H);
 size_t rec_persist_partial_bytes(int n, int H);
-void rec_persist_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int variant, cudaStream_t st);
+void rec_persist_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int HS, int variant, cudaStream_t st);
+int rec_persist_pair_hs(int H, int n, int sm_count);
+void rec_persist_backward_pair(const RecPersistArgs& a, const RecPersistArgs* b, int HS, cudaStream_t st, int sm_count);
 void rec_persist_forward(const RecPersistArgs& a, cudaStream_t st, int sm_count);
 void rec_persist_backward(const RecPersistArgs& a, cudaStream_t st, int sm_count);
 
