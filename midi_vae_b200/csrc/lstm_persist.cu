@@ -113,6 +113,12 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
+// one or two independent recurrences per launch: CTAs [0, ctas0) run recurrence 0, the rest recurrence 1
+struct KsplitPair {
+  RecKP p[2];
+  int ctas0;
+};
+
 // FWD: A = h_{t-1} rows of the group (K = H), B = packed U slice [4*HS gate columns][H] resident, D = [128 rows][4*HS]
 //      packed column n = ublock*32 + gate*8 + u8  <->  unit j*HS + ublock*8 + u8, semantic gate (i,f,g,o)
 // BWD: A = dG_{t+1} rows of the group (K = 4H), B = U rows of the CTA's HS units [HS][4H] resident, D = [128 rows][HS]
@@ -123,7 +129,12 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // SM sub-partition has two epilogue warps to hide each other's latencies.
 template <bool FWD, int HS>
 __global__ void __launch_bounds__(kThreads, 1)
-rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const RecKP p) {
+rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b0, const __grid_constant__ CUtensorMap tma_b1,
+                   const __grid_constant__ KsplitPair pp) {
+  const int which = (int)blockIdx.x >= pp.ctas0 ? 1 : 0;
+  const RecKP& p = pp.p[which];
+  const CUtensorMap* tmb = which ? &tma_b1 : &tma_b0;
+  const int bid = (int)blockIdx.x - (which ? pp.ctas0 : 0);
   constexpr int BN = FWD ? 4 * HS : HS;              // UMMA N
   constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;      // the epilogue reads 32-column chunks
   constexpr int TM_COLS = 2 * ACC_STRIDE;
@@ -141,14 +152,14 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   const uint32_t smem_b = smem_base;                                   // resident weights: kblocks * B_KB_BYTES
   const uint32_t smem_a = smem_base + (uint32_t)kblocks * B_KB_BYTES;   // A ring
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = p.group0 + blockIdx.x / p.cpg, j = blockIdx.x % p.cpg;
+  const int g = p.group0 + bid / p.cpg, j = bid % p.cpg;
   const int row0 = g * BM;
   unsigned* flags = p.flags + (size_t)g * p.flag_stride;
   const int T = p.steps;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
-    ptx::prefetch_tmap(&tma_b);
+    ptx::prefetch_tmap(tmb);
     for (int s = 0; s < A_STAGES; ++s) { ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1); ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), EPI_WARPS); }
     ptx::mbar_init(ptx::smem_u32(&b_full_bar), 1);
@@ -171,7 +182,7 @@ rec_persist_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     if (lane == 0) {   // resident weights, once
       const uint32_t bb = ptx::smem_u32(&b_full_bar);
       ptx::mbar_arrive_expect_tx(bb, (uint32_t)kblocks * B_KB_BYTES);
-      for (int kb = 0; kb < kblocks; ++kb) ptx::tma_load_2d(smem_b + kb * B_KB_BYTES, &tma_b, bb, kb * BK, j * BN);
+      for (int kb = 0; kb < kblocks; ++kb) ptx::tma_load_2d(smem_b + kb * B_KB_BYTES, tmb, bb, kb * BK, j * BN);
     }
     if (lane < p.prod_lanes) {
       const int NL = p.prod_lanes;
@@ -683,11 +694,6 @@ rec_bwd_ksplit_kernel(const __grid_constant__ CUtensorMap tma_b, const RecKP p) 
 // SMs idle ~90 % of the time; two recurrences that do not depend on each other (e.g. the top notes cell and the velocity
 // cell of the decoder) therefore share one launch: CTAs [0, ctas0) run recurrence 0, the rest recurrence 1, each with its
 // own flags / exchange buffer / weights, and with HS = 32 each needs only 16 CTAs per 128-row group.
-struct KsplitPair {
-  RecKP p[2];
-  int ctas0;     // CTAs of recurrence 0 (the launch has ctas0 + ctas1)
-};
-
 template <int HS>
 __global__ void __launch_bounds__(kThreads, 1)
 rec_bwd_ksplit2_kernel(const __grid_constant__ CUtensorMap tma_b0, const __grid_constant__ CUtensorMap tma_b1, const __grid_constant__ KsplitPair pp) {
@@ -997,7 +1003,24 @@ CUtensorMap make_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t l
 }
 
 template <bool FWD, int HS>
-void launch(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
+RecKP rec_params(const RecPersistArgs& a, int stages, int prod_lanes) {
+  const int H = a.H, G = 4 * H;
+  RecKP p{};
+  p.n = a.n; p.H = H; p.G = G; p.steps = a.steps; p.cpg = H / HS; p.HS = HS; p.stages = stages; p.prod_lanes = prod_lanes;
+  { static int rot = -1; if (rot < 0) { const char* e = getenv("MVAE_REC_ROT"); rot = e ? atoi(e) : 1; } p.kb_rot = rot; }
+  p.gate_act = a.gate_act; p.variant = a.variant;
+  p.flags = a.flags; p.flag_stride = a.steps + 2;
+  p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates; p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0;
+  p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last; p.dG = (bf16*)a.dG;
+  p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  p.trace = (long long*)a.trace;
+  p.hx = (bf16*)a.hx; p.groups_total = (a.n + BM - 1) / BM;
+  return p;
+}
+
+// b != nullptr: a second, independent recurrence of the same hidden size shares the launch (forward only)
+template <bool FWD, int HS>
+void launch(const RecPersistArgs& a, const RecPersistArgs* b, cudaStream_t st, int sm_count) {
   constexpr int BN = FWD ? 4 * HS : HS;
   const int H = a.H, G = 4 * H, K = FWD ? H : G, kblocks = K / BK;
   const int cpg = H / HS;
@@ -1015,26 +1038,32 @@ void launch(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) { MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
   MVAE_REQUIRE(cpg <= sm_count, "hidden size too large for a co-resident group");
-  RecKP p{};
-  p.n = a.n; p.H = H; p.G = G; p.steps = a.steps; p.cpg = cpg; p.HS = HS; p.stages = stages; p.prod_lanes = prod_lanes;
-  { static int rot = -1; if (rot < 0) { const char* e = getenv("MVAE_REC_ROT"); rot = e ? atoi(e) : 1; } p.kb_rot = rot; } p.gate_act = a.gate_act; p.variant = a.variant;
-  p.flags = a.flags; p.flag_stride = a.steps + 2;
-  p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates; p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0;
-  p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last; p.dG = (bf16*)a.dG;
-  p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
-  p.trace = (long long*)a.trace;
-  p.hx = (bf16*)a.hx; p.groups_total = groups;
-  if (FWD) MVAE_REQUIRE(a.hx != nullptr, "persistent forward needs the h exchange buffer");
-  MVAE_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)groups * p.flag_stride * sizeof(unsigned), st));
-  // A: forward  = hseq  as a 2-D matrix [(steps+1)*n, H]  ; backward = dG as [steps*n, 4H]
+  if (FWD) MVAE_REQUIRE(a.hx != nullptr && (!b || b->hx != nullptr), "persistent forward needs the h exchange buffer");
+  KsplitPair pp{};
+  pp.p[0] = rec_params<FWD, HS>(a, stages, prod_lanes);
+  MVAE_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)groups * pp.p[0].flag_stride * sizeof(unsigned), st));
+  // A (backward N-split only): dG as [steps*n, 4H]; the forward reads the exchange buffer with bulk copies
   const CUtensorMap ma = FWD ? make_map(a.hseq, H, (uint64_t)(a.steps + 1) * a.n, H, 64, BM) : make_map(a.dG, G, (uint64_t)a.steps * a.n, G, 64, BM);
   // B: forward  = packed U [cpg*4HS, H] ; backward = U shadow [H, 4H] (rows = this CTA's units)
   const CUtensorMap mb = FWD ? make_map(a.upack, H, (uint64_t)cpg * BN, H, 64, BN) : make_map(a.u_shadow, G, H, a.ldu, 64, BN);
+  if (b) {
+    MVAE_REQUIRE(FWD && b->H == H, "only forward recurrences of one hidden size can share a launch");
+    const int gb = (b->n + BM - 1) / BM;
+    MVAE_REQUIRE((groups + gb) * cpg <= sm_count, "paired recurrences must be co-resident");
+    pp.p[1] = rec_params<FWD, HS>(*b, stages, prod_lanes);
+    MVAE_CUDA(cudaMemsetAsync(b->flags, 0, (size_t)gb * pp.p[1].flag_stride * sizeof(unsigned), st));
+    const CUtensorMap mb1 = make_map(b->upack, H, (uint64_t)cpg * BN, H, 64, BN);
+    pp.p[0].group0 = 0; pp.p[1].group0 = 0; pp.ctas0 = groups * cpg;
+    kern<<<(groups + gb) * cpg, kThreads, smem, st>>>(ma, mb, mb1, pp);
+    count_launch();
+    MVAE_CUDA(cudaGetLastError());
+    return;
+  }
   const int gmax = std::max(1, sm_count / cpg);   // groups that can be co-resident
   for (int g0 = 0; g0 < groups; g0 += gmax) {
     const int ng = std::min(gmax, groups - g0);
-    p.group0 = g0;
-    kern<<<ng * cpg, kThreads, smem, st>>>(ma, mb, p);
+    pp.p[0].group0 = g0; pp.ctas0 = ng * cpg;
+    kern<<<ng * cpg, kThreads, smem, st>>>(ma, mb, mb, pp);
     count_launch();
     MVAE_CUDA(cudaGetLastError());
   }
@@ -1068,9 +1097,9 @@ size_t rec_persist_hx_bytes(int n, int H) { return 2 * (size_t)((n + BM - 1) / B
 
 size_t rec_persist_flag_count(int n, int steps) { return (size_t)((n + BM - 1) / BM) * (steps + 2); }
 
-void rec_persist_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st) {
-  const int hs = rec_persist_hs(H);
-  MVAE_REQUIRE(hs > 0, "persistent recurrence unsupported for this hidden size");
+void rec_persist_pack_u(const float* U, int ldu, void* upack, int H, int hs, int variant, cudaStream_t st) {
+  if (hs == 0) hs = rec_persist_hs(H);
+  MVAE_REQUIRE(hs == 16 || hs == 32, "persistent recurrence unsupported for this hidden size");
   pack_u_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack, H, hs, variant);
   count_launch();
   MVAE_CUDA(cudaGetLastError());
@@ -1078,10 +1107,28 @@ void rec_persist_pack_u(const float* U, int ldu, void* upack, int H, int variant
 
 void rec_persist_forward(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
   switch (rec_persist_hs(a.H)) {
-    case 32: launch<true, 32>(a, st, sm_count); break;
-    case 16: launch<true, 16>(a, st, sm_count); break;
+    case 32: launch<true, 32>(a, nullptr, st, sm_count); break;
+    case 16: launch<true, 16>(a, nullptr, st, sm_count); break;
     default: throw Error("persistent recurrence unsupported for this hidden size");
   }
+}
+
+// units per CTA with which TWO forward recurrences of batch n fit into one co-resident launch (0 = they do not)
+int rec_persist_fwd_pair_hs(int H, int n, int sm_count) {
+  if (H % 64) return 0;
+  const int groups = (n + BM - 1) / BM;
+  for (int hs : {16, 32}) {
+    if (H % hs) continue;
+    const size_t b_bytes = (size_t)(H / 64) * (4 * hs) * 64 * 2;
+    if (b_bytes + 4 * A_STAGE_BYTES + 1024 > smem_max_bytes()) continue;
+    if (2 * groups * (H / hs) <= sm_count) return hs;
+  }
+  return 0;
+}
+
+void rec_persist_forward_pair(const RecPersistArgs& a, const RecPersistArgs& b, int HS, cudaStream_t st, int sm_count) {
+  if (HS == 32) launch<true, 32>(a, &b, st, sm_count);
+  else launch<true, 16>(a, &b, st, sm_count);
 }
 
 bool rec_persist_ksplit_ok(int H) {
@@ -1174,8 +1221,8 @@ void rec_persist_backward_pair(const RecPersistArgs& a, const RecPersistArgs* b,
 void rec_persist_backward(const RecPersistArgs& a, cudaStream_t st, int sm_count) {
   if (rec_persist_ksplit_ok(a.H) && a.upack_bwd && a.partial) { rec_persist_backward_pair(a, nullptr, 16, st, sm_count); return; }
   switch (rec_persist_hs(a.H)) {
-    case 32: launch<false, 32>(a, st, sm_count); break;
-    case 16: launch<false, 16>(a, st, sm_count); break;
+    case 32: launch<false, 32>(a, nullptr, st, sm_count); break;
+    case 16: launch<false, 16>(a, nullptr, st, sm_count); break;
     default: throw Error("persistent recurrence unsupported for this hidden size");
   }
 }

@@ -87,7 +87,7 @@ void Model::build_workspace() {
   };
   if (use_persist && rec_persist_ksplit_ok(H)) { rec_partial = alloc(rec_persist_partial_bytes(NB, H)); rec_partial2 = alloc(rec_persist_partial_bytes(NB, H)); }
   if (use_persist) rec_flags2 = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
-  if (use_persist) rec_hx = alloc(rec_persist_hx_bytes(NB, H));
+  if (use_persist) { rec_hx = alloc(rec_persist_hx_bytes(NB, H)); rec_hx2 = alloc(rec_persist_hx_bytes(NB, H)); }
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
@@ -260,38 +260,74 @@ void Model::prepare_inputs(const mvae_batch& b, bool need_target) {
 // --------------------------------------------------------------------------------------------- one recurrence, forward
 // kind: IN_DENSE  X = (steps, n, ldin) act rows;  IN_RANK1  X = per-row scalar (stride VD);  IN_NONE  x == 0 (as_wired decoder)
 void Model::rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, const void* c0, int ld0) {
+  FwdJob j; j.r = &r; j.kind = kind; j.X = X; j.h0 = h0; j.c0 = c0; j.ld0 = ld0;
+  rec_forward_jobs(&j, nullptr, n);
+}
+
+// input projection over the whole sequence (xw = X W + b) and the initial-state slab
+void Model::rec_forward_prepare(const FwdJob& j, int n) {
+  Rec& r = *j.r;
   const long rows = (long)r.steps * n;
   prof_begin(PC_GEMM);
-  if (kind == IN_DENSE) {
-    GemmArgs g; g.M = (int)rows; g.N = G; g.K = r.Din; g.A = X; g.lda = r.ldin; g.B = W(r.iW); g.ldb = ld(r.iW);
+  if (j.kind == IN_DENSE) {
+    GemmArgs g; g.M = (int)rows; g.N = G; g.K = r.Din; g.A = j.X; g.lda = r.ldin; g.B = W(r.iW); g.ldb = ld(r.iW);
     g.C = r.xw; g.ldc = G; g.c_type = act; g.bias = Wf(r.ib);
     gemm(g);
-  } else if (kind == IN_RANK1) {
-    k_rank1_rows(act, r.xw, rows, G, X, VD, Wf(r.iW), Wf(r.ib), st);
+  } else if (j.kind == IN_RANK1) {
+    k_rank1_rows(act, r.xw, rows, G, j.X, VD, Wf(r.iW), Wf(r.ib), st);
   } else {
     k_fill_rows(act, r.xw, rows, G, Wf(r.ib), st);
   }
   prof_end();
   prof_begin(PC_REC_FWD);
-  if (h0) {
-    k_copy2d(act, act, n, H, h0, ld0, r.hseq, H, st);
-    k_copy2d(act, act, n, H, c0, ld0, r.cseq, H, st);
-    k_copy2d(act, DT_F32, n, H, c0, ld0, c_run, H, st);
+  if (j.h0) {
+    k_copy2d(act, act, n, H, j.h0, j.ld0, r.hseq, H, st);
+    if (!use_persist) k_copy2d(act, act, n, H, j.c0, j.ld0, r.cseq, H, st);
   } else {
     MVAE_CUDA(cudaMemsetAsync(r.hseq, 0, (size_t)n * H * asz(), st));
-    MVAE_CUDA(cudaMemsetAsync(r.cseq, 0, (size_t)n * H * asz(), st));
-    MVAE_CUDA(cudaMemsetAsync(c_run, 0, (size_t)n * H * 4, st));
+    if (!use_persist) MVAE_CUDA(cudaMemsetAsync(r.cseq, 0, (size_t)n * H * asz(), st));
   }
+  prof_end();
+}
+
+RecPersistArgs Model::fwd_args(const FwdJob& j, int n, int slot, int hs) {
+  Rec& r = *j.r;
+  rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, hs, r.variant, st);
+  RecPersistArgs a;
+  a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = slot ? rec_flags2 : rec_flags;
+  a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates; a.c0 = j.c0; a.ldc0 = j.ld0;
+  a.hx = slot ? rec_hx2 : rec_hx;
+  a.trace = slot ? nullptr : trace_buf;
+  return a;
+}
+
+// one or two independent recurrences: projections first, then the time loop (paired in one persistent launch when both
+// run the same number of steps and fit on the chip together)
+void Model::rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n) {
+  rec_forward_prepare(*ja, n);
+  if (jb) rec_forward_prepare(*jb, n);
+  prof_begin(PC_REC_FWD);
   if (use_persist) {
-    rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, r.variant, st);
-    RecPersistArgs a;
-    a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = rec_flags;
-    a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates; a.c0 = c0; a.ldc0 = ld0; a.hx = rec_hx;
-    a.trace = trace_buf;
-    rec_persist_forward(a, st, sm_count);
-    dump_trace("fwd", r);
+    const int hs_pair = (jb && pair_recs && ja->r->steps == jb->r->steps) ? rec_persist_fwd_pair_hs(H, n, sm_count) : 0;
+    if (hs_pair) {
+      RecPersistArgs a = fwd_args(*ja, n, 0, hs_pair), b = fwd_args(*jb, n, 1, hs_pair);
+      rec_persist_forward_pair(a, b, hs_pair, st, sm_count);
+      dump_trace("fwd", *ja->r);
+    } else {
+      for (const FwdJob* j : {ja, jb}) {
+        if (!j) continue;
+        RecPersistArgs a = fwd_args(*j, n, 0, 0);
+        rec_persist_forward(a, st, sm_count);
+        dump_trace("fwd", *j->r);
+      }
+    }
   } else {
-    rec_steps_forward(r, n, 0, r.steps);
+    for (const FwdJob* j : {ja, jb}) {
+      if (!j) continue;
+      if (j->c0) k_copy2d(act, DT_F32, n, H, j->c0, j->ld0, c_run, H, st);
+      else MVAE_CUDA(cudaMemsetAsync(c_run, 0, (size_t)n * H * 4, st));
+      rec_steps_forward(*j->r, n, 0, j->r->steps);
+    }
   }
   prof_end();
 }
@@ -415,12 +451,14 @@ void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& 
 
 // --------------------------------------------------------------------------------------------- encoder (vae_definition.py:443-516)
 void Model::encoder_forward(int n) {
+  // the first pitch layer and the velocity stream are independent and equally long: they share a launch
+  FwdJob jv; jv.r = &enc_vel; jv.kind = IN_RANK1; jv.X = slab(Xv_ext, 1, (long)n * VD);
   for (int k = 0; k < ne; ++k) {
-    const void* X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
-    rec_forward(enc_pitch[k], n, IN_DENSE, X, nullptr, nullptr, 0);
+    FwdJob jp; jp.r = &enc_pitch[k]; jp.kind = IN_DENSE;
+    jp.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
+    rec_forward_jobs(&jp, k == 0 ? &jv : nullptr, n);
   }
   rec_forward(enc_instr, n, IN_DENSE, slab(Xi_ext, 1, (long)n * ID), nullptr, nullptr, 0);
-  rec_forward(enc_vel, n, IN_RANK1, slab(Xv_ext, 1, (long)n * VD), nullptr, nullptr, 0);
 }
 
 // concat -> Dense(tanh) -> Dense(tanh) -> split -> z_mean / z_log_var -> KL -> z (vae_definition.py:468-515, 29-37)
@@ -461,12 +499,14 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
   const bool tf = feedback == MVAE_FB_TEACHER_FORCED;
   auto st1 = [&](int r) { return (const char*)S + (size_t)(2 * r) * H * asz(); };
   auto st2 = [&](int r) { return (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
+  FwdJob jv; jv.r = &dec_vel; jv.kind = tf ? IN_RANK1 : IN_NONE; jv.X = tf ? Xv_ext : nullptr; jv.h0 = st1(nd + 1); jv.c0 = st2(nd + 1); jv.ld0 = nS * H;
   for (int k = 0; k < nd; ++k) {
-    if (k == 0) rec_forward(dec_notes[0], n, tf ? IN_DENSE : IN_NONE, tf ? Y_ext_cur : nullptr, st1(0), st2(0), nS * H);
-    else rec_forward(dec_notes[k], n, IN_DENSE, slab(dec_notes[k - 1].hseq, 1, (long)n * H), st1(k), st2(k), nS * H);
+    FwdJob jp; jp.r = &dec_notes[k]; jp.h0 = st1(k); jp.c0 = st2(k); jp.ld0 = nS * H;
+    if (k == 0) { jp.kind = tf ? IN_DENSE : IN_NONE; jp.X = tf ? Y_ext_cur : nullptr; }
+    else { jp.kind = IN_DENSE; jp.X = slab(dec_notes[k - 1].hseq, 1, (long)n * H); }
+    rec_forward_jobs(&jp, k == 0 ? &jv : nullptr, n);
   }
   rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
-  rec_forward(dec_vel, n, tf ? IN_RANK1 : IN_NONE, tf ? Xv_ext : nullptr, st1(nd + 1), st2(nd + 1), nS * H);
   prof_begin(PC_GEMM);
   { GemmArgs g; g.M = T * n; g.N = Dp; g.K = H; g.A = slab(dec_notes[nd - 1].hseq, 1, (long)n * H); g.lda = H; g.B = W(iWy); g.ldb = ld(iWy);
     g.C = Pn; g.ldc = ld_pn; g.c_type = DT_F32; g.bias = Wf(iby); gemm(g); }

@@ -36,6 +36,16 @@ struct Rec {
   void* upack = nullptr;  // (4H, H) bf16 : recurrent weights packed per CTA for the persistent forward kernel
 };
 
+// one forward recurrence: its input sequence and initial states
+struct FwdJob {
+  Rec* r = nullptr;
+  int kind = IN_NONE;
+  const void* X = nullptr;
+  const void* h0 = nullptr;
+  const void* c0 = nullptr;
+  int ld0 = 0;
+};
+
 // one backward recurrence: where its inputs / external gradients come from and where its outputs go
 struct BwdJob {
   Rec* r = nullptr;
@@ -119,6 +129,7 @@ struct Model {
   bool use_persist = false;          // persistent-RNN kernels (bf16 precision, supported hidden size)
   long long* trace_buf = nullptr;    // MVAE_REC_TRACE=1 debugging aid
   int trace_dumps = 0;
+  void* rec_hx2 = nullptr;           // second recurrence of a paired launch
   void* rec_hx = nullptr;            // h exchange buffer of the persistent forward kernel
   void* rec_partial = nullptr;       // bf16 partial-dh exchange buffer of the K-split backward kernel
   unsigned* rec_flags = nullptr;
@@ -158,6 +169,9 @@ struct Model {
   void prepare_inputs(const mvae_batch& b, bool need_target);
   void rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, const void* c0, int ld0);
   void rec_steps_forward(Rec& r, int n, int t0, int t1);
+  void rec_forward_prepare(const FwdJob& j, int n);
+  RecPersistArgs fwd_args(const FwdJob& j, int n, int slot, int hs);
+  void rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n);
   RecPersistArgs bwd_args(const BwdJob& j, int n, int slot, int hs);
   void rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n);
   void rec_backward_gemms(const BwdJob& j, int n);

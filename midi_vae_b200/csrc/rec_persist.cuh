@@ -38,7 +38,9 @@ int rec_persist_hs(int H);                           // hidden units per CTA (0 
 bool rec_persist_supported(int H, int sm_count);
 size_t rec_persist_flag_count(int n, int steps);
 size_t rec_persist_hx_bytes(int n, int H);
-void rec_persist_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st);
+void rec_persist_pack_u(const float* U, int ldu, void* upack, int H, int hs, int variant, cudaStream_t st);   // hs = 0: the single-launch default
+int rec_persist_fwd_pair_hs(int H, int n, int sm_count);
+void rec_persist_forward_pair(const RecPersistArgs& a, const RecPersistArgs& b, int HS, cudaStream_t st, int sm_count);
 bool rec_persist_ksplit_ok(int H);
 size_t rec_persist_partial_bytes(int n, int H);
 void rec_persist_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int HS, int variant, cudaStream_t st);

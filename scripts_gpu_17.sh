@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --maxfail=40 -p no:cacheprovider 2>&1 | tail -3
+for pr in 1 0; do
+echo "=== bench bf16 cfg3 PAIR=$pr"; MVAE_REC_PAIR=$pr timeout 900 python bench.py --workload cfg3 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b17_$pr.log 2>&1; tail -1 gpurun_out/b17_$pr.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['class_ms'])"
+done
