@@ -1,0 +1,421 @@
+// lstm_cluster.cu -- cluster-resident persistent-RNN kernels for the LSTM recurrences (bf16, H = 256 / 512).
+//
+// Same job as lstm_persist.cu (one launch = all timesteps of one recurrence of vae_definition.py:455-474,533-632, the
+// loop the reference runs as a Theano scan), but the per-step exchange of the hidden state never leaves the SMs:
+//
+//   * the batch is cut into groups of 64 rows; one THREAD-BLOCK CLUSTER of CS = H/32 CTAs owns a group for the whole
+//     sequence.  Clusters are independent of each other (no grid-wide flag, no co-residency requirement);
+//   * CTA j of the cluster owns 32 hidden units (all four gates = 128 gate columns).  Its slice of the recurrent
+//     weights, [128 gate columns][H] bf16, stays resident in shared memory as the A operand (M side) of
+//         gates^T [gate column, batch row] = U^T [gate column, k] * h_{t-1}^T [k, batch row]
+//     so the operand that changes every step is the SMALL one (N = 64 batch rows);
+//   * CTAs (2q, 2q+1) form a CTA pair: tcgen05.mma.cta_group::2 (M = 256, N = 64) reads 128 rows of A from each CTA
+//     and HALF of B from each CTA, so every CTA only has to receive the h tile of 32 batch rows (32 x H bf16 = 32 KB at
+//     H = 512) per step instead of the group's whole h;
+//   * the epilogue (8 warps) moves the accumulator from TMEM (lane = gate column) through a swizzled fp32 scratch tile
+//     into a (batch row, 8 units) ownership, applies the gate math with c in registers for the whole sequence, writes
+//     the CTA's new h slice (64 rows x 32 units) into a staging tile in the consumers' operand layout and PUSHES it with
+//     bulk copies (cp.async.bulk shared::cta -> shared::cluster) into the h buffers of all CS CTAs; the copies complete
+//     transaction bytes on the consumers' mbarriers, so there is no flag, no fence to L2 and no polling: a step is
+//     MMA -> TMEM -> gate math -> DSMEM push -> MMA;
+//   * h buffers and the staging tile are double-buffered; every re-use is ordered by the data dependence itself
+//     (nobody can produce h_{t+1} before having received all of h_t), see the comments at each buffer.
+//
+// The stash (gates, c, h) is written in the layouts of lstm_persist.cu, so either backward kernel can follow.
+#include <cuda.h>
+
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "../../include/midivae.h"
+#include "common.cuh"
+#include "ptx.cuh"
+#include "rec_persist.cuh"
+
+namespace mvae {
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int CL_ROWS = 64;                 // batch rows per cluster (UMMA N of the pair)
+constexpr int CL_HALF = 32;                 // batch rows whose operand tile one CTA of a pair holds
+constexpr int CL_HS = 32;                   // hidden units per CTA
+constexpr int CL_GC = 4 * CL_HS;            // gate columns per CTA = UMMA M per CTA
+constexpr int CL_EPI_WARPS = 8;
+constexpr int CL_THREADS = 32 * (2 + CL_EPI_WARPS);
+constexpr uint32_t CL_SLICE = 4 * CL_HALF * 16;   // one pushed piece: 4 k-granules x 32 rows x 16 B = 2 KB
+constexpr uint32_t CL_STAGE = 2 * CL_SLICE;       // staging tile: both row halves of the CTA's h slice
+constexpr uint32_t CL_SCR = CL_ROWS * CL_GC * 4;  // fp32 scratch tile [64 rows][128 gate columns]
+
+struct ClusterP {
+  int n, H, G, steps, gate_act, variant, nswap;
+  const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates; const bf16* c0; int ldc0;
+  long long* trace;
+};
+
+#define CL_TRACE(step, point)                                                                                              \
+  do {                                                                                                                     \
+    if (p.trace && blockIdx.x == 0 && (step) >= 16 && (step) < 24) p.trace[((step) - 16) * 16 + (point)] = clock64();      \
+  } while (0)
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gate_fwd(int gate_act, float x) {
+  return gate_act == MVAE_GATE_HARD_SIGMOID ? fminf(fmaxf(0.2f * x + 0.5f, 0.f), 1.f) : 0.5f * tanh_fast(0.5f * x) + 0.5f;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+// stash layout shared with lstm_persist.cu: [slab][column/8 granules][n rows][8]
+__device__ __forceinline__ size_t gran_off(int slab, int ngran, int gran, int n, int m) {
+  return (((size_t)slab * ngran + gran) * n + m) * 8;
+}
+__device__ __forceinline__ void named_barrier(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Forward.  Buffers in dynamic shared memory (offsets identical in every CTA, as cta_group::2 and mapa require):
+//   U      [H/64 k-blocks][128 gate columns][64 k] bf16, SWIZZLE_128B (TMA), resident          A operand
+//   hbuf b [H/8 k-granules][32 rows][8 k] bf16 (no swizzle: 8 x 16 B core matrices), b = 0, 1     B operand (this CTA's half)
+//   stage b: the CTA's own new h slice as two 2 KB pieces (row half 0 / 1) in hbuf order         source of the pushes
+//   scratch [64 rows][128 gate columns] fp32, 16-byte chunks XOR-swizzled by (row & 7)            TMEM -> row ownership
+// h_t lives in hbuf[t & 1]; MMA t reads hbuf[(t+1) & 1] = h_{t-1} (the initial state is loaded into hbuf[1]).
+// At H = 512 the scratch tile aliases hbuf[(t+1) & 1] during epilogue t: MMA t has finished reading it, and the next
+// writers (pushes of h_{t+1}) cannot start before every CTA of the cluster has received this CTA's h_t, which it
+// pushes only after its scratch reads.
+template <int CS>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+rec_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tma_u, const ClusterP p) {
+  constexpr int H = CS * CL_HS, G = 4 * H, KB = H / 64;
+  constexpr uint32_t U_BYTES = (uint32_t)KB * CL_GC * 64 * 2;
+  constexpr uint32_t HBUF = (uint32_t)CL_HALF * H * 2;
+  constexpr bool ALIAS = (H >= 512);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t u_full, h_full[2], peer_ready[2], tmem_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_u = smem_base;
+  const uint32_t smem_h0 = smem_base + U_BYTES;                    // hbuf[b] = smem_h0 + b * HBUF
+  const uint32_t smem_st0 = smem_h0 + 2 * HBUF;                    // stage[b] = smem_st0 + b * CL_STAGE
+  const uint32_t smem_scr = smem_st0 + 2 * CL_STAGE;               // only when !ALIAS
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int cl = (int)blockIdx.x / CS;
+  const int e = (int)(rank & 1);
+  const int rh = e ^ p.nswap;                                      // which 32 rows of the group this CTA's operand tile holds
+  const int j = (int)rank;                                         // hidden units [32 j, 32 j + 32)
+  const int row0 = cl * CL_ROWS;
+  const int T = p.steps, n = p.n;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tma_u);
+    ptx::mbar_init(ptx::smem_u32(&u_full), 1);
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(ptx::smem_u32(&h_full[b]), 1); ptx::mbar_init(ptx::smem_u32(&peer_ready[b]), 1); }
+    ptx::mbar_init(ptx::smem_u32(&tmem_full), 1);
+    ptx::fence_barrier_init();
+    const uint32_t ub = ptx::smem_u32(&u_full);
+    ptx::mbar_arrive_expect_tx(ub, U_BYTES);
+    for (int kb = 0; kb < KB; ++kb) ptx::tma_load_2d(smem_u + kb * (CL_GC * 128), &tma_u, ub, kb * 64, j * CL_GC);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(ptx::smem_u32(&tmem_base_slot), 64);
+    ptx::tmem_relinquish2();
+  }
+
+  // epilogue ownership (phase B): batch row rr of the group, units [8 q, 8 q + 8) of the CTA's 32
+  const int etid = (int)threadIdx.x - 64;
+  const int rr = etid & 63, q = (etid >> 6) & 3;
+  const int m = row0 + rr;
+  const bool row_ok = warp >= 2 && m < n;
+  const int u0 = j * CL_HS + q * 8, gu = u0 >> 3;
+  const int bi = p.variant == MVAE_CELL_STANDARD ? 0 : 1, bfk = 1 - bi;   // column block of the i and f gates
+  float cst[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) cst[u] = 0.f;
+
+  if (warp >= 2) {
+    // initial hidden state (hseq slab 0, row-major) -> hbuf[1] in operand order
+    for (int idx = etid; idx < CL_HALF * (H / 8); idx += 32 * CL_EPI_WARPS) {
+      const int r = idx / (H / 8), gk = idx % (H / 8);
+      const int mm = row0 + rh * CL_HALF + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (mm < n) v = *reinterpret_cast<const uint4*>(p.hseq + (size_t)mm * H + gk * 8);
+      ptx::st_shared_u4(smem_h0 + HBUF + gk * (CL_HALF * 16) + r * 16, v);
+    }
+    ptx::fence_proxy_async();
+    if (row_ok) {
+      uint4 cv = make_uint4(0u, 0u, 0u, 0u);
+      if (p.c0) cv = *reinterpret_cast<const uint4*>(p.c0 + (size_t)m * p.ldc0 + u0);
+      unpack8(cv, cst);
+      *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m)) = cv;   // stash slab 0 = c0
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  // barriers initialised, initial tiles written and TMEM allocated in EVERY CTA before anyone pushes or issues a pair MMA
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (e == 0) {
+        // ===================== MMA issuer (even CTA of the pair) =====================
+        constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, CL_ROWS, false, false);
+        const uint16_t pair_mask = (uint16_t)(3u << rank);
+        ptx::mbar_wait(ptx::smem_u32(&u_full), 0);
+        for (int t = 0; t < T; ++t) {
+          // arm the barrier that the pushes of h_t will complete (its previous phase, h_{t-2}, completed before MMA t-1)
+          if (t + 1 < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&h_full[t & 1]), HBUF);
+          const int b = (t + 1) & 1;
+          if (t > 0) ptx::mbar_wait(ptx::smem_u32(&h_full[b]), (uint32_t)(((t - 1) >> 1) & 1));
+          ptx::mbar_wait_cluster(ptx::smem_u32(&peer_ready[b]), (uint32_t)((t >> 1) & 1));   // the odd CTA's half of h_{t-1} (and its U) landed
+          ptx::tc_fence_after();
+          CL_TRACE(t, 0);
+          const uint32_t sb = smem_h0 + b * HBUF;
+#pragma unroll 1
+          for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // A: 128 gate columns x 16 k of the swizzled U block; B: 32 rows x 16 k = 2 k-granules, 512 B apart (LBO), 8-row groups 128 B apart (SBO)
+              ptx::umma_bf16_2cta(tmem_base, ptx::umma_desc_sw128(smem_u + kb * (CL_GC * 128) + k * 32, 16, 1024),
+                                  ptx::umma_desc_noswz(sb + (kb * 8 + k * 2) * (CL_HALF * 16), CL_HALF * 16, 128), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit_2cta(ptx::smem_u32(&tmem_full), pair_mask);
+          CL_TRACE(t, 1);
+        }
+      } else {
+        // ===================== relay (odd CTA): tell the pair's MMA issuer when THIS CTA's operands are in place =====================
+        const uint32_t leader = rank - 1;
+        ptx::mbar_wait(ptx::smem_u32(&u_full), 0);
+        ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(&peer_ready[1]), leader));   // U slice + initial h tile (hbuf[1])
+        for (int t = 0; t + 1 < T; ++t) {
+          const uint32_t hb = ptx::smem_u32(&h_full[t & 1]);
+          ptx::mbar_arrive_expect_tx(hb, HBUF);
+          ptx::mbar_wait(hb, (uint32_t)((t >> 1) & 1));
+          ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(&peer_ready[t & 1]), leader));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== push warp: lane d sends this CTA's new h slice to CTA d of the cluster =====================
+    for (int t = 0; t + 1 < T; ++t) {
+      named_barrier(2, 32 * (CL_EPI_WARPS + 1));                    // staging tile of step t written (and fenced) by the epilogue warps
+      if (lane < CS) {
+        const uint32_t d = (uint32_t)lane;
+        const uint32_t src = smem_st0 + (t & 1) * CL_STAGE + (((d & 1) ^ (uint32_t)p.nswap) * CL_SLICE);
+        const uint32_t dst = ptx::mapa(smem_h0 + (t & 1) * HBUF + (uint32_t)j * CL_SLICE, d);
+        ptx::bulk_copy_dsmem(dst, src, CL_SLICE, ptx::mapa(ptx::smem_u32(&h_full[t & 1]), d));
+      }
+      if (lane == 0) CL_TRACE(t, 6);
+    }
+  } else {
+    // ===================== epilogue warps 2..9 =====================
+    // phase A ownership: TMEM lane = gate column c = gate * 32 + unit of this CTA, 32 batch rows (column half ch)
+    const int wq = warp & 3, ch = (warp - 2) >> 2;
+    const int c = wq * 32 + lane;
+    const bool tracer = (etid == 0);
+    const uint32_t swB = (uint32_t)(rr & 7) << 4;
+    for (int t = 0; t < T; ++t) {
+      // the input projection of this step does not depend on the recurrence: fetch it while the MMAs run
+      uint4 xq[4];
+      if (row_ok) {
+        const bf16* xr = p.xw + ((size_t)t * n + m) * G + u0;
+        xq[0] = __ldg(reinterpret_cast<const uint4*>(xr + bi * H));
+        xq[1] = __ldg(reinterpret_cast<const uint4*>(xr + bfk * H));
+        xq[2] = __ldg(reinterpret_cast<const uint4*>(xr + 2 * H));
+        xq[3] = __ldg(reinterpret_cast<const uint4*>(xr + 3 * H));
+      }
+      ptx::mbar_wait(ptx::smem_u32(&tmem_full), (uint32_t)(t & 1));
+      ptx::tc_fence_after();
+      if (tracer) CL_TRACE(t, 2);
+      const uint32_t scr = ALIAS ? (smem_h0 + ((t + 1) & 1) * HBUF) : smem_scr;
+      {
+        float v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ch * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int ra = ch * 32 + i;
+          ptx::st_shared_f32(scr + ra * (CL_GC * 4) + (((uint32_t)c * 4) ^ ((uint32_t)(ra & 7) << 4)), v[i]);
+        }
+      }
+      ptx::tc_fence_before();
+      named_barrier(1, 32 * CL_EPI_WARPS);
+      if (tracer) CL_TRACE(t, 3);
+      // phase B: the four gates of this thread's 8 units for its batch row
+      float pre[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t off = (uint32_t)(g * 32 + q * 8) * 4;
+        const float4 a0 = ptx::ld_shared_f32x4(scr + rr * (CL_GC * 4) + (off ^ swB));
+        const float4 a1 = ptx::ld_shared_f32x4(scr + rr * (CL_GC * 4) + ((off + 16) ^ swB));
+        pre[g][0] = a0.x; pre[g][1] = a0.y; pre[g][2] = a0.z; pre[g][3] = a0.w;
+        pre[g][4] = a1.x; pre[g][5] = a1.y; pre[g][6] = a1.z; pre[g][7] = a1.w;
+      }
+      float xi[8], xf[8], xg[8], xo[8], gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
+      if (row_ok) { unpack8(xq[0], xi); unpack8(xq[1], xf); unpack8(xq[2], xg); unpack8(xq[3], xo); }
+      else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { xi[u] = 0.f; xf[u] = 0.f; xg[u] = 0.f; xo[u] = 0.f; }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        gi[u] = gate_fwd(p.gate_act, pre[0][u] + xi[u]);
+        gf[u] = gate_fwd(p.gate_act, pre[1][u] + xf[u]);
+        gg[u] = tanh_fast(pre[2][u] + xg[u]);
+        go[u] = gate_fwd(p.gate_act, pre[3][u] + xo[u]);
+        const float s = gf[u] * cst[u] + gi[u] * gg[u];
+        if (p.variant == MVAE_CELL_STANDARD) { cn[u] = s; hn[u] = go[u] * tanh_fast(s); }
+        else { cn[u] = tanh_fast(s); hn[u] = go[u] * cn[u]; }
+        cst[u] = cn[u];
+      }
+      uint4 st_h = pack8(hn);
+      if (!row_ok) st_h = make_uint4(0u, 0u, 0u, 0u);
+      if (t + 1 < T) {
+        // stage[t & 1] was last read by the pushes of step t-2; they landed before any CTA could finish MMA t-1
+        ptx::st_shared_u4(smem_st0 + (t & 1) * CL_STAGE + (uint32_t)(rr >> 5) * CL_SLICE + (uint32_t)q * (CL_HALF * 16) + (uint32_t)(rr & 31) * 16, st_h);
+        ptx::fence_proxy_async();
+        if (tracer) CL_TRACE(t, 4);
+        named_barrier(2, 32 * (CL_EPI_WARPS + 1));
+        if (tracer) CL_TRACE(t, 5);
+      }
+      // the stash (read by the backward pass and the batched GEMMs) is written after the push: off the critical path
+      if (row_ok) {
+        *reinterpret_cast<uint4*>(p.hseq + ((size_t)(t + 1) * n + m) * H + u0) = st_h;
+        *reinterpret_cast<uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)) = pack8(cn);
+        *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)) = pack8(gi);
+        *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)) = pack8(gf);
+        *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)) = pack8(gg);
+        *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)) = pack8(go);
+      }
+    }
+  }
+
+  // nobody may leave (and release its shared memory / TMEM) while a peer can still read or write it
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  if (warp == 1) ptx::tmem_dealloc2(tmem_base, 64);
+}
+
+// U (H, 4H) fp32 master, Keras column blocks -> per-CTA bf16 [CS][128 rows][H], K-major:
+// row mrow = gate * 32 + u of CTA j holds column blk(gate) * H + j * 32 + u of U (gate in semantic order i, f, g, o)
+__global__ void pack_u_cluster_kernel(const float* __restrict__ U, int ldu, bf16* __restrict__ out, int H, int variant) {
+  const long total = (long)H * 4 * H;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % H);
+    const long rn = e / H;              // j * 128 + mrow
+    const int mrow = (int)(rn % CL_GC), j = (int)(rn / CL_GC);
+    const int gate = mrow / CL_HS, u = mrow % CL_HS;
+    int blk = gate;
+    if (variant != MVAE_CELL_STANDARD && gate < 2) blk = 1 - gate;
+    out[e] = __float2bfloat16_rn(U[(long)k * ldu + blk * H + j * CL_HS + u]);
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MVAE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    MVAE_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = (EncodeFn)p;
+  }
+  return fn;
+}
+CUtensorMap make_map_sw128(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (rec_cluster)");
+  return m;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+template <int CS>
+void launch_fwd(const RecPersistArgs& a, cudaStream_t st) {
+  constexpr int H = CS * CL_HS, KB = H / 64;
+  constexpr size_t smem = 1024 + (size_t)KB * CL_GC * 128 + 2 * (size_t)CL_HALF * H * 2 + 2 * CL_STAGE + (H >= 512 ? 0 : CL_SCR);
+  auto kern = rec_cluster_fwd_kernel<CS>;
+  static bool configured = false;
+  if (!configured) {
+    MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8) MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured = true;
+  }
+  const int clusters = (a.n + CL_ROWS - 1) / CL_ROWS;
+  ClusterP p{};
+  p.n = a.n; p.H = H; p.G = 4 * H; p.steps = a.steps; p.gate_act = a.gate_act; p.variant = a.variant;
+  p.nswap = env_int("MVAE_CL_NSWAP", 0);
+  p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates; p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0;
+  p.trace = (long long*)a.trace;
+  const CUtensorMap mu = make_map_sw128(a.upack, H, (uint64_t)CS * CL_GC, H, 64, CL_GC);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  static bool reported = false;
+  if (!reported && env_int("MVAE_CL_VERBOSE", 0)) {
+    int nc = -1;
+    cudaError_t err = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    fprintf(stderr, "rec_cluster_fwd<%d>: smem %zu B, max co-resident clusters %d (%s), launching %d\n", CS, smem, nc, cudaGetErrorString(err), clusters);
+    reported = true;
+  }
+  MVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, mu, p));
+  count_launch();
+}
+
+}  // namespace
+
+// cluster kernels: H = 32 * cluster size, cluster size 8 (portable) or 16 (non-portable, one cluster per GPC)
+bool rec_cluster_supported(int H) {
+  static int enabled = -1;
+  if (enabled < 0) enabled = env_int("MVAE_REC_CLUSTER", 1);
+  return enabled && (H == 256 || H == 512);
+}
+
+void rec_cluster_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st) {
+  MVAE_REQUIRE(H == 256 || H == 512, "cluster recurrence: hidden size 256 or 512");
+  pack_u_cluster_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack, H, variant);
+  count_launch();
+  MVAE_CUDA(cudaGetLastError());
+}
+
+void rec_cluster_forward(const RecPersistArgs& a, cudaStream_t st) {
+  switch (a.H) {
+    case 512: launch_fwd<16>(a, st); break;
+    case 256: launch_fwd<8>(a, st); break;
+    default: throw Error("cluster recurrence unsupported for this hidden size");
+  }
+}
+
+}  // namespace mvae

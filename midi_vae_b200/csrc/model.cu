@@ -143,6 +143,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   use_persist = act == DT_BF16 && cfg.rnn_mode != MVAE_RNN_STREAMED && rec_persist_supported(H, sm_count);
   if (cfg.rnn_mode == MVAE_RNN_PERSISTENT)
     MVAE_REQUIRE(use_persist, "rnn_mode=persistent needs bf16 precision and lstm_size % 64 == 0 with a weight slice that fits in shared memory");
+  use_cluster_fwd = use_persist && rec_cluster_supported(H);
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
@@ -292,7 +293,8 @@ void Model::rec_forward_prepare(const FwdJob& j, int n) {
 
 RecPersistArgs Model::fwd_args(const FwdJob& j, int n, int slot, int hs) {
   Rec& r = *j.r;
-  rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, hs, r.variant, st);
+  if (use_cluster_fwd) rec_cluster_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, r.variant, st);
+  else rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, hs, r.variant, st);
   RecPersistArgs a;
   a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = slot ? rec_flags2 : rec_flags;
   a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates; a.c0 = j.c0; a.ldc0 = j.ld0;
@@ -307,7 +309,15 @@ void Model::rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n) {
   rec_forward_prepare(*ja, n);
   if (jb) rec_forward_prepare(*jb, n);
   prof_begin(PC_REC_FWD);
-  if (use_persist) {
+  if (use_cluster_fwd) {
+    // clusters are independent of each other, so there is nothing to pair: each recurrence is one launch
+    for (const FwdJob* j : {ja, jb}) {
+      if (!j) continue;
+      RecPersistArgs a = fwd_args(*j, n, 0, 0);
+      rec_cluster_forward(a, st);
+      dump_trace("fwd(cluster)", *j->r);
+    }
+  } else if (use_persist) {
     const int hs_pair = (jb && pair_recs && ja->r->steps == jb->r->steps) ? rec_persist_fwd_pair_hs(H, n, sm_count) : 0;
     if (hs_pair) {
       RecPersistArgs a = fwd_args(*ja, n, 0, hs_pair), b = fwd_args(*jb, n, 1, hs_pair);

@@ -174,7 +174,7 @@ def test_train_step_bf16_tolerance(feedback):
     _compare_step(ecfg, ocfg, 16, tol=2e-2, grad_tol=6e-2)
 
 
-@pytest.mark.parametrize("shape", [(16, 64, 16, 8), (64, 256, 100, 16), (12, 128, 32, 200), (8, 1024, 64, 40), (4, 192, 24, 130)])
+@pytest.mark.parametrize("shape", [(16, 64, 16, 8), (64, 256, 100, 16), (12, 128, 32, 200), (8, 1024, 64, 40), (4, 192, 24, 130), (12, 512, 48, 70), (8, 256, 40, 150)])
 @pytest.mark.parametrize("feedback,variant", [("as_wired", "standard"), ("teacher_forced", "standard"), ("teacher_forced", "recurrentshop_recalled")])
 def test_persistent_rnn_matches_streamed(shape, feedback, variant):
     """The persistent-RNN kernels (U resident in SMEM, in-kernel time loop, cross-CTA flags) against the step-streamed
