@@ -87,7 +87,10 @@ void Model::build_workspace() {
   };
   if (use_persist && rec_persist_ksplit_ok(H)) { rec_partial = alloc(rec_persist_partial_bytes(NB, H)); rec_partial2 = alloc(rec_persist_partial_bytes(NB, H)); }
   if (use_persist) rec_flags2 = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
-  if (use_persist) { rec_hx = alloc(rec_persist_hx_bytes(NB, H)); rec_hx2 = alloc(rec_persist_hx_bytes(NB, H)); }
+  if (use_persist) {
+    const size_t hxb = std::max(rec_persist_hx_bytes(NB, H), rec_cluster_supported(H) ? rec_cluster_hx_bytes(NB, H) : (size_t)0);
+    rec_hx = alloc(hxb); rec_hx2 = alloc(hxb);
+  }
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
@@ -149,7 +152,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
   build_workspace();
   { const char* e = getenv("MVAE_REC_PAIR"); pair_recs = e ? atoi(e) != 0 : true; }
-  if (getenv("MVAE_REC_TRACE")) trace_buf = (long long*)alloc(128 * sizeof(long long));
+  if (getenv("MVAE_REC_TRACE")) trace_buf = (long long*)alloc(512 * sizeof(long long));
   MVAE_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -192,14 +195,29 @@ void Model::prof_collect() {
 }
 
 // MVAE_REC_TRACE=1: print the per-phase clock64 stamps CTA 0 of a persistent recurrence recorded for 8 steps
-void Model::dump_trace(const char* dir, const Rec& r) {
+void Model::dump_trace(const char* dir, const Rec& r, int nctas) {
   if (!trace_buf || r.steps < 32) return;
   if (trace_dumps >= 16) return;
   ++trace_dumps;
   MVAE_CUDA(cudaStreamSynchronize(st));
-  long long hbuf[128];
+  long long hbuf[512];
   MVAE_CUDA(cudaMemcpy(hbuf, trace_buf, sizeof(hbuf), cudaMemcpyDeviceToHost));
   MVAE_CUDA(cudaMemset(trace_buf, 0, sizeof(hbuf)));
+  if (nctas > 1) {
+    // cluster kernels: CTA 0 (pair leader) and CTA 1 (its partner), each on its own SM clock; cycles relative to the CTA's first stamp of step 17
+    fprintf(stderr, "rec trace %s %s: points 0 mma-issue 1 commit 2 tmem-full-seen 3 scratch-written 4 push-issued(t0) 5 barrier 6 bulk-issued 7 h_full-done 8 relay-sent 9 push-issued(t255)\n",
+            dir, r.name.c_str());
+    for (int c = 0; c < nctas; ++c) {
+      long long base = 0;
+      for (int k = 0; k < 16; ++k) { const long long v = hbuf[(c * 8 + 1) * 16 + k]; if (v && (!base || v < base)) base = v; }
+      for (int sidx = 1; sidx < 5; ++sidx) {
+        fprintf(stderr, "  cta %d step %2d:", c, 16 + sidx);
+        for (int k = 0; k < 10; ++k) fprintf(stderr, " %d:%lld", k, hbuf[(c * 8 + sidx) * 16 + k] ? hbuf[(c * 8 + sidx) * 16 + k] - base : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+    return;
+  }
   fprintf(stderr, "rec trace %s %s: cycles relative to the step's first stamp; points: 0 poll-start 1 flag-seen 2 tma-issued 3 first-kblock-landed "
                   "4 last-kblock-landed 5 epi-wait 6 epi-wake 7 stores-done 8 proxy-fence 9 barrier 10 threadfence 11 flag-published\n", dir, r.name.c_str());
   for (int sidx = 0; sidx < 8; ++sidx) {
@@ -315,7 +333,7 @@ void Model::rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n) {
       if (!j) continue;
       RecPersistArgs a = fwd_args(*j, n, 0, 0);
       rec_cluster_forward(a, st);
-      dump_trace("fwd(cluster)", *j->r);
+      dump_trace("fwd(cluster)", *j->r, 2);
     }
   } else if (use_persist) {
     const int hs_pair = (jb && pair_recs && ja->r->steps == jb->r->steps) ? rec_persist_fwd_pair_hs(H, n, sm_count) : 0;

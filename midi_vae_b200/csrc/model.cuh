@@ -160,7 +160,7 @@ struct Model {
   void prof_begin(int cls);
   void prof_end();
   void prof_collect();
-  void dump_trace(const char* dir, const Rec& r);
+  void dump_trace(const char* dir, const Rec& r, int nctas = 1);
 
   // batch plumbing
   mvae_batch upload(const mvae_batch& hb, const uint8_t* song_start = nullptr);

@@ -125,6 +125,20 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// relaxed form: no fence in front of the arrive (the .release.cluster form drains every outstanding store of the thread through
+// MEMBAR.ALL.GPU, ~1-2 k cycles in a kernel that streams a stash to HBM).  For hand-offs whose payload travelled through
+// the async proxy (bulk copies / st.async / TMA with complete_tx) and is consumed by the async proxy.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// multicast bulk copy global -> the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier
+// (same offset) receives complete_tx of `bytes`
+__device__ __forceinline__ void bulk_load_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -143,11 +157,34 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     }
   }
 }
+// non-blocking probe (mbarrier.test_wait never suspends the thread): for barriers completed by REMOTE arrivals / st.async
+__device__ __forceinline__ void mbar_spin_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 28)) {
+      printf("mbar_spin_cluster timeout: block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
 // bulk copy from this CTA's shared memory into the shared memory of a CTA of the cluster; completes `bytes` of
 // transaction count on an mbarrier of the DESTINATION CTA (both addresses from mapa)
 __device__ __forceinline__ void bulk_copy_dsmem(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster), "r"(src_cta),
                "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+// 16-byte asynchronous store into the shared memory of a CTA of the cluster; completes 16 bytes of transaction count on
+// an mbarrier of the destination CTA (both addresses from mapa)
+__device__ __forceinline__ void st_async_u4(uint32_t dst_cluster, const uint4& v, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst_cluster), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar_cluster)
                : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
@@ -165,6 +202,26 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc,
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in TENSOR MEMORY (lane = M row of this CTA, K packed two bf16 per 32-bit column: 16 k = 8 columns):
+// no shared-memory read of A at all -- an SS-mode MMA with a small N is paced by the 4 KB A fetch (64 B/clk), not by the math
+__device__ __forceinline__ void umma_bf16_2cta_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive (once all previously issued MMAs of this thread completed) on the mbarrier at this offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
