@@ -387,7 +387,7 @@ constexpr int CL2_MAXG = 3;
 constexpr uint32_t CL2_TM_U = 64 * CL2_MAXG;   // TMEM: accumulator of group g at columns 64 g, U from column 192
 
 struct Cluster2P {
-  int n, steps, nswap, ng;
+  int n, steps, nswap, ng, dbg;   // dbg: timing experiments only (bit 0: no gate/c stash stores, bit 1: no xw loads)
   const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates; const bf16* c0; int ldc0;
   const bf16* upack;
   uint8_t* hx;        // exchange buffer [clusters][ng][2][CS][2 row halves][2 KB]
@@ -487,45 +487,47 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
   ptx::tc_fence_after();
 
   if (warp == 0) {
-    if (lane == 0) {
-      if (e == 0) {
-        // ===================== MMA issuer (even CTA of the pair) =====================
-        constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, CL_ROWS, false, false);
-        const uint16_t pair_mask = (uint16_t)(3u << rank);
-        const uint64_t bd0 = ptx::umma_desc_noswz(smem_h0, CL_HALF * 16, 128);
-        for (int t = 0; t < T; ++t) {
-          const int b = (t + 1) & 1;
+    if (e == 0) {
+      // ===================== MMA issuer (even CTA of the pair) =====================
+      // the whole warp walks the loop so that descriptors and addresses stay warp-uniform (uniform datapath); one elected lane issues
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, CL_ROWS, false, false);
+      const uint16_t pair_mask = (uint16_t)(3u << rank);
+      const uint64_t bd0 = ptx::umma_desc_noswz(smem_h0, CL_HALF * 16, 128);
+      for (int t = 0; t < T; ++t) {
+        const int b = (t + 1) & 1;
 #pragma unroll
-          for (int g = 0; g < CL2_MAXG; ++g) {
-            if (g >= nga) break;
-            if (t + 1 < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&h_full[g][t & 1]), HBUF);
-            if (t > 0) ptx::mbar_wait(ptx::smem_u32(&h_full[g][b]), (uint32_t)(((t - 1) >> 1) & 1));
-            if (g == 0) CL_TRACE(t, 7);
-            ptx::mbar_wait(ptx::smem_u32(&peer_ready[g][b]), (uint32_t)((t >> 1) & 1));
-            ptx::tc_fence_after();
-            if (g == 0) CL_TRACE(t, 0);
-            const uint64_t bd = bd0 + (uint64_t)(((2 * g + b) * HBUF) >> 4);
-            const uint32_t d_tmem = tmem_base + (uint32_t)g * 64u, a_tmem = tmem_base + CL2_TM_U;
+        for (int g = 0; g < CL2_MAXG; ++g) {
+          if (g >= nga) break;
+          if (t + 1 < T && lane == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&h_full[g][t & 1]), HBUF);
+          if (t > 0) ptx::mbar_wait(ptx::smem_u32(&h_full[g][b]), (uint32_t)(((t - 1) >> 1) & 1));
+          if (g == 0 && lane == 0) CL_TRACE(t, 7);
+          ptx::mbar_wait(ptx::smem_u32(&peer_ready[g][b]), (uint32_t)((t >> 1) & 1));
+          ptx::tc_fence_after();
+          if (g == 0 && lane == 0) CL_TRACE(t, 0);
+          const uint64_t bd = bd0 + (uint64_t)(((2 * g + b) * HBUF) >> 4);
+          const uint32_t d_tmem = tmem_base + (uint32_t)g * 64u, a_tmem = tmem_base + CL2_TM_U;
+          if (ptx::elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
               ptx::umma_bf16_2cta_ts(d_tmem, a_tmem + (uint32_t)ks * 8u, bd + (uint64_t)(ks * 2 * (CL_HALF * 16) >> 4), idesc, ks > 0 ? 1u : 0u);
             ptx::umma_commit_2cta(ptx::smem_u32(&tmem_full[g]), pair_mask);
-            if (g == 0) CL_TRACE(t, 1);
           }
+          __syncwarp();
+          if (g == 0 && lane == 0) CL_TRACE(t, 1);
         }
-      } else {
-        // ===================== relay (odd CTA) =====================
-        const uint32_t leader = rank - 1;
-        for (int g = 0; g < nga; ++g) ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&peer_ready[g][1]), leader));
-        for (int t = 0; t + 1 < T; ++t) {
-          for (int g = 0; g < nga; ++g) {
-            const uint32_t hb = ptx::smem_u32(&h_full[g][t & 1]);
-            ptx::mbar_arrive_expect_tx(hb, HBUF);
-            ptx::mbar_wait(hb, (uint32_t)((t >> 1) & 1));
-            if (g == 0) CL_TRACE(t + 1, 7);
-            ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&peer_ready[g][t & 1]), leader));
-            if (g == 0) CL_TRACE(t + 1, 8);
-          }
+      }
+    } else if (lane == 0) {
+      // ===================== relay (odd CTA) =====================
+      const uint32_t leader = rank - 1;
+      for (int g = 0; g < nga; ++g) ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&peer_ready[g][1]), leader));
+      for (int t = 0; t + 1 < T; ++t) {
+        for (int g = 0; g < nga; ++g) {
+          const uint32_t hb = ptx::smem_u32(&h_full[g][t & 1]);
+          ptx::mbar_arrive_expect_tx(hb, HBUF);
+          ptx::mbar_wait(hb, (uint32_t)((t >> 1) & 1));
+          if (g == 0) CL_TRACE(t + 1, 7);
+          ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&peer_ready[g][t & 1]), leader));
+          if (g == 0) CL_TRACE(t + 1, 8);
         }
       }
     }
@@ -550,7 +552,7 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
     const uint32_t swB = (uint32_t)(rr & 7) << 4;
     auto load_xw = [&](int t, int g, uint4* xq) {
       const int m = row0 + g * CL_ROWS + rr;
-      if (m < n) {
+      if (m < n && !(p.dbg & 2)) {
         const bf16* xr = p.xw + ((size_t)t * n + m) * G + u0;
         xq[0] = __ldg(reinterpret_cast<const uint4*>(xr + bi * H));
         xq[1] = __ldg(reinterpret_cast<const uint4*>(xr + bfk * H));
@@ -625,11 +627,13 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
         }
         if (row_ok) {
           *reinterpret_cast<uint4*>(p.hseq + ((size_t)(t + 1) * n + m) * H + u0) = st_h;
+          if (!(p.dbg & 1)) {
           *reinterpret_cast<uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)) = pack8(cn);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)) = pack8(gi);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)) = pack8(gf);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)) = pack8(gg);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)) = pack8(go);
+          }
         }
         if (tracer && g == nga - 1) CL_TRACE(t, 9);
       }
@@ -641,6 +645,322 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
   ptx::cluster_arrive();
   ptx::cluster_wait();
   if (warp == 1) ptx::tmem_dealloc2(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward.  dh_{t-1} = dG_t U^T contracts over ALL 4H gate columns, so the weight-stationary split is over K:
+//   * pair q of the cluster owns hidden units [64 q, 64 q + 64) = 256 gate columns.  Within the pair, CTA e does the
+//     gate-gradient math for 32 of the group's 64 batch rows (x the pair's 64 units), so the dG it produces is exactly
+//     ITS half (N split) of the B operand of the pair MMA: nothing is gathered;
+//   * A = U^T restricted to the pair's 256 gate columns, [H output units][256] bf16, resident in TENSOR MEMORY
+//     (CTA e: units 256 mt + 128 e + lane of M tile mt); D (TMEM) = partial dh^T [units of this CTA][64 rows];
+//   * reduce-scatter: the partial for (64 units of pair q', 32 rows of CTA e') is one 4 KB bf16 message; every CTA sends
+//     4 H/256 messages and receives H/64 (one per pair) by bulk copies into the receiver's shared memory (complete_tx
+//     on its barrier), and sums them in fp32.  Messages of step t may overtake a slow receiver by at most... anything,
+//     so receivers ACK what they have read (relaxed remote arrives) and senders wait for the ACKs of the previous
+//     message before they overwrite their staging tile / the receivers' buffers;
+//   * NG = 1..2 independent 64-row groups rotate through the same weights to hide the exchange latency.
+//   iteration it (t = T-1-it), per group:  [sum partials of t+1 -> dh_t] -> gate-gradient math -> dG_t (operand tile + global)
+//                                          -> pair MMA -> TMEM -> bf16 messages -> push ; it == T: dh_{-1}, dc_{-1} -> dS
+constexpr int CLB_MAXG = 2;
+constexpr uint32_t CLB_GS = CL_HALF * 16 + 16;     // 528 B: k-granule stride of the dG operand tile / unit-granule stride of a message (bank padding)
+constexpr uint32_t CLB_MSG = 8 * CLB_GS;           // 4224 B: 8 unit granules x 32 rows x 16 B
+constexpr uint32_t CLB_BT = 32 * CLB_GS;           // 16896 B: 32 k-granules (4 gates x 64 units / 8) x 32 rows x 16 B
+
+struct ClusterBP {
+  int n, steps, nswap, ng;
+  const bf16* gates; const bf16* cseq; const bf16* dhext; const bf16* dh_last; int ld_last;
+  bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
+  const bf16* upack;      // [CS][MT][128 units][256 gate columns of the pair]
+  long long* trace;
+};
+
+template <bool HARD>
+__device__ __forceinline__ float gate_bwd(float s) {
+  return HARD ? ((s > 0.f && s < 1.f) ? 0.2f : 0.f) : s * (1.f - s);
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+
+template <int CS, bool HARD, bool STD>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+rec_cluster_bwd_kernel(const ClusterBP p) {
+  constexpr int H = CS * CL_HS, G = 4 * H, NP = CS / 2, MT = H / 256, ND = 4 * MT;
+  constexpr uint32_t TM_U = CLB_MAXG * MT * 64;                     // TMEM: D(g, mt) at (g MT + mt) 64, U^T tile mt at TM_U + 128 mt
+  constexpr uint32_t GRP = CLB_BT + (ND + NP) * CLB_MSG;            // per group: operand tile | staging (ND messages) | receive (NP messages)
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t b_ready[CLB_MAXG], tmem_full[CLB_MAXG], recv_full[CLB_MAXG], ack[CLB_MAXG];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int cl = (int)blockIdx.x / CS;
+  const int e = (int)(rank & 1), q = (int)(rank >> 1);
+  const int rhs = e ^ p.nswap;                                      // which 32 rows of a group this CTA does the cell math for
+  const int T = p.steps, n = p.n, ng = p.ng;
+  const int row0 = cl * CL_ROWS * ng;
+  const int nga = min(ng, (n - row0 + CL_ROWS - 1) / CL_ROWS);
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < CLB_MAXG; ++g) {
+      ptx::mbar_init(ptx::smem_u32(&b_ready[g]), 2 * CL_EPI_WARPS);
+      ptx::mbar_init(ptx::smem_u32(&tmem_full[g]), 1);
+      ptx::mbar_init(ptx::smem_u32(&recv_full[g]), 1);
+      ptx::mbar_init(ptx::smem_u32(&ack[g]), ND * CL_EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+    for (int g = 0; g < CLB_MAXG; ++g) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&recv_full[g]), NP * CLB_MSG);   // messages of iteration 0
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(ptx::smem_u32(&tmem_base_slot), 512);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp >= 2 && warp < 6) {
+    // U^T tiles -> tensor memory: lane = output unit, 32-bit column c = gate-column pair (2c, 2c+1) of the pair's 256
+    const int mrow = (warp & 3) * 32 + lane;
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.upack + (((size_t)rank * MT + mt) * 128 + mrow) * 256);
+      for (int c32 = 0; c32 < 4; ++c32) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = __ldg(src + c32 * 8 + i);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        ptx::tmem_st_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TM_U + (uint32_t)(mt * 128 + c32 * 32), r);
+      }
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  ptx::tc_fence_after();
+
+  if (warp == 0) {
+    if (e == 0) {
+      // ===================== MMA issuer (even CTA of the pair): warp-uniform loop, one elected lane issues =====================
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, CL_ROWS, false, false);
+      const uint16_t pair_mask = (uint16_t)(3u << rank);
+      const uint64_t bd0 = ptx::umma_desc_noswz(smem_base, CLB_GS, 128);
+      for (int it = 0; it < T; ++it) {
+#pragma unroll
+        for (int g = 0; g < CLB_MAXG; ++g) {
+          if (g >= nga) break;
+          ptx::mbar_wait(ptx::smem_u32(&b_ready[g]), (uint32_t)(it & 1));   // both CTAs wrote (and fenced) their dG_t tiles
+          ptx::tc_fence_after();
+          if (g == 0 && lane == 0) CL_TRACE(it, 0);
+          const uint64_t bd = bd0 + (uint64_t)((g * GRP) >> 4);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int ks = 0; ks < 16; ++ks)
+                ptx::umma_bf16_2cta_ts(tmem_base + (uint32_t)((g * MT + mt) * 64), tmem_base + TM_U + (uint32_t)(mt * 128 + ks * 8),
+                                       bd + (uint64_t)((ks * 2 * CLB_GS) >> 4), idesc, ks > 0 ? 1u : 0u);
+            ptx::umma_commit_2cta(ptx::smem_u32(&tmem_full[g]), pair_mask);
+          }
+          __syncwarp();
+          if (g == 0 && lane == 0) CL_TRACE(it, 1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== push warp: lane x sends message x of the freshly staged partials =====================
+    for (int it = 0; it < T; ++it) {
+      for (int g = 0; g < nga; ++g) {
+        named_barrier(2, 32 * (CL_EPI_WARPS + 1));
+        ptx::fence_proxy_async();            // staging was written with generic stores by the epilogue warps (ordered by the barrier)
+        if (lane < ND) {
+          const int mt = lane >> 2, hp = (lane >> 1) & 1, ep = lane & 1;
+          const uint32_t dest = (uint32_t)(2 * (4 * mt + 2 * e + hp) + (ep ^ p.nswap));
+          const uint32_t gb = smem_base + (uint32_t)g * GRP;
+          ptx::bulk_copy_dsmem(ptx::mapa(gb + CLB_BT + (ND + q) * CLB_MSG, dest), gb + CLB_BT + (uint32_t)lane * CLB_MSG, CLB_MSG,
+                               ptx::mapa(ptx::smem_u32(&recv_full[g]), dest));
+        }
+        if (lane == 0 && g == 0) CL_TRACE(it, 6);
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..9 =====================
+    const int etid = (int)threadIdx.x - 64;
+    const int ew = etid >> 5;
+    // cell ownership: row r of this CTA's 32, unit granule gq of the pair's 8 (4 rows x 8 granules per warp: every global access >= 64 B contiguous)
+    const int r = ew * 4 + (lane >> 3), gq = lane & 7;
+    const int u0 = 64 * q + 8 * gq, gu = u0 >> 3;
+    // drain ownership: TMEM lane = unit 128 e + wq 32 + lane of an M tile, 32 columns = the rows of CTA `ch` of the destination pair
+    const int wq = warp & 3, ch = (warp - 2) >> 2;
+    const int e_src = (q & 3) >> 1;                                 // which CTA of every pair holds the partials for my pair's units
+    constexpr int bi = STD ? 0 : 1, bfk = 1 - bi;
+    const bool tracer = (etid == 0);
+    float dc[CLB_MAXG][8];
+#pragma unroll
+    for (int g = 0; g < CLB_MAXG; ++g)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dc[g][u] = 0.f;
+
+    struct Stash { uint4 g[4], c0, c1, ex; };
+    auto load_stash = [&](int t, int g, Stash& s) {
+      const int m = row0 + g * CL_ROWS + rhs * CL_HALF + r;
+      if (t >= 0 && m < n) {
+        s.g[0] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)));
+        s.g[1] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)));
+        s.g[2] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)));
+        s.g[3] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)));
+        s.c0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t, H / 8, gu, n, m)));
+        s.c1 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)));
+        s.ex = make_uint4(0u, 0u, 0u, 0u);
+        if (p.dhext) s.ex = __ldg(reinterpret_cast<const uint4*>(p.dhext + ((size_t)t * n + m) * H + u0));
+        if (t == T - 1 && p.dh_last) {
+          // extra gradient into the last step's h (encoder heads): fold it into the external term
+          float a[8], b[8];
+          unpack8(s.ex, a);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(p.dh_last + (size_t)m * p.ld_last + u0)), b);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) a[u] += b[u];
+          s.ex = pack8(a);
+        }
+      }
+    };
+    Stash nx;
+    load_stash(T - 1, 0, nx);
+    for (int it = 0; it <= T; ++it) {
+      const int t = T - 1 - it;
+#pragma unroll
+      for (int g = 0; g < CLB_MAXG; ++g) {
+        if (g >= nga) break;
+        const uint32_t gb = smem_base + (uint32_t)g * GRP;
+        const int m = row0 + g * CL_ROWS + rhs * CL_HALF + r;
+        const bool row_ok = m < n;
+        const Stash cur = nx;
+        // ---- dh_t = sum over the pairs of their partial dG_{t+1} U^T for this thread's 8 units
+        float dh[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dh[u] = 0.f;
+        if (it > 0) {
+          ptx::mbar_wait(ptx::smem_u32(&recv_full[g]), (uint32_t)((it - 1) & 1));
+          if (tracer && g == 0) CL_TRACE(it, 2);
+          if (tracer && it < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&recv_full[g]), NP * CLB_MSG);   // arm the phase of iteration `it`
+#pragma unroll
+          for (int s = 0; s < NP; ++s) {
+            float f[8];
+            unpack8(ptx::ld_shared_u4(gb + CLB_BT + (ND + s) * CLB_MSG + (uint32_t)gq * CLB_GS + (uint32_t)r * 16), f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dh[u] += f[u];
+          }
+          if (it < T) {
+            // tell every source that its message has been read: it may overwrite its staging tile and my receive slot
+            __syncwarp();
+            if (lane < NP) ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&ack[g]), (uint32_t)(2 * lane + e_src)));
+          }
+        }
+        if (t < 0) {
+          if (row_ok && p.dS_h) {
+            *reinterpret_cast<uint4*>(p.dS_h + (size_t)m * p.ldS + u0) = pack8(dh);
+            *reinterpret_cast<uint4*>(p.dS_c + (size_t)m * p.ldS + u0) = pack8(dc[g]);
+          }
+          continue;
+        }
+        // ---- gate-gradient math for step t
+        uint4 pk[4];
+        {
+          float gi[8], gf[8], gg[8], go[8], c0[8], c1[8], ex[8], di[8], df[8], dg[8], dob[8];
+          unpack8(cur.g[0], gi); unpack8(cur.g[1], gf); unpack8(cur.g[2], gg); unpack8(cur.g[3], go);
+          unpack8(cur.c0, c0); unpack8(cur.c1, c1); unpack8(cur.ex, ex);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float d = dh[u] + ex[u];
+            float d_o, ds;
+            if (STD) {
+              const float tc = tanh_fast(c1[u]);
+              d_o = d * tc;
+              ds = dc[g][u] + d * go[u] * (1.f - tc * tc);
+            } else {
+              d_o = d * c1[u];
+              ds = (dc[g][u] + d * go[u]) * (1.f - c1[u] * c1[u]);
+            }
+            di[u] = ds * gg[u] * gate_bwd<HARD>(gi[u]);
+            df[u] = ds * c0[u] * gate_bwd<HARD>(gf[u]);
+            dg[u] = ds * gi[u] * (1.f - gg[u] * gg[u]);
+            dob[u] = d_o * gate_bwd<HARD>(go[u]);
+            dc[g][u] = ds * gf[u];
+            if (!row_ok) { di[u] = 0.f; df[u] = 0.f; dg[u] = 0.f; dob[u] = 0.f; dc[g][u] = 0.f; }
+          }
+          pk[0] = pack8(di); pk[1] = pack8(df); pk[2] = pack8(dg); pk[3] = pack8(dob);
+        }
+        // operand tile: k = gate * 64 + unit-in-pair -> k-granule gate * 8 + gq, this CTA's row r
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) ptx::st_shared_u4(gb + (uint32_t)(gt * 8 + gq) * CLB_GS + (uint32_t)r * 16, pk[gt]);
+        // nothing of this thread is in flight to global memory here (see the order below), so the CTA-scope membar inside is cheap
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (e == 0) ptx::mbar_arrive(ptx::smem_u32(&b_ready[g]));
+          else ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&b_ready[g]), rank - 1));
+        }
+        if (tracer && g == 0) CL_TRACE(it, 3);
+        // ---- off the critical path: dG_t for the batched weight-gradient GEMMs, and the stash of the NEXT item
+        if (row_ok) {
+          bf16* dgp = p.dG + ((size_t)t * n + m) * G + u0;
+          *reinterpret_cast<uint4*>(dgp + bi * H) = pk[0];
+          *reinterpret_cast<uint4*>(dgp + bfk * H) = pk[1];
+          *reinterpret_cast<uint4*>(dgp + 2 * H) = pk[2];
+          *reinterpret_cast<uint4*>(dgp + 3 * H) = pk[3];
+        }
+        if (g + 1 < nga) load_stash(t, g + 1, nx);
+        else load_stash(t - 1, 0, nx);
+        // ---- partial dh_{t-1} of this CTA's units: TMEM -> bf16 messages in the staging tile
+        ptx::mbar_wait(ptx::smem_u32(&tmem_full[g]), (uint32_t)(it & 1));
+        ptx::tc_fence_after();
+        if (tracer && g == 0) CL_TRACE(it, 4);
+        if (it > 0) ptx::mbar_wait(ptx::smem_u32(&ack[g]), (uint32_t)((it - 1) & 1));   // every receiver has read message it-1
+        if (tracer && g == 0) CL_TRACE(it, 5);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          float v[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((g * MT + mt) * 64 + ch * 32), v);
+          const uint32_t msg = (uint32_t)(((mt * 2 + (wq >> 1)) * 2) + ch);
+          const uint32_t base = gb + CLB_BT + msg * CLB_MSG + (uint32_t)((wq & 1) * 4 + (lane >> 3)) * CLB_GS + (uint32_t)(lane & 7) * 2;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) st_shared_u16(base + i * 16, __bfloat16_as_ushort(__float2bfloat16_rn(v[i])));
+        }
+        ptx::tc_fence_before();
+        named_barrier(2, 32 * (CL_EPI_WARPS + 1));
+        if (tracer && g == 0) CL_TRACE(it, 9);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  if (warp == 1) ptx::tmem_dealloc2(tmem_base, 512);
+}
+
+// U (H, 4H) fp32 master -> bf16 [CS][MT][128][256] for the cluster backward kernel: CTA rank = 2 q + e, M tile mt, lane l:
+// output unit 256 mt + 128 e + l; column kk = gate * 64 + uu (gate in semantic order i, f, g, o): U[unit, blk(gate) H + 64 q + uu]
+__global__ void pack_u_cluster_bwd_kernel(const float* __restrict__ U, int ldu, bf16* __restrict__ out, int H, int variant) {
+  const long total = (long)H * 4 * H;
+  const int MT = H / 256;
+  for (long x = blockIdx.x * (long)blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int kk = (int)(x % 256);
+    long rest = x / 256;
+    const int l = (int)(rest % 128); rest /= 128;
+    const int mt = (int)(rest % MT);
+    const int rank = (int)(rest / MT);
+    const int q = rank >> 1, e = rank & 1;
+    const int gate = kk / 64, uu = kk % 64;
+    int blk = gate;
+    if (variant != MVAE_CELL_STANDARD && gate < 2) blk = 1 - gate;
+    out[x] = __float2bfloat16_rn(U[(long)(256 * mt + 128 * e + l) * ldu + blk * H + 64 * q + uu]);
+  }
 }
 
 // U (H, 4H) fp32 master, Keras column blocks -> per-CTA bf16 [CS][128 rows][H], K-major:
@@ -742,12 +1062,12 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   }
   const int groups = (a.n + CL_ROWS - 1) / CL_ROWS;
   int ng = env_int("MVAE_CL_NG", 0);
-  if (ng <= 0) ng = CL2_MAXG;
+  if (ng <= 0) ng = 2;
   ng = std::max(1, std::min(std::min(ng, CL2_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
   const size_t smem = 1024 + CL_SCR + (size_t)ng * 2 * CL_HALF * H * 2;
   Cluster2P p{};
-  p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng;
+  p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.dbg = env_int("MVAE_CL_DBG", 0);
   p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates; p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0;
   p.upack = (const bf16*)a.upack; p.hx = (uint8_t*)a.hx; p.trace = (long long*)a.trace;
   MVAE_REQUIRE(p.hx != nullptr, "cluster forward: exchange buffer missing");
@@ -763,6 +1083,48 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
     int nc = -1;
     cudaError_t err = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
     fprintf(stderr, "rec_cluster_fwd2<%d>: smem %zu B, ng %d, max co-resident clusters %d (%s), launching %d\n", CS, smem, ng, nc, cudaGetErrorString(err), clusters);
+    reported = true;
+  }
+  MVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  count_launch();
+}
+
+
+template <int CS, bool HARD, bool STD>
+void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
+  constexpr int H = CS * CL_HS, MT = H / 256, ND = 4 * MT, NP = CS / 2;
+  constexpr size_t grp = CLB_BT + (size_t)(ND + NP) * CLB_MSG;
+  constexpr size_t smem_max = 1024 + CLB_MAXG * grp;
+  auto kern = rec_cluster_bwd_kernel<CS, HARD, STD>;
+  static bool configured = false;
+  if (!configured) {
+    MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    if (CS > 8) MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured = true;
+  }
+  const int groups = (a.n + CL_ROWS - 1) / CL_ROWS;
+  int ng = env_int("MVAE_CLB_NG", 0);
+  if (ng <= 0) ng = CLB_MAXG;
+  ng = std::max(1, std::min(std::min(ng, CLB_MAXG), groups));
+  const int clusters = (groups + ng - 1) / ng;
+  const size_t smem = 1024 + (size_t)ng * grp;
+  ClusterBP p{};
+  p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng;
+  p.gates = (const bf16*)a.gates; p.cseq = (const bf16*)a.cseq; p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last;
+  p.dG = (bf16*)a.dG; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace;
+  MVAE_REQUIRE(p.upack != nullptr, "cluster backward: packed weights missing");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  static bool reported = false;
+  if (!reported && env_int("MVAE_CL_VERBOSE", 0)) {
+    int nc = -1;
+    cudaError_t err = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    fprintf(stderr, "rec_cluster_bwd<%d>: smem %zu B, ng %d, max co-resident clusters %d (%s), launching %d\n", CS, smem, ng, nc, cudaGetErrorString(err), clusters);
     reported = true;
   }
   MVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
@@ -786,6 +1148,34 @@ void rec_cluster_pack_u(const float* U, int ldu, void* upack, int H, int variant
   pack_u_cluster_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack, H, variant);
   count_launch();
   MVAE_CUDA(cudaGetLastError());
+}
+
+void rec_cluster_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int variant, cudaStream_t st) {
+  MVAE_REQUIRE(H == 256 || H == 512, "cluster recurrence: hidden size 256 or 512");
+  pack_u_cluster_bwd_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack_bwd, H, variant);
+  count_launch();
+  MVAE_CUDA(cudaGetLastError());
+}
+
+bool rec_cluster_bwd_supported(int H) {
+  static int enabled = -1;
+  if (enabled < 0) enabled = env_int("MVAE_REC_CLUSTER_BWD", 1);
+  return enabled && rec_cluster_supported(H);
+}
+
+void rec_cluster_backward(const RecPersistArgs& a, cudaStream_t st) {
+  const bool hard = a.gate_act == MVAE_GATE_HARD_SIGMOID, stdc = a.variant == MVAE_CELL_STANDARD;
+  MVAE_REQUIRE(a.H == 512 || a.H == 256, "cluster recurrence unsupported for this hidden size");
+#define MVAE_CL_BWD(CS)                                                        \
+  do {                                                                         \
+    if (hard && stdc) launch_bwd<CS, true, true>(a, st);                       \
+    else if (hard) launch_bwd<CS, true, false>(a, st);                         \
+    else if (stdc) launch_bwd<CS, false, true>(a, st);                         \
+    else launch_bwd<CS, false, false>(a, st);                                  \
+  } while (0)
+  if (a.H == 512) MVAE_CL_BWD(16);
+  else MVAE_CL_BWD(8);
+#undef MVAE_CL_BWD
 }
 
 void rec_cluster_forward(const RecPersistArgs& a, cudaStream_t st) {

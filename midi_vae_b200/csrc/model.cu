@@ -83,7 +83,7 @@ void Model::build_workspace() {
     r.cseq = alloc((size_t)(r.steps + 1) * n * H * a);
     if (need_dhext) r.dhext = alloc((size_t)r.steps * n * H * a);
     if (use_persist) r.upack = alloc((size_t)G * H * 2);
-    if (use_persist && rec_persist_ksplit_ok(H)) r.upack_b = alloc((size_t)G * H * 2);
+    if (use_persist && (rec_persist_ksplit_ok(H) || rec_cluster_bwd_supported(H))) r.upack_b = alloc((size_t)G * H * 2);
   };
   if (use_persist && rec_persist_ksplit_ok(H)) { rec_partial = alloc(rec_persist_partial_bytes(NB, H)); rec_partial2 = alloc(rec_persist_partial_bytes(NB, H)); }
   if (use_persist) rec_flags2 = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
@@ -147,6 +147,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   if (cfg.rnn_mode == MVAE_RNN_PERSISTENT)
     MVAE_REQUIRE(use_persist, "rnn_mode=persistent needs bf16 precision and lstm_size % 64 == 0 with a weight slice that fits in shared memory");
   use_cluster_fwd = use_persist && rec_cluster_supported(H);
+  use_cluster_bwd = use_persist && rec_cluster_bwd_supported(H);
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
@@ -380,7 +381,10 @@ RecPersistArgs Model::bwd_args(const BwdJob& j, int n, int slot, int hs) {
   a.gates = r.gates; a.cseq = r.cseq; a.u_shadow = W(r.iU); a.ldu = ld(r.iU);
   a.dhext = j.use_dhext ? r.dhext : nullptr; a.dh_last = j.dh_last; a.ld_last = j.ld_last; a.dG = r.xw;
   a.dS_h = j.dS_h; a.dS_c = j.dS_c; a.ldS = j.ldS;
-  if (r.upack_b && hs) {
+  if (use_cluster_bwd) {
+    rec_cluster_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, r.variant, st);
+    a.upack_bwd = r.upack_b;
+  } else if (r.upack_b && hs) {
     rec_persist_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, hs, r.variant, st);
     a.upack_bwd = r.upack_b; a.partial = slot ? rec_partial2 : rec_partial;
   }
@@ -393,7 +397,14 @@ RecPersistArgs Model::bwd_args(const BwdJob& j, int n, int slot, int hs) {
 // recurrence fills the idle time of the first).
 void Model::rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n) {
   prof_begin(PC_REC_BWD);
-  if (use_persist) {
+  if (use_cluster_bwd) {
+    for (const BwdJob* j : {ja, jb}) {
+      if (!j) continue;
+      RecPersistArgs a = bwd_args(*j, n, 0, 0);
+      rec_cluster_backward(a, st);
+      dump_trace("bwd(cluster)", *j->r, 2);
+    }
+  } else if (use_persist) {
     // pairing pays only when both recurrences run the same number of steps (a 4-step instrument cell cannot fill the gaps of a T-step one)
     const int hs_pair = (jb && pair_recs && ja->r->steps == jb->r->steps) ? rec_persist_pair_hs(H, n, sm_count) : 0;
     if (hs_pair) {

@@ -127,7 +127,8 @@ struct Model {
   const void* e_cur = nullptr;       // output of the last tanh Dense before the split
   bool stepwise_done = false;
   bool use_persist = false;          // persistent-RNN kernels (bf16 precision, supported hidden size)
-  bool use_cluster_fwd = false;      // cluster / DSMEM forward recurrence kernel (lstm_cluster.cu)
+  bool use_cluster_fwd = false;      // cluster forward recurrence kernel (lstm_cluster.cu)
+  bool use_cluster_bwd = false;      // cluster backward recurrence kernel (lstm_cluster.cu)
   long long* trace_buf = nullptr;    // MVAE_REC_TRACE=1 debugging aid
   int trace_dumps = 0;
   void* rec_hx2 = nullptr;           // second recurrence of a paired launch

@@ -55,5 +55,8 @@ bool rec_cluster_supported(int H);
 size_t rec_cluster_hx_bytes(int n, int H);
 void rec_cluster_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st);
 void rec_cluster_forward(const RecPersistArgs& a, cudaStream_t st);
+bool rec_cluster_bwd_supported(int H);
+void rec_cluster_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int variant, cudaStream_t st);
+void rec_cluster_backward(const RecPersistArgs& a, cudaStream_t st);
 
 }  // namespace mvae
