@@ -681,8 +681,14 @@ __device__ __forceinline__ float gate_bwd(float s) {
 }
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
 
+// Warp roles (19 warps): 0 = MMA issuer (even CTA), 1 / 2 = push warp of group 0 / 1 (warp 1 also owns the TMEM allocation),
+// 3..10 = epilogue warps of group 0, 11..18 = epilogue warps of group 1.  The two groups' epilogues are instruction-bound
+// (~900 instructions per thread and step), so each group gets its own 8 warps: 4 warps per scheduler instead of 2.
+constexpr int CLW_SETS = 2;
+constexpr int CLW_THREADS = 32 * (3 + CLW_SETS * CL_EPI_WARPS);
+
 template <int CS, bool HARD, bool STD>
-__global__ void __launch_bounds__(CL_THREADS, 1)
+__global__ void __launch_bounds__(CLW_THREADS, 1)
 rec_cluster_bwd_kernel(const ClusterBP p) {
   constexpr int H = CS * CL_HS, G = 4 * H, NP = CS / 2, MT = H / 256, ND = 4 * MT;
   constexpr uint32_t TM_U = CLB_MAXG * MT * 64;                     // TMEM: D(g, mt) at (g MT + mt) 64, U^T tile mt at TM_U + 128 mt
@@ -720,7 +726,7 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp >= 2 && warp < 6) {
+  if (warp >= 3 && warp < 7) {
     // U^T tiles -> tensor memory: lane = output unit, 32-bit column c = gate-column pair (2c, 2c+1) of the pair's 256
     const int mrow = (warp & 3) * 32 + lane;
     for (int mt = 0; mt < MT; ++mt) {
@@ -771,16 +777,17 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== push warp: lane x sends message x of the freshly staged partials =====================
-    for (int it = 0; it < T; ++it) {
-      for (int g = 0; g < nga; ++g) {
-        named_barrier(2, 32 * (CL_EPI_WARPS + 1));
+  } else if (warp <= CLW_SETS) {
+    // ===================== push warp of group g: lane x sends message x of the freshly staged partials =====================
+    const int g = warp - 1;
+    if (g < nga) {
+      const uint32_t gb = smem_base + (uint32_t)g * GRP;
+      for (int it = 0; it < T; ++it) {
+        named_barrier(1 + g, 32 * (CL_EPI_WARPS + 1));
         ptx::fence_proxy_async();            // staging was written with generic stores by the epilogue warps (ordered by the barrier)
         if (lane < ND) {
           const int mt = lane >> 2, hp = (lane >> 1) & 1, ep = lane & 1;
           const uint32_t dest = (uint32_t)(2 * (4 * mt + 2 * e + hp) + (ep ^ p.nswap));
-          const uint32_t gb = smem_base + (uint32_t)g * GRP;
           ptx::bulk_copy_dsmem(ptx::mapa(gb + CLB_BT + (ND + q) * CLB_MSG, dest), gb + CLB_BT + (uint32_t)lane * CLB_MSG, CLB_MSG,
                                ptx::mapa(ptx::smem_u32(&recv_full[g]), dest));
         }
@@ -788,61 +795,43 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
       }
     }
   } else {
-    // ===================== epilogue warps 2..9 =====================
-    const int etid = (int)threadIdx.x - 64;
-    const int ew = etid >> 5;
-    // cell ownership: row r of this CTA's 32, unit granule gq of the pair's 8 (4 rows x 8 granules per warp: every global access >= 64 B contiguous)
-    const int r = ew * 4 + (lane >> 3), gq = lane & 7;
-    const int u0 = 64 * q + 8 * gq, gu = u0 >> 3;
-    // drain ownership: TMEM lane = unit 128 e + wq 32 + lane of an M tile, 32 columns = the rows of CTA `ch` of the destination pair
-    const int wq = warp & 3, ch = (warp - 2) >> 2;
-    const int e_src = (q & 3) >> 1;                                 // which CTA of every pair holds the partials for my pair's units
-    constexpr int bi = STD ? 0 : 1, bfk = 1 - bi;
-    const bool tracer = (etid == 0);
-    float dc[CLB_MAXG][8];
-#pragma unroll
-    for (int g = 0; g < CLB_MAXG; ++g)
-#pragma unroll
-      for (int u = 0; u < 8; ++u) dc[g][u] = 0.f;
-
-    struct Stash { uint4 g[4], c0, c1, ex; };
-    auto load_stash = [&](int t, int g, Stash& s) {
+    // ===================== epilogue warps: set s = group s =====================
+    const int g = (warp - 3) >> 3, ew = (warp - 3) & 7;
+    if (g < nga) {
+      const uint32_t gb = smem_base + (uint32_t)g * GRP;
+      // cell ownership: row r of this CTA's 32, unit granule gq of the pair's 8 (4 rows x 8 granules per warp: every global access >= 64 B contiguous)
+      const int r = ew * 4 + (lane >> 3), gq = lane & 7;
+      const int u0 = 64 * q + 8 * gq, gu = u0 >> 3;
       const int m = row0 + g * CL_ROWS + rhs * CL_HALF + r;
-      if (t >= 0 && m < n) {
-        s.g[0] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)));
-        s.g[1] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)));
-        s.g[2] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)));
-        s.g[3] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)));
-        s.c0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t, H / 8, gu, n, m)));
-        s.c1 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)));
-        s.ex = make_uint4(0u, 0u, 0u, 0u);
-        if (p.dhext) s.ex = __ldg(reinterpret_cast<const uint4*>(p.dhext + ((size_t)t * n + m) * H + u0));
-        if (t == T - 1 && p.dh_last) {
-          // extra gradient into the last step's h (encoder heads): fold it into the external term
-          float a[8], b[8];
-          unpack8(s.ex, a);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(p.dh_last + (size_t)m * p.ld_last + u0)), b);
+      const bool row_ok = m < n;
+      // drain ownership: TMEM lane = unit 128 e + wq 32 + lane of an M tile, 32 columns = the rows of CTA `ch` of the destination pair
+      const int wq = warp & 3, ch = ew >> 2;
+      const int e_src = (q & 3) >> 1;                               // which CTA of every pair holds the partials for my pair's units
+      constexpr int bi = STD ? 0 : 1, bfk = 1 - bi;
+      const bool tracer = (ew == 0 && lane == 0);
+      float dc[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) a[u] += b[u];
-          s.ex = pack8(a);
+      for (int u = 0; u < 8; ++u) dc[u] = 0.f;
+
+      for (int it = 0; it <= T; ++it) {
+        const int t = T - 1 - it;
+        // stash of step t: independent of the recurrence, in flight while the partials arrive
+        uint4 sg[4], sc0, sc1, sex;
+        sex = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0 && row_ok) {
+          sg[0] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)));
+          sg[1] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)));
+          sg[2] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)));
+          sg[3] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)));
+          sc0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t, H / 8, gu, n, m)));
+          sc1 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)));
+          if (p.dhext) sex = __ldg(reinterpret_cast<const uint4*>(p.dhext + ((size_t)t * n + m) * H + u0));
         }
-      }
-    };
-    Stash nx;
-    load_stash(T - 1, 0, nx);
-    for (int it = 0; it <= T; ++it) {
-      const int t = T - 1 - it;
-#pragma unroll
-      for (int g = 0; g < CLB_MAXG; ++g) {
-        if (g >= nga) break;
-        const uint32_t gb = smem_base + (uint32_t)g * GRP;
-        const int m = row0 + g * CL_ROWS + rhs * CL_HALF + r;
-        const bool row_ok = m < n;
-        const Stash cur = nx;
         // ---- dh_t = sum over the pairs of their partial dG_{t+1} U^T for this thread's 8 units
         float dh[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) dh[u] = 0.f;
+        if (it == 0 && p.dh_last && row_ok) unpack8(__ldg(reinterpret_cast<const uint4*>(p.dh_last + (size_t)m * p.ld_last + u0)), dh);
         if (it > 0) {
           ptx::mbar_wait(ptx::smem_u32(&recv_full[g]), (uint32_t)((it - 1) & 1));
           if (tracer && g == 0) CL_TRACE(it, 2);
@@ -863,41 +852,49 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
         if (t < 0) {
           if (row_ok && p.dS_h) {
             *reinterpret_cast<uint4*>(p.dS_h + (size_t)m * p.ldS + u0) = pack8(dh);
-            *reinterpret_cast<uint4*>(p.dS_c + (size_t)m * p.ldS + u0) = pack8(dc[g]);
+            *reinterpret_cast<uint4*>(p.dS_c + (size_t)m * p.ldS + u0) = pack8(dc);
           }
-          continue;
+          break;
         }
         // ---- gate-gradient math for step t
         uint4 pk[4];
-        {
-          float gi[8], gf[8], gg[8], go[8], c0[8], c1[8], ex[8], di[8], df[8], dg[8], dob[8];
-          unpack8(cur.g[0], gi); unpack8(cur.g[1], gf); unpack8(cur.g[2], gg); unpack8(cur.g[3], go);
-          unpack8(cur.c0, c0); unpack8(cur.c1, c1); unpack8(cur.ex, ex);
+        if (row_ok) {
+          float gi[8], gf[8], gg[8], go[8], c0[8], c1[8], ex[8], dv[8];
+          unpack8(sg[0], gi); unpack8(sg[1], gf); unpack8(sg[2], gg); unpack8(sg[3], go);
+          unpack8(sc0, c0); unpack8(sc1, c1); unpack8(sex, ex);
+          float ds[8], d_o[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float d = dh[u] + ex[u];
-            float d_o, ds;
             if (STD) {
               const float tc = tanh_fast(c1[u]);
-              d_o = d * tc;
-              ds = dc[g][u] + d * go[u] * (1.f - tc * tc);
+              d_o[u] = d * tc;
+              ds[u] = dc[u] + d * go[u] * (1.f - tc * tc);
             } else {
-              d_o = d * c1[u];
-              ds = (dc[g][u] + d * go[u]) * (1.f - c1[u] * c1[u]);
+              d_o[u] = d * c1[u];
+              ds[u] = (dc[u] + d * go[u]) * (1.f - c1[u] * c1[u]);
             }
-            di[u] = ds * gg[u] * gate_bwd<HARD>(gi[u]);
-            df[u] = ds * c0[u] * gate_bwd<HARD>(gf[u]);
-            dg[u] = ds * gi[u] * (1.f - gg[u] * gg[u]);
-            dob[u] = d_o * gate_bwd<HARD>(go[u]);
-            dc[g][u] = ds * gf[u];
-            if (!row_ok) { di[u] = 0.f; df[u] = 0.f; dg[u] = 0.f; dob[u] = 0.f; dc[g][u] = 0.f; }
+            dc[u] = ds[u] * gf[u];
           }
-          pk[0] = pack8(di); pk[1] = pack8(df); pk[2] = pack8(dg); pk[3] = pack8(dob);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dv[u] = ds[u] * gg[u] * gate_bwd<HARD>(gi[u]);
+          pk[0] = pack8(dv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dv[u] = ds[u] * c0[u] * gate_bwd<HARD>(gf[u]);
+          pk[1] = pack8(dv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dv[u] = ds[u] * gi[u] * (1.f - gg[u] * gg[u]);
+          pk[2] = pack8(dv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dv[u] = d_o[u] * gate_bwd<HARD>(go[u]);
+          pk[3] = pack8(dv);
+        } else {
+          pk[0] = pk[1] = pk[2] = pk[3] = make_uint4(0u, 0u, 0u, 0u);
         }
         // operand tile: k = gate * 64 + unit-in-pair -> k-granule gate * 8 + gq, this CTA's row r
 #pragma unroll
         for (int gt = 0; gt < 4; ++gt) ptx::st_shared_u4(gb + (uint32_t)(gt * 8 + gq) * CLB_GS + (uint32_t)r * 16, pk[gt]);
-        // nothing of this thread is in flight to global memory here (see the order below), so the CTA-scope membar inside is cheap
+        // nothing of this thread is in flight to global memory here except the dG stores of the previous step
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -905,7 +902,7 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
           else ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&b_ready[g]), rank - 1));
         }
         if (tracer && g == 0) CL_TRACE(it, 3);
-        // ---- off the critical path: dG_t for the batched weight-gradient GEMMs, and the stash of the NEXT item
+        // ---- off the critical path: dG_t for the batched weight-gradient GEMMs
         if (row_ok) {
           bf16* dgp = p.dG + ((size_t)t * n + m) * G + u0;
           *reinterpret_cast<uint4*>(dgp + bi * H) = pk[0];
@@ -913,8 +910,6 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
           *reinterpret_cast<uint4*>(dgp + 2 * H) = pk[2];
           *reinterpret_cast<uint4*>(dgp + 3 * H) = pk[3];
         }
-        if (g + 1 < nga) load_stash(t, g + 1, nx);
-        else load_stash(t - 1, 0, nx);
         // ---- partial dh_{t-1} of this CTA's units: TMEM -> bf16 messages in the staging tile
         ptx::mbar_wait(ptx::smem_u32(&tmem_full[g]), (uint32_t)(it & 1));
         ptx::tc_fence_after();
@@ -931,7 +926,7 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
           for (int i = 0; i < 32; ++i) st_shared_u16(base + i * 16, __bfloat16_as_ushort(__float2bfloat16_rn(v[i])));
         }
         ptx::tc_fence_before();
-        named_barrier(2, 32 * (CL_EPI_WARPS + 1));
+        named_barrier(1 + g, 32 * (CL_EPI_WARPS + 1));
         if (tracer && g == 0) CL_TRACE(it, 9);
       }
     }
@@ -1115,7 +1110,7 @@ void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace;
   MVAE_REQUIRE(p.upack != nullptr, "cluster backward: packed weights missing");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

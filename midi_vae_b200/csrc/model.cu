@@ -138,6 +138,9 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   MVAE_REQUIRE(major == 10, "libmidivae.so is built for sm_100a (B200) only");
   MVAE_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   MVAE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  MVAE_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  MVAE_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  MVAE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   act = c.precision == MVAE_PREC_FP32 ? DT_F32 : DT_BF16;
   T = c.input_length; H = c.lstm_size; L = c.latent_rep_size; Dp = c.input_dim; Di = c.meta_instrument_dim; Ti = c.meta_instrument_length;
   C = c.num_composers; ne = c.num_layers_encoder; nd = c.num_layers_decoder; G = 4 * H; NB = c.max_batch;
@@ -148,6 +151,11 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
     MVAE_REQUIRE(use_persist, "rnn_mode=persistent needs bf16 precision and lstm_size % 64 == 0 with a weight slice that fits in shared memory");
   use_cluster_fwd = use_persist && rec_cluster_supported(H);
   use_cluster_bwd = use_persist && rec_cluster_bwd_supported(H);
+  // the cluster recurrences occupy 16 SMs per 64..128 batch rows and leave the rest of the chip idle: the batched weight-gradient
+  // GEMMs (needed only by the optimizer) run next to them on a second stream, on a grid sized for the idle SMs
+  { const char* e = getenv("MVAE_SIDE_STREAM"); use_side = use_cluster_bwd && (e ? atoi(e) != 0 : true); }
+  { const char* e = getenv("MVAE_SIDE_SMS"); side_sms = e ? atoi(e) : 0; }
+  if (side_sms <= 0) side_sms = std::max(16, sm_count - 16 * ((NB + 127) / 128));
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
@@ -165,6 +173,9 @@ Model::~Model() {
   for (void* p : allocs_) cudaFree(p);
   if (pin) cudaFreeHost(pin);
   if (stream) cudaStreamDestroy(stream);
+  if (side) cudaStreamDestroy(side);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
 }
 
 void Model::commit_params() {
@@ -172,16 +183,16 @@ void Model::commit_params() {
 }
 
 // --------------------------------------------------------------------------------------------- profiling
-void Model::prof_begin(int cls) {
+void Model::prof_begin(int cls, cudaStream_t s) {
   if (!profiling) return;
   Ev ev; ev.cls = cls;
   MVAE_CUDA(cudaEventCreate(&ev.a)); MVAE_CUDA(cudaEventCreate(&ev.b));
-  MVAE_CUDA(cudaEventRecord(ev.a, st));
+  MVAE_CUDA(cudaEventRecord(ev.a, s ? s : st));
   evs.push_back(ev);
 }
-void Model::prof_end() {
+void Model::prof_end(cudaStream_t s) {
   if (!profiling) return;
-  MVAE_CUDA(cudaEventRecord(evs.back().b, st));
+  MVAE_CUDA(cudaEventRecord(evs.back().b, s ? s : st));
 }
 void Model::prof_collect() {
   for (int i = 0; i < PC_COUNT; ++i) { prof_ms[i] = 0; prof_n[i] = 0; }
@@ -231,10 +242,11 @@ void Model::dump_trace(const char* dir, const Rec& r, int nctas) {
 }
 
 // --------------------------------------------------------------------------------------------- GEMM routing
-void Model::gemm(GemmArgs g) {
+void Model::gemm(GemmArgs g) { gemm_on(g, st, sm_count); }
+void Model::gemm_on(GemmArgs g, cudaStream_t s, int sms) {
   g.in_type = act;
-  if (act == DT_BF16 && gemm_tc_supported(g)) gemm_tc(g, st, sm_count);
-  else gemm_simt(g, st);
+  if (act == DT_BF16 && gemm_tc_supported(g)) gemm_tc(g, s, sms);
+  else gemm_simt(g, s);
 }
 
 // --------------------------------------------------------------------------------------------- batch plumbing
@@ -444,31 +456,46 @@ void Model::rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n) {
   prof_end();
 }
 
-// batched weight gradients of one recurrence (dU = Hprev^T dG, dW = X^T dG, db = colsum dG) and dx = dG W^T for the layer below
+// batched GEMMs after the reverse sweep of one recurrence: dx = dG W^T for the layer below (on the critical path, main stream) and
+// the weight gradients dU = Hprev^T dG, dW = X^T dG, db = colsum dG (needed only by the optimizer: side stream when enabled)
 void Model::rec_backward_gemms(const BwdJob& j, int n) {
   Rec& r = *j.r;
   const long rows = (long)r.steps * n;
   void* dG = r.xw;  // the pre-activation buffer is dead after the forward sweep
-  prof_begin(PC_GEMM);
+  if (use_side) {
+    MVAE_CUDA(cudaEventRecord(ev_fork, st));          // dG, hseq of this recurrence are final here
+    MVAE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  }
   if (j.need_dx) {  // dx = dG W^T first: the layer below is waiting for it
+    prof_begin(PC_GEMM);
     GemmArgs g; g.M = (int)rows; g.N = r.Din; g.K = G; g.A = dG; g.lda = G; g.B = W(r.iW); g.ldb = ld(r.iW); g.transB = true;
     g.C = j.dx_out; g.ldc = H; g.c_type = act;
     gemm(g);
+    prof_end();
   }
+  if (use_side) rec_backward_wgrads(j, n, side, side_sms);
+  else rec_backward_wgrads(j, n, st, sm_count);
+}
+
+void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms) {
+  Rec& r = *j.r;
+  const long rows = (long)r.steps * n;
+  void* dG = r.xw;
+  prof_begin(PC_GEMM, s);
   {  // dU += Hprev^T dG
     GemmArgs g; g.M = H; g.N = G; g.K = (int)rows; g.A = r.hseq; g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
-    gemm(g);
+    gemm_on(g, s, sms);
   }
   if (j.kind == IN_DENSE) {  // dW += X^T dG
     GemmArgs g; g.M = r.Din; g.N = G; g.K = (int)rows; g.A = j.X; g.lda = r.ldin; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iW); g.ldc = ld(r.iW); g.c_type = DT_F32; g.accumulate = true;
-    gemm(g);
+    gemm_on(g, s, sms);
   } else if (j.kind == IN_RANK1) {
-    k_colsum(act, rows, G, G, dG, j.X, VD, Gp(r.iW), st);
+    k_colsum(act, rows, G, G, dG, j.X, VD, Gp(r.iW), s);
   }
-  k_colsum(act, rows, G, G, dG, nullptr, 0, Gp(r.ib), st);
-  prof_end();
+  k_colsum(act, rows, G, G, dG, nullptr, 0, Gp(r.ib), s);
+  prof_end(s);
 }
 
 // a stack of layers (top first) plus independent side recurrences: pair the i-th stack layer with the i-th side recurrence
@@ -640,6 +667,10 @@ void Model::backward(const mvae_batch& b) {
   const int n = b.n;
   const bool tf = cfg.decoder_feedback == MVAE_FB_TEACHER_FORCED;
   MVAE_CUDA(cudaMemsetAsync(Gr, 0, arena_n * 4, st));
+  if (use_side) {   // the side stream accumulates into the freshly zeroed gradient arena
+    MVAE_CUDA(cudaEventRecord(ev_fork, st));
+    MVAE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  }
   // ---- output heads
   prof_begin(PC_GEMM);
   Rec& top = dec_notes[nd - 1];
@@ -750,6 +781,10 @@ void Model::backward(const mvae_batch& b) {
     { BwdJob j; j.r = &enc_instr; j.kind = IN_DENSE; j.X = slab(Xi_ext, 1, (long)n * ID); j.dh_last = (const char*)du + (size_t)H * asz(); j.ld_last = 3 * H;
       side.push_back(j); }
     rec_backward_group(stack, side, n);
+  }
+  if (use_side) {   // every weight gradient is in the arena before the all-reduce / optimizer
+    MVAE_CUDA(cudaEventRecord(ev_join, this->side));
+    MVAE_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   }
 }
 

@@ -123,6 +123,10 @@ struct Model {
   long long launches = 0;
   size_t h2d_bytes = 0, d2h_bytes = 0;
   cudaStream_t st = nullptr;          // stream of the call in flight
+  cudaStream_t side = nullptr;        // weight-gradient GEMMs run here, next to the (SM-sparse) backward recurrences
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool use_side = false;
+  int side_sms = 0;
   const void* Y_ext_cur = nullptr;   // teacher-forcing source: Yp_ext or (target == pitch) Xp_ext
   const void* e_cur = nullptr;       // output of the last tanh Dense before the split
   bool stepwise_done = false;
@@ -158,8 +162,10 @@ struct Model {
   void build_workspace();
   void commit_params();
   void gemm(GemmArgs g);
-  void prof_begin(int cls);
-  void prof_end();
+  void gemm_on(GemmArgs g, cudaStream_t s, int sms);
+  void prof_begin(int cls, cudaStream_t s = nullptr);
+  void prof_end(cudaStream_t s = nullptr);
+  void rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms);
   void prof_collect();
   void dump_trace(const char* dir, const Rec& r, int nctas = 1);
 
