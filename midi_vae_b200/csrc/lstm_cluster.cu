@@ -394,18 +394,24 @@ struct Cluster2P {
   long long* trace;
 };
 
+// Warp roles (19 warps): 0 = MMA issuer (even CTA) / relay (odd CTA), 1 / 2 = multicast warp of epilogue set 0 / 1 (warp 1 also
+// owns the TMEM allocation), 3..10 = epilogue set 0, 11..18 = epilogue set 1.  Set s works on groups s, s+2: the epilogue
+// is instruction-bound, so two groups are in their epilogue at the same time (4 warps per scheduler instead of 2).
+constexpr int CLF_THREADS = 32 * (3 + 2 * CL_EPI_WARPS);
+
 template <int CS, bool HARD, bool STD>
-__global__ void __launch_bounds__(CL_THREADS, 1)
+__global__ void __launch_bounds__(CLF_THREADS, 1)
 rec_cluster_fwd2_kernel(const Cluster2P p) {
   constexpr int H = CS * CL_HS, G = 4 * H, KS = H / 16;
   constexpr uint32_t HBUF = (uint32_t)CL_HALF * H * 2;
+  constexpr bool ALIAS = (HBUF >= CL_SCR);      // the scratch tile of an item lives in the h tile its MMA has just finished reading
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t h_full[CL2_MAXG][2], peer_ready[CL2_MAXG][2], tmem_full[CL2_MAXG];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_scr = smem_base;                              // fp32 scratch tile, shared by the groups
-  const uint32_t smem_h0 = smem_base + CL_SCR;                      // hbuf(g, b) = smem_h0 + (2 g + b) * HBUF
+  const uint32_t smem_scr0 = smem_base;                              // !ALIAS: scratch tile of set s at smem_scr0 + s * CL_SCR
+  const uint32_t smem_h0 = smem_base + (ALIAS ? 0u : 2u * CL_SCR);   // hbuf(g, b) = smem_h0 + (2 g + b) * HBUF
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const int cl = (int)blockIdx.x / CS;
@@ -432,17 +438,7 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int etid = (int)threadIdx.x - 64;
-  const int rr = etid & 63, q = (etid >> 6) & 3;
-  const int u0 = j * CL_HS + q * 8, gu = u0 >> 3;
-  constexpr int bi = STD ? 0 : 1, bfk = 1 - bi;
-  float cst[CL2_MAXG][8];
-#pragma unroll
-  for (int g = 0; g < CL2_MAXG; ++g)
-#pragma unroll
-    for (int u = 0; u < 8; ++u) cst[g][u] = 0.f;
-
-  if (warp >= 2 && warp < 6) {
+  if (warp >= 3 && warp < 7) {
     // U slice -> tensor memory: lane = gate column, 32-bit column c = k pair (2c, 2c+1); each thread streams its own row
     const int mrow = (warp & 3) * 32 + lane;
     const uint4* src = reinterpret_cast<const uint4*>(p.upack + ((size_t)j * CL_GC + mrow) * H);
@@ -457,10 +453,11 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
     }
     ptx::tmem_st_wait();
   }
-  if (warp >= 2) {
+  if (warp >= 3) {
+    const int etid = (int)threadIdx.x - 96;   // 0..511 over both sets
     for (int g = 0; g < nga; ++g) {
       // initial hidden state (hseq slab 0, row-major) -> hbuf(g, 1) in operand order
-      for (int idx = etid; idx < CL_HALF * (H / 8); idx += 32 * CL_EPI_WARPS) {
+      for (int idx = etid; idx < CL_HALF * (H / 8); idx += 64 * CL_EPI_WARPS) {
         const int r = idx / (H / 8), gk = idx % (H / 8);
         const int mm = row0 + g * CL_ROWS + rh * CL_HALF + r;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -469,16 +466,6 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
       }
     }
     ptx::fence_proxy_async();
-#pragma unroll
-    for (int g = 0; g < CL2_MAXG; ++g) {
-      const int m = row0 + g * CL_ROWS + rr;
-      if (g < nga && m < n) {
-        uint4 cv = make_uint4(0u, 0u, 0u, 0u);
-        if (p.c0) cv = *reinterpret_cast<const uint4*>(p.c0 + (size_t)m * p.ldc0 + u0);
-        unpack8(cv, cst[g]);
-        *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m)) = cv;   // stash slab 0 = c0
-      }
-    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -531,11 +518,12 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== multicast warp: brings this CTA's freshly stored h slice into every consumer's operand tile =====================
+  } else if (warp <= 2) {
+    // ===================== multicast warp of set s: brings this CTA's freshly stored h slice into every consumer's operand tile =====================
+    const int set = warp - 1;
     for (int t = 0; t + 1 < T; ++t) {
-      for (int g = 0; g < nga; ++g) {
-        named_barrier(2, 32 * (CL_EPI_WARPS + 1));
+      for (int g = set; g < nga; g += 2) {
+        named_barrier(2 + 2 * set, 32 * (CL_EPI_WARPS + 1));
         if (lane < 2) {
           const uint8_t* src = p.hx + ((size_t)(((cl * ng + g) * 2 + (t & 1)) * CS + j)) * CL_STAGE + (size_t)lane * CL_SLICE;
           const uint16_t mask = (uint16_t)((((lane ^ p.nswap) & 1) ? 0xAAAAu : 0x5555u) & ((1u << CS) - 1u));
@@ -545,71 +533,91 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
       }
     }
   } else {
-    // ===================== epilogue warps 2..9 =====================
-    const int wq = warp & 3, ch = (warp - 2) >> 2;
+    // ===================== epilogue warps: set s = warps 3 + 8 s .. 10 + 8 s =====================
+    const int set = (warp - 3) >> 3, ew = (warp - 3) & 7;
+    // phase A ownership: TMEM lane = gate column c = gate * 32 + unit, 32 batch rows (column half ch)
+    const int wq = warp & 3, ch = ew >> 2;
     const int c = wq * 32 + lane;
-    const bool tracer = (etid == 0);
+    // phase B ownership: batch row rr of the group, units [8 q, 8 q + 8) of the CTA's 32; a warp = 8 rows x 4 q, so that every
+    // global access of the warp covers whole 64-byte (row-major tensors) or 128-byte (granule-major stash) runs
+    const int rr = ew * 8 + (lane >> 2), q = lane & 3;
+    const int u0 = j * CL_HS + q * 8, gu = u0 >> 3;
+    constexpr int bi = STD ? 0 : 1, bfk = 1 - bi;
+    const bool tracer = (ew == 0 && lane == 0);
     const uint32_t swB = (uint32_t)(rr & 7) << 4;
-    auto load_xw = [&](int t, int g, uint4* xq) {
+    float cst[2][8];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int g = set + 2 * k;
       const int m = row0 + g * CL_ROWS + rr;
-      if (m < n && !(p.dbg & 2)) {
-        const bf16* xr = p.xw + ((size_t)t * n + m) * G + u0;
-        xq[0] = __ldg(reinterpret_cast<const uint4*>(xr + bi * H));
-        xq[1] = __ldg(reinterpret_cast<const uint4*>(xr + bfk * H));
-        xq[2] = __ldg(reinterpret_cast<const uint4*>(xr + 2 * H));
-        xq[3] = __ldg(reinterpret_cast<const uint4*>(xr + 3 * H));
-      } else {
-        xq[0] = xq[1] = xq[2] = xq[3] = make_uint4(0u, 0u, 0u, 0u);
+      uint4 cv = make_uint4(0u, 0u, 0u, 0u);
+      if (g < nga && m < n) {
+        if (p.c0) cv = *reinterpret_cast<const uint4*>(p.c0 + (size_t)m * p.ldc0 + u0);
+        *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m)) = cv;   // stash slab 0 = c0
       }
-    };
-    uint4 xn[4];
-    load_xw(0, 0, xn);
+      unpack8(cv, cst[k]);
+    }
     for (int t = 0; t < T; ++t) {
 #pragma unroll
-      for (int g = 0; g < CL2_MAXG; ++g) {
+      for (int k = 0; k < 2; ++k) {
+        const int g = set + 2 * k;
         if (g >= nga) break;
         const int m = row0 + g * CL_ROWS + rr;
         const bool row_ok = m < n;
-        // the input projection does not depend on the recurrence: this item's was fetched one item ago, fetch the next one's now
-        uint4 xq[4] = {xn[0], xn[1], xn[2], xn[3]};
-        if (g + 1 < nga) load_xw(t, g + 1, xn);
-        else if (t + 1 < T) load_xw(t + 1, 0, xn);
+        // the input projection does not depend on the recurrence: in flight while the MMA of this item runs
+        uint4 xq[4];
+        xq[0] = xq[1] = xq[2] = xq[3] = make_uint4(0u, 0u, 0u, 0u);
+        if (row_ok) {
+          const bf16* xr = p.xw + ((size_t)t * n + m) * G + u0;
+          xq[0] = __ldg(reinterpret_cast<const uint4*>(xr + bi * H));
+          xq[1] = __ldg(reinterpret_cast<const uint4*>(xr + bfk * H));
+          xq[2] = __ldg(reinterpret_cast<const uint4*>(xr + 2 * H));
+          xq[3] = __ldg(reinterpret_cast<const uint4*>(xr + 3 * H));
+        }
         ptx::mbar_wait(ptx::smem_u32(&tmem_full[g]), (uint32_t)(t & 1));
         ptx::tc_fence_after();
         if (tracer && g == 0) CL_TRACE(t, 2);
+        const uint32_t scr = ALIAS ? (smem_h0 + (2 * g + ((t + 1) & 1)) * HBUF) : (smem_scr0 + (uint32_t)set * CL_SCR);
         {
           float v[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 64 + ch * 32), v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int ra = ch * 32 + i;
-            ptx::st_shared_f32(smem_scr + ra * (CL_GC * 4) + (((uint32_t)c * 4) ^ ((uint32_t)(ra & 7) << 4)), v[i]);
+            ptx::st_shared_f32(scr + ra * (CL_GC * 4) + (((uint32_t)c * 4) ^ ((uint32_t)(ra & 7) << 4)), v[i]);
           }
         }
         ptx::tc_fence_before();
-        named_barrier(1, 32 * CL_EPI_WARPS);
+        named_barrier(1 + 2 * set, 32 * CL_EPI_WARPS);
         if (tracer && g == 0) CL_TRACE(t, 3);
         float pre[4][8];
 #pragma unroll
         for (int gt = 0; gt < 4; ++gt) {
           const uint32_t off = (uint32_t)(gt * 32 + q * 8) * 4;
-          const float4 a0 = ptx::ld_shared_f32x4(smem_scr + rr * (CL_GC * 4) + (off ^ swB));
-          const float4 a1 = ptx::ld_shared_f32x4(smem_scr + rr * (CL_GC * 4) + ((off + 16) ^ swB));
+          const float4 a0 = ptx::ld_shared_f32x4(scr + rr * (CL_GC * 4) + (off ^ swB));
+          const float4 a1 = ptx::ld_shared_f32x4(scr + rr * (CL_GC * 4) + ((off + 16) ^ swB));
           pre[gt][0] = a0.x; pre[gt][1] = a0.y; pre[gt][2] = a0.z; pre[gt][3] = a0.w;
           pre[gt][4] = a1.x; pre[gt][5] = a1.y; pre[gt][6] = a1.z; pre[gt][7] = a1.w;
         }
-        float xi[8], xf[8], xg[8], xo[8], gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
-        unpack8(xq[0], xi); unpack8(xq[1], xf); unpack8(xq[2], xg); unpack8(xq[3], xo);
+        float xv[8], gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
+        unpack8(xq[0], xv);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) gi[u] = gate_fwd<HARD>(pre[0][u] + xv[u]);
+        unpack8(xq[1], xv);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) gf[u] = gate_fwd<HARD>(pre[1][u] + xv[u]);
+        unpack8(xq[2], xv);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) gg[u] = tanh_fast(pre[2][u] + xv[u]);
+        unpack8(xq[3], xv);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) go[u] = gate_fwd<HARD>(pre[3][u] + xv[u]);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          gi[u] = gate_fwd<HARD>(pre[0][u] + xi[u]);
-          gf[u] = gate_fwd<HARD>(pre[1][u] + xf[u]);
-          gg[u] = tanh_fast(pre[2][u] + xg[u]);
-          go[u] = gate_fwd<HARD>(pre[3][u] + xo[u]);
-          const float s = gf[u] * cst[g][u] + gi[u] * gg[u];
-          if (STD) { cn[u] = s; hn[u] = go[u] * tanh_fast(s); }
-          else { cn[u] = tanh_fast(s); hn[u] = go[u] * cn[u]; }
-          cst[g][u] = cn[u];
+          const float sv = gf[u] * cst[k][u] + gi[u] * gg[u];
+          if (STD) { cn[u] = sv; hn[u] = go[u] * tanh_fast(sv); }
+          else { cn[u] = tanh_fast(sv); hn[u] = go[u] * cn[u]; }
+          cst[k][u] = cn[u];
         }
         uint4 st_h = pack8(hn);
         if (!row_ok) st_h = make_uint4(0u, 0u, 0u, 0u);
@@ -618,24 +626,24 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
           uint8_t* dst = p.hx + ((size_t)(((cl * ng + g) * 2 + (t & 1)) * CS + j)) * CL_STAGE + (size_t)(rr >> 5) * CL_SLICE +
                          (size_t)q * (CL_HALF * 16) + (size_t)(rr & 31) * 16;
           *reinterpret_cast<uint4*>(dst) = st_h;
+          // generic store -> async-proxy read by the multicast copy; the only other traffic of this thread still in flight is the
+          // stash of the previous item (the input projection above has been consumed)
           ptx::fence_proxy_async_global();
           if (tracer && g == 0) CL_TRACE(t, 4);
-          named_barrier(2, 32 * (CL_EPI_WARPS + 1));   // also: every thread is done reading the scratch tile
+          named_barrier(2 + 2 * set, 32 * (CL_EPI_WARPS + 1));   // also: every thread of the set is done reading the scratch tile
           if (tracer && g == 0) CL_TRACE(t, 5);
         } else {
-          named_barrier(3, 32 * CL_EPI_WARPS);         // last step: only the scratch tile needs protecting
+          named_barrier(5 + set, 32 * CL_EPI_WARPS);             // last step: only the scratch tile needs protecting
         }
-        if (row_ok) {
+        if (row_ok && !(p.dbg & 1)) {
           *reinterpret_cast<uint4*>(p.hseq + ((size_t)(t + 1) * n + m) * H + u0) = st_h;
-          if (!(p.dbg & 1)) {
           *reinterpret_cast<uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)) = pack8(cn);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)) = pack8(gi);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)) = pack8(gf);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)) = pack8(gg);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)) = pack8(go);
-          }
         }
-        if (tracer && g == nga - 1) CL_TRACE(t, 9);
+        if (tracer && g == 0) CL_TRACE(t, 9);
       }
     }
   }
@@ -1047,7 +1055,8 @@ void launch_fwd(const RecPersistArgs& a, cudaStream_t st) {
 template <int CS, bool HARD, bool STD>
 void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   constexpr int H = CS * CL_HS;
-  constexpr size_t smem_max = 1024 + CL_SCR + (size_t)CL2_MAXG * 2 * CL_HALF * H * 2;
+  constexpr size_t hbuf = (size_t)CL_HALF * H * 2, scr_bytes = hbuf >= CL_SCR ? 0 : 2 * CL_SCR;
+  constexpr size_t smem_max = 1024 + scr_bytes + (size_t)CL2_MAXG * 2 * hbuf;
   auto kern = rec_cluster_fwd2_kernel<CS, HARD, STD>;
   static bool configured = false;
   if (!configured) {
@@ -1060,7 +1069,7 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   if (ng <= 0) ng = 2;
   ng = std::max(1, std::min(std::min(ng, CL2_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
-  const size_t smem = 1024 + CL_SCR + (size_t)ng * 2 * CL_HALF * H * 2;
+  const size_t smem = 1024 + scr_bytes + (size_t)ng * 2 * hbuf;
   Cluster2P p{};
   p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.dbg = env_int("MVAE_CL_DBG", 0);
   p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates; p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0;
@@ -1068,7 +1077,7 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   MVAE_REQUIRE(p.hx != nullptr, "cluster forward: exchange buffer missing");
   MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * CL_STAGE <= rec_cluster_hx_bytes(a.n, H), "cluster forward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
