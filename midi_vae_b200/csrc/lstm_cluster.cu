@@ -680,6 +680,8 @@ struct ClusterBP {
   const bf16* gates; const bf16* cseq; const bf16* dhext; const bf16* dh_last; int ld_last;
   bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
   const bf16* upack;      // [CS][MT][128 units][256 gate columns of the pair]
+  uint8_t* xbuf;          // via_l2: global exchange buffer [clusters][ng][CS][ND messages]
+  int via_l2;             // messages travel smem -> L2 -> smem (bulk store, remote arrive, bulk load) instead of DSMEM bulk copies
   long long* trace;
 };
 
@@ -702,7 +704,7 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
   constexpr uint32_t TM_U = CLB_MAXG * MT * 64;                     // TMEM: D(g, mt) at (g MT + mt) 64, U^T tile mt at TM_U + 128 mt
   constexpr uint32_t GRP = CLB_BT + (ND + NP) * CLB_MSG;            // per group: operand tile | staging (ND messages) | receive (NP messages)
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t b_ready[CLB_MAXG], tmem_full[CLB_MAXG], recv_full[CLB_MAXG], ack[CLB_MAXG];
+  __shared__ __align__(8) uint64_t b_ready[CLB_MAXG], tmem_full[CLB_MAXG], recv_full[CLB_MAXG], ack[CLB_MAXG], msg_ready[CLB_MAXG];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -721,6 +723,7 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
       ptx::mbar_init(ptx::smem_u32(&tmem_full[g]), 1);
       ptx::mbar_init(ptx::smem_u32(&recv_full[g]), 1);
       ptx::mbar_init(ptx::smem_u32(&ack[g]), ND * CL_EPI_WARPS);
+      ptx::mbar_init(ptx::smem_u32(&msg_ready[g]), NP);
     }
     ptx::fence_barrier_init();
     for (int g = 0; g < CLB_MAXG; ++g) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&recv_full[g]), NP * CLB_MSG);   // messages of iteration 0
@@ -790,16 +793,37 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
     const int g = warp - 1;
     if (g < nga) {
       const uint32_t gb = smem_base + (uint32_t)g * GRP;
+      const int xl = lane % ND;
+      const int mt = xl >> 2, hp = (xl >> 1) & 1, ep = xl & 1;
+      const uint32_t dest = (uint32_t)(2 * (4 * mt + 2 * e + hp) + (ep ^ p.nswap));
+      const uint32_t dst = ptx::mapa(gb + CLB_BT + (ND + q) * CLB_MSG, dest), dbar = ptx::mapa(ptx::smem_u32(&recv_full[g]), dest);
+      const uint32_t src = gb + CLB_BT + (uint32_t)xl * CLB_MSG;
+      // via_l2: my staging tile goes to slot (cluster, g, rank) of the global exchange buffer in one bulk store; once it is complete the
+      // ND destinations are told (relaxed remote arrives), and when my NP sources have told me I fetch my message out of each one's slot
+      const size_t slot_bytes = (size_t)ND * CLB_MSG;
+      uint8_t* my_slot = p.xbuf + ((size_t)(cl * ng + g) * CS + rank) * slot_bytes;
+      const uint32_t ready_remote = ptx::mapa(ptx::smem_u32(&msg_ready[g]), dest);
+      const int my_msg = (q >> 2) * 4 + (q & 1) * 2 + (e ^ p.nswap);                 // index of the message for me in a source's staging tile
+      const uint8_t* fetch_src = p.xbuf + ((size_t)(cl * ng + g) * CS + (size_t)(2 * (lane % NP) + ((q & 3) >> 1))) * slot_bytes + (size_t)my_msg * CLB_MSG;
       for (int it = 0; it < T; ++it) {
         named_barrier(1 + g, 32 * (CL_EPI_WARPS + 1));
         ptx::fence_proxy_async();            // staging was written with generic stores by the epilogue warps (ordered by the barrier)
-        if (lane < ND) {
-          const int mt = lane >> 2, hp = (lane >> 1) & 1, ep = lane & 1;
-          const uint32_t dest = (uint32_t)(2 * (4 * mt + 2 * e + hp) + (ep ^ p.nswap));
-          ptx::bulk_copy_dsmem(ptx::mapa(gb + CLB_BT + (ND + q) * CLB_MSG, dest), gb + CLB_BT + (uint32_t)lane * CLB_MSG, CLB_MSG,
-                               ptx::mapa(ptx::smem_u32(&recv_full[g]), dest));
+        if (!p.via_l2) {
+          if (lane < ND) ptx::bulk_copy_dsmem(dst, src, CLB_MSG, dbar);
+          if (lane == 0 && g == 0) CL_TRACE(it, 6);
+        } else {
+          if (lane == 0) {
+            ptx::bulk_store(my_slot, gb + CLB_BT, (uint32_t)slot_bytes);
+            ptx::bulk_commit();
+            ptx::bulk_wait_all();
+          }
+          __syncwarp();
+          if (lane < ND) ptx::mbar_arrive_remote_relaxed(ready_remote);
+          if (lane == 0 && g == 0) CL_TRACE(it, 6);
+          ptx::mbar_wait(ptx::smem_u32(&msg_ready[g]), (uint32_t)(it & 1));
+          if (lane < NP) ptx::bulk_load(gb + CLB_BT + (ND + lane) * CLB_MSG, fetch_src, CLB_MSG, ptx::smem_u32(&recv_full[g]));
+          if (lane == 0 && g == 0) CL_TRACE(it, 8);
         }
-        if (lane == 0 && g == 0) CL_TRACE(it, 6);
       }
     }
   } else {
@@ -1118,6 +1142,9 @@ void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
   p.dG = (bf16*)a.dG; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace;
   MVAE_REQUIRE(p.upack != nullptr, "cluster backward: packed weights missing");
+  p.xbuf = (uint8_t*)a.partial;
+  p.via_l2 = env_int("MVAE_CLB_L2", 1) && p.xbuf != nullptr;
+  if (p.via_l2) MVAE_REQUIRE((size_t)clusters * ng * CS * ND * CLB_MSG <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -1143,6 +1170,9 @@ bool rec_cluster_supported(int H) {
   if (enabled < 0) enabled = env_int("MVAE_REC_CLUSTER", 1);
   return enabled && (H == 256 || H == 512);
 }
+
+// global exchange buffer of the backward kernel (via_l2): [64-row groups rounded up to whole clusters][H/32 CTAs][H/64 messages of 4224 B]
+size_t rec_cluster_xbuf_bytes(int n, int H) { return (size_t)((n + CL_ROWS - 1) / CL_ROWS + CLB_MAXG) * (size_t)(H / CL_HS) * (size_t)(H / 64) * CLB_MSG; }
 
 // global exchange buffer of the forward kernel: [64-row groups, rounded up to whole clusters][2][H/32 CTAs][4 KB]
 size_t rec_cluster_hx_bytes(int n, int H) { return (size_t)((n + CL_ROWS - 1) / CL_ROWS + CL2_MAXG) * 2 * (size_t)(H / CL_HS) * CL_STAGE; }

@@ -85,7 +85,10 @@ void Model::build_workspace() {
     if (use_persist) r.upack = alloc((size_t)G * H * 2);
     if (use_persist && (rec_persist_ksplit_ok(H) || rec_cluster_bwd_supported(H))) r.upack_b = alloc((size_t)G * H * 2);
   };
-  if (use_persist && rec_persist_ksplit_ok(H)) { rec_partial = alloc(rec_persist_partial_bytes(NB, H)); rec_partial2 = alloc(rec_persist_partial_bytes(NB, H)); }
+  if (use_persist && (rec_persist_ksplit_ok(H) || rec_cluster_bwd_supported(H))) {
+    const size_t pb = std::max(rec_persist_partial_bytes(NB, H), rec_cluster_bwd_supported(H) ? rec_cluster_xbuf_bytes(NB, H) : (size_t)0);
+    rec_partial = alloc(pb); rec_partial2 = alloc(pb);
+  }
   if (use_persist) rec_flags2 = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   if (use_persist) {
     const size_t hxb = std::max(rec_persist_hx_bytes(NB, H), rec_cluster_supported(H) ? rec_cluster_hx_bytes(NB, H) : (size_t)0);
@@ -395,7 +398,7 @@ RecPersistArgs Model::bwd_args(const BwdJob& j, int n, int slot, int hs) {
   a.dS_h = j.dS_h; a.dS_c = j.dS_c; a.ldS = j.ldS;
   if (use_cluster_bwd) {
     rec_cluster_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, r.variant, st);
-    a.upack_bwd = r.upack_b;
+    a.upack_bwd = r.upack_b; a.partial = slot ? rec_partial2 : rec_partial;
   } else if (r.upack_b && hs) {
     rec_persist_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, hs, r.variant, st);
     a.upack_bwd = r.upack_b; a.partial = slot ? rec_partial2 : rec_partial;

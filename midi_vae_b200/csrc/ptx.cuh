@@ -138,6 +138,13 @@ __device__ __forceinline__ void bulk_load_multicast(uint32_t dst, const void* sr
                "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
                : "memory");
 }
+// bulk copy shared -> global (async proxy), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread COMPLETE (writes performed), not only their source reads
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;

@@ -53,6 +53,7 @@ void rec_persist_backward(const RecPersistArgs& a, cudaStream_t st, int sm_count
 // cluster / DSMEM kernels (lstm_cluster.cu): H = 256 or 512; same stash layouts as the kernels above
 bool rec_cluster_supported(int H);
 size_t rec_cluster_hx_bytes(int n, int H);
+size_t rec_cluster_xbuf_bytes(int n, int H);
 void rec_cluster_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st);
 void rec_cluster_forward(const RecPersistArgs& a, cudaStream_t st);
 bool rec_cluster_bwd_supported(int H);
