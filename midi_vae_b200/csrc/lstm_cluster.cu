@@ -1143,7 +1143,7 @@ void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace;
   MVAE_REQUIRE(p.upack != nullptr, "cluster backward: packed weights missing");
   p.xbuf = (uint8_t*)a.partial;
-  p.via_l2 = env_int("MVAE_CLB_L2", 1) && p.xbuf != nullptr;
+  p.via_l2 = env_int("MVAE_CLB_L2", 0) && p.xbuf != nullptr;
   if (p.via_l2) MVAE_REQUIRE((size_t)clusters * ng * CS * ND * CLB_MSG <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;

@@ -144,6 +144,9 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   MVAE_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
   MVAE_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   MVAE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  MVAE_CUDA(cudaStreamCreateWithFlags(&st_branch, cudaStreamNonBlocking));
+  MVAE_CUDA(cudaEventCreateWithFlags(&ev_bfork, cudaEventDisableTiming));
+  MVAE_CUDA(cudaEventCreateWithFlags(&ev_bjoin, cudaEventDisableTiming));
   act = c.precision == MVAE_PREC_FP32 ? DT_F32 : DT_BF16;
   T = c.input_length; H = c.lstm_size; L = c.latent_rep_size; Dp = c.input_dim; Di = c.meta_instrument_dim; Ti = c.meta_instrument_length;
   C = c.num_composers; ne = c.num_layers_encoder; nd = c.num_layers_decoder; G = 4 * H; NB = c.max_batch;
@@ -158,6 +161,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   // GEMMs (needed only by the optimizer) run next to them on a second stream, on a grid sized for the idle SMs
   { const char* e = getenv("MVAE_SIDE_STREAM"); use_side = use_cluster_bwd && (e ? atoi(e) != 0 : true); }
   { const char* e = getenv("MVAE_SIDE_SMS"); side_sms = e ? atoi(e) : 0; }
+  { const char* e = getenv("MVAE_BRANCH"); use_branch = use_cluster_fwd && use_cluster_bwd && (e ? atoi(e) != 0 : true); }
   if (side_sms <= 0) side_sms = std::max(16, sm_count - 16 * ((NB + 127) / 128));
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
@@ -177,6 +181,9 @@ Model::~Model() {
   if (pin) cudaFreeHost(pin);
   if (stream) cudaStreamDestroy(stream);
   if (side) cudaStreamDestroy(side);
+  if (st_branch) cudaStreamDestroy(st_branch);
+  if (ev_bfork) cudaEventDestroy(ev_bfork);
+  if (ev_bjoin) cudaEventDestroy(ev_bjoin);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
 }
@@ -207,6 +214,28 @@ void Model::prof_collect() {
     cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
   }
   evs.clear();
+}
+
+// --------------------------------------------------------------------------------------------- branch stream
+// fork: remember "now" on the main stream; begin: everything issued until end() goes to the branch stream and starts after the fork point;
+// join: the main stream waits for what the branch did.  Host code stays sequential; only the stream the launches go to changes.
+void Model::branch_fork() {
+  if (!use_branch) return;
+  MVAE_CUDA(cudaEventRecord(ev_bfork, st));
+}
+void Model::branch_begin() {
+  if (!use_branch) return;
+  MVAE_CUDA(cudaStreamWaitEvent(st_branch, ev_bfork, 0));
+  st_saved = st; st = st_branch; cur_slot = 1;
+}
+void Model::branch_end() {
+  if (!use_branch) return;
+  MVAE_CUDA(cudaEventRecord(ev_bjoin, st_branch));
+  st = st_saved; cur_slot = 0;
+}
+void Model::branch_join() {
+  if (!use_branch) return;
+  MVAE_CUDA(cudaStreamWaitEvent(st, ev_bjoin, 0));
 }
 
 // MVAE_REC_TRACE=1: print the per-phase clock64 stamps CTA 0 of a persistent recurrence recorded for 8 steps
@@ -347,7 +376,7 @@ void Model::rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n) {
     // clusters are independent of each other, so there is nothing to pair: each recurrence is one launch
     for (const FwdJob* j : {ja, jb}) {
       if (!j) continue;
-      RecPersistArgs a = fwd_args(*j, n, 0, 0);
+      RecPersistArgs a = fwd_args(*j, n, cur_slot, 0);
       rec_cluster_forward(a, st);
       dump_trace("fwd(cluster)", *j->r, 2);
     }
@@ -415,7 +444,7 @@ void Model::rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n) {
   if (use_cluster_bwd) {
     for (const BwdJob* j : {ja, jb}) {
       if (!j) continue;
-      RecPersistArgs a = bwd_args(*j, n, 0, 0);
+      RecPersistArgs a = bwd_args(*j, n, cur_slot, 0);
       rec_cluster_backward(a, st);
       dump_trace("bwd(cluster)", *j->r, 2);
     }
@@ -503,6 +532,18 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms)
 
 // a stack of layers (top first) plus independent side recurrences: pair the i-th stack layer with the i-th side recurrence
 void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n) {
+  if (use_branch) {
+    // the stack (top layer first) is the critical chain; the independent recurrences run next to it on the branch stream
+    branch_fork();
+    rec_backward_sweep(&stack[0], nullptr, n);
+    rec_backward_gemms(stack[0], n);
+    branch_begin();
+    for (auto& j : side) { rec_backward_sweep(&j, nullptr, n); rec_backward_gemms(j, n); }
+    branch_end();
+    for (size_t k = 1; k < stack.size(); ++k) { rec_backward_sweep(&stack[k], nullptr, n); rec_backward_gemms(stack[k], n); }
+    branch_join();
+    return;
+  }
   size_t si = 0;
   for (size_t k = 0; k < stack.size(); ++k) {
     const BwdJob* partner = si < side.size() ? &side[si] : nullptr;
@@ -522,6 +563,22 @@ void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& 
 void Model::encoder_forward(int n) {
   // the first pitch layer and the velocity stream are independent and equally long: they share a launch
   FwdJob jv; jv.r = &enc_vel; jv.kind = IN_RANK1; jv.X = slab(Xv_ext, 1, (long)n * VD);
+  if (use_branch) {
+    branch_fork();
+    for (int k = 0; k < ne; ++k) {
+      FwdJob jp; jp.r = &enc_pitch[k]; jp.kind = IN_DENSE;
+      jp.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
+      rec_forward_jobs(&jp, nullptr, n);
+      if (k == 0) {   // velocity and instrument streams: next to the pitch stack
+        branch_begin();
+        rec_forward_jobs(&jv, nullptr, n);
+        rec_forward(enc_instr, n, IN_DENSE, slab(Xi_ext, 1, (long)n * ID), nullptr, nullptr, 0);
+        branch_end();
+      }
+    }
+    branch_join();
+    return;
+  }
   for (int k = 0; k < ne; ++k) {
     FwdJob jp; jp.r = &enc_pitch[k]; jp.kind = IN_DENSE;
     jp.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
@@ -569,13 +626,25 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
   auto st1 = [&](int r) { return (const char*)S + (size_t)(2 * r) * H * asz(); };
   auto st2 = [&](int r) { return (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
   FwdJob jv; jv.r = &dec_vel; jv.kind = tf ? IN_RANK1 : IN_NONE; jv.X = tf ? Xv_ext : nullptr; jv.h0 = st1(nd + 1); jv.c0 = st2(nd + 1); jv.ld0 = nS * H;
+  if (use_branch) branch_fork();
   for (int k = 0; k < nd; ++k) {
     FwdJob jp; jp.r = &dec_notes[k]; jp.h0 = st1(k); jp.c0 = st2(k); jp.ld0 = nS * H;
     if (k == 0) { jp.kind = tf ? IN_DENSE : IN_NONE; jp.X = tf ? Y_ext_cur : nullptr; }
     else { jp.kind = IN_DENSE; jp.X = slab(dec_notes[k - 1].hseq, 1, (long)n * H); }
-    rec_forward_jobs(&jp, k == 0 ? &jv : nullptr, n);
+    if (use_branch) {
+      rec_forward_jobs(&jp, nullptr, n);
+      if (k == 0) {
+        branch_begin();
+        rec_forward_jobs(&jv, nullptr, n);
+        rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
+        branch_end();
+      }
+    } else {
+      rec_forward_jobs(&jp, k == 0 ? &jv : nullptr, n);
+    }
   }
-  rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
+  if (use_branch) branch_join();
+  else rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
   prof_begin(PC_GEMM);
   { GemmArgs g; g.M = T * n; g.N = Dp; g.K = H; g.A = slab(dec_notes[nd - 1].hseq, 1, (long)n * H); g.lda = H; g.B = W(iWy); g.ldb = ld(iWy);
     g.C = Pn; g.ldc = ld_pn; g.c_type = DT_F32; g.bias = Wf(iby); gemm(g); }

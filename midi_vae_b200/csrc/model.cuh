@@ -127,6 +127,16 @@ struct Model {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_side = false;
   int side_sms = 0;
+  // independent recurrences (velocity / instrument streams) run on a branch stream next to the pitch stack: a cluster recurrence
+  // occupies 4 of the chip's 7 cluster slots, so two of them overlap almost completely
+  cudaStream_t st_branch = nullptr, st_saved = nullptr;
+  cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
+  bool use_branch = false;
+  int cur_slot = 0;                   // which set of exchange buffers the recurrence being issued uses
+  void branch_fork();
+  void branch_begin();
+  void branch_end();
+  void branch_join();
   const void* Y_ext_cur = nullptr;   // teacher-forcing source: Yp_ext or (target == pitch) Xp_ext
   const void* e_cur = nullptr;       // output of the last tanh Dense before the split
   bool stepwise_done = false;
