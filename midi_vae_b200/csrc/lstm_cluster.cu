@@ -391,6 +391,7 @@ struct Cluster2P {
   const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates; const bf16* c0; int ldc0;
   const bf16* upack;
   uint8_t* hx;        // exchange buffer [clusters][ng][2][CS][2 row halves][2 KB]
+  int x_mode; const bf16* xtab; const unsigned char* x_idx; int x_ld, x_shift; const bf16* x_scalar; const float* x_w; const float* x_b;
   long long* trace;
 };
 
@@ -408,6 +409,7 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t h_full[CL2_MAXG][2], peer_ready[CL2_MAXG][2], tmem_full[CL2_MAXG];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float x_wb[2][CL_GC];   // x_mode 2: input kernel row / bias of this CTA's 128 gate columns (gate-major, semantic gate order)
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_scr0 = smem_base;                              // !ALIAS: scratch tile of set s at smem_scr0 + s * CL_SCR
@@ -432,6 +434,12 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
   if (warp == 1) {
     ptx::tmem_alloc2(ptx::smem_u32(&tmem_base_slot), 512);
     ptx::tmem_relinquish2();
+  }
+  if (p.x_mode == 2 && threadIdx.x >= 96 && threadIdx.x < 96 + CL_GC) {
+    const int cc = (int)threadIdx.x - 96, gt = cc >> 5, uu = cc & 31;
+    const int blk = (gt < 2 && !STD) ? 1 - gt : gt;
+    x_wb[0][cc] = p.x_w[blk * H + j * CL_HS + uu];
+    x_wb[1][cc] = p.x_b[blk * H + j * CL_HS + uu];
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -567,12 +575,26 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
         // the input projection does not depend on the recurrence: in flight while the MMA of this item runs
         uint4 xq[4];
         xq[0] = xq[1] = xq[2] = xq[3] = make_uint4(0u, 0u, 0u, 0u);
+        float xs = 0.f;
         if (row_ok) {
-          const bf16* xr = p.xw + ((size_t)t * n + m) * G + u0;
-          xq[0] = __ldg(reinterpret_cast<const uint4*>(xr + bi * H));
-          xq[1] = __ldg(reinterpret_cast<const uint4*>(xr + bfk * H));
-          xq[2] = __ldg(reinterpret_cast<const uint4*>(xr + 2 * H));
-          xq[3] = __ldg(reinterpret_cast<const uint4*>(xr + 3 * H));
+          if (p.x_mode == 0) {
+            const bf16* xr = p.xw + ((size_t)t * n + m) * G + u0;
+            xq[0] = __ldg(reinterpret_cast<const uint4*>(xr + bi * H));
+            xq[1] = __ldg(reinterpret_cast<const uint4*>(xr + bfk * H));
+            xq[2] = __ldg(reinterpret_cast<const uint4*>(xr + 2 * H));
+            xq[3] = __ldg(reinterpret_cast<const uint4*>(xr + 3 * H));
+          } else if (p.x_mode == 1) {
+            // one-hot input: x W + b is row `class` of the (64, 4H) table (row 63 = bias only = zero input)
+            int cls = 63;
+            if (p.x_idx && t >= p.x_shift) cls = (int)__ldg(p.x_idx + (size_t)m * p.x_ld + (t - p.x_shift));
+            const bf16* xr = p.xtab + (size_t)cls * G + u0;
+            xq[0] = __ldg(reinterpret_cast<const uint4*>(xr + bi * H));
+            xq[1] = __ldg(reinterpret_cast<const uint4*>(xr + bfk * H));
+            xq[2] = __ldg(reinterpret_cast<const uint4*>(xr + 2 * H));
+            xq[3] = __ldg(reinterpret_cast<const uint4*>(xr + 3 * H));
+          } else {
+            xs = __bfloat162float(p.x_scalar[((size_t)t * n + m) * p.x_ld]);
+          }
         }
         ptx::mbar_wait(ptx::smem_u32(&tmem_full[g]), (uint32_t)(t & 1));
         ptx::tc_fence_after();
@@ -600,6 +622,13 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
           pre[gt][4] = a1.x; pre[gt][5] = a1.y; pre[gt][6] = a1.z; pre[gt][7] = a1.w;
         }
         float xv[8], gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
+        if (p.x_mode == 2) {
+          // scalar input: x w + b from the CTA's shared copy of the kernel row and bias (fp32, no intermediate rounding)
+#pragma unroll
+          for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pre[gt][u] += xs * x_wb[0][gt * 32 + q * 8 + u] + x_wb[1][gt * 32 + q * 8 + u];
+        }
         unpack8(xq[0], xv);
 #pragma unroll
         for (int u = 0; u < 8; ++u) gi[u] = gate_fwd<HARD>(pre[0][u] + xv[u]);
@@ -1098,6 +1127,9 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.dbg = env_int("MVAE_CL_DBG", 0);
   p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates; p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0;
   p.upack = (const bf16*)a.upack; p.hx = (uint8_t*)a.hx; p.trace = (long long*)a.trace;
+  p.x_mode = a.x_mode; p.xtab = (const bf16*)a.xtab; p.x_idx = a.x_idx; p.x_ld = a.x_ld; p.x_shift = a.x_shift;
+  p.x_scalar = (const bf16*)a.x_scalar; p.x_w = a.x_w; p.x_b = a.x_b;
+  MVAE_REQUIRE(p.x_mode == 0 ? p.xw != nullptr : (p.x_mode == 1 ? p.xtab != nullptr : (p.x_scalar && p.x_w && p.x_b)), "cluster forward: input projection source missing");
   MVAE_REQUIRE(p.hx != nullptr, "cluster forward: exchange buffer missing");
   MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * CL_STAGE <= rec_cluster_hx_bytes(a.n, H), "cluster forward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
@@ -1187,6 +1219,22 @@ void rec_cluster_pack_u(const float* U, int ldu, void* upack, int H, int variant
 void rec_cluster_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int variant, cudaStream_t st) {
   MVAE_REQUIRE(H == 256 || H == 512, "cluster recurrence: hidden size 256 or 512");
   pack_u_cluster_bwd_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack_bwd, H, variant);
+  count_launch();
+  MVAE_CUDA(cudaGetLastError());
+}
+
+// x_mode 1 table: row i < din = bf16( bf16(W[i, :]) + b ) (exactly what the bf16 GEMM of a one-hot row stores), rows din..63 = bf16(b)
+__global__ void build_xtab_kernel(const bf16* __restrict__ W, int ldw, int din, const float* __restrict__ bias, bf16* __restrict__ out, int G) {
+  const int total = 64 * G;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < total; x += gridDim.x * blockDim.x) {
+    const int i = x / G, c = x % G;
+    const float w = i < din ? __bfloat162float(W[(size_t)i * ldw + c]) : 0.f;
+    out[x] = __float2bfloat16_rn(w + bias[c]);
+  }
+}
+void rec_cluster_build_xtab(const void* W_bf16, int ldw, int din, const float* bias, void* xtab, int H, cudaStream_t st) {
+  MVAE_REQUIRE(din <= 63, "one-hot input projection table: at most 63 classes");
+  build_xtab_kernel<<<64, 256, 0, st>>>((const bf16*)W_bf16, ldw, din, bias, (bf16*)xtab, 4 * H);
   count_launch();
   MVAE_CUDA(cudaGetLastError());
 }

@@ -83,6 +83,7 @@ void Model::build_workspace() {
     r.cseq = alloc((size_t)(r.steps + 1) * n * H * a);
     if (need_dhext) r.dhext = alloc((size_t)r.steps * n * H * a);
     if (use_persist) r.upack = alloc((size_t)G * H * 2);
+    if (use_persist && rec_cluster_supported(H)) r.xtab = alloc((size_t)64 * G * 2);
     if (use_persist && (rec_persist_ksplit_ok(H) || rec_cluster_bwd_supported(H))) r.upack_b = alloc((size_t)G * H * 2);
   };
   if (use_persist && (rec_persist_ksplit_ok(H) || rec_cluster_bwd_supported(H))) {
@@ -140,11 +141,13 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   MVAE_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   MVAE_REQUIRE(major == 10, "libmidivae.so is built for sm_100a (B200) only");
   MVAE_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  MVAE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  MVAE_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  int prio_least = 0, prio_greatest = 0;
+  MVAE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  MVAE_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_greatest));   // the critical chain
+  MVAE_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_least));
   MVAE_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   MVAE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-  MVAE_CUDA(cudaStreamCreateWithFlags(&st_branch, cudaStreamNonBlocking));
+  MVAE_CUDA(cudaStreamCreateWithPriority(&st_branch, cudaStreamNonBlocking, prio_least));
   MVAE_CUDA(cudaEventCreateWithFlags(&ev_bfork, cudaEventDisableTiming));
   MVAE_CUDA(cudaEventCreateWithFlags(&ev_bjoin, cudaEventDisableTiming));
   act = c.precision == MVAE_PREC_FP32 ? DT_F32 : DT_BF16;
@@ -161,6 +164,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   // GEMMs (needed only by the optimizer) run next to them on a second stream, on a grid sized for the idle SMs
   { const char* e = getenv("MVAE_SIDE_STREAM"); use_side = use_cluster_bwd && (e ? atoi(e) != 0 : true); }
   { const char* e = getenv("MVAE_SIDE_SMS"); side_sms = e ? atoi(e) : 0; }
+  { const char* e = getenv("MVAE_FUSE_XPROJ"); fuse_xproj = use_cluster_fwd && (e ? atoi(e) != 0 : true); }
   { const char* e = getenv("MVAE_BRANCH"); use_branch = use_cluster_fwd && use_cluster_bwd && (e ? atoi(e) != 0 : true); }
   if (side_sms <= 0) side_sms = std::max(16, sm_count - 16 * ((NB + 127) / 128));
   build_params();
@@ -206,13 +210,20 @@ void Model::prof_end(cudaStream_t s) {
 }
 void Model::prof_collect() {
   for (int i = 0; i < PC_COUNT; ++i) { prof_ms[i] = 0; prof_n[i] = 0; }
+  const bool timeline = getenv("MVAE_TIMELINE") != nullptr && !evs.empty();
+  static const char* cls_name[PC_COUNT] = {"rec_fwd", "rec_bwd", "gemm", "pointwise", "adam", "allreduce"};
   for (auto& ev : evs) {
     MVAE_CUDA(cudaEventSynchronize(ev.b));
     float ms = 0;
     MVAE_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    if (timeline) {
+      float t0 = 0;
+      MVAE_CUDA(cudaEventElapsedTime(&t0, evs[0].a, ev.a));
+      fprintf(stderr, "timeline %-9s start %8.3f ms  dur %7.3f ms\n", cls_name[ev.cls], t0, ms);
+    }
     prof_ms[ev.cls] += ms; prof_n[ev.cls] += 1;
-    cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
   }
+  for (auto& ev : evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   evs.clear();
 }
 
@@ -221,10 +232,18 @@ void Model::prof_collect() {
 // join: the main stream waits for what the branch did.  Host code stays sequential; only the stream the launches go to changes.
 void Model::branch_fork() {
   if (!use_branch) return;
+  fork_pending = true;
+}
+// called right before a recurrence kernel is launched: the branch may start once the main stream's preparation kernels are done, so that the
+// main recurrence (launched next) gets its cluster slots first and the branch recurrence takes what is left
+void Model::fork_if_pending() {
+  if (!fork_pending) return;
   MVAE_CUDA(cudaEventRecord(ev_bfork, st));
+  fork_pending = false;
 }
 void Model::branch_begin() {
   if (!use_branch) return;
+  fork_if_pending();
   MVAE_CUDA(cudaStreamWaitEvent(st_branch, ev_bfork, 0));
   st_saved = st; st = st_branch; cur_slot = 1;
 }
@@ -318,6 +337,7 @@ void Model::prepare_inputs(const mvae_batch& b, bool need_target) {
   const bool distinct_target = need_target && b.target && b.target != b.pitch;
   k_expand_inputs(act, b.n, T, Ti, PD, ID, VD, b.pitch, b.target, b.instr, b.velocity, Xp_ext, distinct_target ? Yp_ext : nullptr, Xi_ext, Xv_ext, st);
   Y_ext_cur = distinct_target ? Yp_ext : Xp_ext;
+  cur_pitch = b.pitch; cur_target = distinct_target ? b.target : b.pitch;
   prof_end();
 }
 
@@ -332,8 +352,12 @@ void Model::rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, 
 void Model::rec_forward_prepare(const FwdJob& j, int n) {
   Rec& r = *j.r;
   const long rows = (long)r.steps * n;
+  const bool fused = fuse_xproj && r.steps > 8 && ((j.kind == IN_DENSE && j.onehot) || j.kind == IN_RANK1 || j.kind == IN_NONE);
   prof_begin(PC_GEMM);
-  if (j.kind == IN_DENSE) {
+  if (fused) {
+    // the cluster kernel computes x W + b itself: a row gather for one-hot inputs (table built here), x w + b for the scalar stream
+    if (j.kind != IN_RANK1) rec_cluster_build_xtab(W(r.iW), ld(r.iW), j.kind == IN_DENSE ? r.Din : 0, Wf(r.ib), r.xtab, H, st);
+  } else if (j.kind == IN_DENSE) {
     GemmArgs g; g.M = (int)rows; g.N = G; g.K = r.Din; g.A = j.X; g.lda = r.ldin; g.B = W(r.iW); g.ldb = ld(r.iW);
     g.C = r.xw; g.ldc = G; g.c_type = act; g.bias = Wf(r.ib);
     gemm(g);
@@ -363,6 +387,14 @@ RecPersistArgs Model::fwd_args(const FwdJob& j, int n, int slot, int hs) {
   a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates; a.c0 = j.c0; a.ldc0 = j.ld0;
   a.hx = slot ? rec_hx2 : rec_hx;
   a.trace = slot ? nullptr : trace_buf;
+  if (fuse_xproj && r.steps > 8) {
+    if ((j.kind == IN_DENSE && j.onehot) || j.kind == IN_NONE) {
+      a.x_mode = 1; a.xtab = r.xtab;
+      a.x_idx = j.kind == IN_DENSE ? j.idx : nullptr; a.x_ld = j.idx_ld; a.x_shift = j.idx_shift;
+    } else if (j.kind == IN_RANK1) {
+      a.x_mode = 2; a.x_scalar = j.X; a.x_ld = VD; a.x_w = Wf(r.iW); a.x_b = Wf(r.ib);
+    }
+  }
   return a;
 }
 
@@ -377,6 +409,7 @@ void Model::rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n) {
     for (const FwdJob* j : {ja, jb}) {
       if (!j) continue;
       RecPersistArgs a = fwd_args(*j, n, cur_slot, 0);
+      fork_if_pending();
       rec_cluster_forward(a, st);
       dump_trace("fwd(cluster)", *j->r, 2);
     }
@@ -445,6 +478,7 @@ void Model::rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n) {
     for (const BwdJob* j : {ja, jb}) {
       if (!j) continue;
       RecPersistArgs a = bwd_args(*j, n, cur_slot, 0);
+      fork_if_pending();
       rec_cluster_backward(a, st);
       dump_trace("bwd(cluster)", *j->r, 2);
     }
@@ -490,7 +524,7 @@ void Model::rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n) {
 
 // batched GEMMs after the reverse sweep of one recurrence: dx = dG W^T for the layer below (on the critical path, main stream) and
 // the weight gradients dU = Hprev^T dG, dW = X^T dG, db = colsum dG (needed only by the optimizer: side stream when enabled)
-void Model::rec_backward_gemms(const BwdJob& j, int n) {
+void Model::rec_backward_gemms(const BwdJob& j, int n, bool tail) {
   Rec& r = *j.r;
   const long rows = (long)r.steps * n;
   void* dG = r.xw;  // the pre-activation buffer is dead after the forward sweep
@@ -505,7 +539,7 @@ void Model::rec_backward_gemms(const BwdJob& j, int n) {
     gemm(g);
     prof_end();
   }
-  if (use_side) rec_backward_wgrads(j, n, side, side_sms);
+  if (use_side) rec_backward_wgrads(j, n, side, tail ? sm_count : side_sms);   // tail: nothing else is left to run next to them
   else rec_backward_wgrads(j, n, st, sm_count);
 }
 
@@ -531,7 +565,7 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms)
 }
 
 // a stack of layers (top first) plus independent side recurrences: pair the i-th stack layer with the i-th side recurrence
-void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n) {
+void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n, bool last_group) {
   if (use_branch) {
     // the stack (top layer first) is the critical chain; the independent recurrences run next to it on the branch stream
     branch_fork();
@@ -540,7 +574,7 @@ void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& 
     branch_begin();
     for (auto& j : side) { rec_backward_sweep(&j, nullptr, n); rec_backward_gemms(j, n); }
     branch_end();
-    for (size_t k = 1; k < stack.size(); ++k) { rec_backward_sweep(&stack[k], nullptr, n); rec_backward_gemms(stack[k], n); }
+    for (size_t k = 1; k < stack.size(); ++k) { rec_backward_sweep(&stack[k], nullptr, n); rec_backward_gemms(stack[k], n, last_group && k + 1 == stack.size()); }
     branch_join();
     return;
   }
@@ -568,6 +602,7 @@ void Model::encoder_forward(int n) {
     for (int k = 0; k < ne; ++k) {
       FwdJob jp; jp.r = &enc_pitch[k]; jp.kind = IN_DENSE;
       jp.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
+      if (k == 0) { jp.onehot = true; jp.idx = cur_pitch; jp.idx_ld = T; jp.idx_shift = 0; }
       rec_forward_jobs(&jp, nullptr, n);
       if (k == 0) {   // velocity and instrument streams: next to the pitch stack
         branch_begin();
@@ -631,6 +666,7 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
     FwdJob jp; jp.r = &dec_notes[k]; jp.h0 = st1(k); jp.c0 = st2(k); jp.ld0 = nS * H;
     if (k == 0) { jp.kind = tf ? IN_DENSE : IN_NONE; jp.X = tf ? Y_ext_cur : nullptr; }
     else { jp.kind = IN_DENSE; jp.X = slab(dec_notes[k - 1].hseq, 1, (long)n * H); }
+    if (k == 0 && tf) { jp.onehot = true; jp.idx = cur_target; jp.idx_ld = T; jp.idx_shift = 1; }   // x_t = y_{t-1}, x_0 = 0
     if (use_branch) {
       rec_forward_jobs(&jp, nullptr, n);
       if (k == 0) {
@@ -852,7 +888,7 @@ void Model::backward(const mvae_batch& b) {
       side.push_back(j); }
     { BwdJob j; j.r = &enc_instr; j.kind = IN_DENSE; j.X = slab(Xi_ext, 1, (long)n * ID); j.dh_last = (const char*)du + (size_t)H * asz(); j.ld_last = 3 * H;
       side.push_back(j); }
-    rec_backward_group(stack, side, n);
+    rec_backward_group(stack, side, n, true);
   }
   if (use_side) {   // every weight gradient is in the arena before the all-reduce / optimizer
     MVAE_CUDA(cudaEventRecord(ev_join, this->side));

@@ -34,6 +34,7 @@ struct Rec {
   void* dhext = nullptr;  // (steps, n, H) act : gradient arriving from the layer / head above
   void* upack_b = nullptr;  // (cpg, H, 64) bf16 : recurrent weights packed for the K-split persistent backward kernel
   void* upack = nullptr;  // (4H, H) bf16 : recurrent weights packed per CTA for the persistent forward kernel
+  void* xtab = nullptr;   // (64, 4H) bf16 : one-hot input projection table of the cluster forward kernel
 };
 
 // one forward recurrence: its input sequence and initial states
@@ -44,6 +45,10 @@ struct FwdJob {
   const void* h0 = nullptr;
   const void* c0 = nullptr;
   int ld0 = 0;
+  // cluster forward: the one-hot input as class indices (u8 [n][idx_ld], step t reads column t - idx_shift), instead of the dense rows X
+  const unsigned char* idx = nullptr;
+  int idx_ld = 0, idx_shift = 0;
+  bool onehot = false;
 };
 
 // one backward recurrence: where its inputs / external gradients come from and where its outputs go
@@ -133,10 +138,15 @@ struct Model {
   cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
   bool use_branch = false;
   int cur_slot = 0;                   // which set of exchange buffers the recurrence being issued uses
+  bool fork_pending = false;          // the fork point is the launch of the next main-stream recurrence (it must win the cluster slots)
+  void fork_if_pending();
   void branch_fork();
   void branch_begin();
   void branch_end();
   void branch_join();
+  const unsigned char* cur_pitch = nullptr;   // device u8 rolls of the batch in flight (class indices)
+  const unsigned char* cur_target = nullptr;
+  bool fuse_xproj = false;          // cluster forward computes one-hot / scalar input projections itself
   const void* Y_ext_cur = nullptr;   // teacher-forcing source: Yp_ext or (target == pitch) Xp_ext
   const void* e_cur = nullptr;       // output of the last tanh Dense before the split
   bool stepwise_done = false;
@@ -192,8 +202,8 @@ struct Model {
   void rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n);
   RecPersistArgs bwd_args(const BwdJob& j, int n, int slot, int hs);
   void rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n);
-  void rec_backward_gemms(const BwdJob& j, int n);
-  void rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n);
+  void rec_backward_gemms(const BwdJob& j, int n, bool tail = false);
+  void rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n, bool last_group = false);
   void encoder_forward(int n);
   void head_forward(const mvae_batch& b, bool with_style_loss);
   void decoder_forward(const mvae_batch& b, int feedback);

@@ -31,6 +31,14 @@ struct RecPersistArgs {
   const void* upack_bwd = nullptr;    // K-split backward: packed weights, rec_persist_pack_u_bwd
   void* partial = nullptr;            // K-split backward: exchange buffer, rec_persist_partial_bytes
   void* trace = nullptr;              // optional: 8 steps x 16 clock64 stamps of CTA 0 (profiling aid)
+  // cluster forward only: input projection computed inside the kernel instead of streamed from the (steps, n, 4H) xw buffer
+  int x_mode = 0;                     // 0: xw buffer; 1: one-hot input = row gather from xtab; 2: scalar input (x w + b)
+  const void* xtab = nullptr;         // x_mode 1: (64, 4H) bf16: row i = W[i] + b for the one-hot class i, row 63 = b (zero input)
+  const unsigned char* x_idx = nullptr;   // x_mode 1: class index of row m at step t-x_shift at x_idx[m * x_ld + t - x_shift]; null or t < x_shift: zero input
+  int x_ld = 0, x_shift = 0;
+  const void* x_scalar = nullptr;     // x_mode 2: bf16 scalar input of row m at step t at x_scalar[(t * n + m) * x_ld]
+  const float* x_w = nullptr;         // x_mode 2: (4H) input kernel row and bias, fp32
+  const float* x_b = nullptr;
 };
 
 size_t smem_max_bytes();
@@ -56,6 +64,7 @@ size_t rec_cluster_hx_bytes(int n, int H);
 size_t rec_cluster_xbuf_bytes(int n, int H);
 void rec_cluster_pack_u(const float* U, int ldu, void* upack, int H, int variant, cudaStream_t st);
 void rec_cluster_forward(const RecPersistArgs& a, cudaStream_t st);
+void rec_cluster_build_xtab(const void* W_bf16, int ldw, int din, const float* bias, void* xtab, int H, cudaStream_t st);
 bool rec_cluster_bwd_supported(int H);
 void rec_cluster_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int variant, cudaStream_t st);
 void rec_cluster_backward(const RecPersistArgs& a, cudaStream_t st);
