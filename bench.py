@@ -264,10 +264,10 @@ def main():
         # kernel classes and their algorithmic FLOPs per step (B sequences): the forward recurrences do h*U, the backward
         # recurrences dG*U^T (same count), everything else (input projections, heads, all weight gradients) is batched GEMM
         classes = {
-            "rec_bwd": ("persistent backward recurrence (dG*U^T per step + gate-gradient math)" if args.rnn_mode != "streamed" and args.precision == "bf16"
-                        else "step-streamed backward recurrence", rec_fwd * B),
-            "rec_fwd": ("persistent forward recurrence (h*U per step + gate math)" if args.rnn_mode != "streamed" and args.precision == "bf16"
-                        else "step-streamed forward recurrence", rec_fwd * B),
+            "rec_bwd": ((("rec_cluster_bwd_kernel: cluster-resident" if H in (256, 512) else "persistent") + " backward recurrence (dG*U^T per step on tcgen05 + gate-gradient math)")
+                        if args.rnn_mode != "streamed" and args.precision == "bf16" else "step-streamed backward recurrence", rec_fwd * B),
+            "rec_fwd": ((("rec_cluster_fwd2_kernel: cluster-resident" if H in (256, 512) else "persistent") + " forward recurrence (h*U per step on tcgen05 + gate math)")
+                        if args.rnn_mode != "streamed" and args.precision == "bf16" else "step-streamed forward recurrence", rec_fwd * B),
             "gemm": ("batched tcgen05 GEMMs (input projections, heads, weight gradients)", (train - 2 * rec_fwd) * B),
         }
         dom = max(classes, key=lambda k: kms[k][0])
@@ -275,12 +275,13 @@ def main():
         peak = pk["bf16_sustained"]
         achieved = classes[dom][1] / (dom_ms / 1e3) / 1e12
         traffic = None
-        ncu_file = os.path.join(ROOT, "profiles", "r1", "ncu_rec_bwd_ksplit_cfg3.json")
-        if dom == "rec_bwd" and args.workload == "cfg3" and os.path.exists(ncu_file):
-            ks = [k for k in json.load(open(ncu_file))["kernels"] if k["gpu__time_duration.sum"] > 1.0]   # the T=256 launches
+        ncu_file = os.path.join(ROOT, "profiles", "r1", "ncu_rec_cluster_cfg3.json")
+        if dom in ("rec_bwd", "rec_fwd") and args.workload == "cfg3" and os.path.exists(ncu_file):
+            pat = "rec_cluster_bwd" if dom == "rec_bwd" else "rec_cluster_fwd"
+            ks = [k for k in json.load(open(ncu_file))["kernels"] if pat in k["Kernel Name"] and k["gpu__time_duration.sum"] > 0.3]   # the T=256 launches
             if ks:
                 traffic = {"dram_bytes_per_launch": sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in ks) / len(ks) * 1e6,
-                           "launches_per_step": 6, "source": "profiles/r1/ncu_rec_bwd_ksplit_cfg3.json (ncu --set full)"}
+                           "launches_per_step": 6, "source": "profiles/r1/ncu_rec_cluster_cfg3.json (ncu --set full, per launch of one T=256 recurrence)"}
         roof = {"bound": "tensor", "kernel": classes[dom][0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "kernel_ms_per_step": dom_ms, "kernel_flops_per_step": classes[dom][1],
