@@ -64,7 +64,7 @@ struct GemmArgs {
 void gemm_simt(const GemmArgs& g, cudaStream_t st);
 // tcgen05 / TMA / TMEM GEMM (bf16 inputs, fp32 accumulate).  Throws if the shape is unsupported.
 bool gemm_tc_supported(const GemmArgs& g);
-void gemm_tc(const GemmArgs& g, cudaStream_t st, int sm_count);
+void gemm_tc(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched = nullptr);   // sched: 2 zeroed ints owned by the calling stream (dynamic tile scheduler)
 int gemm_tc_selftest(int device, int verbose);
 
 // launch accounting (bench.py reports gpu_launches)

@@ -41,6 +41,7 @@ struct TcParams {
   const void* addend; int ldadd; int add_bf16;
   int act; int atomic_acc;
   int m_tiles, n_tiles, k_splits, kb_total, kb_per_split;
+  int* sched;   // [0] next tile, [1] finished CTAs (both zero between launches that share them): dynamic tile scheduler
 };
 
 template <int BN>
@@ -59,6 +60,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  // tiles are handed out by an atomic counter (a CTA that becomes resident late -- other kernels may hold part of the chip -- simply finds
+  // nothing left); the producer warp draws the tile and passes it to the MMA and epilogue warps through this ring
+  constexpr int RS = 4;
+  __shared__ __align__(8) uint64_t sched_full[RS], sched_empty[RS];
+  __shared__ int sched_tile[RS];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
@@ -70,6 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     ptx::prefetch_tmap(&tma_b);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1); ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), 4); }
+    for (int r = 0; r < RS; ++r) { ptx::mbar_init(ptx::smem_u32(&sched_full[r]), 1); ptx::mbar_init(ptx::smem_u32(&sched_empty[r]), 5); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -85,7 +92,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int sit = 0;; ++sit) {
+        const int rs = sit % RS;
+        ptx::mbar_wait(ptx::smem_u32(&sched_empty[rs]), (uint32_t)(((sit / RS) & 1) ^ 1));
+        const int tile = atomicAdd(p.sched, 1);
+        sched_tile[rs] = tile;
+        ptx::mbar_arrive(ptx::smem_u32(&sched_full[rs]));
+        if (tile >= num_tiles) break;
         const int ks = tile % p.k_splits, mn = tile / p.k_splits;
         const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -116,8 +129,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int it = 0;; ++it) {
+        const int rs = it % RS;
+        ptx::mbar_wait(ptx::smem_u32(&sched_full[rs]), (uint32_t)((it / RS) & 1));
+        const int tile = sched_tile[rs];
+        ptx::mbar_arrive(ptx::smem_u32(&sched_empty[rs]));
+        if (tile >= num_tiles) break;
         const int ks = tile % p.k_splits;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
@@ -145,8 +162,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else {
     // ===================== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====================
     const int quad = warp & 3;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0;; ++it) {
+      const int rs = it % RS;
+      int tile = 0;
+      if (lane == 0) {
+        ptx::mbar_wait(ptx::smem_u32(&sched_full[rs]), (uint32_t)((it / RS) & 1));
+        tile = sched_tile[rs];
+        ptx::mbar_arrive(ptx::smem_u32(&sched_empty[rs]));
+      }
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= num_tiles) break;
       const int mn = tile / p.k_splits;
       const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
       const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
@@ -230,6 +255,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
+  if (threadIdx.x == 0) {   // the last CTA to leave re-arms the scheduler for the next launch that uses it (launches sharing it are stream-ordered)
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; __threadfence(); }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -267,7 +296,7 @@ CUtensorMap make_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t l
 }
 
 template <bool A_MN, bool B_MN, int BN>
-void launch(const GemmArgs& g, cudaStream_t st, int sm_count) {
+void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
   using L = SmemLayout<BN>;
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_type == DT_BF16;
@@ -281,6 +310,7 @@ void launch(const GemmArgs& g, cudaStream_t st, int sm_count) {
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.atomic_acc = g.accumulate ? 1 : 0;
+  p.sched = sched;
   const CUtensorMap ma = A_MN ? make_map(g.A, g.M, g.K, g.lda, 64, 64) : make_map(g.A, g.K, g.M, g.lda, 64, BM);
   const CUtensorMap mb = B_MN ? make_map(g.B, g.N, g.K, g.ldb, 64, 64) : make_map(g.B, g.K, g.N, g.ldb, 64, BN);
   auto kern = gemm_tc_kernel<A_MN, B_MN, BN>;
@@ -308,24 +338,33 @@ bool gemm_tc_supported(const GemmArgs& g) {
   return true;
 }
 
-void gemm_tc(const GemmArgs& g, cudaStream_t st, int sm_count) {
+// scheduler words of launches that are NOT given their own: one pair per (device, stream) would be needed for concurrent launches, so callers
+// that run GEMMs on several streams pass their own (Model does); this default pair serves single-stream users such as the self test
+static int* default_sched() {
+  static int* d = nullptr;
+  if (!d) { MVAE_CUDA(cudaMalloc(&d, 2 * sizeof(int))); MVAE_CUDA(cudaMemset(d, 0, 2 * sizeof(int))); }
+  return d;
+}
+
+void gemm_tc(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
   MVAE_REQUIRE(gemm_tc_supported(g), "shape / alignment not supported by the tcgen05 GEMM");
+  if (!sched) sched = default_sched();
   const bool a_mn = g.transA, b_mn = !g.transB;
   // 128x256 tiles (87 FLOP per operand byte instead of 64) when N is wide enough to fill them
   static int wide = -1;
   if (wide < 0) { const char* e = getenv("MVAE_GEMM_BN256"); wide = e ? atoi(e) : 1; }
   const bool bn256 = wide && g.N >= 256 && (g.N % 256 == 0 || g.N >= 1024);
   if (bn256) {
-    if (!a_mn && !b_mn) launch<false, false, 256>(g, st, sm_count);
-    else if (!a_mn && b_mn) launch<false, true, 256>(g, st, sm_count);
-    else if (a_mn && !b_mn) launch<true, false, 256>(g, st, sm_count);
-    else launch<true, true, 256>(g, st, sm_count);
+    if (!a_mn && !b_mn) launch<false, false, 256>(g, st, sm_count, sched);
+    else if (!a_mn && b_mn) launch<false, true, 256>(g, st, sm_count, sched);
+    else if (a_mn && !b_mn) launch<true, false, 256>(g, st, sm_count, sched);
+    else launch<true, true, 256>(g, st, sm_count, sched);
     return;
   }
-  if (!a_mn && !b_mn) launch<false, false, 128>(g, st, sm_count);
-  else if (!a_mn && b_mn) launch<false, true, 128>(g, st, sm_count);
-  else if (a_mn && !b_mn) launch<true, false, 128>(g, st, sm_count);
-  else launch<true, true, 128>(g, st, sm_count);
+  if (!a_mn && !b_mn) launch<false, false, 128>(g, st, sm_count, sched);
+  else if (!a_mn && b_mn) launch<false, true, 128>(g, st, sm_count, sched);
+  else if (a_mn && !b_mn) launch<true, false, 128>(g, st, sm_count, sched);
+  else launch<true, true, 128>(g, st, sm_count, sched);
 }
 
 // ------------------------------------------------------------------------------------------------ self test

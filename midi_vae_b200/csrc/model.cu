@@ -171,6 +171,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
   build_workspace();
+  gemm_sched = (int*)alloc(8 * sizeof(int));
   { const char* e = getenv("MVAE_REC_PAIR"); pair_recs = e ? atoi(e) != 0 : true; }
   if (getenv("MVAE_REC_TRACE")) trace_buf = (long long*)alloc(512 * sizeof(long long));
   MVAE_CUDA(cudaStreamSynchronize(stream));
@@ -296,7 +297,9 @@ void Model::dump_trace(const char* dir, const Rec& r, int nctas) {
 void Model::gemm(GemmArgs g) { gemm_on(g, st, sm_count); }
 void Model::gemm_on(GemmArgs g, cudaStream_t s, int sms) {
   g.in_type = act;
-  if (act == DT_BF16 && gemm_tc_supported(g)) gemm_tc(g, s, sms);
+  // one scheduler word pair per stream: launches that share a pair must be stream-ordered
+  int* sched = gemm_sched + (s == side ? 2 : (s == st_branch ? 4 : 0));
+  if (act == DT_BF16 && gemm_tc_supported(g)) gemm_tc(g, s, sms, sched);
   else gemm_simt(g, s);
 }
 

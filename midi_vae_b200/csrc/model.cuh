@@ -131,6 +131,7 @@ struct Model {
   cudaStream_t side = nullptr;        // weight-gradient GEMMs run here, next to the (SM-sparse) backward recurrences
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_side = false;
+  int* gemm_sched = nullptr;          // dynamic tile scheduler words of the GEMM kernel, one pair per stream
   int side_sms = 0;
   // independent recurrences (velocity / instrument streams) run on a branch stream next to the pitch stack: a cluster recurrence
   // occupies 4 of the chip's 7 cluster slots, so two of them overlap almost completely
