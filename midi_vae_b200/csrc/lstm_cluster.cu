@@ -391,6 +391,7 @@ struct Cluster2P {
   const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates; const bf16* c0; int ldc0;
   const bf16* upack;
   uint8_t* hx;        // exchange buffer [clusters][ng][2][CS][2 row halves][2 KB]
+  int c0_stash;       // this launch continues a sequence: initial c = stash slab 0 (granule layout) of the (offset) cseq pointer, h = hseq slab 0
   int x_mode; const bf16* xtab; const unsigned char* x_idx; int x_ld, x_shift; const bf16* x_scalar; const float* x_w; const float* x_b;
   long long* trace;
 };
@@ -560,8 +561,12 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
       const int m = row0 + g * CL_ROWS + rr;
       uint4 cv = make_uint4(0u, 0u, 0u, 0u);
       if (g < nga && m < n) {
-        if (p.c0) cv = *reinterpret_cast<const uint4*>(p.c0 + (size_t)m * p.ldc0 + u0);
-        *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m)) = cv;   // stash slab 0 = c0
+        if (p.c0_stash) {
+          cv = *reinterpret_cast<const uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m));
+        } else {
+          if (p.c0) cv = *reinterpret_cast<const uint4*>(p.c0 + (size_t)m * p.ldc0 + u0);
+          *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m)) = cv;   // stash slab 0 = c0
+        }
       }
       unpack8(cv, cst[k]);
     }
@@ -1125,10 +1130,14 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   const size_t smem = 1024 + scr_bytes + (size_t)ng * 2 * hbuf;
   Cluster2P p{};
   p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.dbg = env_int("MVAE_CL_DBG", 0);
-  p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates; p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0;
+  // a.t0 > 0: this launch continues the sequence at step t0 (time-chunked recurrences): every time-indexed buffer is simply offset
+  const size_t t0 = (size_t)a.t0, nn = (size_t)a.n;
+  p.xw = a.xw ? (const bf16*)a.xw + t0 * nn * 4 * H : nullptr;
+  p.hseq = (bf16*)a.hseq + t0 * nn * H; p.cseq = (bf16*)a.cseq + t0 * nn * H; p.gates = (bf16*)a.gates + t0 * nn * 4 * H;
+  p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0; p.c0_stash = a.t0 > 0;
   p.upack = (const bf16*)a.upack; p.hx = (uint8_t*)a.hx; p.trace = (long long*)a.trace;
-  p.x_mode = a.x_mode; p.xtab = (const bf16*)a.xtab; p.x_idx = a.x_idx; p.x_ld = a.x_ld; p.x_shift = a.x_shift;
-  p.x_scalar = (const bf16*)a.x_scalar; p.x_w = a.x_w; p.x_b = a.x_b;
+  p.x_mode = a.x_mode; p.xtab = (const bf16*)a.xtab; p.x_idx = a.x_idx; p.x_ld = a.x_ld; p.x_shift = a.x_shift - a.t0;
+  p.x_scalar = a.x_scalar ? (const bf16*)a.x_scalar + t0 * nn * a.x_ld : nullptr; p.x_w = a.x_w; p.x_b = a.x_b;
   MVAE_REQUIRE(p.x_mode == 0 ? p.xw != nullptr : (p.x_mode == 1 ? p.xtab != nullptr : (p.x_scalar && p.x_w && p.x_b)), "cluster forward: input projection source missing");
   MVAE_REQUIRE(p.hx != nullptr, "cluster forward: exchange buffer missing");
   MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * CL_STAGE <= rec_cluster_hx_bytes(a.n, H), "cluster forward: exchange buffer too small");
