@@ -782,24 +782,35 @@ void Model::backward(const mvae_batch& b) {
     MVAE_CUDA(cudaEventRecord(ev_fork, st));
     MVAE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
   }
+  // weight gradients are needed only by the optimizer: they go to the side stream (when enabled), the activations' gradients stay on the
+  // critical chain.  fork_side(): everything issued so far on the main stream is visible to the side stream.
+  cudaStream_t ws = use_side ? side : st;
+  const int wsms = use_side ? side_sms : sm_count;
+  auto fork_side = [&]() {
+    if (!use_side) return;
+    MVAE_CUDA(cudaEventRecord(ev_fork, st));
+    MVAE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  };
   // ---- output heads
-  prof_begin(PC_GEMM);
   Rec& top = dec_notes[nd - 1];
+  prof_begin(PC_GEMM, ws);
   { GemmArgs g; g.M = H; g.N = Dp; g.K = T * n; g.A = slab(top.hseq, 1, (long)n * H); g.lda = H; g.transA = true; g.B = dlog_n; g.ldb = ld_pn;
-    g.C = Gp(iWy); g.ldc = ld(iWy); g.c_type = DT_F32; g.accumulate = true; gemm(g); }
-  k_colsum(act, (long)T * n, Dp, ld_pn, dlog_n, nullptr, 0, Gp(iby), st);
+    g.C = Gp(iWy); g.ldc = ld(iWy); g.c_type = DT_F32; g.accumulate = true; gemm_on(g, ws, wsms); }
+  k_colsum(act, (long)T * n, Dp, ld_pn, dlog_n, nullptr, 0, Gp(iby), ws);
+  { GemmArgs g; g.M = H; g.N = Di; g.K = Ti * n; g.A = slab(dec_instr.hseq, 1, (long)n * H); g.lda = H; g.transA = true; g.B = dlog_i; g.ldb = ld_pi;
+    g.C = Gp(iWio); g.ldc = ld(iWio); g.c_type = DT_F32; g.accumulate = true; gemm_on(g, ws, wsms); }
+  k_colsum(act, (long)Ti * n, Di, ld_pi, dlog_i, nullptr, 0, Gp(ibio), ws);
+  // velocity head (N = 1): rank-1 forms instead of GEMMs
+  k_colsum(act, (long)T * n, H, H, slab(dec_vel.hseq, 1, (long)n * H), dlog_v, ld_pv, Gp(iWvo), ws);   // dWv[j] = sum_r dlog[r] h[r,j]
+  k_colsum(act, (long)T * n, 1, ld_pv, dlog_v, nullptr, 0, Gp(ibvo), ws);
+  prof_end(ws);
+  prof_begin(PC_GEMM);
   { GemmArgs g; g.M = T * n; g.N = H; g.K = Dp; g.A = dlog_n; g.lda = ld_pn; g.B = W(iWy); g.ldb = ld(iWy); g.transB = true;
     g.C = top.dhext; g.ldc = H; g.c_type = act; gemm(g); }
-  { GemmArgs g; g.M = H; g.N = Di; g.K = Ti * n; g.A = slab(dec_instr.hseq, 1, (long)n * H); g.lda = H; g.transA = true; g.B = dlog_i; g.ldb = ld_pi;
-    g.C = Gp(iWio); g.ldc = ld(iWio); g.c_type = DT_F32; g.accumulate = true; gemm(g); }
-  k_colsum(act, (long)Ti * n, Di, ld_pi, dlog_i, nullptr, 0, Gp(ibio), st);
   { GemmArgs g; g.M = Ti * n; g.N = H; g.K = Di; g.A = dlog_i; g.lda = ld_pi; g.B = W(iWio); g.ldb = ld(iWio); g.transB = true;
     g.C = dec_instr.dhext; g.ldc = H; g.c_type = act; gemm(g); }
   prof_end();
-  // velocity head (N = 1): rank-1 forms instead of GEMMs
   prof_begin(PC_POINTWISE);
-  k_colsum(act, (long)T * n, H, H, slab(dec_vel.hseq, 1, (long)n * H), dlog_v, ld_pv, Gp(iWvo), st);   // dWv[j] = sum_r dlog[r] h[r,j]
-  k_colsum(act, (long)T * n, 1, ld_pv, dlog_v, nullptr, 0, Gp(ibvo), st);
   k_rank1_rows(act, dec_vel.dhext, (long)T * n, H, dlog_v, ld_pv, Wf(iWvo), nullptr, st);              // dh[r,:] = dlog[r] * Wv
   prof_end();
   // ---- decoder recurrences (top layer first)
@@ -825,10 +836,13 @@ void Model::backward(const mvae_batch& b) {
   prof_begin(PC_POINTWISE);
   k_tanh_bwd(act, (long)n * nS * H, dS, S, dSpre, st);
   prof_end();
-  prof_begin(PC_GEMM);
+  fork_side();
+  prof_begin(PC_GEMM, ws);
   { GemmArgs g; g.M = Q; g.N = nS * H; g.K = n; g.A = q; g.lda = ldq; g.transA = true; g.B = dSpre; g.ldb = nS * H;
-    g.C = Gp(iWinit); g.ldc = ld(iWinit); g.c_type = DT_F32; g.accumulate = true; gemm(g); }
-  k_colsum(act, n, nS * H, nS * H, dSpre, nullptr, 0, Gp(ibinit), st);
+    g.C = Gp(iWinit); g.ldc = ld(iWinit); g.c_type = DT_F32; g.accumulate = true; gemm_on(g, ws, wsms); }
+  k_colsum(act, n, nS * H, nS * H, dSpre, nullptr, 0, Gp(ibinit), ws);
+  prof_end(ws);
+  prof_begin(PC_GEMM);
   { GemmArgs g; g.M = n; g.N = Q; g.K = nS * H; g.A = dSpre; g.lda = nS * H; g.B = W(iWinit); g.ldb = ld(iWinit); g.transB = true;
     g.C = dq; g.ldc = ldq; g.c_type = act; gemm(g); }
   prof_end();
@@ -838,15 +852,18 @@ void Model::backward(const mvae_batch& b) {
                dlv, st);
   prof_end();
   // ---- latent head Denses
-  prof_begin(PC_GEMM);
   const void* e1 = e_cur;
   const void* e2 = (const char*)e_cur + (size_t)half * asz();
+  fork_side();
+  prof_begin(PC_GEMM, ws);
   { GemmArgs g; g.M = half; g.N = L; g.K = n; g.A = e1; g.lda = H; g.transA = true; g.B = dmu; g.ldb = ldl; g.C = Gp(iWmu); g.ldc = ld(iWmu);
-    g.c_type = DT_F32; g.accumulate = true; gemm(g); }
-  k_colsum(act, n, L, ldl, dmu, nullptr, 0, Gp(ibmu), st);
+    g.c_type = DT_F32; g.accumulate = true; gemm_on(g, ws, wsms); }
+  k_colsum(act, n, L, ldl, dmu, nullptr, 0, Gp(ibmu), ws);
   { GemmArgs g; g.M = H - half; g.N = L; g.K = n; g.A = e2; g.lda = H; g.transA = true; g.B = dlv; g.ldb = ldl; g.C = Gp(iWlv); g.ldc = ld(iWlv);
-    g.c_type = DT_F32; g.accumulate = true; gemm(g); }
-  k_colsum(act, n, L, ldl, dlv, nullptr, 0, Gp(iblv), st);
+    g.c_type = DT_F32; g.accumulate = true; gemm_on(g, ws, wsms); }
+  k_colsum(act, n, L, ldl, dlv, nullptr, 0, Gp(iblv), ws);
+  prof_end(ws);
+  prof_begin(PC_GEMM);
   { GemmArgs g; g.M = n; g.N = half; g.K = L; g.A = dmu; g.lda = ldl; g.B = W(iWmu); g.ldb = ld(iWmu); g.transB = true; g.C = de; g.ldc = H;
     g.c_type = act; gemm(g); }
   { GemmArgs g; g.M = n; g.N = H - half; g.K = L; g.A = dlv; g.lda = ldl; g.B = W(iWlv); g.ldb = ld(iWlv); g.transB = true;
@@ -857,10 +874,13 @@ void Model::backward(const mvae_batch& b) {
     prof_begin(PC_POINTWISE);
     k_tanh_bwd(act, (long)n * H, de, e, dpre_e, st);
     prof_end();
-    prof_begin(PC_GEMM);
+    fork_side();
+    prof_begin(PC_GEMM, ws);
     { GemmArgs g; g.M = H; g.N = H; g.K = n; g.A = a1; g.lda = H; g.transA = true; g.B = dpre_e; g.ldb = H; g.C = Gp(iWe); g.ldc = ld(iWe);
-      g.c_type = DT_F32; g.accumulate = true; gemm(g); }
-    k_colsum(act, n, H, H, dpre_e, nullptr, 0, Gp(ibe), st);
+      g.c_type = DT_F32; g.accumulate = true; gemm_on(g, ws, wsms); }
+    k_colsum(act, n, H, H, dpre_e, nullptr, 0, Gp(ibe), ws);
+    prof_end(ws);
+    prof_begin(PC_GEMM);
     { GemmArgs g; g.M = n; g.N = H; g.K = H; g.A = dpre_e; g.lda = H; g.B = W(iWe); g.ldb = ld(iWe); g.transB = true; g.C = da1; g.ldc = H;
       g.c_type = act; gemm(g); }
     prof_end();
@@ -869,10 +889,13 @@ void Model::backward(const mvae_batch& b) {
   prof_begin(PC_POINTWISE);
   k_tanh_bwd(act, (long)n * H, d_a1, a1, dpre_a, st);
   prof_end();
-  prof_begin(PC_GEMM);
+  fork_side();
+  prof_begin(PC_GEMM, ws);
   { GemmArgs g; g.M = 3 * H; g.N = H; g.K = n; g.A = u; g.lda = 3 * H; g.transA = true; g.B = dpre_a; g.ldb = H; g.C = Gp(iWa); g.ldc = ld(iWa);
-    g.c_type = DT_F32; g.accumulate = true; gemm(g); }
-  k_colsum(act, n, H, H, dpre_a, nullptr, 0, Gp(iba), st);
+    g.c_type = DT_F32; g.accumulate = true; gemm_on(g, ws, wsms); }
+  k_colsum(act, n, H, H, dpre_a, nullptr, 0, Gp(iba), ws);
+  prof_end(ws);
+  prof_begin(PC_GEMM);
   { GemmArgs g; g.M = n; g.N = 3 * H; g.K = H; g.A = dpre_a; g.lda = H; g.B = W(iWa); g.ldb = ld(iWa); g.transB = true; g.C = du; g.ldc = 3 * H;
     g.c_type = act; gemm(g); }
   prof_end();

@@ -174,12 +174,14 @@ def test_train_step_bf16_tolerance(feedback):
     _compare_step(ecfg, ocfg, 16, tol=2e-2, grad_tol=6e-2)
 
 
-@pytest.mark.parametrize("shape", [(16, 64, 16, 8), (64, 256, 100, 16), (12, 128, 32, 200), (8, 1024, 64, 40), (4, 192, 24, 130), (12, 512, 48, 70), (8, 256, 40, 150)])
+@pytest.mark.parametrize("shape", [(16, 64, 16, 8), (64, 256, 100, 16), (12, 128, 32, 200), (8, 1024, 64, 40), (4, 192, 24, 130), (12, 512, 48, 70), (8, 256, 40, 150), (4, 512, 24, 65), (4, 256, 24, 1)])
 @pytest.mark.parametrize("feedback,variant", [("as_wired", "standard"), ("teacher_forced", "standard"), ("teacher_forced", "recurrentshop_recalled")])
 def test_persistent_rnn_matches_streamed(shape, feedback, variant):
     """The persistent-RNN kernels (U resident in SMEM, in-kernel time loop, cross-CTA flags) against the step-streamed
     form (one tcgen05 GEMM + one pointwise launch per step): same bf16 operands, so only accumulation order and the
-    tanh.approx gate math differ.  Also covers a ragged 2-group batch (200 rows = 128 + 72)."""
+    tanh.approx gate math differ.  Also covers a ragged 2-group batch (200 rows = 128 + 72).  H = 256 / 512 run the cluster
+    kernels (lstm_cluster.cu: 8 / 16-CTA clusters, CTA-pair MMA, multicast / DSMEM exchange, in-kernel input projections), with
+    ragged groups (70 = 64 + 6, 150 = 2 x 64 + 22, 65 = 64 + 1 rows), a single row and 4-step sequences."""
     T, H, L, n = shape
     res = {}
     for mode in ("streamed", "persistent"):
@@ -193,6 +195,27 @@ def test_persistent_rnn_matches_streamed(shape, feedback, variant):
     ms, gs = res["streamed"]; mp, gp = res["persistent"]
     for k in METRIC_KEYS:
         # accuracies are counts of argmax hits over few rows: allow a couple of near-tie flips on an untrained model
+        tol_k = 0.05 if "acc" in k else 5e-3 * max(1.0, abs(ms[k]))
+        assert abs(ms[k] - mp[k]) <= tol_k, (k, ms[k], mp[k])
+    for k in gs:
+        scale = max(np.abs(gs[k]).max(), 1e-6)
+        assert np.abs(gs[k] - gp[k]).max() <= 3e-2 * scale + 1e-9, (k, float(np.abs(gs[k] - gp[k]).max()), float(scale))
+
+
+def test_cluster_rnn_sigmoid_gates():
+    """The logistic-sigmoid gate variant (north_star's wording; the reference default is hard_sigmoid) through the cluster kernels."""
+    T, H, L, n = 16, 256, 32, 70
+    res = {}
+    for mode in ("streamed", "persistent"):
+        ecfg, _ = util.make_cfgs(T=T, H=H, L=L, feedback="teacher_forced", gate="sigmoid", precision="bf16", max_batch=n, rnn_mode=mode)
+        w = util.make_weights(ecfg)
+        eng = _engine(ecfg, w)
+        r, hist, eps, sw = util.make_batch(ecfg, n, weights=True)
+        m = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)
+        res[mode] = (m, eng.get_grads())
+        eng.close()
+    ms, gs = res["streamed"]; mp, gp = res["persistent"]
+    for k in METRIC_KEYS:
         tol_k = 0.05 if "acc" in k else 5e-3 * max(1.0, abs(ms[k]))
         assert abs(ms[k] - mp[k]) <= tol_k, (k, ms[k], mp[k])
     for k in gs:
