@@ -13,8 +13,8 @@
 // handled by the UMMA shared-memory descriptors (major-ness bits in the instruction descriptor), with the
 // TMA boxes chosen so that the smem image is the canonical SWIZZLE_128B layout of the respective major-ness.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2..5 epilogue
-// (TMEM -> registers -> global, one output row per thread).  Two TMEM accumulators (2 x BN columns) let
+// CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2..9 epilogue
+// (TMEM -> registers -> global, one output row per thread, two warps per lane quadrant).  Two TMEM accumulators (2 x BN columns) let
 // the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 
@@ -32,7 +32,8 @@ namespace {
 using bf16 = __nv_bfloat16;
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;             // two per TMEM lane quadrant: the epilogue of a K = 512 tile is as long as its MMAs
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 
 struct TcParams {
   int M, N, K;
@@ -75,8 +76,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1); ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), 4); }
-    for (int r = 0; r < RS; ++r) { ptx::mbar_init(ptx::smem_u32(&sched_full[r]), 1); ptx::mbar_init(ptx::smem_u32(&sched_empty[r]), 5); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), kEpiWarps); }
+    for (int r = 0; r < RS; ++r) { ptx::mbar_init(ptx::smem_u32(&sched_full[r]), 1); ptx::mbar_init(ptx::smem_u32(&sched_empty[r]), 1 + kEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -160,8 +161,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====================
-    const int quad = warp & 3;
+    // ===================== epilogue: warps 2..9, TMEM lane quadrant = warp % 4, 32-column chunks c with c % 2 == ehalf =====================
+    const int quad = warp & 3, ehalf = (warp - 2) >> 2;
     for (int it = 0;; ++it) {
       const int rs = it % RS;
       int tile = 0;
@@ -180,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int m = m0 + quad * 32 + lane;
       const bool row_ok = m < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = ehalf; c < BN / 32; c += 2) {
         const int nb = n0 + c * 32;
         if (nb >= p.N) break;                                   // warp-uniform
         float v[32];
@@ -188,8 +189,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (!row_ok) continue;
         const int nvalid = min(32, p.N - nb);
         if (p.bias) {
+          if (nvalid == 32 && (reinterpret_cast<uintptr_t>(p.bias + nb) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
+              v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
+          }
         }
         if (p.addend) {
           if (p.add_bf16) {
