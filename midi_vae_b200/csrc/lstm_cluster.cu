@@ -714,6 +714,7 @@ struct ClusterBP {
   const bf16* gates; const bf16* cseq; const bf16* dhext; const bf16* dh_last; int ld_last;
   bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
   const bf16* upack;      // [CS][MT][128 units][256 gate columns of the pair]
+  int l2_prefetch;        // > 0: prefetch the stash of step t - l2_prefetch into L2
   uint8_t* xbuf;          // via_l2: global exchange buffer [clusters][ng][CS][ND messages]
   int via_l2;             // messages travel smem -> L2 -> smem (bulk store, remote arrive, bulk load) instead of DSMEM bulk copies
   long long* trace;
@@ -723,6 +724,7 @@ template <bool HARD>
 __device__ __forceinline__ float gate_bwd(float s) {
   return HARD ? ((s > 0.f && s < 1.f) ? 0.2f : 0.f) : s * (1.f - s);
 }
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
 
 // Warp roles (19 warps): 0 = MMA issuer (even CTA), 1 / 2 = push warp of group 0 / 1 (warp 1 also owns the TMEM allocation),
@@ -892,6 +894,16 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
           sc0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t, H / 8, gu, n, m)));
           sc1 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)));
           if (p.dhext) sex = __ldg(reinterpret_cast<const uint4*>(p.dhext + ((size_t)t * n + m) * H + u0));
+        }
+        if (p.l2_prefetch && t >= p.l2_prefetch && row_ok) {
+          // the stash streams from HBM next to the weight-gradient GEMMs of the side stream: pull the lines of a later step into L2 now
+          const int tp = t - p.l2_prefetch;
+          prefetch_l2(p.gates + gran_off(tp, G / 8, bi * (H / 8) + gu, n, m));
+          prefetch_l2(p.gates + gran_off(tp, G / 8, bfk * (H / 8) + gu, n, m));
+          prefetch_l2(p.gates + gran_off(tp, G / 8, 2 * (H / 8) + gu, n, m));
+          prefetch_l2(p.gates + gran_off(tp, G / 8, 3 * (H / 8) + gu, n, m));
+          prefetch_l2(p.cseq + gran_off(tp, H / 8, gu, n, m));
+          if (p.dhext) prefetch_l2(p.dhext + ((size_t)tp * n + m) * H + u0);
         }
         // ---- dh_t = sum over the pairs of their partial dG_{t+1} U^T for this thread's 8 units
         float dh[8];
@@ -1183,6 +1195,7 @@ void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
   p.dG = (bf16*)a.dG; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace;
   MVAE_REQUIRE(p.upack != nullptr, "cluster backward: packed weights missing");
+  p.l2_prefetch = env_int("MVAE_CLB_PREFETCH", 2);
   p.xbuf = (uint8_t*)a.partial;
   p.via_l2 = env_int("MVAE_CLB_L2", 0) && p.xbuf != nullptr;
   if (p.via_l2) MVAE_REQUIRE((size_t)clusters * ng * CS * ND * CLB_MSG <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
