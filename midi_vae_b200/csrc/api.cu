@@ -68,6 +68,8 @@ void Model::style_transfer(const mvae_batch& b, const uint8_t* song_start, int c
   MVAE_REQUIRE(c_from >= 0 && c_from < L && c_to >= 0 && c_to < L, "latent dims to swap out of range");
   MVAE_REQUIRE(feedback == MVAE_FB_AS_WIRED || feedback == MVAE_FB_FREE_RUNNING, "style transfer decodes as_wired or free_running (no targets exist)");
   MVAE_CUDA(cudaMemsetAsync(acc, 0, ACC_COUNT * sizeof(double), st));
+  inference_pass = true;    // no backward pass follows: the recurrences skip the BPTT stash
+  struct Reset { bool& f; ~Reset() { f = false; } } reset{inference_pass};
   prepare_inputs(b, false);
   encoder_forward(b.n);
   mvae_batch b0 = b; b0.eps = nullptr; b0.history = nullptr;   // eps = 0: z = mu (vae_evaluation.py:482-485)

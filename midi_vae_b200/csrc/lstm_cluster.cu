@@ -391,6 +391,7 @@ struct Cluster2P {
   const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates; const bf16* c0; int ldc0;
   const bf16* upack;
   uint8_t* hx;        // exchange buffer [clusters][ng][2][CS][2 row halves][2 KB]
+  int no_stash;       // inference: h only, no BPTT stash
   int c0_stash;       // this launch continues a sequence: initial c = stash slab 0 (granule layout) of the (offset) cseq pointer, h = hseq slab 0
   int x_mode; const bf16* xtab; const unsigned char* x_idx; int x_ld, x_shift; const bf16* x_scalar; const float* x_w; const float* x_b;
   long long* trace;
@@ -669,8 +670,8 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
         } else {
           named_barrier(5 + set, 32 * CL_EPI_WARPS);             // last step: only the scratch tile needs protecting
         }
-        if (row_ok && !(p.dbg & 1)) {
-          *reinterpret_cast<uint4*>(p.hseq + ((size_t)(t + 1) * n + m) * H + u0) = st_h;
+        if (row_ok) *reinterpret_cast<uint4*>(p.hseq + ((size_t)(t + 1) * n + m) * H + u0) = st_h;
+        if (row_ok && !p.no_stash) {   // gates and c are read only by the backward pass
           *reinterpret_cast<uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)) = pack8(cn);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)) = pack8(gi);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)) = pack8(gf);
@@ -1136,7 +1137,12 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   }
   const int groups = (a.n + CL_ROWS - 1) / CL_ROWS;
   int ng = env_int("MVAE_CL_NG", 0);
-  if (ng <= 0) ng = 2;
+  if (ng <= 0) {
+    // 2 groups per cluster is the fastest per step; when that needs more 16-CTA clusters than are ever co-resident (7 on a B200) a third
+    // group per cluster (one warp set then serves two groups: ~1.65x per step) still beats a second wave (2x)
+    ng = 2;
+    if (CS == 16 && (groups + 1) / 2 > 7 && (groups + 2) / 3 <= 7) ng = 3;
+  }
   ng = std::max(1, std::min(std::min(ng, CL2_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
   const size_t smem = 1024 + scr_bytes + (size_t)ng * 2 * hbuf;
@@ -1146,7 +1152,7 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   const size_t t0 = (size_t)a.t0, nn = (size_t)a.n;
   p.xw = a.xw ? (const bf16*)a.xw + t0 * nn * 4 * H : nullptr;
   p.hseq = (bf16*)a.hseq + t0 * nn * H; p.cseq = (bf16*)a.cseq + t0 * nn * H; p.gates = (bf16*)a.gates + t0 * nn * 4 * H;
-  p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0; p.c0_stash = a.t0 > 0;
+  p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0; p.c0_stash = a.t0 > 0; p.no_stash = a.no_stash;
   p.upack = (const bf16*)a.upack; p.hx = (uint8_t*)a.hx; p.trace = (long long*)a.trace;
   p.x_mode = a.x_mode; p.xtab = (const bf16*)a.xtab; p.x_idx = a.x_idx; p.x_ld = a.x_ld; p.x_shift = a.x_shift - a.t0;
   p.x_scalar = a.x_scalar ? (const bf16*)a.x_scalar + t0 * nn * a.x_ld : nullptr; p.x_w = a.x_w; p.x_b = a.x_b;

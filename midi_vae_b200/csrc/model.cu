@@ -390,6 +390,7 @@ RecPersistArgs Model::fwd_args(const FwdJob& j, int n, int slot, int hs) {
   a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates; a.c0 = j.c0; a.ldc0 = j.ld0;
   a.hx = slot ? rec_hx2 : rec_hx;
   a.trace = slot ? nullptr : trace_buf;
+  a.no_stash = inference_pass ? 1 : 0;
   if (fuse_xproj && r.steps > 8) {
     if ((j.kind == IN_DENSE && j.onehot) || j.kind == IN_NONE) {
       a.x_mode = 1; a.xtab = r.xtab;

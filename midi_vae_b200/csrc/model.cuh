@@ -147,6 +147,7 @@ struct Model {
   void branch_join();
   const unsigned char* cur_pitch = nullptr;   // device u8 rolls of the batch in flight (class indices)
   const unsigned char* cur_target = nullptr;
+  bool inference_pass = false;      // forward only (style transfer / predict): the recurrences skip the BPTT stash
   bool fuse_xproj = false;          // cluster forward computes one-hot / scalar input projections itself
   const void* Y_ext_cur = nullptr;   // teacher-forcing source: Yp_ext or (target == pitch) Xp_ext
   const void* e_cur = nullptr;       // output of the last tanh Dense before the split

@@ -31,6 +31,7 @@ struct RecPersistArgs {
   const void* upack_bwd = nullptr;    // K-split backward: packed weights, rec_persist_pack_u_bwd
   void* partial = nullptr;            // K-split backward: exchange buffer, rec_persist_partial_bytes
   void* trace = nullptr;              // optional: 8 steps x 16 clock64 stamps of CTA 0 (profiling aid)
+  int no_stash = 0;                   // cluster forward: inference, do not write the gates / c stash
   int t0 = 0;                         // cluster kernels: this launch covers steps [t0, t0 + steps) of the sequence (time-chunked recurrences)
   // cluster forward only: input projection computed inside the kernel instead of streamed from the (steps, n, 4H) xw buffer
   int x_mode = 0;                     // 0: xw buffer; 1: one-hot input = row gather from xtab; 2: scalar input (x w + b)

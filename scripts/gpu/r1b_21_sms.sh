@@ -1,0 +1,5 @@
+#!/bin/bash
+for sms in 84 112 148 60; do
+echo "=== side_sms=$sms"
+MVAE_SIDE_SMS=$sms timeout 600 python bench.py --workload cfg3 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['class_ms'])"
+done
