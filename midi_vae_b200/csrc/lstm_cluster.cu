@@ -1142,6 +1142,7 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
     // group per cluster (one warp set then serves two groups: ~1.65x per step) still beats a second wave (2x)
     ng = 2;
     if (CS == 16 && (groups + 1) / 2 > 7 && (groups + 2) / 3 <= 7) ng = 3;
+    if (CS == 8 && groups <= env_int("MVAE_CL_NG1_MAX", 8)) ng = 1;   // 8-CTA clusters are plentiful: one group each has the shortest chain
   }
   ng = std::max(1, std::min(std::min(ng, CL2_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
@@ -1191,7 +1192,7 @@ void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
   }
   const int groups = (a.n + CL_ROWS - 1) / CL_ROWS;
   int ng = env_int("MVAE_CLB_NG", 0);
-  if (ng <= 0) ng = CLB_MAXG;
+  if (ng <= 0) ng = (CS == 8 && groups <= env_int("MVAE_CL_NG1_MAX", 8)) ? 1 : CLB_MAXG;
   ng = std::max(1, std::min(std::min(ng, CLB_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
   const size_t smem = 1024 + (size_t)ng * grp;
