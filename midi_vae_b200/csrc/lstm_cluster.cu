@@ -1018,6 +1018,331 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
   if (warp == 1) ptx::tmem_dealloc2(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward, second form (H = 512, 16-CTA clusters): K split over QUADS instead of pairs, so that half of the exchange becomes an
+// all-gather that can ride the multicast path and the DSMEM reduce-scatter shrinks from 8 x 4 KB to 4 x 4 KB per CTA and step.
+//   * cell ownership as in the forward kernel: CTA `rank` does the gate-gradient math of units [32 rank, 32 rank + 32) for all 64 rows
+//     of a group ((row, 8 units) per thread);
+//   * quad kq = CTAs 4 kq .. 4 kq + 3 owns units [128 kq, +128) = 512 gate columns = one K quarter.  Its four dG pieces (64 rows x 128
+//     gate columns each) are ALL-GATHERED inside the quad: every CTA stores its piece to a global slot and multicasts each row half
+//     (8 KB) into the B-operand tiles of the two quad CTAs that hold that half; a tile is 32 rows x 512 k, double-buffered, and a
+//     buffer is re-used only after both pair MMAs that read it have committed (tcgen05.commit multicast to the quad's b_free barriers);
+//   * pair (mt, kq) = CTAs 4 kq + 2 mt + {0, 1}: A = U^T [256 output units of M tile mt][512 k of quarter kq] in tensor memory,
+//     D = partial dh^T [128 units per CTA][64 rows], ONE M tile, 32 MMAs (M256 N64 K16) per step as before;
+//   * reduce-scatter: CTA (kq, c) sends the 32-unit blocks of its D to the four CTAs of quad #c and receives one 4 KB bf16 message per
+//     K quarter (from CTAs 4 s + kq): bulk copies + ACKs exactly as in the first form, with half the bytes and half the drain work.
+constexpr uint32_t CLQ_BT = 64 * CL_HALF * 16;         // 32 KB: B tile [64 k-granules][32 rows][16 B]
+constexpr uint32_t CLQ_PIECE = 16 * CL_HALF * 16;      // 8 KB: one CTA's dG piece for one row half (16 k-granules)
+constexpr uint32_t CLQ_MGS = CL_ROWS * 16 + 16;        // 1040 B: unit-granule stride of a message (64 rows x 16 B + bank padding)
+constexpr uint32_t CLQ_MSG = 4 * CLQ_MGS;              // 4160 B: 32 units x 64 rows bf16
+constexpr uint32_t CLQ_GRP = 2 * CLQ_BT + 8 * CLQ_MSG; // per group: 2 B tiles | staging (4 messages) | receive (4 messages)
+
+struct ClusterQP {
+  int n, steps, nswap, ng, l2_prefetch;
+  const bf16* gates; const bf16* cseq; const bf16* dhext; const bf16* dh_last; int ld_last;
+  bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
+  const bf16* upack;      // [16][128 output units][512 k]
+  uint8_t* xbuf;          // dG exchange slots [clusters][ng][2][16 CTAs][2 row halves][8 KB]
+  long long* trace;
+};
+
+template <bool HARD, bool STD>
+__global__ void __launch_bounds__(CLW_THREADS, 1)
+rec_cluster_bwd4_kernel(const ClusterQP p) {
+  constexpr int CS = 16, H = 512, G = 4 * H;
+  constexpr uint32_t TM_U = CLB_MAXG * 64;                            // TMEM: D(g) at 64 g, U^T tile from column 128
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t b_full[CLB_MAXG][2], b_free[CLB_MAXG][2], peer_ready[CLB_MAXG][2], tmem_full[CLB_MAXG], recv_full[CLB_MAXG], ack[CLB_MAXG];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int cl = (int)blockIdx.x / CS;
+  const int e = (int)(rank & 1), kq = (int)(rank >> 2), c = (int)(rank & 3);
+  const int T = p.steps, n = p.n, ng = p.ng;
+  const int row0 = cl * CL_ROWS * ng;
+  const int nga = min(ng, (n - row0 + CL_ROWS - 1) / CL_ROWS);
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < CLB_MAXG; ++g) {
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(ptx::smem_u32(&b_full[g][b]), 1);
+        ptx::mbar_init(ptx::smem_u32(&b_free[g][b]), 2);
+        ptx::mbar_init(ptx::smem_u32(&peer_ready[g][b]), 1);
+      }
+      ptx::mbar_init(ptx::smem_u32(&tmem_full[g]), 1);
+      ptx::mbar_init(ptx::smem_u32(&recv_full[g]), 1);
+      ptx::mbar_init(ptx::smem_u32(&ack[g]), 4 * CL_EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+    for (int g = 0; g < CLB_MAXG; ++g) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&recv_full[g]), 4 * CLQ_MSG);   // messages of iteration 0
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(ptx::smem_u32(&tmem_base_slot), 512);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp >= 3 && warp < 7) {
+    // U^T tile -> tensor memory: lane = output unit 256 mt + 128 e + lane, 32-bit column = k pair of the quad's 512 k
+    const int mrow = (warp & 3) * 32 + lane;
+    const uint4* src = reinterpret_cast<const uint4*>(p.upack + ((size_t)rank * 128 + mrow) * 512);
+    for (int c32 = 0; c32 < 8; ++c32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 v = __ldg(src + c32 * 8 + i);
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+      }
+      ptx::tmem_st_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TM_U + (uint32_t)c32 * 32u, r);
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  ptx::tc_fence_after();
+
+  if (warp == 0) {
+    if (e == 0) {
+      // ===================== MMA issuer (even CTA of the pair) =====================
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, CL_ROWS, false, false);
+      const uint16_t pair_mask = (uint16_t)(3u << rank);
+      const uint16_t quad_mask = (uint16_t)(0xFu << (4 * kq));
+      const uint64_t bd0 = ptx::umma_desc_noswz(smem_base, CL_HALF * 16, 128);
+      for (int it = 0; it < T; ++it) {
+        const int b = it & 1;
+#pragma unroll
+        for (int g = 0; g < CLB_MAXG; ++g) {
+          if (g >= nga) break;
+          if (lane == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&b_full[g][b]), CLQ_BT);
+          ptx::mbar_wait(ptx::smem_u32(&b_full[g][b]), (uint32_t)((it >> 1) & 1));          // my half of the quad's dG_t
+          ptx::mbar_wait(ptx::smem_u32(&peer_ready[g][b]), (uint32_t)((it >> 1) & 1));      // the odd CTA's half
+          ptx::tc_fence_after();
+          if (g == 0 && lane == 0) CL_TRACE(it, 0);
+          const uint64_t bd = bd0 + (uint64_t)((g * CLQ_GRP + b * CLQ_BT) >> 4);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 32; ++ks)
+              ptx::umma_bf16_2cta_ts(tmem_base + (uint32_t)g * 64u, tmem_base + TM_U + (uint32_t)ks * 8u,
+                                     bd + (uint64_t)((ks * 2 * (CL_HALF * 16)) >> 4), idesc, ks > 0 ? 1u : 0u);
+            ptx::umma_commit_2cta(ptx::smem_u32(&tmem_full[g]), pair_mask);
+            ptx::umma_commit_2cta(ptx::smem_u32(&b_free[g][b]), quad_mask);   // both B tiles of this pair may be overwritten (by anyone in the quad)
+          }
+          __syncwarp();
+          if (g == 0 && lane == 0) CL_TRACE(it, 1);
+        }
+      }
+    } else if (lane == 0) {
+      // ===================== relay (odd CTA): "my half of dG_t landed" -> the pair's MMA issuer =====================
+      const uint32_t leader = rank - 1;
+      for (int it = 0; it < T; ++it) {
+        const int b = it & 1;
+        for (int g = 0; g < nga; ++g) {
+          const uint32_t bb = ptx::smem_u32(&b_full[g][b]);
+          ptx::mbar_arrive_expect_tx(bb, CLQ_BT);
+          ptx::mbar_wait(bb, (uint32_t)((it >> 1) & 1));
+          ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&peer_ready[g][b]), leader));
+        }
+      }
+    }
+  } else if (warp <= CLW_SETS) {
+    // ===================== helper warp of group g: multicasts this CTA's dG piece, later pushes its partial messages =====================
+    const int g = warp - 1;
+    if (g < nga) {
+      const uint32_t gb = smem_base + (uint32_t)g * CLQ_GRP;
+      // push: message w goes to CTA 4 c + w (quad #c), slot kq of its receive buffer
+      const int xl = lane & 3;
+      const uint32_t dest = (uint32_t)(4 * c + xl);
+      const uint32_t pdst = ptx::mapa(gb + 2 * CLQ_BT + (4 + kq) * CLQ_MSG, dest), pbar = ptx::mapa(ptx::smem_u32(&recv_full[g]), dest);
+      const uint32_t psrc = gb + 2 * CLQ_BT + (uint32_t)xl * CLQ_MSG;
+      for (int it = 0; it < T; ++it) {
+        const int b = it & 1;
+        named_barrier(1 + g, 32 * (CL_EPI_WARPS + 1));                      // dG piece of step t stored to the exchange slot (and fenced)
+        if (it >= 2) ptx::mbar_wait(ptx::smem_u32(&b_free[g][b]), (uint32_t)((((it >> 1) - 1)) & 1));   // every MMA that read buffer b is done
+        if (lane < 2) {
+          const int ed = (lane ^ p.nswap) & 1;                              // parity of the quad CTAs that hold row half `lane`
+          const uint16_t mask = (uint16_t)(((1u << ed) | (1u << (2 + ed))) << (4 * kq));
+          const uint8_t* src = p.xbuf + ((size_t)(((cl * ng + g) * 2 + b) * CS + rank)) * (2 * CLQ_PIECE) + (size_t)lane * CLQ_PIECE;
+          ptx::bulk_load_multicast(gb + b * CLQ_BT + (uint32_t)c * CLQ_PIECE, src, CLQ_PIECE, ptx::smem_u32(&b_full[g][b]), mask);
+        }
+        if (lane == 0 && g == 0) CL_TRACE(it, 8);
+        named_barrier(3 + g, 32 * (CL_EPI_WARPS + 1));                      // partial messages staged
+        ptx::fence_proxy_async();
+        if (lane < 4) ptx::bulk_copy_dsmem(pdst, psrc, CLQ_MSG, pbar);
+        if (lane == 0 && g == 0) CL_TRACE(it, 6);
+      }
+    }
+  } else {
+    // ===================== epilogue warps: set s = group s =====================
+    const int g = (warp - 3) >> 3, ew = (warp - 3) & 7;
+    if (g < nga) {
+      const uint32_t gb = smem_base + (uint32_t)g * CLQ_GRP;
+      // cell ownership (as in the forward kernel): batch row rr, units [8 q, 8 q + 8) of this CTA's 32
+      const int rr = ew * 8 + (lane >> 2), q = lane & 3;
+      const int u0 = (int)rank * CL_HS + q * 8, gu = u0 >> 3;
+      const int m = row0 + g * CL_ROWS + rr;
+      const bool row_ok = m < n;
+      // drain ownership: TMEM lane = output unit 128 (rank & 3) + 32 wq + lane -> message wq, 32 columns = batch rows ch * 32 ..
+      const int wq = warp & 3, ch = ew >> 2;
+      constexpr int bi = STD ? 0 : 1, bfk = 1 - bi;
+      const bool tracer = (ew == 0 && lane == 0);
+      float dc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dc[u] = 0.f;
+
+      for (int it = 0; it <= T; ++it) {
+        const int t = T - 1 - it;
+        uint4 sg[4], sc0, sc1, sex;
+        sex = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0 && row_ok) {
+          sg[0] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)));
+          sg[1] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)));
+          sg[2] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)));
+          sg[3] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)));
+          sc0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t, H / 8, gu, n, m)));
+          sc1 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)));
+          if (p.dhext) sex = __ldg(reinterpret_cast<const uint4*>(p.dhext + ((size_t)t * n + m) * H + u0));
+        }
+        if (p.l2_prefetch && t >= p.l2_prefetch && row_ok) {
+          const int tp = t - p.l2_prefetch;
+          prefetch_l2(p.gates + gran_off(tp, G / 8, bi * (H / 8) + gu, n, m));
+          prefetch_l2(p.gates + gran_off(tp, G / 8, bfk * (H / 8) + gu, n, m));
+          prefetch_l2(p.gates + gran_off(tp, G / 8, 2 * (H / 8) + gu, n, m));
+          prefetch_l2(p.gates + gran_off(tp, G / 8, 3 * (H / 8) + gu, n, m));
+          prefetch_l2(p.cseq + gran_off(tp, H / 8, gu, n, m));
+          if (p.dhext) prefetch_l2(p.dhext + ((size_t)tp * n + m) * H + u0);
+        }
+        // ---- dh_t = sum over the K quarters of their partial dG_{t+1} U^T for this thread's 8 units
+        float dh[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dh[u] = 0.f;
+        if (it == 0 && p.dh_last && row_ok) unpack8(__ldg(reinterpret_cast<const uint4*>(p.dh_last + (size_t)m * p.ld_last + u0)), dh);
+        if (it > 0) {
+          ptx::mbar_wait(ptx::smem_u32(&recv_full[g]), (uint32_t)((it - 1) & 1));
+          if (tracer && g == 0) CL_TRACE(it, 2);
+          if (tracer && it < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&recv_full[g]), 4 * CLQ_MSG);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            float f[8];
+            unpack8(ptx::ld_shared_u4(gb + 2 * CLQ_BT + (4 + s) * CLQ_MSG + (uint32_t)q * CLQ_MGS + (uint32_t)rr * 16), f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dh[u] += f[u];
+          }
+          if (it < T) {
+            __syncwarp();
+            if (lane < 4) ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&ack[g]), (uint32_t)(4 * lane + kq)));   // sources: CTAs 4 s + kq
+          }
+        }
+        if (t < 0) {
+          if (row_ok && p.dS_h) {
+            *reinterpret_cast<uint4*>(p.dS_h + (size_t)m * p.ldS + u0) = pack8(dh);
+            *reinterpret_cast<uint4*>(p.dS_c + (size_t)m * p.ldS + u0) = pack8(dc);
+          }
+          break;
+        }
+        // ---- gate-gradient math for step t
+        uint4 pk[4];
+        if (row_ok) {
+          float gi[8], gf[8], gg[8], go[8], c0[8], c1[8], ex[8], dv[8];
+          unpack8(sg[0], gi); unpack8(sg[1], gf); unpack8(sg[2], gg); unpack8(sg[3], go);
+          unpack8(sc0, c0); unpack8(sc1, c1); unpack8(sex, ex);
+          float ds[8], d_o[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float d = dh[u] + ex[u];
+            if (STD) {
+              const float tc = tanh_fast(c1[u]);
+              d_o[u] = d * tc;
+              ds[u] = dc[u] + d * go[u] * (1.f - tc * tc);
+            } else {
+              d_o[u] = d * c1[u];
+              ds[u] = (dc[u] + d * go[u]) * (1.f - c1[u] * c1[u]);
+            }
+            dc[u] = ds[u] * gf[u];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dv[u] = ds[u] * gg[u] * gate_bwd<HARD>(gi[u]);
+          pk[0] = pack8(dv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dv[u] = ds[u] * c0[u] * gate_bwd<HARD>(gf[u]);
+          pk[1] = pack8(dv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dv[u] = ds[u] * gi[u] * (1.f - gg[u] * gg[u]);
+          pk[2] = pack8(dv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dv[u] = d_o[u] * gate_bwd<HARD>(go[u]);
+          pk[3] = pack8(dv);
+        } else {
+          pk[0] = pk[1] = pk[2] = pk[3] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // this CTA's dG piece -> exchange slot (k within the piece = gate * 32 + unit: k-granule gate * 4 + q), one 8 KB block per row half
+        {
+          uint8_t* slot = p.xbuf + ((size_t)(((cl * ng + g) * 2 + (it & 1)) * CS + rank)) * (2 * CLQ_PIECE) + (size_t)(rr >> 5) * CLQ_PIECE + (size_t)(rr & 31) * 16;
+#pragma unroll
+          for (int gt = 0; gt < 4; ++gt) *reinterpret_cast<uint4*>(slot + (size_t)(gt * 4 + q) * (CL_HALF * 16)) = pk[gt];
+        }
+        ptx::fence_proxy_async_global();       // generic stores -> the multicast copy (async proxy); nothing else of this thread is in flight but old dG rows
+        named_barrier(1 + g, 32 * (CL_EPI_WARPS + 1));
+        if (tracer && g == 0) CL_TRACE(it, 3);
+        // ---- off the critical path: dG_t for the batched weight-gradient GEMMs
+        if (row_ok) {
+          bf16* dgp = p.dG + ((size_t)t * n + m) * G + u0;
+          *reinterpret_cast<uint4*>(dgp + bi * H) = pk[0];
+          *reinterpret_cast<uint4*>(dgp + bfk * H) = pk[1];
+          *reinterpret_cast<uint4*>(dgp + 2 * H) = pk[2];
+          *reinterpret_cast<uint4*>(dgp + 3 * H) = pk[3];
+        }
+        // ---- partial dh_{t-1} of this CTA's 128 output units: TMEM -> bf16 messages in the staging tile
+        ptx::mbar_wait(ptx::smem_u32(&tmem_full[g]), (uint32_t)(it & 1));
+        ptx::tc_fence_after();
+        if (tracer && g == 0) CL_TRACE(it, 4);
+        if (it > 0) ptx::mbar_wait(ptx::smem_u32(&ack[g]), (uint32_t)((it - 1) & 1));   // every receiver has read message it-1
+        if (tracer && g == 0) CL_TRACE(it, 5);
+        {
+          float v[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 64 + ch * 32), v);
+          const uint32_t base = gb + 2 * CLQ_BT + (uint32_t)wq * CLQ_MSG + (uint32_t)(lane >> 3) * CLQ_MGS + (uint32_t)(ch * 32) * 16 + (uint32_t)(lane & 7) * 2;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) st_shared_u16(base + i * 16, __bfloat16_as_ushort(__float2bfloat16_rn(v[i])));
+        }
+        ptx::tc_fence_before();
+        named_barrier(3 + g, 32 * (CL_EPI_WARPS + 1));
+        if (tracer && g == 0) CL_TRACE(it, 9);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  if (warp == 1) ptx::tmem_dealloc2(tmem_base, 512);
+}
+
+// U (512, 2048) fp32 master -> bf16 [16 CTAs][128 lanes][512 k] for the quad backward kernel: CTA rank (kq = rank / 4, mt = (rank / 2) % 2,
+// e = rank % 2), lane l: output unit 256 mt + 128 e + l; k = cs * 128 + gate * 32 + uu: U[unit, blk(gate) * 512 + 128 kq + 32 cs + uu]
+__global__ void pack_u_cluster_bwd4_kernel(const float* __restrict__ U, int ldu, bf16* __restrict__ out, int variant) {
+  const int H = 512;
+  const long total = (long)H * 4 * H;
+  for (long x = blockIdx.x * (long)blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int kk = (int)(x % 512);
+    long rest = x / 512;
+    const int l = (int)(rest % 128);
+    const int rank = (int)(rest / 128);
+    const int kq = rank >> 2, mt = (rank >> 1) & 1, e = rank & 1;
+    const int cs = kk >> 7, gate = (kk >> 5) & 3, uu = kk & 31;
+    int blk = gate;
+    if (variant != MVAE_CELL_STANDARD && gate < 2) blk = 1 - gate;
+    out[x] = __float2bfloat16_rn(U[(long)(256 * mt + 128 * e + l) * ldu + blk * H + 128 * kq + 32 * cs + uu]);
+  }
+}
+
 // U (H, 4H) fp32 master -> bf16 [CS][MT][128][256] for the cluster backward kernel: CTA rank = 2 q + e, M tile mt, lane l:
 // output unit 256 mt + 128 e + l; column kk = gate * 64 + uu (gate in semantic order i, f, g, o): U[unit, blk(gate) H + 64 q + uu]
 __global__ void pack_u_cluster_bwd_kernel(const float* __restrict__ U, int ldu, bf16* __restrict__ out, int H, int variant) {
@@ -1223,6 +1548,41 @@ void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
   count_launch();
 }
 
+
+template <bool HARD, bool STD>
+void launch_bwd4(const RecPersistArgs& a, cudaStream_t st) {
+  constexpr int CS = 16, H = 512;
+  constexpr size_t smem_max = 1024 + (size_t)CLB_MAXG * CLQ_GRP;
+  auto kern = rec_cluster_bwd4_kernel<HARD, STD>;
+  static bool configured = false;
+  if (!configured) {
+    MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured = true;
+  }
+  const int groups = (a.n + CL_ROWS - 1) / CL_ROWS;
+  int ng = env_int("MVAE_CLB_NG", 0);
+  if (ng <= 0) ng = CLB_MAXG;
+  ng = std::max(1, std::min(std::min(ng, CLB_MAXG), groups));
+  const int clusters = (groups + ng - 1) / ng;
+  const size_t smem = 1024 + (size_t)ng * CLQ_GRP;
+  ClusterQP p{};
+  p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.l2_prefetch = env_int("MVAE_CLB_PREFETCH", 2);
+  p.gates = (const bf16*)a.gates; p.cseq = (const bf16*)a.cseq; p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last;
+  p.dG = (bf16*)a.dG; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace; p.xbuf = (uint8_t*)a.partial;
+  MVAE_REQUIRE(p.upack != nullptr && p.xbuf != nullptr, "cluster backward: packed weights / exchange buffer missing");
+  MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * 2 * CLQ_PIECE <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  MVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  count_launch();
+}
+
 }  // namespace
 
 // cluster kernels: H = 32 * cluster size, cluster size 8 (portable) or 16 (non-portable, one cluster per GPC)
@@ -1233,7 +1593,10 @@ bool rec_cluster_supported(int H) {
 }
 
 // global exchange buffer of the backward kernel (via_l2): [64-row groups rounded up to whole clusters][H/32 CTAs][H/64 messages of 4224 B]
-size_t rec_cluster_xbuf_bytes(int n, int H) { return (size_t)((n + CL_ROWS - 1) / CL_ROWS + CLB_MAXG) * (size_t)(H / CL_HS) * (size_t)(H / 64) * CLB_MSG; }
+size_t rec_cluster_xbuf_bytes(int n, int H) {
+  const size_t groups = (size_t)((n + CL_ROWS - 1) / CL_ROWS + CLB_MAXG), ctas = (size_t)(H / CL_HS);
+  return std::max(groups * ctas * (size_t)(H / 64) * CLB_MSG, groups * 2 * ctas * 2 * (size_t)CLQ_PIECE);
+}
 
 // global exchange buffer of the forward kernel: [64-row groups, rounded up to whole clusters][2][H/32 CTAs][4 KB]
 size_t rec_cluster_hx_bytes(int n, int H) { return (size_t)((n + CL_ROWS - 1) / CL_ROWS + CL2_MAXG) * 2 * (size_t)(H / CL_HS) * CL_STAGE; }
@@ -1245,8 +1608,17 @@ void rec_cluster_pack_u(const float* U, int ldu, void* upack, int H, int variant
   MVAE_CUDA(cudaGetLastError());
 }
 
+// which backward form runs: the quad form exists for H = 512 only
+static bool use_bwd4(int H) { return H == 512 && env_int("MVAE_CLB_V", 4) == 4; }
+
 void rec_cluster_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int variant, cudaStream_t st) {
   MVAE_REQUIRE(H == 256 || H == 512, "cluster recurrence: hidden size 256 or 512");
+  if (use_bwd4(H)) {
+    pack_u_cluster_bwd4_kernel<<<148 * 8, 256, 0, st>>>(U, ldu, (bf16*)upack_bwd, variant);
+    count_launch();
+    MVAE_CUDA(cudaGetLastError());
+    return;
+  }
   pack_u_cluster_bwd_kernel<<<std::min(148 * 8, (int)(((long)H * 4 * H + 255) / 256)), 256, 0, st>>>(U, ldu, (bf16*)upack_bwd, H, variant);
   count_launch();
   MVAE_CUDA(cudaGetLastError());
@@ -1277,6 +1649,13 @@ bool rec_cluster_bwd_supported(int H) {
 void rec_cluster_backward(const RecPersistArgs& a, cudaStream_t st) {
   const bool hard = a.gate_act == MVAE_GATE_HARD_SIGMOID, stdc = a.variant == MVAE_CELL_STANDARD;
   MVAE_REQUIRE(a.H == 512 || a.H == 256, "cluster recurrence unsupported for this hidden size");
+  if (use_bwd4(a.H)) {
+    if (hard && stdc) launch_bwd4<true, true>(a, st);
+    else if (hard) launch_bwd4<true, false>(a, st);
+    else if (stdc) launch_bwd4<false, true>(a, st);
+    else launch_bwd4<false, false>(a, st);
+    return;
+  }
 #define MVAE_CL_BWD(CS)                                                        \
   do {                                                                         \
     if (hard && stdc) launch_bwd<CS, true, true>(a, st);                       \
