@@ -5,17 +5,23 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu-baseline /
 (``midi_vae_b200``) never imports it and fails loudly when its CUDA library is
 missing.
 
-PARITY UNPINNED.  The reference (brunnergino/MIDI-VAE) executes this graph inside
-Keras 2.0.8 (Theano backend) + recurrentshop (un-pinned master); neither is
-vendored under /root/reference nor installed here, and the reference ships no
-tests, golden vectors or input/output fixtures.  This
-file is therefore a restatement of the reference's *graph wiring*
-(vae_definition.py, cited per function) plus the published Keras-2.0.8
-semantics for LSTM / Dense / categorical_crossentropy / weighted objectives /
-Adam.  The golden vectors under tests/golden are "oracle-derived, not
-reference-derived".  What *is* pinned against the reference: the weight names,
-shapes and ordering, checked against the shipped HDF5 checkpoints
-(tests/test_checkpoint_layout.py).
+PARITY PINNED ON THE REFERENCE'S OWN GRAPH CODE, THIRD-PARTY LAYER MATH RESTATED.  The reference
+(brunnergino/MIDI-VAE) executes this graph inside Keras 2.0.8 (Theano backend) + recurrentshop
+(un-pinned master); neither is vendored under /root/reference nor installed here, and the
+reference ships no tests or input/output fixtures.  What pins this file:
+  * tests/golden/reference_cfg1.npz -- produced by importing the reference's UNMODIFIED
+    vae_definition.py and running VAE.create / prepare_* / predict / evaluate / fit on top of a
+    restated slice of Keras 2.0.8 + recurrentshop (oracle/keras_shim, see its README).  This file
+    matches those vectors to 1e-9 in float64 (tests/test_reference_pin.py): wiring, positional
+    lists, loss composition, metric names, Adam trajectory, both recalled decoder-cell conventions.
+  * the shipped HDF5 checkpoints: layer / weight names, shapes and save order reproduced by the
+    reference's graph code through the shim (reference_layout.json == checkpoint_layout.json);
+    the decoders' untrained first-cell input kernels (=> ``as_wired`` feedback); first decoder
+    step of two shipped models on known chords.
+What stays un-pinned: the per-layer arithmetic of Keras / recurrentshop is restated from their
+published behaviour in BOTH this file and the shim (same author, so not independent), and
+recurrentshop's multi-step decode semantics could not be confirmed on the shipped GRU models.
+The vectors under tests/golden/cfg1_step.npz are "oracle-derived".
 
 Everything is plain PyTorch on the CPU, written with dense one-hot matmuls as
 the reference does (no gather tricks), generic in dtype (float64 for golden

@@ -1,0 +1,206 @@
+"""Generate REFERENCE-EXECUTED golden vectors: the reference's own, unmodified ``vae_definition.py`` is imported from
+/root/reference and run -- ``VAE().create(**the kwargs vae_training.py:47-109 passes)``, ``prepare_*`` list builders,
+``encoder/decoder/autoencoder.predict``, ``autoencoder.evaluate``, ``autoencoder.fit`` -- on top of the restated Keras 2.0.8 /
+recurrentshop slice in oracle/keras_shim (neither library exists offline; see that directory's README for what is and is not
+independent evidence).  Run where /root/reference exists:
+
+    python tests/golden/make_reference_golden.py
+
+Writes tests/golden/reference_cfg1.npz (LSTM branch, BASELINE configs[0] shapes: seq_len 16, hidden 64, latent 16, batch 8) and
+tests/golden/reference_layout.json (layer / weight names, shapes and save order produced by the reference's graph code for
+its DEFAULT GRU configuration -- compared in the tests with the shipped HDF5 checkpoints).
+"""
+import json
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("MIDIVAE_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    """vae_definition.py, unmodified, with keras / recurrentshop resolved to oracle/keras_shim."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "keras_shim"))
+    sys.path.insert(0, ROOT)
+    sys.path.append(REF)
+    # data_class.py (plots; imports matplotlib, matplotlib2tikz, pretty_midi) is imported by vae_definition.py:11 but never used in it
+    sys.modules.setdefault("data_class", types.ModuleType("data_class"))
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix="mvae_ref_"))      # settings.py:60-63 creates ./pickles/<timestamp>/ at import
+    try:
+        import vae_definition as vd
+    finally:
+        os.chdir(cwd)
+    return vd
+
+
+def create_kwargs(vd, **over):
+    """Exactly the keyword list of vae_training.py:47-109, values taken from the reference's settings module."""
+    S = sys.modules["settings"]
+    names = ["input_dim", "output_dim", "use_embedding", "embedding_dim", "input_length", "output_length", "vae_loss", "optimizer",
+             "activation", "lstm_activation", "lstm_state_activation", "epsilon_std", "epsilon_factor", "include_composer_decoder",
+             "num_composers", "composer_weight", "lstm_size", "cell_type", "num_layers_encoder", "num_layers_decoder", "bidirectional",
+             "decode", "teacher_force", "learning_rate", "split_lstm_vector", "history", "beta", "prior_mean", "prior_std",
+             "decoder_additional_input", "decoder_additional_input_dim", "extra_layer", "meta_instrument", "meta_instrument_dim",
+             "meta_instrument_length", "meta_instrument_activation", "meta_instrument_weight", "signature_decoder", "signature_dim",
+             "signature_activation", "signature_weight", "composer_decoder_at_notes_output", "composer_decoder_at_notes_weight",
+             "composer_decoder_at_notes_activation", "composer_decoder_at_instrument_output", "composer_decoder_at_instrument_weight",
+             "composer_decoder_at_instrument_activation", "meta_velocity", "meta_velocity_length", "meta_velocity_activation",
+             "meta_velocity_weight", "meta_held_notes", "meta_held_notes_length", "meta_held_notes_activation", "meta_held_notes_weight",
+             "meta_next_notes", "meta_next_notes_output_length", "meta_next_notes_weight", "meta_next_notes_teacher_force",
+             "activation_before_splitting"]
+    kw = {n: getattr(S, n) for n in names}
+    kw["latent_rep_size"] = S.latent_dim
+    kw.update(over)
+    return kw
+
+
+def set_module_lengths(vd, T):
+    """prepare_* (vae_definition.py:770-1045) read the sequence length from the settings globals star-imported into the module."""
+    vd.input_length = T
+    vd.output_length = T
+    vd.meta_velocity_length = T
+    vd.meta_held_notes_length = T
+
+
+def keras_name_map(cfg):
+    """our parameter name -> (sub-model, keras layer, index inside layer.weights) for the LSTM branch."""
+    m = {}
+    enc = [f"lstm_{k}" for k in range(1, cfg.num_layers_encoder + 1)] + ["lstm_meta_instrument", "lstm_meta_velocity"]
+    for l in enc:
+        for i, t in enumerate(["kernel", "recurrent_kernel", "bias"]):
+            m[f"{l}/{t}"] = ("encoder", l, i)
+    for l in ["extra_instrument_after_concat_layer", "extra_layer", "z_mean", "z_log_var"]:
+        for i, t in enumerate(["kernel", "bias"]):
+            m[f"{l}/{t}"] = ("encoder", l, i)
+    return m
+
+
+def load_into_reference(model, cfg, w):
+    """Copy our named weights into the reference-built Keras models.  Encoder layers are named by the reference; decoder tensors
+    are positional: the 'decoder' model saves [init-state Denses (notes l1 s1, s2, l2 s1, s2, instr s1, s2, vel s1, s2)], then per
+    RecurrentModel [cells (kernel, bias, recurrent kernel), output Dense] -- the order oracle.param_specs lists them in."""
+    for k, (sub, layer, idx) in keras_name_map(cfg).items():
+        l = model.encoder.get_layer(layer)
+        arrs = l.get_weights()
+        arrs[idx] = w[k]
+        l.set_weights(arrs)
+    from oracle import midivae_oracle as O
+    dec_names = [n for n, _, _ in O.param_specs(cfg) if n.startswith(("dec_init/", "notes/", "meta_instrument/", "meta_velocity/"))]
+    model.decoder.set_weights([w[n] for n in dec_names])
+    return dec_names
+
+
+def main():
+    vd = import_reference()
+    import keras
+    from keras import backend as K
+    import recurrentshop.cells as rs_cells
+    from midi_vae_b200 import METRIC_KEYS, marshal, synth  # noqa: F401
+    from oracle import midivae_oracle as O
+    from tests import util
+
+    out_layout = {}
+    # ---- 1. the reference's DEFAULT configuration (GRU, T 64, H 256, L 256): names / shapes / save order
+    K.clear_session()
+    ref = vd.VAE()
+    ref.create(**create_kwargs(vd))
+    for part in ("encoder", "decoder", "autoencoder"):
+        out_layout[part] = [[l, n, list(s)] for l, n, s in getattr(ref, part).weight_layout()]
+    out_layout["metrics_names"] = ref.autoencoder.metrics_names
+    out_layout["autoencoder_inputs"] = ref.autoencoder.input_names
+    out_layout["decoder_inputs"] = ref.decoder.input_names
+    out_layout["encoder_inputs"] = ref.encoder.input_names
+    # the decoders' first-cell input kernels in every shipped checkpoint: still at their Glorot-uniform initialisation (max |w| = the
+    # initialiser's limit, std = limit / sqrt(3)) after hundreds of epochs => their input was identically zero => decoder_feedback 'as_wired'
+    from midi_vae_b200 import hdf5
+    stats = {}
+    for mdl in sorted(os.listdir(os.path.join(REF, "models"))):
+        for f in sorted(os.listdir(os.path.join(REF, "models", mdl))):
+            if f.startswith("decoderEpoch"):
+                t = hdf5.read_weights(os.path.join(REF, "models", mdl, f))
+                for ln in t["layer_names"]:
+                    for wn, a in t["layers"][ln]:
+                        if a.ndim == 2:
+                            stats[f"{mdl}/{wn.replace(':0', '')}"] = [list(a.shape), float(np.abs(a).max()), float(a.std())]
+    out_layout["shipped_decoder_kernel_stats"] = stats
+    json.dump(out_layout, open(os.path.join(HERE, "reference_layout.json"), "w"), indent=0)
+
+    # ---- 2. LSTM branch at cfg1 shapes, weights = the seeded test weights, run through the reference's own prepare_* + models
+    T, H, L, n = 16, 64, 16, 8
+    out = {}
+    for variant, shim_variant in (("standard", "standard"), ("recurrentshop_recalled", "recalled")):
+        ecfg, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant=variant, max_batch=n)
+        w = util.make_weights(ecfg, seed=42, jitter=0.1)
+        # one synthetic SONG of n chunks: the reference's prepare_* take one style class and one instrument matrix per song
+        r = synth.make_song(np.random.default_rng(1235), n, T, 1)
+        rng = np.random.default_rng(1335)
+        hist = (rng.standard_normal((n, L)) * 0.1).astype(np.float32)
+        eps = synth.make_eps(n, L, 1235, 0.01)
+        rs_cells.LSTM_VARIANT = shim_variant
+        K.clear_session()
+        set_module_lengths(vd, T)
+        model = vd.VAE()
+        model.create(**create_kwargs(vd, cell_type="LSTM", input_length=T, output_length=T, lstm_size=H, latent_rep_size=L,
+                                     meta_velocity_length=T, meta_held_notes_length=T, meta_next_notes_output_length=T))
+        load_into_reference(model, ocfg, w)
+        K.set_random_normal_hook(lambda shp, mean, std: eps.astype(np.float64)[:shp[0]] * (std / 0.01) + mean)
+
+        # the reference's per-song tensors (vae_definition.py:765-769): X/Y (N,T,61) one-hot, C int, I (4,16), V (N,T), D (N,T), S, H (N,L)
+        X, I_, V3, C1 = r.dense(np.float64)
+        Y = X
+        I_song = I_[0]                                   # one instrument matrix per song (tiled by prepare_*)
+        V = V3[..., 0]
+        D = np.zeros_like(V)
+        S = np.zeros((n, 15))
+        C = int(r.style[0])
+        in_list, out_list, sw = vd.prepare_autoencoder_input_and_output_list(X, Y, C, I_song, V, D, S, hist.astype(np.float64), return_sample_weight=True)
+        enc_in = vd.prepare_encoder_input_list(X, I_song, V, D)
+        z = model.encoder.predict(enc_in, batch_size=n)
+        dec_in = vd.prepare_decoder_input(z, C, S, hist.astype(np.float64))
+        dec_out = model.decoder.predict(dec_in, batch_size=n)
+        ae_out = model.autoencoder.predict(in_list, batch_size=n)
+        ev = model.autoencoder.evaluate(in_list, out_list, batch_size=n, sample_weight=sw, verbose=0)
+        hist_fit = []
+        for _ in range(3):
+            h = model.autoencoder.fit(in_list, out_list, epochs=1, batch_size=n, shuffle=False, sample_weight=sw, verbose=0)
+            hist_fit.append({k: v[0] for k, v in h.history.items()})
+        g0 = None
+        p = variant + "/"
+        out[p + "z"] = z
+        for k, a in zip(("Y", "I", "V"), dec_out):
+            out[p + "dec_" + k] = a
+        for k, a in zip(("Y", "I", "V", "C"), ae_out):
+            out[p + "ae_" + k] = a
+        out[p + "evaluate"] = np.array(ev)
+        out[p + "metrics_names"] = np.array(model.autoencoder.metrics_names)
+        out[p + "fit_keys"] = np.array(sorted(hist_fit[0]))
+        out[p + "fit"] = np.array([[hf[k] for k in sorted(hf)] for hf in hist_fit])
+        out[p + "in_shapes"] = np.array([str(np.asarray(a).shape) for a in in_list])
+        out[p + "out_shapes"] = np.array([str(np.asarray(a).shape) for a in out_list])
+        out[p + "sw_shapes"] = np.array([str(np.asarray(a).shape) for a in sw])
+        if variant == "standard":                     # the lists themselves, as the reference's prepare_* built them
+            for tag, lst in (("in", in_list), ("out", out_list), ("sw", sw), ("enc_in", enc_in), ("dec_in", dec_in)):
+                for i, a in enumerate(lst):
+                    out[f"lists/{tag}_{i}"] = np.asarray(a)
+        # weights after the 3 Adam steps, by our names
+        dec_names = [nm for nm, _, _ in O.param_specs(ocfg) if nm.startswith(("dec_init/", "notes/", "meta_instrument/", "meta_velocity/"))]
+        for nm, a in zip(dec_names, model.decoder.get_weights()):
+            out[p + "w3/" + nm] = a
+        for k, (sub, layer, idx) in keras_name_map(ocfg).items():
+            out[p + "w3/" + k] = model.encoder.get_layer(layer).get_weights()[idx]
+        del g0
+    out["pitch"], out["instr"], out["velocity"], out["style"], out["hist"], out["eps"] = r.pitch, r.instr, r.velocity, r.style, hist, eps
+    path = os.path.join(HERE, "reference_cfg1.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+    print("keras shim", keras.__version__, "evaluate(standard):", dict(zip(out["standard/metrics_names"], out["standard/evaluate"])))
+
+
+if __name__ == "__main__":
+    main()
