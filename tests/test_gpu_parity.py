@@ -160,6 +160,55 @@ def test_golden_fixture_cfg1():
     eng.close()
 
 
+@pytest.mark.parametrize("variant", ["standard", "recurrentshop_recalled"])
+def test_reference_executed_fixture_cfg1(variant):
+    """The CUDA path, through the reference-shaped facade and the reference's own positional lists, against vectors produced by
+    EXECUTING the reference's vae_definition.py (tests/golden/make_reference_golden.py; Keras / recurrentshop restated in
+    oracle/keras_shim): encoder / decoder / autoencoder predict, evaluate, three fit steps and the weights they leave behind.
+    fp32 precision, 1e-4 relative (north_star's tolerance)."""
+    import os
+    from midi_vae_b200 import VAE, marshal
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cfg1.npz"))
+    T, H, L, n = 16, 64, 16, 8
+    vae = VAE().create(input_dim=61, output_dim=61, input_length=T, output_length=T, latent_rep_size=L, lstm_size=H, activation='softmax',
+                       include_composer_decoder=True, num_composers=2, composer_weight=0.1, num_layers_encoder=2, num_layers_decoder=2,
+                       learning_rate=2e-4, beta=0.1, extra_layer=True, meta_instrument=True, meta_instrument_dim=16, meta_instrument_length=4,
+                       meta_instrument_activation='softmax', meta_instrument_weight=0.1, meta_velocity=True, meta_velocity_length=T,
+                       meta_velocity_weight=1.0, epsilon_std=0.01, teacher_force=False, max_batch=n, dec_cell_variant=variant,
+                       decoder_feedback="as_wired", precision="fp32")
+    ecfg, _ = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant=variant, max_batch=n)
+    vae.engine.set_weights(util.make_weights(ecfg, seed=42, jitter=0.1))
+    pre = variant + "/"
+    lists = {tag: [g[f"lists/{tag}_{i}"] for i in range(sum(1 for k in g.files if k.startswith(f"lists/{tag}_")))]
+             for tag in ("in", "out", "sw", "enc_in")}
+    eps = g["eps"]
+    z = vae.encoder.predict(lists["enc_in"], batch_size=n, eps=eps)
+    assert util.rel_err(z, g[pre + "z"]) <= TOL32
+    hist = lists["in"][2]
+    Y, Ih, Vh = vae.decoder.predict(marshal.prepare_decoder_input(g[pre + "z"], H=hist), batch_size=n)
+    for mine, name in ((Y, "Y"), (Ih, "I"), (Vh, "V")):
+        assert util.rel_err(mine, g[pre + "dec_" + name]) <= 2 * TOL32, name
+    outs = vae.autoencoder.predict(lists["in"], batch_size=n, eps=eps)
+    for mine, name in zip(outs, ("Y", "I", "V", "C")):
+        assert util.rel_err(mine, g[pre + "ae_" + name]) <= 2 * TOL32, name
+    ev = vae.autoencoder.evaluate(lists["in"], lists["out"], batch_size=n, sample_weight=lists["sw"], eps=eps)
+    for k, a, b in zip(vae.autoencoder.metrics_names, ev, g[pre + "evaluate"]):
+        assert abs(a - b) <= TOL32 * max(1.0, abs(b)), (k, a, b)
+    keys = list(g[pre + "fit_keys"])
+    for step in range(3):
+        h = vae.autoencoder.fit(lists["in"], lists["out"], epochs=1, batch_size=n, shuffle=False, sample_weight=lists["sw"], eps=eps)
+        for k, b in zip(keys, g[pre + "fit"][step]):
+            a = h.history[k][0]
+            assert abs(a - b) <= TOL32 * max(1.0, abs(b)), (step, k, a, b)
+    w0 = util.make_weights(ecfg, seed=42, jitter=0.1)
+    w3 = vae.engine.get_weights()
+    for k in w3:      # three Adam steps of ~lr each: compare the UPDATE
+        d_ref = g[pre + "w3/" + k] - w0[k]
+        d = w3[k] - w0[k]
+        assert np.abs(d - d_ref).max() <= 0.1 * 3 * 2e-4 + 1e-7, k
+    vae.engine.close()
+
+
 def test_gemm_tc_selftest():
     """tcgen05 GEMM (all four major-ness cases, ragged edges, all epilogues) against the SIMT GEMM."""
     from midi_vae_b200 import _lib
