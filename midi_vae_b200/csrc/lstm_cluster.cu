@@ -392,6 +392,7 @@ struct Cluster2P {
   const bf16* upack;
   uint8_t* hx;        // exchange buffer [clusters][ng][2][CS][2 row halves][2 KB]
   int no_stash;       // inference: h only, no BPTT stash
+  int cl0;            // first cluster of this launch (a launch may cover a sub-range of the batch's clusters)
   int c0_stash;       // this launch continues a sequence: initial c = stash slab 0 (granule layout) of the (offset) cseq pointer, h = hseq slab 0
   int x_mode; const bf16* xtab; const unsigned char* x_idx; int x_ld, x_shift; const bf16* x_scalar; const float* x_w; const float* x_b;
   long long* trace;
@@ -418,7 +419,7 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
   const uint32_t smem_h0 = smem_base + (ALIAS ? 0u : 2u * CL_SCR);   // hbuf(g, b) = smem_h0 + (2 g + b) * HBUF
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int cl = (int)blockIdx.x / CS;
+  const int cl = (int)blockIdx.x / CS + p.cl0;
   const int e = (int)(rank & 1);
   const int rh = e ^ p.nswap;
   const int j = (int)rank;
@@ -713,6 +714,8 @@ constexpr uint32_t CLB_BT = 32 * CLB_GS;           // 16896 B: 32 k-granules (4 
 struct ClusterBP {
   int n, steps, nswap, ng;
   const bf16* gates; const bf16* cseq; const bf16* dhext; const bf16* dh_last; int ld_last;
+  int cl0;                // first cluster of this launch (a launch may cover a sub-range of the batch's clusters)
+  const bf16* dc_last;    // time-chunked sweeps: cell-state gradient carried in from the chunk after this one (same leading dimension as dh_last)
   bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
   const bf16* upack;      // [CS][MT][128 units][256 gate columns of the pair]
   int l2_prefetch;        // > 0: prefetch the stash of step t - l2_prefetch into L2
@@ -747,7 +750,7 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int cl = (int)blockIdx.x / CS;
+  const int cl = (int)blockIdx.x / CS + p.cl0;
   const int e = (int)(rank & 1), q = (int)(rank >> 1);
   const int rhs = e ^ p.nswap;                                      // which 32 rows of a group this CTA does the cell math for
   const int T = p.steps, n = p.n, ng = p.ng;
@@ -881,6 +884,7 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
       float dc[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) dc[u] = 0.f;
+      if (p.dc_last && row_ok) unpack8(__ldg(reinterpret_cast<const uint4*>(p.dc_last + (size_t)m * p.ld_last + u0)), dc);
 
       for (int it = 0; it <= T; ++it) {
         const int t = T - 1 - it;
@@ -1040,6 +1044,8 @@ constexpr uint32_t CLQ_GRP = 2 * CLQ_BT + 8 * CLQ_MSG; // per group: 2 B tiles |
 struct ClusterQP {
   int n, steps, nswap, ng, l2_prefetch;
   const bf16* gates; const bf16* cseq; const bf16* dhext; const bf16* dh_last; int ld_last;
+  int cl0;                // first cluster of this launch (a launch may cover a sub-range of the batch's clusters)
+  const bf16* dc_last;    // time-chunked sweeps: cell-state gradient carried in from the chunk after this one (same leading dimension as dh_last)
   bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
   const bf16* upack;      // [16][128 output units][512 k]
   uint8_t* xbuf;          // dG exchange slots [clusters][ng][2][16 CTAs][2 row halves][8 KB]
@@ -1058,7 +1064,7 @@ rec_cluster_bwd4_kernel(const ClusterQP p) {
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int cl = (int)blockIdx.x / CS;
+  const int cl = (int)blockIdx.x / CS + p.cl0;
   const int e = (int)(rank & 1), kq = (int)(rank >> 2), c = (int)(rank & 3);
   const int T = p.steps, n = p.n, ng = p.ng;
   const int row0 = cl * CL_ROWS * ng;
@@ -1195,6 +1201,7 @@ rec_cluster_bwd4_kernel(const ClusterQP p) {
       float dc[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) dc[u] = 0.f;
+      if (p.dc_last && row_ok) unpack8(__ldg(reinterpret_cast<const uint4*>(p.dc_last + (size_t)m * p.ld_last + u0)), dc);
 
       for (int it = 0; it <= T; ++it) {
         const int t = T - 1 - it;
@@ -1469,10 +1476,14 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
     if (CS == 16 && (groups + 1) / 2 > 7 && (groups + 2) / 3 <= 7) ng = 3;
     if (CS == 8 && groups <= env_int("MVAE_CL_NG1_MAX", 8)) ng = 1;   // 8-CTA clusters are plentiful: one group each has the shortest chain
   }
+  if (a.ng > 0) ng = a.ng;
   ng = std::max(1, std::min(std::min(ng, CL2_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
+  const int cl0 = std::min(std::max(a.cl0, 0), clusters), ncl = a.ncl > 0 ? std::min(a.ncl, clusters - cl0) : clusters - cl0;
+  if (ncl <= 0) return;
   const size_t smem = 1024 + scr_bytes + (size_t)ng * 2 * hbuf;
   Cluster2P p{};
+  p.cl0 = cl0;
   p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.dbg = env_int("MVAE_CL_DBG", 0);
   // a.t0 > 0: this launch continues the sequence at step t0 (time-chunked recurrences): every time-indexed buffer is simply offset
   const size_t t0 = (size_t)a.t0, nn = (size_t)a.n;
@@ -1486,7 +1497,7 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   MVAE_REQUIRE(p.hx != nullptr, "cluster forward: exchange buffer missing");
   MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * CL_STAGE <= rec_cluster_hx_bytes(a.n, H), "cluster forward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(ncl * CS)); cfg.blockDim = dim3(CLF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1520,11 +1531,20 @@ void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
   if (ng <= 0) ng = (CS == 8 && groups <= env_int("MVAE_CL_NG1_MAX", 8)) ? 1 : CLB_MAXG;
   ng = std::max(1, std::min(std::min(ng, CLB_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
+  const int cl0 = std::min(std::max(a.cl0, 0), clusters), ncl = a.ncl > 0 ? std::min(a.ncl, clusters - cl0) : clusters - cl0;
+  if (ncl <= 0) return;
   const size_t smem = 1024 + (size_t)ng * grp;
   ClusterBP p{};
+  p.cl0 = cl0;
   p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng;
-  p.gates = (const bf16*)a.gates; p.cseq = (const bf16*)a.cseq; p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last;
-  p.dG = (bf16*)a.dG; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  {
+    // a.t0 > 0: this launch sweeps steps [t0, t0 + steps) of the sequence in reverse (time-chunked sweeps): every time-indexed buffer is offset,
+    // the carry from the later chunk arrives through dh_last / dc_last and leaves through dS_h / dS_c
+    const size_t t0 = (size_t)a.t0, nn = (size_t)a.n, Hh = (size_t)a.H;
+    p.gates = (const bf16*)a.gates + t0 * nn * 4 * Hh; p.cseq = (const bf16*)a.cseq + t0 * nn * Hh;
+    p.dhext = a.dhext ? (const bf16*)a.dhext + t0 * nn * Hh : nullptr; p.dh_last = (const bf16*)a.dh_last; p.dc_last = (const bf16*)a.dc_last; p.ld_last = a.ld_last;
+    p.dG = (bf16*)a.dG + t0 * nn * 4 * Hh; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  }
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace;
   MVAE_REQUIRE(p.upack != nullptr, "cluster backward: packed weights missing");
   p.l2_prefetch = env_int("MVAE_CLB_PREFETCH", 2);
@@ -1532,7 +1552,7 @@ void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
   p.via_l2 = env_int("MVAE_CLB_L2", 0) && p.xbuf != nullptr;
   if (p.via_l2) MVAE_REQUIRE((size_t)clusters * ng * CS * ND * CLB_MSG <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(ncl * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1565,16 +1585,25 @@ void launch_bwd4(const RecPersistArgs& a, cudaStream_t st) {
   if (ng <= 0) ng = CLB_MAXG;
   ng = std::max(1, std::min(std::min(ng, CLB_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
+  const int cl0 = std::min(std::max(a.cl0, 0), clusters), ncl = a.ncl > 0 ? std::min(a.ncl, clusters - cl0) : clusters - cl0;
+  if (ncl <= 0) return;
   const size_t smem = 1024 + (size_t)ng * CLQ_GRP;
   ClusterQP p{};
+  p.cl0 = cl0;
   p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.l2_prefetch = env_int("MVAE_CLB_PREFETCH", 2);
-  p.gates = (const bf16*)a.gates; p.cseq = (const bf16*)a.cseq; p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last;
-  p.dG = (bf16*)a.dG; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  {
+    // a.t0 > 0: this launch sweeps steps [t0, t0 + steps) of the sequence in reverse (time-chunked sweeps): every time-indexed buffer is offset,
+    // the carry from the later chunk arrives through dh_last / dc_last and leaves through dS_h / dS_c
+    const size_t t0 = (size_t)a.t0, nn = (size_t)a.n, Hh = (size_t)a.H;
+    p.gates = (const bf16*)a.gates + t0 * nn * 4 * Hh; p.cseq = (const bf16*)a.cseq + t0 * nn * Hh;
+    p.dhext = a.dhext ? (const bf16*)a.dhext + t0 * nn * Hh : nullptr; p.dh_last = (const bf16*)a.dh_last; p.dc_last = (const bf16*)a.dc_last; p.ld_last = a.ld_last;
+    p.dG = (bf16*)a.dG + t0 * nn * 4 * Hh; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
+  }
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace; p.xbuf = (uint8_t*)a.partial;
   MVAE_REQUIRE(p.upack != nullptr && p.xbuf != nullptr, "cluster backward: packed weights / exchange buffer missing");
   MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * 2 * CLQ_PIECE <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(ncl * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

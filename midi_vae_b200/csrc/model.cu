@@ -96,6 +96,7 @@ void Model::build_workspace() {
     rec_hx = alloc(hxb); rec_hx2 = alloc(hxb);
   }
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
+  if (chunks > 1) for (int i = 0; i < 4; ++i) rec_carry[i] = alloc(n * H * a);
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
   for (int k = 0; k < nd; ++k) rec_bufs(dec_notes[k], true);
@@ -167,6 +168,9 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_FUSE_XPROJ"); fuse_xproj = use_cluster_fwd && (e ? atoi(e) != 0 : true); }
   { const char* e = getenv("MVAE_BRANCH"); use_branch = use_cluster_fwd && use_cluster_bwd && (e ? atoi(e) != 0 : true); }
   if (side_sms <= 0) side_sms = std::max(16, sm_count - 16 * ((NB + 127) / 128));
+  { const char* e = getenv("MVAE_CHUNKS"); chunks = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
+  { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
+  if (chunks > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
@@ -187,6 +191,8 @@ Model::~Model() {
   if (stream) cudaStreamDestroy(stream);
   if (side) cudaStreamDestroy(side);
   if (st_branch) cudaStreamDestroy(st_branch);
+  if (st_pipe) cudaStreamDestroy(st_pipe);
+  for (auto& ev : ev_pool) cudaEventDestroy(ev);
   if (ev_bfork) cudaEventDestroy(ev_bfork);
   if (ev_bjoin) cudaEventDestroy(ev_bjoin);
   if (ev_fork) cudaEventDestroy(ev_fork);
@@ -298,7 +304,7 @@ void Model::gemm(GemmArgs g) { gemm_on(g, st, sm_count); }
 void Model::gemm_on(GemmArgs g, cudaStream_t s, int sms) {
   g.in_type = act;
   // one scheduler word pair per stream: launches that share a pair must be stream-ordered
-  int* sched = gemm_sched + (s == side ? 2 : (s == st_branch ? 4 : 0));
+  int* sched = gemm_sched + (s == side ? 2 : (s == st_branch ? 4 : (s == st_pipe && st_pipe ? 6 : 0)));
   if (act == DT_BF16 && gemm_tc_supported(g)) gemm_tc(g, s, sms, sched);
   else gemm_simt(g, s);
 }
@@ -381,9 +387,10 @@ void Model::rec_forward_prepare(const FwdJob& j, int n) {
   prof_end();
 }
 
-RecPersistArgs Model::fwd_args(const FwdJob& j, int n, int slot, int hs) {
+RecPersistArgs Model::fwd_args(const FwdJob& j, int n, int slot, int hs, bool pack) {
   Rec& r = *j.r;
-  if (use_cluster_fwd) rec_cluster_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, r.variant, st);
+  if (!pack) {}
+  else if (use_cluster_fwd) rec_cluster_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, r.variant, st);
   else rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, hs, r.variant, st);
   RecPersistArgs a;
   a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = slot ? rec_flags2 : rec_flags;
@@ -454,7 +461,7 @@ void Model::rec_steps_forward(Rec& r, int n, int t0, int t1) {
 }
 
 // --------------------------------------------------------------------------------------------- one recurrence, backward
-RecPersistArgs Model::bwd_args(const BwdJob& j, int n, int slot, int hs) {
+RecPersistArgs Model::bwd_args(const BwdJob& j, int n, int slot, int hs, bool pack) {
   Rec& r = *j.r;
   RecPersistArgs a;
   a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant;
@@ -463,7 +470,7 @@ RecPersistArgs Model::bwd_args(const BwdJob& j, int n, int slot, int hs) {
   a.dhext = j.use_dhext ? r.dhext : nullptr; a.dh_last = j.dh_last; a.ld_last = j.ld_last; a.dG = r.xw;
   a.dS_h = j.dS_h; a.dS_c = j.dS_c; a.ldS = j.ldS;
   if (use_cluster_bwd) {
-    rec_cluster_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, r.variant, st);
+    if (pack) rec_cluster_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, r.variant, st);
     a.upack_bwd = r.upack_b; a.partial = slot ? rec_partial2 : rec_partial;
   } else if (r.upack_b && hs) {
     rec_persist_pack_u_bwd(Wf(r.iU), ld(r.iU), r.upack_b, H, hs, r.variant, st);
@@ -570,6 +577,7 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms)
 
 // a stack of layers (top first) plus independent side recurrences: pair the i-th stack layer with the i-th side recurrence
 void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n, bool last_group) {
+  if (stack.size() >= 2 && chunked_ok(stack[0].r->steps)) { stack_backward_chunked(stack, side, n, last_group); return; }
   if (use_branch) {
     // the stack (top layer first) is the critical chain; the independent recurrences run next to it on the branch stream
     branch_fork();
@@ -597,10 +605,169 @@ void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& 
   }
 }
 
+// --------------------------------------------------------------------------------------------- time-chunked layer pipeline
+cudaEvent_t Model::next_event() {
+  if (ev_next == ev_pool.size()) {
+    cudaEvent_t e;
+    MVAE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_pool.push_back(e);
+  }
+  return ev_pool[ev_next++];
+}
+
+bool Model::chunked_ok(int steps) const {
+  return chunks > 1 && use_branch && use_cluster_fwd && use_cluster_bwd && steps % chunks == 0 && steps / chunks >= 8;
+}
+
+// Forward over a stack of layers (jobs[0] = bottom).  Layer k runs as `chunks` launches of T / chunks steps (the cluster kernel continues from the
+// h slab / c stash the previous launch left); the moment chunk c of layer k is done, the input projection of chunk c of layer k + 1 starts on
+// the pipe stream, and layer k + 1 chunk c waits only for that.  The independent velocity / instrument recurrences go to the branch stream at
+// the first launch of layer `branch_at`, limited to the cluster slots the stack leaves free (a straggling branch cluster would otherwise take
+// a slot between two chunks of the stack and halve its width).
+void Model::stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel, FwdJob* binstr) {
+  const int L = (int)jobs.size(), NC = chunks, Tc = jobs[0].r->steps / NC;
+  const int bat = std::min(branch_at, L - 1);
+  ev_next = 0;
+  rec_forward_prepare(jobs[0], n);                      // one-hot table / whole projection of the bottom layer + its initial-state slab
+  prof_begin(PC_REC_FWD);
+  for (int k = 1; k < L; ++k) {
+    Rec& r = *jobs[k].r;
+    if (jobs[k].h0) k_copy2d(act, act, n, H, jobs[k].h0, jobs[k].ld0, r.hseq, H, st);
+    else MVAE_CUDA(cudaMemsetAsync(r.hseq, 0, (size_t)n * H * asz(), st));
+  }
+  std::vector<RecPersistArgs> base((size_t)L);
+  for (int k = 0; k < L; ++k) base[(size_t)k] = fwd_args(jobs[k], n, 0, 0, true);   // packs U (main stream, before the first launch)
+  // cluster slots the branch may hold while the stack runs: 16-CTA clusters: 7 co-resident, the stack uses ceil(groups / 2)
+  const int groups = (n + 63) / 64;
+  const int free_slots = H == 512 ? std::max(1, 7 - (groups + 1) / 2) : 0;
+  auto launch_branch = [&]() {
+    branch_begin();
+    for (FwdJob* j : {bvel, binstr}) {
+      if (!j) continue;
+      rec_forward_prepare(*j, n);
+      RecPersistArgs a = fwd_args(*j, n, cur_slot, 0, true);
+      if (free_slots > 0 && (groups + 1) / 2 > free_slots) a.ng = 3;     // fewer, wider clusters
+      const int ngb = a.ng > 0 ? a.ng : 2, ncl_all = (groups + ngb - 1) / ngb;
+      if (free_slots > 0 && ncl_all > free_slots) {
+        for (int c0 = 0; c0 < ncl_all; c0 += free_slots) { a.cl0 = c0; a.ncl = free_slots; rec_cluster_forward(a, st); }
+      } else {
+        rec_cluster_forward(a, st);
+      }
+    }
+    branch_end();
+  };
+  std::vector<cudaEvent_t> proj_done((size_t)NC), proj_next((size_t)NC);
+  for (int k = 0; k < L; ++k) {
+    for (int c = 0; c < NC; ++c) {
+      if (k > 0) MVAE_CUDA(cudaStreamWaitEvent(st, proj_done[(size_t)c], 0));
+      RecPersistArgs a = base[(size_t)k];
+      a.t0 = c * Tc; a.steps = Tc;
+      if (k == bat && c == 0) fork_if_pending();
+      rec_cluster_forward(a, st);
+      if (k == bat && c == 0 && (bvel || binstr)) launch_branch();
+      if (k + 1 < L) {
+        Rec& rn = *jobs[k + 1].r;
+        cudaEvent_t e = next_event();
+        MVAE_CUDA(cudaEventRecord(e, st));
+        MVAE_CUDA(cudaStreamWaitEvent(st_pipe, e, 0));
+        GemmArgs g; g.M = Tc * n; g.N = G; g.K = rn.Din; g.A = slab(jobs[k].r->hseq, (long)c * Tc + 1, (long)n * H); g.lda = rn.ldin;
+        g.B = W(rn.iW); g.ldb = ld(rn.iW); g.C = slab(rn.xw, (long)c * Tc, (long)n * G); g.ldc = G; g.c_type = act; g.bias = Wf(rn.ib);
+        gemm_on(g, st_pipe, sm_count);
+        cudaEvent_t d = next_event();
+        MVAE_CUDA(cudaEventRecord(d, st_pipe));
+        proj_next[(size_t)c] = d;
+      }
+    }
+    proj_done.swap(proj_next);
+  }
+  prof_end();
+}
+
+// Reverse sweeps over a stack of layers (stack[0] = top).  Chunks run latest-first; the (dh, dc) carry between two chunks of a layer goes
+// through rec_carry (bf16, ping-pong); dx = dG W^T of a chunk starts on the pipe stream as soon as the chunk's dG is complete, and the layer
+// below waits per chunk.  Weight gradients of a layer are whole-sequence GEMMs on the side stream after its last chunk.
+void Model::stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJob>& sidej, int n, bool last_group) {
+  const int L = (int)stack.size(), NC = chunks, Tc = stack[0].r->steps / NC;
+  ev_next = 0;
+  std::vector<RecPersistArgs> base((size_t)L);
+  for (int k = 0; k < L; ++k) base[(size_t)k] = bwd_args(stack[k], n, 0, 0, true);   // packs U^T (main stream)
+  const int groups = (n + 63) / 64;
+  const int free_slots = H == 512 ? std::max(1, 7 - (groups + 1) / 2) : 0;
+  auto launch_branch = [&]() {
+    branch_begin();
+    for (auto& j : sidej) {
+      prof_begin(PC_REC_BWD);
+      RecPersistArgs a = bwd_args(j, n, cur_slot, 0, true);
+      const int ncl_all = (groups + 1) / 2;
+      if (free_slots > 0 && ncl_all > free_slots) {
+        for (int c0 = 0; c0 < ncl_all; c0 += free_slots) { a.cl0 = c0; a.ncl = free_slots; rec_cluster_backward(a, st); }
+      } else {
+        rec_cluster_backward(a, st);
+      }
+      prof_end();
+      rec_backward_gemms(j, n);
+    }
+    branch_end();
+  };
+  branch_fork();
+  std::vector<cudaEvent_t> dx_done((size_t)NC), dx_next((size_t)NC);
+  for (int k = 0; k < L; ++k) {
+    BwdJob& j = stack[k];
+    Rec& r = *j.r;
+    prof_begin(PC_REC_BWD);
+    for (int i = 0; i < NC; ++i) {
+      const int c = NC - 1 - i;                         // chunk of steps [c Tc, (c + 1) Tc)
+      if (k > 0) MVAE_CUDA(cudaStreamWaitEvent(st, dx_done[(size_t)c], 0));
+      RecPersistArgs a = base[(size_t)k];
+      a.t0 = c * Tc; a.steps = Tc;
+      if (i > 0) { a.dh_last = rec_carry[(i - 1) & 1]; a.dc_last = rec_carry[2 + ((i - 1) & 1)]; a.ld_last = H; }
+      if (i + 1 < NC) { a.dS_h = rec_carry[i & 1]; a.dS_c = rec_carry[2 + (i & 1)]; a.ldS = H; }
+      if (k == 0 && i == 0) fork_if_pending();
+      rec_cluster_backward(a, st);
+      if (j.need_dx) {
+        cudaEvent_t e = next_event();
+        MVAE_CUDA(cudaEventRecord(e, st));
+        MVAE_CUDA(cudaStreamWaitEvent(st_pipe, e, 0));
+        GemmArgs g; g.M = Tc * n; g.N = r.Din; g.K = G; g.A = slab(r.xw, (long)c * Tc, (long)n * G); g.lda = G; g.B = W(r.iW); g.ldb = ld(r.iW);
+        g.transB = true; g.C = slab(j.dx_out, (long)c * Tc, (long)n * H); g.ldc = H; g.c_type = act;
+        gemm_on(g, st_pipe, sm_count);
+        cudaEvent_t d = next_event();
+        MVAE_CUDA(cudaEventRecord(d, st_pipe));
+        dx_next[(size_t)c] = d;
+      }
+    }
+    prof_end();
+    dx_done.swap(dx_next);
+    const bool tail = last_group && k + 1 == L;
+    if (use_side) {
+      MVAE_CUDA(cudaEventRecord(ev_fork, st));          // dG of this layer is final here
+      MVAE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      rec_backward_wgrads(j, n, side, tail ? sm_count : side_sms);
+    } else {
+      rec_backward_wgrads(j, n, st, sm_count);
+    }
+    if (k == 0 && !sidej.empty()) launch_branch();      // issued after the top layer's weight gradients so that those are first in the side stream
+  }
+  branch_join();
+}
+
 // --------------------------------------------------------------------------------------------- encoder (vae_definition.py:443-516)
 void Model::encoder_forward(int n) {
   // the first pitch layer and the velocity stream are independent and equally long: they share a launch
   FwdJob jv; jv.r = &enc_vel; jv.kind = IN_RANK1; jv.X = slab(Xv_ext, 1, (long)n * VD);
+  if (ne >= 2 && !inference_pass && chunked_ok(T)) {
+    std::vector<FwdJob> jobs((size_t)ne);
+    for (int k = 0; k < ne; ++k) {
+      FwdJob& jp = jobs[(size_t)k]; jp.r = &enc_pitch[k]; jp.kind = IN_DENSE;
+      jp.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
+      if (k == 0) { jp.onehot = true; jp.idx = cur_pitch; jp.idx_ld = T; jp.idx_shift = 0; }
+    }
+    FwdJob ji; ji.r = &enc_instr; ji.kind = IN_DENSE; ji.X = slab(Xi_ext, 1, (long)n * ID);
+    branch_fork();
+    stack_forward_chunked(jobs, n, &jv, &ji);
+    branch_join();
+    return;
+  }
   if (use_branch) {
     branch_fork();
     for (int k = 0; k < ne; ++k) {
@@ -665,8 +832,22 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
   auto st1 = [&](int r) { return (const char*)S + (size_t)(2 * r) * H * asz(); };
   auto st2 = [&](int r) { return (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
   FwdJob jv; jv.r = &dec_vel; jv.kind = tf ? IN_RANK1 : IN_NONE; jv.X = tf ? Xv_ext : nullptr; jv.h0 = st1(nd + 1); jv.c0 = st2(nd + 1); jv.ld0 = nS * H;
-  if (use_branch) branch_fork();
-  for (int k = 0; k < nd; ++k) {
+  const bool chunked = nd >= 2 && !inference_pass && chunked_ok(T);
+  if (chunked) {
+    std::vector<FwdJob> jobs((size_t)nd);
+    for (int k = 0; k < nd; ++k) {
+      FwdJob& jp = jobs[(size_t)k]; jp.r = &dec_notes[k]; jp.h0 = st1(k); jp.c0 = st2(k); jp.ld0 = nS * H;
+      if (k == 0) { jp.kind = tf ? IN_DENSE : IN_NONE; jp.X = tf ? Y_ext_cur : nullptr; }
+      else { jp.kind = IN_DENSE; jp.X = slab(dec_notes[k - 1].hseq, 1, (long)n * H); }
+      if (k == 0 && tf) { jp.onehot = true; jp.idx = cur_target; jp.idx_ld = T; jp.idx_shift = 1; }
+    }
+    FwdJob ji; ji.r = &dec_instr; ji.kind = tf ? IN_DENSE : IN_NONE; ji.X = tf ? Xi_ext : nullptr; ji.h0 = st1(nd); ji.c0 = st2(nd); ji.ld0 = nS * H;
+    branch_fork();
+    stack_forward_chunked(jobs, n, &jv, &ji);
+    branch_join();
+  }
+  if (use_branch && !chunked) branch_fork();
+  for (int k = 0; k < nd && !chunked; ++k) {
     FwdJob jp; jp.r = &dec_notes[k]; jp.h0 = st1(k); jp.c0 = st2(k); jp.ld0 = nS * H;
     if (k == 0) { jp.kind = tf ? IN_DENSE : IN_NONE; jp.X = tf ? Y_ext_cur : nullptr; }
     else { jp.kind = IN_DENSE; jp.X = slab(dec_notes[k - 1].hseq, 1, (long)n * H); }
@@ -683,7 +864,8 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
       rec_forward_jobs(&jp, k == 0 ? &jv : nullptr, n);
     }
   }
-  if (use_branch) branch_join();
+  if (chunked) {}
+  else if (use_branch) branch_join();
   else rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
   prof_begin(PC_GEMM);
   { GemmArgs g; g.M = T * n; g.N = Dp; g.K = H; g.A = slab(dec_notes[nd - 1].hseq, 1, (long)n * H); g.lda = H; g.B = W(iWy); g.ldb = ld(iWy);

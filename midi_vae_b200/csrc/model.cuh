@@ -145,6 +145,19 @@ struct Model {
   void branch_begin();
   void branch_end();
   void branch_join();
+  // time-chunked layer pipeline (MVAE_CHUNKS > 1): a stack of layers runs its recurrences in `chunks` launches of T / chunks steps each, so that
+  // the batched GEMM between two layers (input projection forward, dx backward) of chunk c runs on the pipe stream while the producing
+  // layer is already working on chunk c + 1: the GEMMs leave the critical chain
+  int chunks = 1;
+  int branch_at = 0;                  // the branch recurrences fork at the first launch of this layer of the stack (0 = first layer)
+  cudaStream_t st_pipe = nullptr;
+  std::vector<cudaEvent_t> ev_pool;   // disable-timing events, handed out round-robin within a step
+  size_t ev_next = 0;
+  cudaEvent_t next_event();
+  void* rec_carry[4] = {nullptr, nullptr, nullptr, nullptr};   // (n, H) act: dh / dc carried between the chunks of a reverse sweep (ping-pong)
+  bool chunked_ok(int steps) const;
+  void stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel, FwdJob* binstr);
+  void stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n, bool last_group);
   const unsigned char* cur_pitch = nullptr;   // device u8 rolls of the batch in flight (class indices)
   const unsigned char* cur_target = nullptr;
   bool inference_pass = false;      // forward only (style transfer / predict): the recurrences skip the BPTT stash
@@ -200,9 +213,9 @@ struct Model {
   void rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, const void* c0, int ld0);
   void rec_steps_forward(Rec& r, int n, int t0, int t1);
   void rec_forward_prepare(const FwdJob& j, int n);
-  RecPersistArgs fwd_args(const FwdJob& j, int n, int slot, int hs);
+  RecPersistArgs fwd_args(const FwdJob& j, int n, int slot, int hs, bool pack = true);
   void rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n);
-  RecPersistArgs bwd_args(const BwdJob& j, int n, int slot, int hs);
+  RecPersistArgs bwd_args(const BwdJob& j, int n, int slot, int hs, bool pack = true);
   void rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n);
   void rec_backward_gemms(const BwdJob& j, int n, bool tail = false);
   void rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n, bool last_group = false);

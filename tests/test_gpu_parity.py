@@ -251,6 +251,37 @@ def test_persistent_rnn_matches_streamed(shape, feedback, variant):
         assert np.abs(gs[k] - gp[k]).max() <= 3e-2 * scale + 1e-9, (k, float(np.abs(gs[k] - gp[k]).max()), float(scale))
 
 
+@pytest.mark.parametrize("shape,chunks", [((64, 256, 32, 70), 4), ((32, 512, 48, 130), 2), ((64, 512, 48, 520), 4), ((48, 512, 24, 65), 3)])
+@pytest.mark.parametrize("feedback,variant", [("teacher_forced", "standard"), ("as_wired", "recurrentshop_recalled")])
+def test_time_chunked_layer_pipeline_matches_whole_sequence_launches(shape, chunks, feedback, variant, monkeypatch):
+    """MVAE_CHUNKS > 1: the layer stacks run their cluster recurrences as several launches of T / chunks steps (forward: continue from the h slab /
+    c stash; backward: (dh, dc) carried through a bf16 buffer), with the inter-layer GEMMs of a chunk on a pipe stream and the branch
+    recurrences limited to the free cluster slots (sub-range launches, 3 groups per cluster).  Same arithmetic as the whole-sequence
+    launches except for the bf16 rounding of c / dc at the chunk boundaries.  520 rows = 9 groups = 5 clusters (ragged last one)."""
+    T, H, L, n = shape
+    res = {}
+    for nc in (1, chunks):
+        monkeypatch.setenv("MVAE_CHUNKS", str(nc))
+        ecfg, _ = util.make_cfgs(T=T, H=H, L=L, feedback=feedback, variant=variant, precision="bf16", max_batch=n, rnn_mode="persistent")
+        w = util.make_weights(ecfg)
+        eng = _engine(ecfg, w)
+        r, hist, eps, sw = util.make_batch(ecfg, n, weights=True)
+        m = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)
+        g = eng.get_grads()
+        m2 = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)      # a second step: buffers / events are reused
+        res[nc] = (m, g, m2)
+        eng.close()
+    monkeypatch.delenv("MVAE_CHUNKS")
+    (ma, ga, ma2), (mb, gb, mb2) = res[1], res[chunks]
+    for k in METRIC_KEYS:
+        tol_k = 0.05 if "acc" in k else 2e-3 * max(1.0, abs(ma[k]))
+        assert abs(ma[k] - mb[k]) <= tol_k, (k, ma[k], mb[k])
+        assert abs(ma2[k] - mb2[k]) <= (0.05 if "acc" in k else 5e-3 * max(1.0, abs(ma2[k]))), (k, ma2[k], mb2[k])
+    for k in ga:
+        scale = max(np.abs(ga[k]).max(), 1e-6)
+        assert np.abs(ga[k] - gb[k]).max() <= 1e-2 * scale + 1e-9, (k, float(np.abs(ga[k] - gb[k]).max()), float(scale))
+
+
 def test_cluster_rnn_sigmoid_gates():
     """The logistic-sigmoid gate variant (north_star's wording; the reference default is hard_sigmoid) through the cluster kernels."""
     T, H, L, n = 16, 256, 32, 70
