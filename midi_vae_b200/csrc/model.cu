@@ -96,7 +96,7 @@ void Model::build_workspace() {
     rec_hx = alloc(hxb); rec_hx2 = alloc(hxb);
   }
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
-  if (chunks > 1) for (int i = 0; i < 4; ++i) rec_carry[i] = alloc(n * H * a);
+  if (chunks_bwd > 1) for (int i = 0; i < 4; ++i) rec_carry[i] = alloc(n * H * a);
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
   for (int k = 0; k < nd; ++k) rec_bufs(dec_notes[k], true);
@@ -169,8 +169,10 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_BRANCH"); use_branch = use_cluster_fwd && use_cluster_bwd && (e ? atoi(e) != 0 : true); }
   if (side_sms <= 0) side_sms = std::max(16, sm_count - 16 * ((NB + 127) / 128));
   { const char* e = getenv("MVAE_CHUNKS"); chunks = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
+  { const char* e = getenv("MVAE_CHUNKS_BWD"); chunks_bwd = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
+  { const char* e = getenv("MVAE_PIPE_SMS"); pipe_sms = e ? atoi(e) : 0; }
   { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
-  if (chunks > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
+  if (chunks > 1 || chunks_bwd > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
@@ -577,7 +579,7 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms)
 
 // a stack of layers (top first) plus independent side recurrences: pair the i-th stack layer with the i-th side recurrence
 void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n, bool last_group) {
-  if (stack.size() >= 2 && chunked_ok(stack[0].r->steps)) { stack_backward_chunked(stack, side, n, last_group); return; }
+  if (stack.size() >= 2 && chunked_ok(stack[0].r->steps, chunks_bwd)) { stack_backward_chunked(stack, side, n, last_group); return; }
   if (use_branch) {
     // the stack (top layer first) is the critical chain; the independent recurrences run next to it on the branch stream
     branch_fork();
@@ -615,8 +617,18 @@ cudaEvent_t Model::next_event() {
   return ev_pool[ev_next++];
 }
 
-bool Model::chunked_ok(int steps) const {
-  return chunks > 1 && use_branch && use_cluster_fwd && use_cluster_bwd && steps % chunks == 0 && steps / chunks >= 8;
+bool Model::chunked_ok(int steps, int nc) const {
+  return nc > 1 && use_branch && use_cluster_fwd && use_cluster_bwd && steps % nc == 0 && steps / nc >= 8;
+}
+
+// grid of a pipe-stream GEMM: only the SMs that stay free while the stack's and the branch's clusters are resident.  A larger grid would leave
+// CTAs pending; those take the SMs a finishing chunk releases and hold them until the GEMM runs out of tiles, so the next chunk's clusters
+// (16 free SMs in one GPC each) could not form
+int Model::pipe_grid(int n) const {
+  if (pipe_sms > 0) return std::min(pipe_sms, sm_count);
+  const int groups = (n + 63) / 64;
+  const int held = H == 512 ? 16 * 7 : 8 * 2 * std::min(groups, 8);
+  return std::max(16, sm_count - held);
 }
 
 // Forward over a stack of layers (jobs[0] = bottom).  Layer k runs as `chunks` launches of T / chunks steps (the cluster kernel continues from the
@@ -625,7 +637,7 @@ bool Model::chunked_ok(int steps) const {
 // the first launch of layer `branch_at`, limited to the cluster slots the stack leaves free (a straggling branch cluster would otherwise take
 // a slot between two chunks of the stack and halve its width).
 void Model::stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel, FwdJob* binstr) {
-  const int L = (int)jobs.size(), NC = chunks, Tc = jobs[0].r->steps / NC;
+  const int L = (int)jobs.size(), NC = chunks, Tc = jobs[0].r->steps / NC, psms = pipe_grid(n);
   const int bat = std::min(branch_at, L - 1);
   ev_next = 0;
   rec_forward_prepare(jobs[0], n);                      // one-hot table / whole projection of the bottom layer + its initial-state slab
@@ -672,7 +684,7 @@ void Model::stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel
         MVAE_CUDA(cudaStreamWaitEvent(st_pipe, e, 0));
         GemmArgs g; g.M = Tc * n; g.N = G; g.K = rn.Din; g.A = slab(jobs[k].r->hseq, (long)c * Tc + 1, (long)n * H); g.lda = rn.ldin;
         g.B = W(rn.iW); g.ldb = ld(rn.iW); g.C = slab(rn.xw, (long)c * Tc, (long)n * G); g.ldc = G; g.c_type = act; g.bias = Wf(rn.ib);
-        gemm_on(g, st_pipe, sm_count);
+        gemm_on(g, st_pipe, psms);
         cudaEvent_t d = next_event();
         MVAE_CUDA(cudaEventRecord(d, st_pipe));
         proj_next[(size_t)c] = d;
@@ -687,7 +699,7 @@ void Model::stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel
 // through rec_carry (bf16, ping-pong); dx = dG W^T of a chunk starts on the pipe stream as soon as the chunk's dG is complete, and the layer
 // below waits per chunk.  Weight gradients of a layer are whole-sequence GEMMs on the side stream after its last chunk.
 void Model::stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJob>& sidej, int n, bool last_group) {
-  const int L = (int)stack.size(), NC = chunks, Tc = stack[0].r->steps / NC;
+  const int L = (int)stack.size(), NC = chunks_bwd, Tc = stack[0].r->steps / NC, psms = pipe_grid(n);
   ev_next = 0;
   std::vector<RecPersistArgs> base((size_t)L);
   for (int k = 0; k < L; ++k) base[(size_t)k] = bwd_args(stack[k], n, 0, 0, true);   // packs U^T (main stream)
@@ -730,7 +742,7 @@ void Model::stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJo
         MVAE_CUDA(cudaStreamWaitEvent(st_pipe, e, 0));
         GemmArgs g; g.M = Tc * n; g.N = r.Din; g.K = G; g.A = slab(r.xw, (long)c * Tc, (long)n * G); g.lda = G; g.B = W(r.iW); g.ldb = ld(r.iW);
         g.transB = true; g.C = slab(j.dx_out, (long)c * Tc, (long)n * H); g.ldc = H; g.c_type = act;
-        gemm_on(g, st_pipe, sm_count);
+        gemm_on(g, st_pipe, psms);
         cudaEvent_t d = next_event();
         MVAE_CUDA(cudaEventRecord(d, st_pipe));
         dx_next[(size_t)c] = d;
@@ -755,7 +767,7 @@ void Model::stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJo
 void Model::encoder_forward(int n) {
   // the first pitch layer and the velocity stream are independent and equally long: they share a launch
   FwdJob jv; jv.r = &enc_vel; jv.kind = IN_RANK1; jv.X = slab(Xv_ext, 1, (long)n * VD);
-  if (ne >= 2 && !inference_pass && chunked_ok(T)) {
+  if (ne >= 2 && !inference_pass && chunked_ok(T, chunks)) {
     std::vector<FwdJob> jobs((size_t)ne);
     for (int k = 0; k < ne; ++k) {
       FwdJob& jp = jobs[(size_t)k]; jp.r = &enc_pitch[k]; jp.kind = IN_DENSE;
@@ -832,7 +844,7 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
   auto st1 = [&](int r) { return (const char*)S + (size_t)(2 * r) * H * asz(); };
   auto st2 = [&](int r) { return (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
   FwdJob jv; jv.r = &dec_vel; jv.kind = tf ? IN_RANK1 : IN_NONE; jv.X = tf ? Xv_ext : nullptr; jv.h0 = st1(nd + 1); jv.c0 = st2(nd + 1); jv.ld0 = nS * H;
-  const bool chunked = nd >= 2 && !inference_pass && chunked_ok(T);
+  const bool chunked = nd >= 2 && !inference_pass && chunked_ok(T, chunks);
   if (chunked) {
     std::vector<FwdJob> jobs((size_t)nd);
     for (int k = 0; k < nd; ++k) {

@@ -148,14 +148,16 @@ struct Model {
   // time-chunked layer pipeline (MVAE_CHUNKS > 1): a stack of layers runs its recurrences in `chunks` launches of T / chunks steps each, so that
   // the batched GEMM between two layers (input projection forward, dx backward) of chunk c runs on the pipe stream while the producing
   // layer is already working on chunk c + 1: the GEMMs leave the critical chain
-  int chunks = 1;
+  int chunks = 1, chunks_bwd = 1;     // forward / backward (MVAE_CHUNKS / MVAE_CHUNKS_BWD)
+  int pipe_sms = 0;                   // MVAE_PIPE_SMS: grid of a pipe-stream GEMM (0 = the SMs the resident clusters leave free)
+  int pipe_grid(int n) const;
   int branch_at = 0;                  // the branch recurrences fork at the first launch of this layer of the stack (0 = first layer)
   cudaStream_t st_pipe = nullptr;
   std::vector<cudaEvent_t> ev_pool;   // disable-timing events, handed out round-robin within a step
   size_t ev_next = 0;
   cudaEvent_t next_event();
   void* rec_carry[4] = {nullptr, nullptr, nullptr, nullptr};   // (n, H) act: dh / dc carried between the chunks of a reverse sweep (ping-pong)
-  bool chunked_ok(int steps) const;
+  bool chunked_ok(int steps, int nc) const;
   void stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel, FwdJob* binstr);
   void stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n, bool last_group);
   const unsigned char* cur_pitch = nullptr;   // device u8 rolls of the batch in flight (class indices)

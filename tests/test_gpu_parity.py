@@ -254,7 +254,7 @@ def test_persistent_rnn_matches_streamed(shape, feedback, variant):
 @pytest.mark.parametrize("shape,chunks", [((64, 256, 32, 70), 4), ((32, 512, 48, 130), 2), ((64, 512, 48, 520), 4), ((48, 512, 24, 65), 3)])
 @pytest.mark.parametrize("feedback,variant", [("teacher_forced", "standard"), ("as_wired", "recurrentshop_recalled")])
 def test_time_chunked_layer_pipeline_matches_whole_sequence_launches(shape, chunks, feedback, variant, monkeypatch):
-    """MVAE_CHUNKS > 1: the layer stacks run their cluster recurrences as several launches of T / chunks steps (forward: continue from the h slab /
+    """MVAE_CHUNKS / MVAE_CHUNKS_BWD > 1: the layer stacks run their cluster recurrences as several launches of T / chunks steps (forward: continue from the h slab /
     c stash; backward: (dh, dc) carried through a bf16 buffer), with the inter-layer GEMMs of a chunk on a pipe stream and the branch
     recurrences limited to the free cluster slots (sub-range launches, 3 groups per cluster).  Same arithmetic as the whole-sequence
     launches except for the bf16 rounding of c / dc at the chunk boundaries.  520 rows = 9 groups = 5 clusters (ragged last one)."""
@@ -262,6 +262,7 @@ def test_time_chunked_layer_pipeline_matches_whole_sequence_launches(shape, chun
     res = {}
     for nc in (1, chunks):
         monkeypatch.setenv("MVAE_CHUNKS", str(nc))
+        monkeypatch.setenv("MVAE_CHUNKS_BWD", str(nc))
         ecfg, _ = util.make_cfgs(T=T, H=H, L=L, feedback=feedback, variant=variant, precision="bf16", max_batch=n, rnn_mode="persistent")
         w = util.make_weights(ecfg)
         eng = _engine(ecfg, w)
@@ -272,6 +273,7 @@ def test_time_chunked_layer_pipeline_matches_whole_sequence_launches(shape, chun
         res[nc] = (m, g, m2)
         eng.close()
     monkeypatch.delenv("MVAE_CHUNKS")
+    monkeypatch.delenv("MVAE_CHUNKS_BWD")
     (ma, ga, ma2), (mb, gb, mb2) = res[1], res[chunks]
     for k in METRIC_KEYS:
         tol_k = 0.05 if "acc" in k else 2e-3 * max(1.0, abs(ma[k]))
