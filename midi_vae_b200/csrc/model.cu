@@ -649,6 +649,7 @@ void Model::stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel
   }
   std::vector<RecPersistArgs> base((size_t)L);
   for (int k = 0; k < L; ++k) base[(size_t)k] = fwd_args(jobs[k], n, 0, 0, true);   // packs U (main stream, before the first launch)
+  prof_end();
   // cluster slots the branch may hold while the stack runs: 16-CTA clusters: 7 co-resident, the stack uses ceil(groups / 2)
   const int groups = (n + 63) / 64;
   const int free_slots = H == 512 ? std::max(1, 7 - (groups + 1) / 2) : 0;
@@ -675,7 +676,9 @@ void Model::stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel
       RecPersistArgs a = base[(size_t)k];
       a.t0 = c * Tc; a.steps = Tc;
       if (k == bat && c == 0) fork_if_pending();
+      prof_begin(PC_REC_FWD);               // (prof_begin / prof_end pairs do not nest: the branch work below opens its own)
       rec_cluster_forward(a, st);
+      prof_end();
       if (k == bat && c == 0 && (bvel || binstr)) launch_branch();
       if (k + 1 < L) {
         Rec& rn = *jobs[k + 1].r;
@@ -692,7 +695,6 @@ void Model::stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel
     }
     proj_done.swap(proj_next);
   }
-  prof_end();
 }
 
 // Reverse sweeps over a stack of layers (stack[0] = top).  Chunks run latest-first; the (dh, dc) carry between two chunks of a layer goes
