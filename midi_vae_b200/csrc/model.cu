@@ -171,6 +171,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_CHUNKS"); chunks = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
   { const char* e = getenv("MVAE_CHUNKS_BWD"); chunks_bwd = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
   { const char* e = getenv("MVAE_PIPE_SMS"); pipe_sms = e ? atoi(e) : 0; }
+  { const char* e = getenv("MVAE_WGRAD_CHUNKS"); wgrad_per_chunk = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
   if (chunks > 1 || chunks_bwd > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
   build_params();
@@ -556,22 +557,26 @@ void Model::rec_backward_gemms(const BwdJob& j, int n, bool tail) {
   else rec_backward_wgrads(j, n, st, sm_count);
 }
 
-void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms) {
+void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms, int t0, int nsteps) {
+  // steps [t0, t0 + nsteps) of the sequence (default: all): every product accumulates into the zeroed gradient arena, so a sequence may be
+  // covered by several calls (time-chunked sweeps hand their chunks over as soon as they are complete)
   Rec& r = *j.r;
-  const long rows = (long)r.steps * n;
-  void* dG = r.xw;
+  if (nsteps < 0) nsteps = r.steps - t0;
+  const long rows = (long)nsteps * n;
+  const void* dG = slab(r.xw, t0, (long)n * G);
+  const void* Xc = j.X ? (const char*)j.X + (size_t)t0 * n * (j.kind == IN_RANK1 ? VD : r.ldin) * asz() : nullptr;
   prof_begin(PC_GEMM, s);
   {  // dU += Hprev^T dG
-    GemmArgs g; g.M = H; g.N = G; g.K = (int)rows; g.A = r.hseq; g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
+    GemmArgs g; g.M = H; g.N = G; g.K = (int)rows; g.A = slab(r.hseq, t0, (long)n * H); g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
     gemm_on(g, s, sms);
   }
   if (j.kind == IN_DENSE) {  // dW += X^T dG
-    GemmArgs g; g.M = r.Din; g.N = G; g.K = (int)rows; g.A = j.X; g.lda = r.ldin; g.transA = true; g.B = dG; g.ldb = G;
+    GemmArgs g; g.M = r.Din; g.N = G; g.K = (int)rows; g.A = Xc; g.lda = r.ldin; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iW); g.ldc = ld(r.iW); g.c_type = DT_F32; g.accumulate = true;
     gemm_on(g, s, sms);
   } else if (j.kind == IN_RANK1) {
-    k_colsum(act, rows, G, G, dG, j.X, VD, Gp(r.iW), s);
+    k_colsum(act, rows, G, G, dG, Xc, VD, Gp(r.iW), s);
   }
   k_colsum(act, rows, G, G, dG, nullptr, 0, Gp(r.ib), s);
   prof_end(s);
@@ -738,9 +743,9 @@ void Model::stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJo
       if (i + 1 < NC) { a.dS_h = rec_carry[i & 1]; a.dS_c = rec_carry[2 + (i & 1)]; a.ldS = H; }
       if (k == 0 && i == 0) fork_if_pending();
       rec_cluster_backward(a, st);
+      cudaEvent_t e = nullptr;
+      if (j.need_dx || (use_side && wgrad_per_chunk)) { e = next_event(); MVAE_CUDA(cudaEventRecord(e, st)); }
       if (j.need_dx) {
-        cudaEvent_t e = next_event();
-        MVAE_CUDA(cudaEventRecord(e, st));
         MVAE_CUDA(cudaStreamWaitEvent(st_pipe, e, 0));
         GemmArgs g; g.M = Tc * n; g.N = r.Din; g.K = G; g.A = slab(r.xw, (long)c * Tc, (long)n * G); g.lda = G; g.B = W(r.iW); g.ldb = ld(r.iW);
         g.transB = true; g.C = slab(j.dx_out, (long)c * Tc, (long)n * H); g.ldc = H; g.c_type = act;
@@ -749,11 +754,18 @@ void Model::stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJo
         MVAE_CUDA(cudaEventRecord(d, st_pipe));
         dx_next[(size_t)c] = d;
       }
+      if (use_side && wgrad_per_chunk) {   // the chunk's dG is final: its share of the weight gradients can start now
+        prof_end();
+        MVAE_CUDA(cudaStreamWaitEvent(side, e, 0));
+        rec_backward_wgrads(j, n, side, (last_group && k + 1 == L && i + 1 == NC) ? sm_count : side_sms, c * Tc, Tc);
+        prof_begin(PC_REC_BWD);
+      }
     }
     prof_end();
     dx_done.swap(dx_next);
     const bool tail = last_group && k + 1 == L;
-    if (use_side) {
+    if (use_side && wgrad_per_chunk) {
+    } else if (use_side) {
       MVAE_CUDA(cudaEventRecord(ev_fork, st));          // dG of this layer is final here
       MVAE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
       rec_backward_wgrads(j, n, side, tail ? sm_count : side_sms);
