@@ -171,7 +171,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_CHUNKS"); chunks = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
   { const char* e = getenv("MVAE_CHUNKS_BWD"); chunks_bwd = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
   { const char* e = getenv("MVAE_PIPE_SMS"); pipe_sms = e ? atoi(e) : 0; }
-  { const char* e = getenv("MVAE_WGRAD_CHUNKS"); wgrad_per_chunk = e ? atoi(e) != 0 : true; }
+  { const char* e = getenv("MVAE_WGRAD_CHUNKS"); wgrad_per_chunk = e ? atoi(e) != 0 : false; }
   { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
   if (chunks > 1 || chunks_bwd > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
   build_params();

@@ -151,7 +151,7 @@ struct Model {
   int chunks = 1, chunks_bwd = 1;     // forward / backward (MVAE_CHUNKS / MVAE_CHUNKS_BWD)
   int pipe_sms = 0;                   // MVAE_PIPE_SMS: grid of a pipe-stream GEMM (0 = the SMs the resident clusters leave free)
   int pipe_grid(int n) const;
-  bool wgrad_per_chunk = true;        // chunked reverse sweeps: weight-gradient GEMMs per chunk (MVAE_WGRAD_CHUNKS=0: per layer)
+  bool wgrad_per_chunk = false;       // chunked reverse sweeps: MVAE_WGRAD_CHUNKS=1 hands the weight-gradient GEMMs over per chunk (measured slower)
   int branch_at = 0;                  // the branch recurrences fork at the first launch of this layer of the stack (0 = first layer)
   cudaStream_t st_pipe = nullptr;
   std::vector<cudaEvent_t> ev_pool;   // disable-timing events, handed out round-robin within a step

@@ -263,6 +263,7 @@ def test_time_chunked_layer_pipeline_matches_whole_sequence_launches(shape, chun
     for nc in (1, chunks):
         monkeypatch.setenv("MVAE_CHUNKS", str(nc))
         monkeypatch.setenv("MVAE_CHUNKS_BWD", str(nc))
+        monkeypatch.setenv("MVAE_WGRAD_CHUNKS", "1" if chunks == 4 else "0")      # per-chunk / per-layer weight-gradient GEMMs
         ecfg, _ = util.make_cfgs(T=T, H=H, L=L, feedback=feedback, variant=variant, precision="bf16", max_batch=n, rnn_mode="persistent")
         w = util.make_weights(ecfg)
         eng = _engine(ecfg, w)
@@ -274,6 +275,7 @@ def test_time_chunked_layer_pipeline_matches_whole_sequence_launches(shape, chun
         eng.close()
     monkeypatch.delenv("MVAE_CHUNKS")
     monkeypatch.delenv("MVAE_CHUNKS_BWD")
+    monkeypatch.delenv("MVAE_WGRAD_CHUNKS")
     (ma, ga, ma2), (mb, gb, mb2) = res[1], res[chunks]
     for k in METRIC_KEYS:
         tol_k = 0.05 if "acc" in k else 2e-3 * max(1.0, abs(ma[k]))
