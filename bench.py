@@ -264,7 +264,7 @@ def main():
         # kernel classes and their algorithmic FLOPs per step (B sequences): the forward recurrences do h*U, the backward
         # recurrences dG*U^T (same count), everything else (input projections, heads, all weight gradients) is batched GEMM
         classes = {
-            "rec_bwd": ((("rec_cluster_bwd_kernel: cluster-resident" if H in (256, 512) else "persistent") + " backward recurrence (dG*U^T per step on tcgen05 + gate-gradient math)")
+            "rec_bwd": ((("rec_cluster_bwd4_kernel (H=512) / rec_cluster_bwd_kernel (H=256): cluster-resident" if H in (256, 512) else "persistent") + " backward recurrence (dG*U^T per step on tcgen05 + gate-gradient math)")
                         if args.rnn_mode != "streamed" and args.precision == "bf16" else "step-streamed backward recurrence", rec_fwd * B),
             "rec_fwd": ((("rec_cluster_fwd2_kernel: cluster-resident" if H in (256, 512) else "persistent") + " forward recurrence (h*U per step on tcgen05 + gate math)")
                         if args.rnn_mode != "streamed" and args.precision == "bf16" else "step-streamed forward recurrence", rec_fwd * B),
@@ -274,16 +274,18 @@ def main():
         dom_ms = kms[dom][0]
         peak = pk["bf16_sustained"]
         achieved = classes[dom][1] / (dom_ms / 1e3) / 1e12
-        traffic = None
-        ncu_file = os.path.join(ROOT, "profiles", "r1", "ncu_rec_cluster_cfg3.json")
+        traffic, traffic_detail = None, None
+        ncu_file = os.path.join(ROOT, "profiles", "r1", "ncu_rec_cluster_cfg3_r1h.json" if dom == "rec_bwd" else "ncu_rec_cluster_cfg3.json")
         if dom in ("rec_bwd", "rec_fwd") and args.workload == "cfg3" and os.path.exists(ncu_file):
             pat = "rec_cluster_bwd" if dom == "rec_bwd" else "rec_cluster_fwd"
             ks = [k for k in json.load(open(ncu_file))["kernels"] if pat in k["Kernel Name"] and k["gpu__time_duration.sum"] > 0.3]   # the T=256 launches
             if ks:
-                traffic = {"dram_bytes_per_launch": sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in ks) / len(ks) * 1e6,
-                           "launches_per_step": 6, "source": "profiles/r1/ncu_rec_cluster_cfg3.json (ncu --set full, per launch of one T=256 recurrence)"}
+                traffic = sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in ks) / len(ks) * 1e6      # bytes per launch
+                traffic_detail = {"launches_per_step": 6, "algorithmic_stash_bytes_per_launch": T * B * H * 2 * (5 + 1 + 4),
+                                  "source": f"profiles/r1/{os.path.basename(ncu_file)} (ncu --set full, mean over the captured T={T} launches; the stash read "
+                                            "(gates 4H + c H per step), dh_ext H and the dG written 4H, all bf16, are the algorithmic bytes)"}
         roof = {"bound": "tensor", "kernel": classes[dom][0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "kernel_ms_per_step": dom_ms, "kernel_flops_per_step": classes[dom][1],
                 "step": {"achieved": value / world * train / 1e12, "frac": value / world * train / 1e12 / peak,
                          "frac_of_burst": value / world * train / 1e12 / pk["bf16_burst"], "train_flops_per_seq": train},
