@@ -393,6 +393,8 @@ struct Cluster2P {
   uint8_t* hx;        // exchange buffer [clusters][ng][2][CS][2 row halves][2 KB]
   int no_stash;       // inference: h only, no BPTT stash
   int cl0;            // first cluster of this launch (a launch may cover a sub-range of the batch's clusters)
+  unsigned* progress; // != null: counter c is incremented once per (CTA, active row group) when the h rows of steps < (c + 1) * progress_every are in global memory
+  int progress_every;
   int c0_stash;       // this launch continues a sequence: initial c = stash slab 0 (granule layout) of the (offset) cseq pointer, h = hseq slab 0
   int x_mode; const bf16* xtab; const unsigned char* x_idx; int x_ld, x_shift; const bf16* x_scalar; const float* x_w; const float* x_b;
   long long* trace;
@@ -678,6 +680,13 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)) = pack8(gf);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)) = pack8(gg);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)) = pack8(go);
+        }
+        if (p.progress && (t + 1) % p.progress_every == 0) {
+          // time-chunk boundary: this (CTA, group)'s h rows up to step t are written; publish them (gpu scope) and count, so that a consumer
+          // gated by a stream wait on the counter (the next layer's input projection of this chunk) may start while the recurrence goes on
+          __threadfence();
+          named_barrier(7 + set, 32 * CL_EPI_WARPS);
+          if (ew == 0 && lane == 0) atomicAdd(p.progress + ((t + 1) / p.progress_every - 1), 1u);
         }
         if (tracer && g == 0) CL_TRACE(t, 9);
       }
@@ -1484,6 +1493,7 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
   const size_t smem = 1024 + scr_bytes + (size_t)ng * 2 * hbuf;
   Cluster2P p{};
   p.cl0 = cl0;
+  p.progress = a.progress_every > 0 ? a.progress : nullptr; p.progress_every = a.progress_every;
   p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.dbg = env_int("MVAE_CL_DBG", 0);
   // a.t0 > 0: this launch continues the sequence at step t0 (time-chunked recurrences): every time-indexed buffer is simply offset
   const size_t t0 = (size_t)a.t0, nn = (size_t)a.n;

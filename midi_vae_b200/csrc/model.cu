@@ -11,6 +11,8 @@
 // The hand-derived backward is restated (and checked against autograd) in oracle/manual_bptt.py.
 #include "model.cuh"
 
+#include <cuda.h>
+
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -97,6 +99,7 @@ void Model::build_workspace() {
   }
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   if (chunks_bwd > 1) for (int i = 0; i < 4; ++i) rec_carry[i] = alloc(n * H * a);
+  if (xw_overlap > 1) rec_progress = (unsigned*)alloc(2 * 16 * sizeof(unsigned));
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
   for (int k = 0; k < nd; ++k) rec_bufs(dec_notes[k], true);
@@ -171,9 +174,10 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_CHUNKS"); chunks = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
   { const char* e = getenv("MVAE_CHUNKS_BWD"); chunks_bwd = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
   { const char* e = getenv("MVAE_PIPE_SMS"); pipe_sms = e ? atoi(e) : 0; }
+  { const char* e = getenv("MVAE_XW_OVERLAP"); xw_overlap = (use_cluster_fwd && e) ? std::max(0, std::min(16, atoi(e))) : 0; }
   { const char* e = getenv("MVAE_WGRAD_CHUNKS"); wgrad_per_chunk = e ? atoi(e) != 0 : false; }
   { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
-  if (chunks > 1 || chunks_bwd > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
+  if (chunks > 1 || chunks_bwd > 1 || xw_overlap > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
@@ -366,7 +370,9 @@ void Model::rec_forward_prepare(const FwdJob& j, int n) {
   const long rows = (long)r.steps * n;
   const bool fused = fuse_xproj && r.steps > 8 && ((j.kind == IN_DENSE && j.onehot) || j.kind == IN_RANK1 || j.kind == IN_NONE);
   prof_begin(PC_GEMM);
-  if (fused) {
+  if (j.xw_ready) {
+    // the input projection was (or is being) written chunk by chunk on the pipe stream; the caller has made this stream wait for it
+  } else if (fused) {
     // the cluster kernel computes x W + b itself: a row gather for one-hot inputs (table built here), x w + b for the scalar stream
     if (j.kind != IN_RANK1) rec_cluster_build_xtab(W(r.iW), ld(r.iW), j.kind == IN_DENSE ? r.Din : 0, Wf(r.ib), r.xtab, H, st);
   } else if (j.kind == IN_DENSE) {
@@ -401,6 +407,7 @@ RecPersistArgs Model::fwd_args(const FwdJob& j, int n, int slot, int hs, bool pa
   a.hx = slot ? rec_hx2 : rec_hx;
   a.trace = slot ? nullptr : trace_buf;
   a.no_stash = inference_pass ? 1 : 0;
+  a.progress = j.progress; a.progress_every = j.progress_every;
   if (fuse_xproj && r.steps > 8) {
     if ((j.kind == IN_DENSE && j.onehot) || j.kind == IN_NONE) {
       a.x_mode = 1; a.xtab = r.xtab;
@@ -612,6 +619,52 @@ void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& 
   }
 }
 
+// --------------------------------------------------------------------------------------------- projection overlap (stream-ordered memory waits)
+namespace {
+typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+WaitValueFn get_wait_value() {
+  static WaitValueFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MVAE_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qres));
+    MVAE_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuStreamWaitValue32 not available from the driver");
+    fn = (WaitValueFn)p;
+  }
+  return fn;
+}
+}  // namespace
+
+// The producer's counters are zeroed on the main stream before its launch; the pipe stream picks up from there.
+void Model::overlap_arm(FwdJob& producer, int n) {
+  (void)n;
+  progress_flip ^= 1;
+  producer.progress = rec_progress + 16 * progress_flip;
+  producer.progress_every = producer.r->steps / xw_overlap;
+  MVAE_CUDA(cudaMemsetAsync(producer.progress, 0, 16 * sizeof(unsigned), st));
+  cudaEvent_t e = next_event();
+  MVAE_CUDA(cudaEventRecord(e, st));
+  MVAE_CUDA(cudaStreamWaitEvent(st_pipe, e, 0));
+}
+
+// Input projection of the consumer layer, one GEMM per time chunk on the pipe stream, each gated by a stream wait until every (CTA, row group)
+// of the producer has published that chunk.  The main stream then waits for the last GEMM only.
+void Model::overlap_project(const FwdJob& producer, Rec& rn, int n) {
+  const int NC = xw_overlap, Tc = producer.progress_every;
+  const unsigned expected = (unsigned)((H / 32) * ((n + 63) / 64));
+  const int psms = pipe_grid(n);
+  for (int c = 0; c < NC; ++c) {     // (not timed by the profiling events: the span would include the wait)
+    const CUresult r = get_wait_value()((CUstream)st_pipe, (CUdeviceptr)(uintptr_t)(producer.progress + c), expected, CU_STREAM_WAIT_VALUE_GEQ);
+    MVAE_REQUIRE(r == CUDA_SUCCESS, "cuStreamWaitValue32 failed");
+    GemmArgs g; g.M = Tc * n; g.N = G; g.K = rn.Din; g.A = slab(producer.r->hseq, (long)c * Tc + 1, (long)n * H); g.lda = rn.ldin;
+    g.B = W(rn.iW); g.ldb = ld(rn.iW); g.C = slab(rn.xw, (long)c * Tc, (long)n * G); g.ldc = G; g.c_type = act; g.bias = Wf(rn.ib);
+    gemm_on(g, st_pipe, c + 1 < NC ? psms : sm_count);     // the last chunk starts when the producer is done: the whole chip
+  }
+  cudaEvent_t d = next_event();
+  MVAE_CUDA(cudaEventRecord(d, st_pipe));
+  MVAE_CUDA(cudaStreamWaitEvent(st, d, 0));
+}
+
 // --------------------------------------------------------------------------------------------- time-chunked layer pipeline
 cudaEvent_t Model::next_event() {
   if (ev_next == ev_pool.size()) {
@@ -796,11 +849,17 @@ void Model::encoder_forward(int n) {
   }
   if (use_branch) {
     branch_fork();
+    ev_next = 0;
+    bool xw_ready = false;
     for (int k = 0; k < ne; ++k) {
       FwdJob jp; jp.r = &enc_pitch[k]; jp.kind = IN_DENSE;
       jp.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
       if (k == 0) { jp.onehot = true; jp.idx = cur_pitch; jp.idx_ld = T; jp.idx_shift = 0; }
+      jp.xw_ready = xw_ready; xw_ready = false;
+      const bool ov = k + 1 < ne && overlap_ok(T);
+      if (ov) overlap_arm(jp, n);
       rec_forward_jobs(&jp, nullptr, n);
+      if (ov) { overlap_project(jp, enc_pitch[k + 1], n); xw_ready = true; }
       if (k == 0) {   // velocity and instrument streams: next to the pitch stack
         branch_begin();
         rec_forward_jobs(&jv, nullptr, n);
@@ -873,13 +932,19 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
     branch_join();
   }
   if (use_branch && !chunked) branch_fork();
+  bool dec_xw_ready = false;
+  if (!chunked) ev_next = 0;
   for (int k = 0; k < nd && !chunked; ++k) {
     FwdJob jp; jp.r = &dec_notes[k]; jp.h0 = st1(k); jp.c0 = st2(k); jp.ld0 = nS * H;
     if (k == 0) { jp.kind = tf ? IN_DENSE : IN_NONE; jp.X = tf ? Y_ext_cur : nullptr; }
     else { jp.kind = IN_DENSE; jp.X = slab(dec_notes[k - 1].hseq, 1, (long)n * H); }
     if (k == 0 && tf) { jp.onehot = true; jp.idx = cur_target; jp.idx_ld = T; jp.idx_shift = 1; }   // x_t = y_{t-1}, x_0 = 0
     if (use_branch) {
+      jp.xw_ready = dec_xw_ready; dec_xw_ready = false;
+      const bool ov = k + 1 < nd && overlap_ok(T);
+      if (ov) overlap_arm(jp, n);
       rec_forward_jobs(&jp, nullptr, n);
+      if (ov) { overlap_project(jp, dec_notes[k + 1], n); dec_xw_ready = true; }
       if (k == 0) {
         branch_begin();
         rec_forward_jobs(&jv, nullptr, n);

@@ -49,6 +49,10 @@ struct FwdJob {
   const unsigned char* idx = nullptr;
   int idx_ld = 0, idx_shift = 0;
   bool onehot = false;
+  // projection overlap (MVAE_XW_OVERLAP): this recurrence publishes per-time-chunk progress counters / its xw buffer is filled elsewhere
+  unsigned* progress = nullptr;
+  int progress_every = 0;
+  bool xw_ready = false;
 };
 
 // one backward recurrence: where its inputs / external gradients come from and where its outputs go
@@ -151,6 +155,14 @@ struct Model {
   int chunks = 1, chunks_bwd = 1;     // forward / backward (MVAE_CHUNKS / MVAE_CHUNKS_BWD)
   int pipe_sms = 0;                   // MVAE_PIPE_SMS: grid of a pipe-stream GEMM (0 = the SMs the resident clusters leave free)
   int pipe_grid(int n) const;
+  // projection overlap: a layer's recurrence stays ONE launch but publishes a counter per time chunk; the next layer's input projection of that
+  // chunk is a GEMM on the pipe stream gated by a stream wait (cuStreamWaitValue32) on the counter: no relaunch, no slot churn, no carry
+  int xw_overlap = 0;                 // MVAE_XW_OVERLAP = number of chunks (0 = off)
+  unsigned* rec_progress = nullptr;   // 2 x 16 counters (ping-pong between consecutive producing layers)
+  int progress_flip = 0;
+  bool overlap_ok(int steps) const { return xw_overlap > 1 && use_cluster_fwd && st_pipe && steps % xw_overlap == 0 && steps / xw_overlap >= 8; }
+  void overlap_arm(FwdJob& producer, int n);                                  // before the producer is launched
+  void overlap_project(const FwdJob& producer, Rec& consumer, int n);         // after the producer is launched
   bool wgrad_per_chunk = false;       // chunked reverse sweeps: MVAE_WGRAD_CHUNKS=1 hands the weight-gradient GEMMs over per chunk (measured slower)
   int branch_at = 0;                  // the branch recurrences fork at the first launch of this layer of the stack (0 = first layer)
   cudaStream_t st_pipe = nullptr;

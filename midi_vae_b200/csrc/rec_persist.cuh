@@ -34,6 +34,8 @@ struct RecPersistArgs {
   void* trace = nullptr;              // optional: 8 steps x 16 clock64 stamps of CTA 0 (profiling aid)
   int no_stash = 0;                   // cluster forward: inference, do not write the gates / c stash
   int t0 = 0;                         // cluster kernels: this launch covers steps [t0, t0 + steps) of the sequence (time-chunked recurrences); time-indexed buffers are passed un-offset
+  unsigned* progress = nullptr;       // cluster forward: per-time-chunk completion counters (see Cluster2P::progress); expected value = (H / 32) * ceil(n / 64)
+  int progress_every = 0;             //   steps per chunk (0 = no publishing)
   int ng = 0;                         // cluster forward: row groups per cluster (0 = the launcher's choice)
   int cl0 = 0, ncl = 0;               // cluster kernels: launch only clusters [cl0, cl0 + ncl) of the batch (ncl = 0: all from cl0)
   // cluster forward only: input projection computed inside the kernel instead of streamed from the (steps, n, 4H) xw buffer

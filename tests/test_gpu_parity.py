@@ -286,6 +286,37 @@ def test_time_chunked_layer_pipeline_matches_whole_sequence_launches(shape, chun
         assert np.abs(ga[k] - gb[k]).max() <= 1e-2 * scale + 1e-9, (k, float(np.abs(ga[k] - gb[k]).max()), float(scale))
 
 
+@pytest.mark.parametrize("shape,nc", [((64, 256, 32, 70), 4), ((32, 512, 48, 130), 2), ((64, 512, 48, 520), 8), ((48, 512, 24, 65), 3)])
+def test_projection_overlap_is_exact(shape, nc, monkeypatch):
+    """MVAE_XW_OVERLAP = nc: a layer's forward recurrence stays one launch but publishes a counter per time chunk; the next layer's input
+    projection runs per chunk on the pipe stream behind cuStreamWaitValue32 on that counter.  Same kernels, same arithmetic per element:
+    metrics and gradients must be identical to the un-overlapped schedule (train step, second train step, and the inference path)."""
+    T, H, L, n = shape
+    res = {}
+    for v in (0, nc):
+        monkeypatch.setenv("MVAE_XW_OVERLAP", str(v))
+        ecfg, _ = util.make_cfgs(T=T, H=H, L=L, feedback="teacher_forced", precision="bf16", max_batch=n, rnn_mode="persistent")
+        w = util.make_weights(ecfg)
+        eng = _engine(ecfg, w)
+        r, hist, eps, sw = util.make_batch(ecfg, n, weights=True)
+        P, Ii, Vv = eng.style_transfer(r.pitch, r.instr, r.velocity, 0, 1, None, "as_wired")      # inference pass (no stash)
+        m = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)
+        g = eng.get_grads()
+        m2 = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)
+        res[v] = (m, g, m2, P, Vv)
+        eng.close()
+    monkeypatch.delenv("MVAE_XW_OVERLAP")
+    (ma, ga, ma2, Pa, Va), (mb, gb, mb2, Pb, Vb) = res[0], res[nc]
+    assert np.array_equal(Pa, Pb) and np.array_equal(Va, Vb)
+    for k in METRIC_KEYS:
+        assert ma[k] == mb[k] or abs(ma[k] - mb[k]) <= 1e-6 * max(1.0, abs(ma[k])), (k, ma[k], mb[k])
+        assert abs(ma2[k] - mb2[k]) <= 1e-5 * max(1.0, abs(ma2[k])), (k, ma2[k], mb2[k])
+    for k in ga:
+        # weight gradients accumulate with fp32 atomics (split-K): order-dependent in the last bits
+        scale = max(np.abs(ga[k]).max(), 1e-6)
+        assert np.abs(ga[k] - gb[k]).max() <= 1e-5 * scale + 1e-9, (k, float(np.abs(ga[k] - gb[k]).max()), float(scale))
+
+
 def test_cluster_rnn_sigmoid_gates():
     """The logistic-sigmoid gate variant (north_star's wording; the reference default is hard_sigmoid) through the cluster kernels."""
     T, H, L, n = 16, 256, 32, 70
