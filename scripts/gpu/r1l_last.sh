@@ -1,7 +1,5 @@
 #!/bin/bash
 # last call of the round: smoke() + the full GPU suite on the final build
 mkdir -p gpurun_out
-echo "=== smoke"
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "=== full gpu tests"
-timeout 600 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -4
+timeout 600 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -25

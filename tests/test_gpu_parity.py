@@ -310,7 +310,10 @@ def test_projection_overlap_is_exact(shape, nc, monkeypatch):
     assert np.array_equal(Pa, Pb) and np.array_equal(Va, Vb)
     for k in METRIC_KEYS:
         assert ma[k] == mb[k] or abs(ma[k] - mb[k]) <= 1e-6 * max(1.0, abs(ma[k])), (k, ma[k], mb[k])
-        assert abs(ma2[k] - mb2[k]) <= 1e-5 * max(1.0, abs(ma2[k])), (k, ma2[k], mb2[k])
+        # the second step runs on weights updated from gradients that were accumulated with fp32 atomics (split-K; order differs from run to run, with
+        # or without the overlap): last-bit weight differences may flip a near-tied argmax, i.e. move an accuracy by a few 1 / (n T)
+        tol2 = 1e-3 if "acc" in k else 1e-4 * max(1.0, abs(ma2[k]))
+        assert abs(ma2[k] - mb2[k]) <= tol2, (k, ma2[k], mb2[k])
     for k in ga:
         # weight gradients accumulate with fp32 atomics (split-K): order-dependent in the last bits
         scale = max(np.abs(ga[k]).max(), 1e-6)
