@@ -154,10 +154,12 @@ def test_shipped_checkpoint_runs_through_the_reference_graph_and_decodes_the_fir
     shim) loads a shipped autoencoder checkpoint positionally (load_weights(by_name=False), vae_training.py:120-123) and, fed
     sustained four-voice chords, reproduces the top voice's pitch at the first decoder step for at least half of the chords (chance: 1/61 each).
     That exercises the restated Keras GRU encoder, the tanh head + split, z_mean, the initial-state Denses, one GRUCell step and
-    the softmax head on weights the restatement had no hand in.  KNOWN GAP, stated here rather than hidden: from the second decoder
-    step on the restated recurrentshop unrolling does not reproduce these chords (it predicts silence), for every GRUCell
-    gate-order / mixing convention tried -- recurrentshop's multi-step decode semantics for GRU cells remain unverified offline.
-    This build ships the LSTM branch; the decoder cell conventions it offers are listed in SURVEY.md A.3."""
+    the softmax head on weights the restatement had no hand in.  OPEN, stated here rather than hidden: from the second decoder
+    step on the shim-run models predict silence for these chords, for every GRUCell gate-order / mixing / state-threading convention
+    tried (96 cell variants x 6 threadings, also on the 1-layer velocity decoder, all four shipped models).  Whether that is
+    recurrentshop's multi-step decode semantics differing from the restatement, or simply how these models behave on synthetic rolls
+    far from their training data (no data ships with the reference), cannot be decided offline.  This build ships the LSTM branch;
+    the decoder cell conventions it offers are listed in SURVEY.md A.3."""
     import sys
     sys.path.insert(0, GOLD)
     import make_reference_golden as G
