@@ -288,7 +288,7 @@ __global__ void softmax_ce_kernel(int steps, int n, int D, float* logits, int ld
       float wt = w ? w[(long)b * steps + t] : 1.f;
       if (lane == 0) {
         ce_sum += (double)(-logf(fminf(fmaxf(py, 1e-7f), 1.f - 1e-7f)) * wt);
-        acc_sum += (bi == y) ? (double)wt : 0.0;
+        acc_sum += (bi == y) ? 1.0 : 0.0;      // Keras 2.0.8 metrics are plain means: sample weights do not enter
       }
       if (dlogits) {
         float live = (py > 1e-7f && py < 1.f - 1e-7f) ? 1.f : 0.f;
@@ -437,7 +437,7 @@ __global__ void finalize_metrics_kernel(const double* acc, int n, int T, int Ti,
   out[MVAE_M_LOSS] = (float)(w_notes * l_notes + w_instr * l_instr + w_vel * l_vel + w_style * l_style + kl);
   out[MVAE_M_NOTES_LOSS] = (float)l_notes; out[MVAE_M_INSTR_LOSS] = (float)l_instr; out[MVAE_M_VEL_LOSS] = (float)l_vel;
   out[MVAE_M_STYLE_LOSS] = (float)l_style;
-  out[MVAE_M_NOTES_ACC] = (float)(acc[ACC_ACC_NOTES] / wnz);
+  out[MVAE_M_NOTES_ACC] = (float)(acc[ACC_ACC_NOTES] / ((double)T * n));
   out[MVAE_M_INSTR_ACC] = (float)(acc[ACC_ACC_INSTR] / ((double)Ti * n));
   out[MVAE_M_VEL_ACC] = (float)(acc[ACC_ACC_VEL] / ((double)T * n));
   out[MVAE_M_STYLE_ACC] = (float)(acc[ACC_ACC_STYLE] / n);

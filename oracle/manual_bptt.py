@@ -201,7 +201,7 @@ def train_step_manual(cfg: OracleConfig, p: Dict[str, Tensor], pitch_idx, instr_
     metrics = {
         "loss": float(total), "decoder_loss_1": float(l_notes), "decoder_loss_2": float(l_instr), "decoder_loss_3": float(l_vel),
         "composer_decoder_loss": float(l_style),
-        "decoder_acc_1": float((((Pn.argmax(-1) == tgt_t).to(dt)) * wt).mean() / wnorm),
+        "decoder_acc_1": float((Pn.argmax(-1) == tgt_t).to(dt).mean()),      # Keras 2.0.8 metrics: plain mean, not sample-weighted
         "decoder_acc_2": float((Pi.argmax(-1) == ins_t).to(dt).mean()),
         "decoder_acc_3": float((torch.round(Pv) == vt).to(dt).mean()),
         "composer_decoder_acc": float((Pc.argmax(-1) == sty).to(dt).mean()), "kl": float(kl),

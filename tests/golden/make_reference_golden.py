@@ -75,7 +75,7 @@ def keras_name_map(cfg):
     for l in enc:
         for i, t in enumerate(["kernel", "recurrent_kernel", "bias"]):
             m[f"{l}/{t}"] = ("encoder", l, i)
-    for l in ["extra_instrument_after_concat_layer", "extra_layer", "z_mean", "z_log_var"]:
+    for l in ["extra_instrument_after_concat_layer"] + (["extra_layer"] if cfg.extra_layer else []) + ["z_mean", "z_log_var"]:
         for i, t in enumerate(["kernel", "bias"]):
             m[f"{l}/{t}"] = ("encoder", l, i)
     return m
@@ -94,6 +94,92 @@ def load_into_reference(model, cfg, w):
     dec_names = [n for n, _, _ in O.param_specs(cfg) if n.startswith(("dec_init/", "notes/", "meta_instrument/", "meta_velocity/"))]
     model.decoder.set_weights([w[n] for n in dec_names])
     return dec_names
+
+
+VARIANTS = {
+    # name: (create-kwarg overrides, oracle-config overrides, module globals read by prepare_*, batch_size)
+    "tf_list": (dict(teacher_force=True), dict(), dict(teacher_force=True), 8),                       # extra ground-truth input, same computation
+    "plain": (dict(history=False, extra_layer=False, num_layers_encoder=1, num_layers_decoder=1),
+              dict(history=False, extra_layer=False, num_layers_encoder=1, num_layers_decoder=1), dict(history=False), 8),
+    "deep": (dict(num_layers_encoder=3, num_layers_decoder=3), dict(num_layers_encoder=3, num_layers_decoder=3), dict(), 8),
+    "weights": (dict(), dict(), dict(silent_weight=0.25), 3),                                          # temporal weights != 1, ragged mini-batches 3 + 3 + 2
+}
+
+
+def run_variants(vd):
+    """Non-default corners of the reference's own graph / list code (vae_definition.py:262-266, 483-487, 548-551, 928-933) -> reference_cfg1_variants.npz"""
+    from keras import backend as K
+    import recurrentshop.cells as rs_cells
+    from dataclasses import replace
+    from midi_vae_b200 import synth
+    from oracle import midivae_oracle as O
+    from tests import util
+    T, H, L, n = 16, 64, 16, 8
+    out = {}
+    r = synth.make_song(np.random.default_rng(4321), n, T, 0)
+    rng = np.random.default_rng(4322)
+    hist = (rng.standard_normal((n, L)) * 0.1).astype(np.float32)
+    eps = synth.make_eps(n, L, 4321, 0.01)
+    X, I_, V3, _ = r.dense(np.float64)
+    for name, (kw, okw, glob, bs) in VARIANTS.items():
+        _, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant="standard", max_batch=n)
+        ocfg = replace(ocfg, **okw)
+        w = {k: v.numpy().astype(np.float32) for k, v in O.init_params(ocfg, seed=77).items()}
+        jit = np.random.default_rng(78)
+        w = {k: (v + 0.1 * jit.standard_normal(v.shape)).astype(np.float32) for k, v in w.items()}
+        rs_cells.LSTM_VARIANT = "standard"
+        K.clear_session()
+        set_module_lengths(vd, T)
+        saved = {k: getattr(vd, k) for k in glob}
+        for k, v in glob.items():
+            setattr(vd, k, v)
+        try:
+            model = vd.VAE()
+            model.create(**create_kwargs(vd, cell_type="LSTM", input_length=T, output_length=T, lstm_size=H, latent_rep_size=L,
+                                         meta_velocity_length=T, meta_held_notes_length=T, meta_next_notes_output_length=T, **kw))
+            load_into_reference(model, ocfg, w)
+            K.set_random_normal_hook(lambda shp, mean, std: eps.astype(np.float64)[:shp[0]] * (std / 0.01) + mean)
+            V = V3[..., 0]
+            D = np.zeros_like(V); S = np.zeros((n, 15))
+            in_list, out_list, sw = vd.prepare_autoencoder_input_and_output_list(X, X, int(r.style[0]), I_[0], V, D, S, hist.astype(np.float64), return_sample_weight=True)
+            z = model.encoder.predict(vd.prepare_encoder_input_list(X, I_[0], V, D), batch_size=n)
+            dec_out = model.decoder.predict(vd.prepare_decoder_input(z, int(r.style[0]), S, hist.astype(np.float64)), batch_size=n)
+            # mini-batches of bs: the hook hands out eps rows from 0 for every call, so feed the batches' eps explicitly through a cursor
+            cursor = {"i": 0}
+            def hook(shp, mean, std):
+                i = cursor["i"]; cursor["i"] = (i + shp[0]) % n
+                return eps.astype(np.float64)[i:i + shp[0]] * (std / 0.01) + mean
+            K.set_random_normal_hook(hook)
+            ev = model.autoencoder.evaluate(in_list, out_list, batch_size=bs, sample_weight=sw, verbose=0)
+            fits = []
+            for _ in range(2):
+                cursor["i"] = 0
+                h = model.autoencoder.fit(in_list, out_list, epochs=1, batch_size=bs, shuffle=False, sample_weight=sw, verbose=0)
+                fits.append([h.history[k][0] for k in sorted(h.history)])
+            p = f"{name}/"
+            out[p + "z"] = z
+            for k, a in zip(("Y", "I", "V"), dec_out):
+                out[p + "dec_" + k] = a
+            out[p + "evaluate"] = np.array(ev)
+            out[p + "fit_keys"] = np.array(sorted(h.history))
+            out[p + "fit"] = np.array(fits)
+            out[p + "n_inputs"] = np.array(len(in_list))
+            out[p + "in_shapes"] = np.array([str(np.asarray(a).shape) for a in in_list])
+            out[p + "sw_notes"] = np.asarray(sw[0])
+            out[p + "batch_size"] = np.array(bs)
+            if name in ("plain", "weights"):          # updated weights after the two epochs (kept for two variants only: fixture size)
+                dec_names = [nm for nm, _, _ in O.param_specs(ocfg) if nm.startswith(("dec_init/", "notes/", "meta_instrument/", "meta_velocity/"))]
+                for nm, a in zip(dec_names, model.decoder.get_weights()):
+                    out[p + "w2/" + nm] = a
+                for k, (sub, layer, idx) in keras_name_map(ocfg).items():
+                    out[p + "w2/" + k] = model.encoder.get_layer(layer).get_weights()[idx]
+        finally:
+            for k, v in saved.items():
+                setattr(vd, k, v)
+    out["pitch"], out["instr"], out["velocity"], out["style"], out["hist"], out["eps"] = r.pitch, r.instr, r.velocity, r.style, hist, eps
+    path = os.path.join(HERE, "reference_cfg1_variants.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
 
 
 def main():
@@ -199,6 +285,7 @@ def main():
     path = os.path.join(HERE, "reference_cfg1.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
+    run_variants(vd)
     print("keras shim", keras.__version__, "evaluate(standard):", dict(zip(out["standard/metrics_names"], out["standard/evaluate"])))
 
 

@@ -186,3 +186,66 @@ def test_shipped_checkpoint_runs_through_the_reference_graph_and_decodes_the_fir
     first = Y[:, 0].argmax(-1)
     hits = int((first == pitch[:, 0]).sum())
     assert hits >= 4, (first, pitch[:, 0])          # measured: JvP 4 of 8, CvJ 7 of 8 (CvP 4, BvM 1); by chance (1/61 per chord) even 2 hits have p < 0.01
+
+
+# ------------------------------------------------------------------------------------------------ non-default corners of the reference's code
+VARIANT_CFG = {
+    "tf_list": dict(),
+    "plain": dict(history=False, extra_layer=False, num_layers_encoder=1, num_layers_decoder=1),
+    "deep": dict(num_layers_encoder=3, num_layers_decoder=3),
+    "weights": dict(),
+}
+
+
+@pytest.mark.parametrize("name", list(VARIANT_CFG))
+def test_reference_executed_variants(name):
+    """tests/golden/reference_cfg1_variants.npz: the reference's graph / list code run (through the shim) with teacher_force=True (extra
+    ground-truth input, same computation: vae_definition.py:262-266), without history / extra layer and with 1 + 1 layers (:483-487, 548-551),
+    with 3 + 3 layers, and with silent_weight = 0.25 over ragged mini-batches of 3 + 3 + 2 chunks (:928-933; Keras' batch-size-weighted
+    epoch means; accuracies are NOT sample-weighted in Keras 2.0.8).  The oracle follows all of them to 1e-9."""
+    from dataclasses import replace
+    g = np.load(os.path.join(GOLD, "reference_cfg1_variants.npz"))
+    _, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant="standard", max_batch=N)
+    ocfg = replace(ocfg, **VARIANT_CFG[name])
+    w = {k: v.numpy().astype(np.float32) for k, v in O.init_params(ocfg, seed=77).items()}
+    jit = np.random.default_rng(78)
+    p = util.to_torch({k: (v + 0.1 * jit.standard_normal(v.shape)).astype(np.float32) for k, v in w.items()})
+    r = synth.Rolls(g["pitch"], g["instr"], g["velocity"], g["style"])
+    X, I, V, C, th, te, _ = util.oracle_inputs(ocfg, r, g["hist"], g["eps"], None)
+    if not ocfg.history:
+        th = None
+    pre = name + "/"
+    assert int(g[pre + "n_inputs"]) == {"tf_list": 8, "plain": 6, "deep": 7, "weights": 7}[name]
+    with torch.no_grad():
+        z, _, _ = O.encode(ocfg, p, X, I, V, te)
+        Yh, Ih, Vh = O.decode(ocfg, p, z, th, feedback="as_wired")[:3]
+    assert np.abs(z.numpy() - g[pre + "z"]).max() < TOL
+    for nm, mine in (("Y", Yh), ("I", Ih), ("V", Vh)):
+        assert np.abs(mine.numpy() - g[pre + "dec_" + nm]).max() < TOL, nm
+    bs = int(g[pre + "batch_size"])
+    wn = torch.tensor(g[pre + "sw_notes"])
+    if name == "weights":
+        assert set(np.unique(g[pre + "sw_notes"])) == {0.25, 1.0}
+
+    def epoch(fn):
+        tot, acc = 0, {}
+        for a in range(0, N, bs):
+            sl = slice(a, min(N, a + bs))
+            m = fn(X[sl], I[sl], V[sl], C[sl], None if th is None else th[sl], te[sl], (wn[sl], None, None, None))
+            k = sl.stop - sl.start
+            for key, v in m.items():
+                acc[key] = acc.get(key, 0.0) + v * k
+            tot += k
+        return {key: v / tot for key, v in acc.items()}
+
+    ev = epoch(lambda *a: O.evaluate_batch(ocfg, p, a[0], a[1], a[2], a[3], a[4], a[5], sample_weight=a[6])[0])
+    for k, v in zip(METRIC_KEYS[:9], g[pre + "evaluate"]):
+        assert abs(ev[k] - v) < TOL, (k, ev[k], v)
+    opt = O.KerasAdam(p, lr=ocfg.learning_rate)
+    keys = list(g[pre + "fit_keys"])
+    for e in range(2):
+        m = epoch(lambda *a: O.train_on_batch(ocfg, p, opt, a[0], a[1], a[2], a[3], a[4], a[5], sample_weight=a[6])[0])
+        for k, v in zip(keys, g[pre + "fit"][e]):
+            assert abs(m[k] - v) < TOL, (e, k, m[k], v)
+    for k in [f for f in g.files if f.startswith(pre + "w2/")]:
+        assert np.abs(p[k[len(pre) + 3:]].numpy() - g[k]).max() < TOL, k
