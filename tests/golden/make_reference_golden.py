@@ -182,6 +182,25 @@ def run_variants(vd):
     print(path, os.path.getsize(path), "bytes")
 
 
+def run_postprocess(vd):
+    """The reference's process_decoder_outputs (vae_definition.py:1131-1225, pure numpy, sample_method='argmax') on random decoder outputs
+    -> reference_postprocess.npz.  No restated library is involved in this one."""
+    T, n = 32, 6
+    set_module_lengths(vd, T)
+    rng = np.random.default_rng(2024)
+    Yp = rng.random((n, T, 61)) ** 4
+    Yp[..., 60] *= 3.0                                   # a good share of silent steps
+    Yp /= Yp.sum(-1, keepdims=True)
+    Ip = rng.random((n, 4, 16)); Ip /= Ip.sum(-1, keepdims=True)
+    Vp = rng.random((n, T, 1))                           # velocities on both sides of the 0.5 played-note threshold
+    Vp[rng.random((n, T, 1)) < 0.3] *= 0.4
+    Y, I, V, D, N = vd.process_decoder_outputs([Yp.copy(), Ip.copy(), Vp.copy()], "argmax")
+    path = os.path.join(HERE, "reference_postprocess.npz")
+    np.savez_compressed(path, Yp=Yp.astype(np.float32), Ip=Ip.astype(np.float32), Vp=Vp.astype(np.float32)[..., 0],
+                        Y=Y.astype(np.uint8), I=I.astype(np.uint8), V=V, D=D.astype(np.uint8), T=np.array(T))
+    print(path, os.path.getsize(path), "bytes; sounding steps", int(Y.sum()), "of", Y.shape[0])
+
+
 def main():
     vd = import_reference()
     import keras
@@ -286,6 +305,7 @@ def main():
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
     run_variants(vd)
+    run_postprocess(vd)
     print("keras shim", keras.__version__, "evaluate(standard):", dict(zip(out["standard/metrics_names"], out["standard/evaluate"])))
 
 
