@@ -398,9 +398,10 @@ void Model::rec_forward_prepare(const FwdJob& j, int n) {
 
 RecPersistArgs Model::fwd_args(const FwdJob& j, int n, int slot, int hs, bool pack) {
   Rec& r = *j.r;
-  if (!pack) {}
-  else if (use_cluster_fwd) rec_cluster_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, r.variant, st);
-  else rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, hs, r.variant, st);
+  if (pack) {
+    if (use_cluster_fwd) rec_cluster_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, r.variant, st);
+    else rec_persist_pack_u(Wf(r.iU), ld(r.iU), r.upack, H, hs, r.variant, st);
+  }
   RecPersistArgs a;
   a.n = n; a.H = H; a.steps = r.steps; a.gate_act = cfg.gate_act; a.variant = r.variant; a.flags = slot ? rec_flags2 : rec_flags;
   a.upack = r.upack; a.xw = r.xw; a.hseq = r.hseq; a.cseq = r.cseq; a.gates = r.gates; a.c0 = j.c0; a.ldc0 = j.ld0;
@@ -818,6 +819,7 @@ void Model::stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJo
     dx_done.swap(dx_next);
     const bool tail = last_group && k + 1 == L;
     if (use_side && wgrad_per_chunk) {
+      // already handed over chunk by chunk above
     } else if (use_side) {
       MVAE_CUDA(cudaEventRecord(ev_fork, st));          // dG of this layer is final here
       MVAE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
@@ -955,9 +957,10 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
       rec_forward_jobs(&jp, k == 0 ? &jv : nullptr, n);
     }
   }
-  if (chunked) {}
-  else if (use_branch) branch_join();
-  else rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
+  if (!chunked) {
+    if (use_branch) branch_join();
+    else rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
+  }
   prof_begin(PC_GEMM);
   { GemmArgs g; g.M = T * n; g.N = Dp; g.K = H; g.A = slab(dec_notes[nd - 1].hseq, 1, (long)n * H); g.lda = H; g.B = W(iWy); g.ldb = ld(iWy);
     g.C = Pn; g.ldc = ld_pn; g.c_type = DT_F32; g.bias = Wf(iby); gemm(g); }
