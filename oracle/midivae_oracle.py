@@ -71,6 +71,9 @@ class OracleConfig:
     gate_act: str = "hard_sigmoid"            # Keras 2.0.8 default; "sigmoid" = north_star wording
     dec_cell_variant: str = "standard"        # or "recurrentshop_recalled"
     decoder_feedback: str = "as_wired"        # "as_wired" | "teacher_forced" | "free_running"
+    # the reference's shipped default (settings.py:155) is GRU; the CUDA build implements the LSTM branch, the oracle restates both
+    # (GRU = groundwork for SURVEY.md 8(f-1); GRUCell conventions as recalled: blocks [z|r|h], h' = (1 - z) h + z hh)
+    cell_type: str = "LSTM"                   # "LSTM" | "GRU"
 
     @property
     def T(self): return self.input_length
@@ -91,19 +94,21 @@ class OracleConfig:
 # --------------------------------------------------------------------------------------
 def param_specs(cfg: OracleConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
     """(name, shape, init) in canonical (reference checkpoint) order."""
-    H, L, G = cfg.H, cfg.L, 4 * cfg.H
+    gru = cfg.cell_type == "GRU"
+    H, L, G = cfg.H, cfg.L, (3 if gru else 4) * cfg.H
     Dp, Di = cfg.input_dim, cfg.meta_instrument_dim
     s: List[Tuple[str, Tuple[int, ...], str]] = []
+    pre = "gru" if gru else "lstm"
 
     def keras_lstm(name, D):
         s.append((f"{name}/kernel", (D, G), "glorot"))
         s.append((f"{name}/recurrent_kernel", (H, G), "orthogonal"))
-        s.append((f"{name}/bias", (G,), "lstm_bias"))
+        s.append((f"{name}/bias", (G,), "zeros" if gru else "lstm_bias"))
 
     for k in range(1, cfg.num_layers_encoder + 1):           # vae_definition.py:455-460
-        keras_lstm(f"lstm_{k}", Dp if k == 1 else H)
-    keras_lstm("lstm_meta_instrument", Di)                   # :464-468
-    keras_lstm("lstm_meta_velocity", 1)                      # :470-474
+        keras_lstm(f"{pre}_{k}", Dp if k == 1 else H)
+    keras_lstm(f"{pre}_meta_instrument", Di)                 # :464-468
+    keras_lstm(f"{pre}_meta_velocity", 1)                    # :470-474
     s.append(("extra_instrument_after_concat_layer/kernel", (3 * H, H), "glorot"))  # :483-484
     s.append(("extra_instrument_after_concat_layer/bias", (H,), "zeros"))
     if cfg.extra_layer:
@@ -118,7 +123,7 @@ def param_specs(cfg: OracleConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
 
     Q = 2 * L if cfg.history else L                          # :548-551
     def init_dense(name):
-        for j in (1, 2):                                     # :563-568 (state 1, state 2)
+        for j in ((1,) if gru else (1, 2)):                  # :563-568 (state 1, state 2; a GRU cell has one state)
             s.append((f"dec_init/{name}_s{j}/kernel", (Q, H), "glorot"))
             s.append((f"dec_init/{name}_s{j}/bias", (H,), "zeros"))
     for k in range(1, cfg.num_layers_decoder + 1):
@@ -129,7 +134,11 @@ def param_specs(cfg: OracleConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
     def rs_cell(name, D):                                    # recurrentshop LSTMCell: Dense(4H,bias) on x, Dense(4H,no bias) on h
         s.append((f"{name}/kernel", (D, G), "glorot"))
         s.append((f"{name}/bias", (G,), "zeros"))
-        s.append((f"{name}/recurrent_kernel", (H, G), "glorot"))
+        if gru:                                              # GRUCell: Dense(3H,bias) on x, Dense(2H) on h for z, r, Dense(H) on r*h (shipped shapes)
+            s.append((f"{name}/recurrent_kernel_1", (H, 2 * H), "glorot"))
+            s.append((f"{name}/recurrent_kernel_2", (H, H), "glorot"))
+        else:
+            s.append((f"{name}/recurrent_kernel", (H, G), "glorot"))
     for k in range(1, cfg.num_layers_decoder + 1):           # :533-540
         rs_cell(f"notes/cell_{k}", Dp if k == 1 else H)
     s.append(("notes/out/kernel", (H, Dp), "glorot"))        # :542
@@ -219,17 +228,37 @@ def keras_lstm(cfg: OracleConfig, p: Dict[str, Tensor], name: str, x: Tensor, re
     return torch.stack(hs, 1) if return_sequences else h
 
 
+def keras_gru(cfg: OracleConfig, p: Dict[str, Tensor], name: str, x: Tensor, return_sequences: bool) -> Tensor:
+    """keras.layers.GRU (2.0.8): blocks [z|r|h]; z, r = gate(x W + h U + b); hh = tanh(x W_h + (r*h) U_h + b_h); h' = z*h + (1-z)*hh."""
+    B, T, _ = x.shape
+    H = cfg.H
+    W, U, b = p[f"{name}/kernel"], p[f"{name}/recurrent_kernel"], p[f"{name}/bias"]
+    act = _gate(cfg)
+    h = x.new_zeros(B, H)
+    xw = x @ W + b
+    hs = []
+    for t in range(T):
+        z = act(xw[:, t, :H] + h @ U[:, :H])
+        r = act(xw[:, t, H:2 * H] + h @ U[:, H:2 * H])
+        hh = torch.tanh(xw[:, t, 2 * H:] + (r * h) @ U[:, 2 * H:])
+        h = z * h + (1 - z) * hh
+        hs.append(h)
+    return torch.stack(hs, 1) if return_sequences else h
+
+
 # --------------------------------------------------------------------------------------
 # encoder  (vae_definition.py:443-516)
 # --------------------------------------------------------------------------------------
 def encoder_heads(cfg: OracleConfig, p: Dict[str, Tensor], X: Tensor, I: Tensor, V: Tensor) -> Tuple[Tensor, Tensor]:
     """X (B,T,61) one-hot, I (B,4,16) one-hot, V (B,T,1)  ->  (z_mean, z_log_var)  each (B,L)."""
+    gru = cfg.cell_type == "GRU"
+    rnn, pre = (keras_gru, "gru") if gru else (keras_lstm, "lstm")
     h = X
     for k in range(1, cfg.num_layers_encoder):
-        h = keras_lstm(cfg, p, f"lstm_{k}", h, True)
-    h = keras_lstm(cfg, p, f"lstm_{cfg.num_layers_encoder}", h, False)
-    m_i = keras_lstm(cfg, p, "lstm_meta_instrument", I, False)
-    m_v = keras_lstm(cfg, p, "lstm_meta_velocity", V, False)
+        h = rnn(cfg, p, f"{pre}_{k}", h, True)
+    h = rnn(cfg, p, f"{pre}_{cfg.num_layers_encoder}", h, False)
+    m_i = rnn(cfg, p, f"{pre}_meta_instrument", I, False)
+    m_v = rnn(cfg, p, f"{pre}_meta_velocity", V, False)
     u = torch.cat([h, m_i, m_v], dim=1)                                   # :468,:474
     a = torch.tanh(u @ p["extra_instrument_after_concat_layer/kernel"] + p["extra_instrument_after_concat_layer/bias"])
     if cfg.extra_layer:
@@ -268,11 +297,24 @@ def encode(cfg, p, X, I, V, eps=None):
 # --------------------------------------------------------------------------------------
 def _init_states(cfg, p, q, name):
     s1 = torch.tanh(q @ p[f"dec_init/{name}_s1/kernel"] + p[f"dec_init/{name}_s1/bias"])
+    if cfg.cell_type == "GRU":
+        return s1, None
     s2 = torch.tanh(q @ p[f"dec_init/{name}_s2/kernel"] + p[f"dec_init/{name}_s2/bias"])
     return s1, s2            # (state1, state2) = (h, c)
 
 
 def _rs_cell(cfg, p, name, x, h, c):
+    if cfg.cell_type == "GRU":
+        # recurrentshop GRUCell as recalled (structure = the shipped checkpoints): blocks [z|r|h]; h' = (1 - z) h + z hh  -- note the mix is
+        # the opposite of Keras' GRU layer; the first decoder step of the shipped models decodes correctly only with this one
+        H = cfg.H
+        act = _gate(cfg)
+        xa = x @ p[f"{name}/kernel"] + p[f"{name}/bias"]
+        ra = h @ p[f"{name}/recurrent_kernel_1"]
+        z = act(xa[:, :H] + ra[:, :H])
+        r = act(xa[:, H:2 * H] + ra[:, H:])
+        hh = torch.tanh(xa[:, 2 * H:] + (r * h) @ p[f"{name}/recurrent_kernel_2"])
+        return (1 - z) * h + z * hh, None
     a = x @ p[f"{name}/kernel"] + p[f"{name}/bias"] + h @ p[f"{name}/recurrent_kernel"]
     return lstm_step(cfg, a, c, cfg.dec_cell_variant)
 

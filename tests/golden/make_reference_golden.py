@@ -71,7 +71,8 @@ def set_module_lengths(vd, T):
 def keras_name_map(cfg):
     """our parameter name -> (sub-model, keras layer, index inside layer.weights) for the LSTM branch."""
     m = {}
-    enc = [f"lstm_{k}" for k in range(1, cfg.num_layers_encoder + 1)] + ["lstm_meta_instrument", "lstm_meta_velocity"]
+    pre = "gru" if getattr(cfg, "cell_type", "LSTM") == "GRU" else "lstm"
+    enc = [f"{pre}_{k}" for k in range(1, cfg.num_layers_encoder + 1)] + [f"{pre}_meta_instrument", f"{pre}_meta_velocity"]
     for l in enc:
         for i, t in enumerate(["kernel", "recurrent_kernel", "bias"]):
             m[f"{l}/{t}"] = ("encoder", l, i)
@@ -103,6 +104,7 @@ VARIANTS = {
               dict(history=False, extra_layer=False, num_layers_encoder=1, num_layers_decoder=1), dict(history=False), 8),
     "deep": (dict(num_layers_encoder=3, num_layers_decoder=3), dict(num_layers_encoder=3, num_layers_decoder=3), dict(), 8),
     "weights": (dict(), dict(), dict(silent_weight=0.25), 3),                                          # temporal weights != 1, ragged mini-batches 3 + 3 + 2
+    "gru": (dict(cell_type="GRU"), dict(cell_type="GRU"), dict(), 8),                                  # the reference's shipped default cell (settings.py:155)
 }
 
 
@@ -135,8 +137,11 @@ def run_variants(vd):
             setattr(vd, k, v)
         try:
             model = vd.VAE()
-            model.create(**create_kwargs(vd, cell_type="LSTM", input_length=T, output_length=T, lstm_size=H, latent_rep_size=L,
-                                         meta_velocity_length=T, meta_held_notes_length=T, meta_next_notes_output_length=T, **kw))
+            ckw = dict(cell_type="LSTM", input_length=T, output_length=T, lstm_size=H, latent_rep_size=L, meta_velocity_length=T,
+                       meta_held_notes_length=T, meta_next_notes_output_length=T)
+            ckw.update(kw)
+            rs_cells.GRU_GATE_ORDER, rs_cells.GRU_MIX = "zr", "z_takes_new"
+            model.create(**create_kwargs(vd, **ckw))
             load_into_reference(model, ocfg, w)
             K.set_random_normal_hook(lambda shp, mean, std: eps.astype(np.float64)[:shp[0]] * (std / 0.01) + mean)
             V = V3[..., 0]
@@ -167,7 +172,7 @@ def run_variants(vd):
             out[p + "in_shapes"] = np.array([str(np.asarray(a).shape) for a in in_list])
             out[p + "sw_notes"] = np.asarray(sw[0])
             out[p + "batch_size"] = np.array(bs)
-            if name in ("plain", "weights"):          # updated weights after the two epochs (kept for two variants only: fixture size)
+            if name in ("plain", "weights", "gru"):          # updated weights after the two epochs (kept for two variants only: fixture size)
                 dec_names = [nm for nm, _, _ in O.param_specs(ocfg) if nm.startswith(("dec_init/", "notes/", "meta_instrument/", "meta_velocity/"))]
                 for nm, a in zip(dec_names, model.decoder.get_weights()):
                     out[p + "w2/" + nm] = a

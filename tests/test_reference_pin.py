@@ -194,6 +194,7 @@ VARIANT_CFG = {
     "plain": dict(history=False, extra_layer=False, num_layers_encoder=1, num_layers_decoder=1),
     "deep": dict(num_layers_encoder=3, num_layers_decoder=3),
     "weights": dict(),
+    "gru": dict(cell_type="GRU"),          # the reference's shipped default cell; the oracle's GRU branch is groundwork for SURVEY.md 8(f-1)
 }
 
 
@@ -215,7 +216,7 @@ def test_reference_executed_variants(name):
     if not ocfg.history:
         th = None
     pre = name + "/"
-    assert int(g[pre + "n_inputs"]) == {"tf_list": 8, "plain": 6, "deep": 7, "weights": 7}[name]
+    assert int(g[pre + "n_inputs"]) == {"tf_list": 8, "plain": 6, "deep": 7, "weights": 7, "gru": 7}[name]
     with torch.no_grad():
         z, _, _ = O.encode(ocfg, p, X, I, V, te)
         Yh, Ih, Vh = O.decode(ocfg, p, z, th, feedback="as_wired")[:3]
@@ -267,3 +268,45 @@ def test_postprocess_matches_the_reference_function():
     assert np.array_equal(I, g["I"])
     assert np.allclose(V, g["V"], atol=1e-7)
     assert np.array_equal(D, g["D"])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/JvP/autoencoderEpoch440.pickle"), reason="reference checkout not present")
+def test_oracle_gru_branch_runs_a_shipped_checkpoint_like_the_reference_graph():
+    """The oracle's GRU branch at the reference's default sizes (T 64, H 256, L 256) takes the 50 tensors of a shipped autoencoder file
+    positionally (its parameter inventory IS the file's: names, shapes, order, 2 966 094 values) and reproduces what the reference's own
+    graph code, run through the shim on the same file, predicts -- to 1e-9."""
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_reference_golden as G
+    from midi_vae_b200 import hdf5
+    vd = G.import_reference()
+    from keras import backend as K
+    import recurrentshop.cells as rc
+    rc.GRU_GATE_ORDER, rc.GRU_MIX = "zr", "z_takes_new"
+    path = "/root/reference/models/JvP/autoencoderEpoch440.pickle"
+    ocfg = O.OracleConfig(input_length=64, lstm_size=256, latent_rep_size=256, cell_type="GRU")
+    t = hdf5.read_weights(path)
+    flat = [a for ln in t["layer_names"] for _, a in t["layers"][ln]]
+    specs = O.param_specs(ocfg)
+    assert len(flat) == len(specs) == 50 and O.param_count(ocfg) == sum(a.size for a in flat) == 2966094
+    p = {}
+    for (name, shape, _), a in zip(specs, flat):
+        assert tuple(a.shape) == tuple(shape), (name, a.shape, shape)
+        p[name] = torch.tensor(a, dtype=torch.float64)
+    Tq, n = 64, 4
+    r = synth.make_song(np.random.default_rng(11), n, Tq, 0)
+    X, I, V, C = [torch.tensor(a) for a in r.dense(np.float64)]
+    hist = torch.zeros(n, 256, dtype=torch.float64)
+    with torch.no_grad():
+        z, _, _ = O.encode(ocfg, p, X, I, V, None)
+        Yh, Ih, Vh = O.decode(ocfg, p, z, hist, feedback="as_wired")
+    K.clear_session()
+    m = vd.VAE()
+    m.create(**G.create_kwargs(vd, epsilon_std=0.0))
+    m.autoencoder.load_weights(path)
+    G.set_module_lengths(vd, Tq)
+    Xn, In, Vn, _ = r.dense(np.float64)
+    ins, _ = vd.prepare_autoencoder_input_and_output_list(Xn, Xn, 0, In[0], Vn[..., 0], np.zeros((n, Tq)), np.zeros((n, 15)), np.zeros((n, 256)))
+    Yr, Ir, Vr, Cr = m.autoencoder.predict(ins, batch_size=n)
+    assert np.abs(Yh.numpy() - Yr).max() < TOL and np.abs(Ih.numpy() - Ir).max() < TOL and np.abs(Vh.numpy() - Vr).max() < TOL
+    assert np.abs(O.style_head(ocfg, z).numpy() - Cr).max() < TOL
