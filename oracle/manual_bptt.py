@@ -301,3 +301,60 @@ def train_step_manual(cfg: OracleConfig, p: Dict[str, Tensor], pitch_idx, instr_
     rec_bwd(side[0], last_only(du[:, H:2 * H], Ti), "standard", "lstm_meta_instrument/bias", False)
     rec_bwd(side[1], last_only(du[:, 2 * H:], T), "standard", "lstm_meta_velocity/bias", False)
     return metrics, g
+
+
+# --------------------------------------------------------------------------------------
+# GRU primitives (groundwork for SURVEY.md 8(f-1); no CUDA counterpart yet).  One step is TWO dependent products:
+#   a_zr = xw[:, :2H] + h U_zr ;  z, r = act(a_zr)          a_h = xw[:, 2H:] + (r*h) U_h ;  hh = tanh(a_h)
+#   mix "keep" (keras.layers.GRU 2.0.8):  h' = z*h + (1-z)*hh        mix "new" (recurrentshop GRUCell as recalled):  h' = (1-z)*h + z*hh
+# The stash a reverse sweep needs is (z, r, hh) per step plus hseq; dG = [da_z | da_r | da_h] plays the role the 4H gate gradient plays for
+# the LSTM: dW = X^T dG, db = colsum dG, dU_zr = Hprev^T dG[:, :2H], dU_h = (r*Hprev)^T dG[:, 2H:].
+# --------------------------------------------------------------------------------------
+def gru_seq_fwd(cfg, xw: Tensor, U_zr: Tensor, U_h: Tensor, h0: Tensor, mix="keep"):
+    """xw (T,B,3H) pre-activations incl. bias, blocks [z|r|h].  Returns hseq (T+1,B,H) [slot 0 = h0] and gates (T,B,3H) = post-activation (z, r, hh)."""
+    T, B, G = xw.shape
+    H = G // 3
+    hseq = xw.new_zeros(T + 1, B, H); gates = xw.new_zeros(T, B, G)
+    hseq[0] = h0
+    for t in range(T):
+        h = hseq[t]
+        a = xw[t, :, :2 * H] + h @ U_zr
+        z = _act(cfg, a[:, :H]); r = _act(cfg, a[:, H:])
+        hh = torch.tanh(xw[t, :, 2 * H:] + (r * h) @ U_h)
+        hseq[t + 1] = z * h + (1 - z) * hh if mix == "keep" else (1 - z) * h + z * hh
+        gates[t, :, :H] = z; gates[t, :, H:2 * H] = r; gates[t, :, 2 * H:] = hh
+    return hseq, gates
+
+
+def gru_seq_bwd(cfg, dh_ext: Tensor, gates: Tensor, hseq: Tensor, U_zr: Tensor, U_h: Tensor, mix="keep"):
+    """dh_ext (T,B,H): gradient arriving at h_t from outside the recurrence (slot t = h after step t).
+    Returns dG (T,B,3H) pre-activation gradients [da_z|da_r|da_h] and dh0 (B,H)."""
+    T, B, G = gates.shape
+    H = G // 3
+    dG = gates.new_zeros(T, B, G)
+    carry = gates.new_zeros(B, H)
+    for t in range(T - 1, -1, -1):
+        z, r, hh = gates[t, :, :H], gates[t, :, H:2 * H], gates[t, :, 2 * H:]
+        h = hseq[t]
+        d = dh_ext[t] + carry
+        if mix == "keep":
+            dz = d * (h - hh); dhh = d * (1 - z); carry = d * z
+        else:
+            dz = d * (hh - h); dhh = d * z; carry = d * (1 - z)
+        da_h = dhh * (1 - hh * hh)
+        drh = da_h @ U_h.t()                       # gradient wrt (r*h)
+        da_r = drh * h * _dact(cfg, r)
+        da_z = dz * _dact(cfg, z)
+        carry = carry + drh * r + torch.cat([da_z, da_r], dim=1) @ U_zr.t()
+        dG[t, :, :H] = da_z; dG[t, :, H:2 * H] = da_r; dG[t, :, 2 * H:] = da_h
+    return dG, carry
+
+
+def gru_weight_grads(X: Tensor, hseq: Tensor, gates: Tensor, dG: Tensor):
+    """Batched weight gradients of one GRU recurrence from the reverse sweep's dG: X (T,B,D) inputs.  -> dW (D,3H), db (3H), dU_zr (H,2H), dU_h (H,H)."""
+    T, B, G = dG.shape
+    H = G // 3
+    Xf, Gf = X.reshape(T * B, -1), dG.reshape(T * B, G)
+    Hp = hseq[:T].reshape(T * B, H)
+    R = gates[:, :, H:2 * H].reshape(T * B, H)
+    return Xf.t() @ Gf, Gf.sum(0), Hp.t() @ Gf[:, :2 * H], (R * Hp).t() @ Gf[:, 2 * H:]

@@ -121,3 +121,46 @@ def test_golden_vectors_reproduce():
     assert np.allclose([m[k] for k in METRIC_KEYS], g["metrics"], rtol=0, atol=1e-12)
     for k, v in gr.items():
         assert np.abs(v.numpy() - g["g/" + k]).max() <= 1e-6 * max(1.0, float(v.abs().max())), k
+
+
+@pytest.mark.parametrize("mix", ["keep", "new"])
+@pytest.mark.parametrize("gate", ["hard_sigmoid", "sigmoid"])
+def test_manual_gru_bptt_matches_autograd(mix, gate):
+    """The hand-derived GRU reverse sweep (two dependent products per step; stash = z, r, hh) against autograd, for the Keras GRU mix and for
+    the recalled recurrentshop GRUCell mix: blueprint of the GRU kernels of SURVEY.md 8(f-1)."""
+    from oracle import manual_bptt as MB
+    torch.manual_seed(3)
+    T_, B_, H_, D_ = 7, 5, 12, 9
+    cfg = O.OracleConfig(input_length=T_, lstm_size=H_, gate_act=gate)
+    dt = torch.float64
+    X = torch.randn(T_, B_, D_, dtype=dt)
+    leaves = [torch.randn(D_, 3 * H_, dtype=dt) * 0.4, torch.randn(3 * H_, dtype=dt) * 0.2, torch.randn(H_, 2 * H_, dtype=dt) * 0.4,
+              torch.randn(H_, H_, dtype=dt) * 0.4, torch.randn(B_, H_, dtype=dt) * 0.5]
+    W, b, Uzr, Uh, h0 = [l.requires_grad_(True) for l in leaves]
+    probe = torch.randn(T_, B_, H_, dtype=dt)
+    act = O.hard_sigmoid if gate == "hard_sigmoid" else torch.sigmoid
+    h, hs = h0, []
+    xw = X @ W + b
+    for t in range(T_):                     # autograd-friendly restatement of the same step (no in-place writes)
+        a = xw[t, :, :2 * H_] + h @ Uzr
+        z, r = act(a[:, :H_]), act(a[:, H_:])
+        hh = torch.tanh(xw[t, :, 2 * H_:] + (r * h) @ Uh)
+        h = z * h + (1 - z) * hh if mix == "keep" else (1 - z) * h + z * hh
+        hs.append(h)
+    loss = (torch.stack(hs) * probe).sum()
+    gW, gb, gUzr, gUh, gh0 = torch.autograd.grad(loss, [W, b, Uzr, Uh, h0])
+    with torch.no_grad():
+        hseq, gates = MB.gru_seq_fwd(cfg, xw.detach(), Uzr.detach(), Uh.detach(), h0.detach(), mix)
+        assert (hseq[1:] - torch.stack(hs)).abs().max() < 1e-12
+    with torch.no_grad():
+        dG, dh0 = MB.gru_seq_bwd(cfg, probe, gates, hseq, Uzr.detach(), Uh.detach(), mix)
+        dW, db, dUzr, dUh = MB.gru_weight_grads(X, hseq, gates, dG)
+    for mine, ref in ((dW, gW), (db, gb), (dUzr, gUzr), (dUh, gUh), (dh0, gh0)):
+        assert (mine - ref).abs().max() < 1e-10 * max(1.0, float(ref.abs().max()))
+    # and the forward is the oracle's: Keras GRU layer (keep) / recalled GRUCell (new)
+    if mix == "keep":
+        p = {"g/kernel": W.detach(), "g/recurrent_kernel": torch.cat([Uzr, Uh], 1).detach(), "g/bias": b.detach()}
+        ref_h = O.keras_gru(cfg, p, "g", X.permute(1, 0, 2), True)
+        # keras_gru starts from h = 0: compare a run from h0 = 0
+        hs0, _ = MB.gru_seq_fwd(cfg, (X @ W + b).detach(), Uzr.detach(), Uh.detach(), torch.zeros(B_, H_, dtype=dt), mix)
+        assert (hs0[1:].permute(1, 0, 2) - ref_h).abs().max() < 1e-12
