@@ -686,7 +686,10 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
           // gated by a stream wait on the counter (the next layer's input projection of this chunk) may start while the recurrence goes on
           __threadfence();
           named_barrier(7 + set, 32 * CL_EPI_WARPS);
-          if (ew == 0 && lane == 0) atomicAdd(p.progress + ((t + 1) / p.progress_every - 1), 1u);
+          if (ew == 0 && lane == 0) {
+            __threadfence();      // cumulative over the set's stores observed through the barrier: fence and counter update by the SAME thread
+            atomicAdd(p.progress + ((t + 1) / p.progress_every - 1), 1u);
+          }
         }
         if (tracer && g == 0) CL_TRACE(t, 9);
       }
