@@ -164,3 +164,52 @@ def test_manual_gru_bptt_matches_autograd(mix, gate):
         # keras_gru starts from h = 0: compare a run from h0 = 0
         hs0, _ = MB.gru_seq_fwd(cfg, (X @ W + b).detach(), Uzr.detach(), Uh.detach(), torch.zeros(B_, H_, dtype=dt), mix)
         assert (hs0[1:].permute(1, 0, 2) - ref_h).abs().max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ independent witnesses (PyTorch's own layers)
+def test_lstm_equations_agree_with_torch_nn_lstm():
+    """An implementation nobody here wrote: torch.nn.LSTM (gate blocks i, f, g, o; logistic gates) against the oracle's Keras-LSTM restatement
+    with gate_act='sigmoid' (Keras blocks [i|f|c|o] are the same order).  Pins the cell equations, the block order and the bias handling;
+    the Keras default hard_sigmoid differs from this only in the gate non-linearity (oracle.hard_sigmoid = clip(0.2 x + 0.5, 0, 1))."""
+    torch.manual_seed(0)
+    T_, B_, D_, H_ = 9, 4, 7, 10
+    cfg = O.OracleConfig(input_length=T_, lstm_size=H_, gate_act="sigmoid")
+    ref = torch.nn.LSTM(D_, H_, batch_first=True).double()
+    p = {"l/kernel": ref.weight_ih_l0.detach().t().contiguous(), "l/recurrent_kernel": ref.weight_hh_l0.detach().t().contiguous(),
+         "l/bias": (ref.bias_ih_l0 + ref.bias_hh_l0).detach()}
+    x = torch.randn(B_, T_, D_, dtype=torch.float64)
+    with torch.no_grad():
+        want, (h_n, _) = ref(x)
+        got = O.keras_lstm(cfg, p, "l", x, True)
+        last = O.keras_lstm(cfg, p, "l", x, False)
+    assert (got - want).abs().max() < 1e-12 and (last - h_n[0]).abs().max() < 1e-12
+
+
+def test_keras_adam_agrees_with_torch_adam_up_to_the_epsilon_placement():
+    """keras.optimizers.Adam (2.0.8) and torch.optim.Adam are the same recursion; they differ only in where epsilon enters
+    (Keras: lr_t m / (sqrt(v) + eps) with the bias corrections folded into lr_t; torch: eps is added to sqrt(v_hat)).  With eps -> 0 the
+    trajectories must coincide."""
+    torch.manual_seed(1)
+    w0 = torch.randn(6, 5, dtype=torch.float64)
+    p = {"w": w0.clone()}
+    opt = O.KerasAdam(p, lr=2e-4, epsilon=1e-300)
+    wt = w0.clone().requires_grad_(True)
+    topt = torch.optim.Adam([wt], lr=2e-4, betas=(0.9, 0.999), eps=1e-300)
+    for step in range(25):
+        g = torch.sin(torch.arange(30, dtype=torch.float64).reshape(6, 5) * (step + 1)) + 0.3
+        opt.step(p, {"w": g})
+        wt.grad = g.clone()
+        topt.step()
+    assert (p["w"] - wt.detach()).abs().max() < 1e-12
+
+
+def test_crossentropy_agrees_with_torch_cross_entropy():
+    """Theano-backend categorical_crossentropy on softmax outputs (renormalise, clip to [1e-7, 1 - 1e-7], -sum y log p) equals
+    torch.nn.functional.cross_entropy on the logits wherever the clip is inactive."""
+    torch.manual_seed(2)
+    logits = torch.randn(5, 8, 61, dtype=torch.float64) * 2
+    idx = torch.randint(0, 61, (5, 8))
+    y = torch.nn.functional.one_hot(idx, 61).double()
+    got = O.categorical_crossentropy(y, torch.softmax(logits, -1))
+    want = torch.nn.functional.cross_entropy(logits.reshape(-1, 61), idx.reshape(-1), reduction="none").reshape(5, 8)
+    assert (got - want).abs().max() < 1e-10
