@@ -292,7 +292,7 @@ def main():
                 "class_ms": {k: round(v[0], 4) for k, v in kms.items()}, "class_launch_groups": {k: v[1] for k, v in kms.items()}}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is timed at N = 1 only (the other ranks would idle in a barrier)
         sample = max(1, min(B, args.cpu_sample))
         rate, ms, cores = cpu_oracle_rate(wl, args.feedback, sample, 2, 1)
         cpu = {"value": rate, "unit": "sequences/s", "cores": cores, "kind": "port",
