@@ -206,6 +206,75 @@ def run_postprocess(vd):
     print(path, os.path.getsize(path), "bytes; sounding steps", int(Y.sum()), "of", Y.shape[0])
 
 
+def run_training_loop(vd):
+    """The reference's OWN training loop -- the source lines of vae_training.py from "# Train model" (:723) to the end of the per-epoch train
+    aggregation (:959), exec'd unmodified -- over five synthetic songs for three epochs with the shim-built LSTM model: history latents (zeros in
+    epoch 0, encoder.predict rolled by one chunk afterwards), one fit per song, per-song means, KL recovery.  -> reference_training_loop.npz"""
+    import contextlib
+    import io
+    import re
+    from keras import backend as K
+    import recurrentshop.cells as rs_cells
+    from midi_vae_b200 import synth
+    from oracle import midivae_oracle as O
+    from tests import util
+    T, H, L, bs, epochs, n_songs = 16, 64, 16, 8, 3, 5
+    src_lines = open(os.path.join(REF, "vae_training.py")).read().split("\n")
+    first = next(i for i, l in enumerate(src_lines) if l.startswith("# Train model"))
+    last = next(i for i, l in enumerate(src_lines) if l.startswith('    print("Total train loss: "'))
+    code = "\n".join(src_lines[first:last + 1])
+    assert "autoencoder.fit(input_list, output_list" in code and "H[1:] = representation_list[:-1]" in code
+    ecfg, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant="standard", max_batch=bs, lr=2e-3)
+    w = util.make_weights(ecfg, seed=52, jitter=0.1)
+    rs_cells.LSTM_VARIANT = "standard"
+    K.clear_session()
+    set_module_lengths(vd, T)
+    model = vd.VAE()
+    model.create(**create_kwargs(vd, cell_type="LSTM", input_length=T, output_length=T, lstm_size=H, latent_rep_size=L, meta_velocity_length=T,
+                                 meta_held_notes_length=T, meta_next_notes_output_length=T, learning_rate=2e-3))
+    load_into_reference(model, ocfg, w)
+    songs = synth.make_songs(n_songs, T, seed=777, min_chunks=5, max_chunks=19)
+    draws = []                                     # every K.random_normal draw, in call order (the test replays them)
+    rng = np.random.default_rng(4242)
+
+    def hook(shp, mean, std):
+        e = rng.standard_normal(shp) * std + mean
+        draws.append(e)
+        return e
+    K.set_random_normal_hook(hook)
+
+    class _Bar:
+        def __init__(self, **k): pass
+        def update(self, *a): pass
+    ns = {k: getattr(vd, k) for k in dir(vd) if not k.startswith("__")}           # the script's `from settings import *` names
+    ns.update(np=np, vae_definition=vd, progressbar=types.SimpleNamespace(ProgressBar=_Bar), encoder=model.encoder, autoencoder=model.autoencoder,
+              latent_dim=L, batch_size=bs, epochs=epochs, shuffle_train_set=False, load_previous_checkpoint=False, history=True, reset_states=True,
+              train_set_size=n_songs, train_paths=[f"song{i}" for i in range(n_songs)],
+              X_train=[s.dense(np.float64)[0] for s in songs], Y_train=[s.dense(np.float64)[0] for s in songs], C_train=[int(s.style[0]) for s in songs],
+              I_train=[s.dense(np.float64)[1][0] for s in songs], V_train=[s.velocity.astype(np.float64) for s in songs],
+              D_train=[np.zeros(s.velocity.shape) for s in songs], S_train=[np.zeros((len(s), 15)) for s in songs],
+              normalized_S_train=[np.zeros((len(s), 15)) for s in songs], T_train=[120.0] * n_songs)
+    for name in set(re.findall(r"\b(total_(?:train|test)_\w+_array)\b", code)):
+        ns[name] = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(code, "vae_training.py[train loop]", "exec"), ns)
+    out = {"loss": np.array(ns["total_train_loss_array"]), "notes_acc": np.array(ns["total_train_accuracy_array"]),
+           "notes_loss": np.array(ns["total_train_notes_loss_array"]), "instr_acc": np.array(ns["total_train_meta_instrument_accuracy_array"]),
+           "instr_loss": np.array(ns["total_train_meta_instrument_loss_array"]), "vel_loss": np.array(ns["total_train_meta_velocity_loss_array"]),
+           "style_acc": np.array(ns["total_train_composer_accuracy_array"]), "style_loss": np.array(ns["total_train_composer_loss_array"]),
+           "kl": np.array(ns["total_train_kl_loss_array"]), "n_draws": np.array(len(draws)),
+           "draws": np.concatenate([d.reshape(-1) for d in draws]), "draw_rows": np.array([d.shape[0] for d in draws]),
+           "song_lengths": np.array([len(s) for s in songs])}
+    dec_names = [nm for nm, _, _ in O.param_specs(ocfg) if nm.startswith(("dec_init/", "notes/", "meta_instrument/", "meta_velocity/"))]
+    for nm, a in zip(dec_names, model.decoder.get_weights()):
+        out["w/" + nm] = a
+    for k, (sub, layer, idx) in keras_name_map(ocfg).items():
+        out["w/" + k] = model.encoder.get_layer(layer).get_weights()[idx]
+    path = os.path.join(HERE, "reference_training_loop.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes; epochs", epochs, "loss per epoch", np.round(out["loss"], 4), "draws", len(draws))
+
+
 def main():
     vd = import_reference()
     import keras
@@ -311,6 +380,7 @@ def main():
     print(path, os.path.getsize(path), "bytes")
     run_variants(vd)
     run_postprocess(vd)
+    run_training_loop(vd)
     print("keras shim", keras.__version__, "evaluate(standard):", dict(zip(out["standard/metrics_names"], out["standard/evaluate"])))
 
 

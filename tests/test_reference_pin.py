@@ -310,3 +310,59 @@ def test_oracle_gru_branch_runs_a_shipped_checkpoint_like_the_reference_graph():
     Yr, Ir, Vr, Cr = m.autoencoder.predict(ins, batch_size=n)
     assert np.abs(Yh.numpy() - Yr).max() < TOL and np.abs(Ih.numpy() - Ir).max() < TOL and np.abs(Vh.numpy() - Vr).max() < TOL
     assert np.abs(O.style_head(ocfg, z).numpy() - Cr).max() < TOL
+
+
+def test_training_loop_matches_the_reference_script_lines():
+    """tests/golden/reference_training_loop.npz comes from exec'ing the reference's OWN loop (vae_training.py:723-959, unmodified source lines)
+    around the shim-built model: 5 songs x 3 epochs, history latents from encoder.predict after epoch 0, one fit per song, per-song means, KL
+    recovered as (loss - sum w_i loss_i) / beta.  The oracle, driven by the restatement of that loop below (the same one
+    midi_vae_b200/training.py implements on the engine), reproduces every per-epoch aggregate and the final weights to 1e-9."""
+    g = np.load(os.path.join(GOLD, "reference_training_loop.npz"))
+    bs, epochs = 8, 3
+    ecfg, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant="standard", max_batch=bs, lr=2e-3)
+    p = util.to_torch(util.make_weights(ecfg, seed=52, jitter=0.1))
+    songs = synth.make_songs(5, T, seed=777, min_chunks=5, max_chunks=19)
+    assert [len(s) for s in songs] == list(g["song_lengths"])
+    rows = list(g["draw_rows"])
+    flat = g["draws"]
+    cursor = {"i": 0, "off": 0}
+
+    def next_eps(n):
+        i = cursor["i"]
+        assert rows[i] == n, (i, rows[i], n)
+        e = torch.tensor(flat[cursor["off"]:cursor["off"] + n * L].reshape(n, L))
+        cursor["i"] += 1
+        cursor["off"] += n * L
+        return e
+
+    opt = O.KerasAdam(p, lr=ocfg.learning_rate)
+    agg = {k: [] for k in ("loss", "notes_acc", "notes_loss", "instr_acc", "instr_loss", "vel_loss", "style_acc", "style_loss", "kl")}
+    for e in range(epochs):
+        per_song = []
+        for s in songs:
+            X, I, V, C = [torch.tensor(a) for a in s.dense(np.float64)]
+            n = len(s)
+            if e == 0:
+                Hh = torch.zeros(n, L, dtype=torch.float64)                      # vae_training.py:789-790
+            else:
+                with torch.no_grad():
+                    z = torch.cat([O.encode(ocfg, p, X[a:a + bs], I[a:a + bs], V[a:a + bs], next_eps(min(n, a + bs) - a))[0] for a in range(0, n, bs)])
+                Hh = O.shift_history(z)                                          # :791-798
+            tot = {}
+            for a in range(0, n, bs):
+                b = min(n, a + bs)
+                m, _ = O.train_on_batch(ocfg, p, opt, X[a:b], I[a:b], V[a:b], C[a:b], Hh[a:b], next_eps(b - a))
+                for k, v in m.items():
+                    tot[k] = tot.get(k, 0.0) + v * (b - a)
+            per_song.append({k: v / n for k, v in tot.items()})
+        mean = {k: float(np.mean([ps[k] for ps in per_song])) for k in per_song[0]}
+        agg["loss"].append(mean["loss"]); agg["notes_acc"].append(mean["decoder_acc_1"]); agg["notes_loss"].append(mean["decoder_loss_1"])
+        agg["instr_acc"].append(mean["decoder_acc_2"]); agg["instr_loss"].append(mean["decoder_loss_2"]); agg["vel_loss"].append(mean["decoder_loss_3"])
+        agg["style_acc"].append(mean["composer_decoder_acc"]); agg["style_loss"].append(mean["composer_decoder_loss"])
+        agg["kl"].append((mean["loss"] - mean["decoder_loss_1"] - 0.1 * mean["composer_decoder_loss"] - 0.1 * mean["decoder_loss_2"]
+                          - 1.0 * mean["decoder_loss_3"]) / 0.1)                 # :946-957
+    assert cursor["i"] == int(g["n_draws"])
+    for k, v in agg.items():
+        assert np.abs(np.array(v) - g[k]).max() < 1e-8, (k, v, g[k])
+    for k, v in p.items():
+        assert np.abs(v.numpy() - g["w/" + k]).max() < 1e-8, k
