@@ -9,6 +9,10 @@ and the velocity roll f32 [n,T]; the remaining rules are cheap integer bookkeepi
         play it as loud as the previous played note;
       - velocity above the threshold but no pitch: velocity 0;
   * D (held-note roll) is 0 where the velocity says "struck", else 1 (:1214-1221).
+
+The per-voice "previous pitch / previous velocity" memory of the override runs over whatever is passed in ONE call: the reference's
+style-switch loop (vae_evaluation.py:2469-2483) calls it once per chunk, its whole-song call sites (:799, :814) once per song.  Call this
+function the same way (tests/test_reference_pin.py pins both uses to reference-executed outputs).
 """
 from __future__ import annotations
 

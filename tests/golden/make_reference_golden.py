@@ -275,6 +275,46 @@ def run_training_loop(vd):
     print(path, os.path.getsize(path), "bytes; epochs", epochs, "loss per epoch", np.round(out["loss"], 4), "draws", len(draws))
 
 
+def run_style_transfer_loop(vd):
+    """The reference's style-switch loop (vae_evaluation.py:2469-2483 and :2549-2550: switch the two style dimensions of every chunk's latent, decode
+    it with the PREVIOUS SWITCHED latent as history, post-process) -- those source lines exec'd unmodified (the classifier / harmonicity
+    bookkeeping between them left out) around the shim-built LSTM model.  -> reference_style_transfer.npz"""
+    from keras import backend as K
+    import recurrentshop.cells as rs_cells
+    from midi_vae_b200 import synth
+    from oracle import midivae_oracle as O
+    from tests import util
+    T, H, L, n = 16, 64, 16, 12
+    lines = open(os.path.join(REF, "vae_evaluation.py")).read().split("\n")
+    a = next(i for i, l in enumerate(lines) if l.strip() == "for i in range(len(encoded_representation)):")
+    b = next(i for i in range(a, len(lines)) if lines[i].strip() == "D_list_switched.extend(D_switched)")
+    c = next(i for i in range(b, len(lines)) if lines[i].strip() == "previous_switched_rep = switched_rep")
+    body = lines[a:b + 1] + [lines[c]]
+    assert any("switched_rep[C] = original_rep[C_switch]" in l for l in body) and any("prepare_decoder_input(switched_rep, C_switch, S[i], previous_switched_rep)" in l for l in body)
+    indent = len(lines[a]) - len(lines[a].lstrip())
+    code = "\n".join(l[indent:] for l in body)
+    ecfg, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant="standard", max_batch=n)
+    w = util.make_weights(ecfg, seed=62, jitter=0.2)
+    rs_cells.LSTM_VARIANT = "standard"
+    K.clear_session()
+    set_module_lengths(vd, T)
+    K.set_random_normal_hook(None)
+    model = vd.VAE()
+    model.create(**create_kwargs(vd, cell_type="LSTM", input_length=T, output_length=T, lstm_size=H, latent_rep_size=L, meta_velocity_length=T,
+                                 meta_held_notes_length=T, meta_next_notes_output_length=T, epsilon_std=0.0))     # vae_evaluation.py:482-485
+    load_into_reference(model, ocfg, w)
+    song = synth.make_song(np.random.default_rng(909), n, T, 0)
+    X, I_, V3, _ = song.dense(np.float64)
+    enc = model.encoder.predict(vd.prepare_encoder_input_list(X, I_[0], V3[..., 0], np.zeros((n, T))), batch_size=n)
+    ns = dict(np=np, vae_definition=vd, decoder=model.decoder, batch_size=n, sample_method="argmax", encoded_representation=enc, C=0, C_switch=1,
+              S=np.zeros((n, 15)), previous_switched_rep=np.zeros((1, L)), Y_list_switched=[], I_list_switched=[], V_list_switched=[], D_list_switched=[])
+    exec(compile(code, "vae_evaluation.py[style switch loop]", "exec"), ns)
+    path = os.path.join(HERE, "reference_style_transfer.npz")
+    np.savez_compressed(path, pitch=song.pitch, instr=song.instr, velocity=song.velocity, encoded=enc, Y=np.asarray(ns["Y_list_switched"]).astype(np.uint8),
+                        I=np.asarray(ns["I_list_switched"]).astype(np.uint8), V=np.asarray(ns["V_list_switched"]), D=np.asarray(ns["D_list_switched"]).astype(np.uint8))
+    print(path, os.path.getsize(path), "bytes; sounding steps", int(np.asarray(ns["Y_list_switched"]).sum()), "of", n * T)
+
+
 def main():
     vd = import_reference()
     import keras
@@ -381,6 +421,7 @@ def main():
     run_variants(vd)
     run_postprocess(vd)
     run_training_loop(vd)
+    run_style_transfer_loop(vd)
     print("keras shim", keras.__version__, "evaluate(standard):", dict(zip(out["standard/metrics_names"], out["standard/evaluate"])))
 
 

@@ -366,3 +366,29 @@ def test_training_loop_matches_the_reference_script_lines():
         assert np.abs(np.array(v) - g[k]).max() < 1e-8, (k, v, g[k])
     for k, v in p.items():
         assert np.abs(v.numpy() - g["w/" + k]).max() < 1e-8, k
+
+
+def test_style_transfer_matches_the_reference_loop_lines():
+    """tests/golden/reference_style_transfer.npz comes from exec'ing the reference's own style-switch loop lines (vae_evaluation.py:2469-2483,
+    :2549-2550) around the shim-built model: per chunk, swap latent dimensions C and C', decode with the PREVIOUS SWITCHED latent as history,
+    process_decoder_outputs.  The oracle's batched style_transfer + the host post-processing reproduce the rolls the loop collected."""
+    from midi_vae_b200 import postprocess
+    g = np.load(os.path.join(GOLD, "reference_style_transfer.npz"))
+    n = g["pitch"].shape[0]
+    ecfg, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant="standard", max_batch=n)
+    p = util.to_torch(util.make_weights(ecfg, seed=62, jitter=0.2))
+    song = synth.Rolls(g["pitch"], g["instr"], g["velocity"], np.zeros(n, np.uint8))
+    X, I, V, _ = [torch.tensor(a) for a in song.dense(np.float64)]
+    start = np.zeros(n, bool)
+    start[0] = True
+    st = O.style_transfer(ocfg, p, X, I, V, 0, 1, start, "as_wired")
+    assert np.abs(st["z"].numpy() - g["encoded"]).max() < TOL                      # encoder.predict with epsilon_std = 0
+    assert float(O.top2_margin(st["Yh"]).min()) > 1e-9
+    # the loop post-processes CHUNK BY CHUNK (one decoder.predict + process_decoder_outputs per chunk), so the per-voice "previous pitch /
+    # previous velocity" memory of the velocity override restarts at every chunk: call the host post-processing the same way
+    pit, ins, vel = st["pitch"].numpy().astype(np.uint8), st["instr"].numpy().astype(np.uint8), st["Vh"].numpy()[..., 0]
+    parts = [postprocess.process_decoder_outputs(pit[i:i + 1], ins[i:i + 1], vel[i:i + 1]) for i in range(n)]
+    Y, Ih, Vv, D = [np.concatenate([q[k] for q in parts]) for k in range(4)]
+    assert np.array_equal(Y, g["Y"]) and np.array_equal(Ih, g["I"]) and np.array_equal(D, g["D"])
+    assert np.abs(Vv - g["V"]).max() < 1e-9
+    assert not np.array_equal(postprocess.process_decoder_outputs(pit, ins, vel)[3], g["D"])      # (whole-song post-processing is a different thing)
