@@ -315,6 +315,60 @@ def run_style_transfer_loop(vd):
     print(path, os.path.getsize(path), "bytes; sounding steps", int(np.asarray(ns["Y_list_switched"]).sum()), "of", n * T)
 
 
+def run_test_loop(vd):
+    """The reference's evaluation pass: the metric-name enumeration (vae_training.py:172-187) and the body of test() from its accumulators (:246)
+    to the end of the per-song loop -- source lines exec'd unmodified -- over four synthetic songs.  -> reference_test_loop.npz"""
+    import textwrap
+    from keras import backend as K
+    import recurrentshop.cells as rs_cells
+    from midi_vae_b200 import synth
+    from tests import util
+    T, H, L, bs, n_songs = 16, 64, 16, 8, 4
+    lines = open(os.path.join(REF, "vae_training.py")).read().split("\n")
+    a = next(i for i, l in enumerate(lines) if l.startswith("enumerated_metric_names = []"))
+    b = next(i for i in range(a, len(lines)) if lines[i].startswith("# initialize loss arrays"))
+    c = next(i for i, l in enumerate(lines) if l.startswith("    total_test_loss = 0"))
+    d = next(i for i in range(c, len(lines)) if lines[i].strip() == "bar.update(test_song_num+1)")
+    code = "\n".join(lines[a:b]) + "\n" + textwrap.dedent("\n".join(lines[c:d + 1]))
+    assert "autoencoder.evaluate(input_list, output_list" in code and "enumerated_metric_names.append" in code
+    ecfg, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant="standard", max_batch=bs)
+    w = util.make_weights(ecfg, seed=72, jitter=0.15)
+    rs_cells.LSTM_VARIANT = "standard"
+    K.clear_session()
+    set_module_lengths(vd, T)
+    model = vd.VAE()
+    model.create(**create_kwargs(vd, cell_type="LSTM", input_length=T, output_length=T, lstm_size=H, latent_rep_size=L, meta_velocity_length=T,
+                                 meta_held_notes_length=T, meta_next_notes_output_length=T))
+    load_into_reference(model, ocfg, w)
+    songs = synth.make_songs(n_songs, T, seed=888, min_chunks=5, max_chunks=19)
+    draws = []
+    rng = np.random.default_rng(5151)
+
+    def hook(shp, mean, std):
+        e = rng.standard_normal(shp) * std + mean
+        draws.append(e)
+        return e
+    K.set_random_normal_hook(hook)
+
+    class _Bar:
+        def __init__(self, **k): pass
+        def update(self, *a): pass
+    ns = {k: getattr(vd, k) for k in dir(vd) if not k.startswith("__")}
+    ns.update(np=np, vae_definition=vd, progressbar=types.SimpleNamespace(ProgressBar=_Bar), encoder=model.encoder, autoencoder=model.autoencoder,
+              latent_dim=L, batch_size=bs, history=True, reset_states=True, test_set_size=n_songs,
+              X_test=[s.dense(np.float64)[0] for s in songs], Y_test=[s.dense(np.float64)[0] for s in songs], C_test=[int(s.style[0]) for s in songs],
+              I_test=[s.dense(np.float64)[1][0] for s in songs], V_test=[s.velocity.astype(np.float64) for s in songs],
+              D_test=[np.zeros(s.velocity.shape) for s in songs], normalized_S_test=[np.zeros((len(s), 15)) for s in songs], T_test=[120.0] * n_songs)
+    exec(compile(code, "vae_training.py[test loop]", "exec"), ns)
+    keys = ["total_test_loss", "total_test_notes_loss", "total_test_accuracy", "total_test_meta_instrument_loss", "total_test_meta_instrument_accuracy",
+            "total_test_meta_velocity_loss", "total_test_meta_velocity_accuracy", "total_test_loss_composer", "total_test_accuracy_composer"]
+    path = os.path.join(HERE, "reference_test_loop.npz")
+    np.savez_compressed(path, totals=np.array([ns[k] for k in keys]), total_names=np.array(keys), enumerated=np.array(ns["enumerated_metric_names"]),
+                        draws=np.concatenate([x.reshape(-1) for x in draws]), draw_rows=np.array([x.shape[0] for x in draws]),
+                        song_lengths=np.array([len(s) for s in songs]))
+    print(path, os.path.getsize(path), "bytes;", ns["enumerated_metric_names"])
+
+
 def main():
     vd = import_reference()
     import keras
@@ -422,6 +476,7 @@ def main():
     run_postprocess(vd)
     run_training_loop(vd)
     run_style_transfer_loop(vd)
+    run_test_loop(vd)
     print("keras shim", keras.__version__, "evaluate(standard):", dict(zip(out["standard/metrics_names"], out["standard/evaluate"])))
 
 

@@ -392,3 +392,49 @@ def test_style_transfer_matches_the_reference_loop_lines():
     assert np.array_equal(Y, g["Y"]) and np.array_equal(Ih, g["I"]) and np.array_equal(D, g["D"])
     assert np.abs(Vv - g["V"]).max() < 1e-9
     assert not np.array_equal(postprocess.process_decoder_outputs(pit, ins, vel)[3], g["D"])      # (whole-song post-processing is a different thing)
+
+
+def test_evaluation_pass_matches_the_reference_script_lines():
+    """tests/golden/reference_test_loop.npz: the reference's metric-name enumeration (vae_training.py:172-187) and the per-song loop of its
+    test() (:246-351) exec'd unmodified around the shim-built model.  The enumerated names are METRIC_KEYS; the accumulated totals are what
+    the oracle gives when driven the way midi_vae_b200.training.evaluate_songs drives the engine (history ALWAYS from encoder.predict rolled
+    by one chunk, batch-size-weighted means per song, sums over songs)."""
+    g = np.load(os.path.join(GOLD, "reference_test_loop.npz"))
+    assert list(g["enumerated"]) == METRIC_KEYS[:9]
+    bs = 8
+    ecfg, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="as_wired", variant="standard", max_batch=bs)
+    p = util.to_torch(util.make_weights(ecfg, seed=72, jitter=0.15))
+    songs = synth.make_songs(4, T, seed=888, min_chunks=5, max_chunks=19)
+    assert [len(s) for s in songs] == list(g["song_lengths"])
+    rows, flat, cur = list(g["draw_rows"]), g["draws"], {"i": 0, "off": 0}
+
+    def next_eps(n):
+        assert rows[cur["i"]] == n
+        e = torch.tensor(flat[cur["off"]:cur["off"] + n * L].reshape(n, L))
+        cur["i"] += 1
+        cur["off"] += n * L
+        return e
+
+    tot = {}
+    for s in songs:
+        X, I, V, C = [torch.tensor(a) for a in s.dense(np.float64)]
+        n = len(s)
+        with torch.no_grad():
+            z = torch.cat([O.encode(ocfg, p, X[a:a + bs], I[a:a + bs], V[a:a + bs], next_eps(min(n, a + bs) - a))[0] for a in range(0, n, bs)])
+        Hh = O.shift_history(z)
+        acc = {}
+        for a in range(0, n, bs):
+            b = min(n, a + bs)
+            m, _, _ = O.evaluate_batch(ocfg, p, X[a:b], I[a:b], V[a:b], C[a:b], Hh[a:b], next_eps(b - a))
+            for k, v in m.items():
+                acc[k] = acc.get(k, 0.0) + v * (b - a)
+        for k, v in acc.items():
+            tot[k] = tot.get(k, 0.0) + v / n
+    assert cur["i"] == len(rows)
+    want = dict(zip(g["total_names"], g["totals"]))
+    pairs = [("total_test_loss", "loss"), ("total_test_notes_loss", "decoder_loss_1"), ("total_test_accuracy", "decoder_acc_1"),
+             ("total_test_meta_instrument_loss", "decoder_loss_2"), ("total_test_meta_instrument_accuracy", "decoder_acc_2"),
+             ("total_test_meta_velocity_loss", "decoder_loss_3"), ("total_test_meta_velocity_accuracy", "decoder_acc_3"),
+             ("total_test_loss_composer", "composer_decoder_loss"), ("total_test_accuracy_composer", "composer_decoder_acc")]
+    for ref_name, key in pairs:
+        assert abs(want[ref_name] - tot[key]) < 1e-8, (ref_name, want[ref_name], tot[key])
