@@ -294,9 +294,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is timed at N = 1 only (the other ranks would idle in a barrier)
         sample = max(1, min(B, args.cpu_sample))
-        rate, ms, cores = cpu_oracle_rate(wl, args.feedback, sample, 2, 1)
+        rate, ms, cores = cpu_oracle_rate(wl, args.feedback, sample, 10, 1)       # ~10 s of CPU work at cfg3
         cpu = {"value": rate, "unit": "sequences/s", "cores": cores, "kind": "port",
-               "sample": f"oracle fp32 torch-CPU train step on {sample} of {B} sequences of the workload, median of 2 steps ({ms:.0f} ms/step)"}
+               "sample": f"oracle fp32 torch-CPU train step on {sample} of {B} sequences of the workload, median of 10 steps after 1 warm-up ({ms:.0f} ms/step)"}
 
     if world > 1:
         dist.barrier()
