@@ -599,7 +599,8 @@ void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& 
     rec_backward_sweep(&stack[0], nullptr, n);
     rec_backward_gemms(stack[0], n);
     branch_begin();
-    for (auto& j : side) { rec_backward_sweep(&j, nullptr, n); rec_backward_gemms(j, n); }
+    // last group: by the time the side stream reaches the branch recurrences' weight gradients only the tail of the step is left: whole chip
+    for (auto& j : side) { rec_backward_sweep(&j, nullptr, n); rec_backward_gemms(j, n, last_group); }
     branch_end();
     for (size_t k = 1; k < stack.size(); ++k) { rec_backward_sweep(&stack[k], nullptr, n); rec_backward_gemms(stack[k], n, last_group && k + 1 == stack.size()); }
     branch_join();
