@@ -361,6 +361,9 @@ class VAE(object):
 
     def _eps(self, n: int) -> Optional[np.ndarray]:
         """K.random_normal(stddev=epsilon_std) of the sampling Lambda (vae_definition.py:498-502), drawn on the host."""
+        src = getattr(self, "eps_source", None)
+        if src is not None:                 # tests replay a recorded sequence of draws (tests/golden/reference_training_loop.npz)
+            return np.asarray(src(n), np.float32).reshape(n, self.engine.cfg.latent_rep_size)
         if self.epsilon_std == 0:
             return None
         return (self._rng.standard_normal((n, self.engine.cfg.latent_rep_size)) * self.epsilon_std).astype(np.float32)
