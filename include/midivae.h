@@ -36,6 +36,7 @@ enum { MVAE_CELL_STANDARD = 0, MVAE_CELL_RECURRENTSHOP_RECALLED = 1 };  /* SURVE
 enum { MVAE_FB_AS_WIRED = 0, MVAE_FB_TEACHER_FORCED = 1, MVAE_FB_FREE_RUNNING = 2 };  /* SURVEY.md 8(a) row D-fb */
 enum { MVAE_PREC_FP32 = 0, MVAE_PREC_BF16 = 1 };   /* fp32 SIMT parity path / bf16 tcgen05 tensor-core path */
 enum { MVAE_RNN_STREAMED = 0, MVAE_RNN_PERSISTENT = 1, MVAE_RNN_AUTO = 2 };
+enum { MVAE_CELLTYPE_LSTM = 0, MVAE_CELLTYPE_GRU = 1 };                 /* vae_definition.py:457-472,535,585,623; settings.py:155 ships GRU */
 
 /* Mirrors the VAE.create(...) kwargs that are live on the hot path (vae_definition.py:40-102). */
 typedef struct mvae_config {
@@ -60,6 +61,9 @@ typedef struct mvae_config {
   float beta, prior_mean, prior_std;                     /* KLDivergenceLayer, vae_definition.py:15-37 */
   float notes_weight, meta_instrument_weight, meta_velocity_weight, composer_weight; /* loss_weights, :336-397 */
   float learning_rate, adam_beta_1, adam_beta_2, adam_epsilon;  /* keras.optimizers.Adam, :174-175 */
+  int cell_type;               /* MVAE_CELLTYPE_*: LSTM (north_star; cluster / persistent kernels) or GRU (the reference's shipped default;
+                                  step-streamed kernels).  GRU: Keras 2.0.8 GRU encoders (blocks [z|r|h], h' = z h + (1-z) hh) and recurrentshop
+                                  GRUCell decoders (as recalled: h' = (1-z) h + z hh; dec_cell_variant applies to the LSTM cells only)      */
 } mvae_config;
 
 /* One mini-batch = a consecutive slice of <= batch_size chunks of a song

@@ -17,6 +17,7 @@ CELL = {"standard": 0, "recurrentshop_recalled": 1}
 FEEDBACK = {"as_wired": 0, "teacher_forced": 1, "free_running": 2}
 PRECISION = {"fp32": 0, "bf16": 1}
 RNN_MODE = {"streamed": 0, "persistent": 1, "auto": 2}
+CELL_TYPE = {"LSTM": 0, "GRU": 1}
 PROF_CLASSES = ["rec_fwd", "rec_bwd", "gemm", "pointwise", "adam", "allreduce"]
 
 
@@ -26,7 +27,7 @@ class MvaeConfig(C.Structure):
         "num_composers", "num_layers_encoder", "num_layers_decoder", "history", "extra_layer", "split_lstm_vector",
         "gate_act", "dec_cell_variant", "decoder_feedback", "precision", "rnn_mode", "max_batch")] + [(n, C.c_float) for n in (
         "beta", "prior_mean", "prior_std", "notes_weight", "meta_instrument_weight", "meta_velocity_weight", "composer_weight",
-        "learning_rate", "adam_beta_1", "adam_beta_2", "adam_epsilon")]
+        "learning_rate", "adam_beta_1", "adam_beta_2", "adam_epsilon")] + [("cell_type", C.c_int)]
 
 
 class MvaeBatch(C.Structure):

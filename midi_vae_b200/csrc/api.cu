@@ -181,7 +181,7 @@ int mvae_default_config(mvae_config* c) {
   c->input_length = 64; c->lstm_size = 256; c->latent_rep_size = 256; c->input_dim = 61; c->meta_instrument_dim = 16;
   c->meta_instrument_length = 4; c->num_composers = 2; c->num_layers_encoder = 2; c->num_layers_decoder = 2;
   c->history = 1; c->extra_layer = 1; c->split_lstm_vector = 1;
-  c->gate_act = MVAE_GATE_HARD_SIGMOID; c->dec_cell_variant = MVAE_CELL_STANDARD; c->decoder_feedback = MVAE_FB_AS_WIRED;
+  c->gate_act = MVAE_GATE_HARD_SIGMOID; c->dec_cell_variant = MVAE_CELL_RECURRENTSHOP_RECALLED; c->decoder_feedback = MVAE_FB_AS_WIRED;
   c->precision = MVAE_PREC_FP32; c->rnn_mode = MVAE_RNN_AUTO; c->max_batch = 256;
   c->beta = 0.1f; c->prior_mean = 0.f; c->prior_std = 1.f;
   c->notes_weight = 1.f; c->meta_instrument_weight = 0.1f; c->meta_velocity_weight = 1.f; c->composer_weight = 0.1f;

@@ -157,6 +157,81 @@ __global__ void cell_bwd_kernel(CellCfg cc, int n, int H, const float* __restric
   }
 }
 
+// ------------------------------------------------------------------ GRU cell math (row f-1: the reference's shipped cell type, settings.py:155)
+// Blocks [z|r|h] (Keras 2.0.8 GRU, vae_definition.py:457-472; recurrentshop GRUCell, :535,585,623).  A step is TWO dependent products:
+//   pre[:, 0:2H] = x W_zr + h U_zr + b_zr -> z, r;   rh = r * h;   pre[:, 2H:3H] = x W_h + rh U_h + b_h -> hh = tanh;
+//   mix 0 (Keras GRU):             h' = z h + (1 - z) hh
+//   mix 1 (recurrentshop GRUCell): h' = (1 - z) h + z hh          (as recalled; the shipped decoders' first step decodes only with this one)
+// Stash for the reverse sweep: gates_t (n,3H) = [z|r|hh], rh_t (n,H), h sequence.
+template <typename AT>
+__global__ void gru_gates_kernel(int gate_act, int n, int H, const float* __restrict__ pre, const AT* __restrict__ h_prev, AT* __restrict__ gates,
+                                 AT* __restrict__ rh) {
+  long total = (long)n * H;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int j = (int)(e % H);
+    long b = e / H;
+    const float* pr = pre + b * 3 * H;
+    float z = gate_fn(gate_act, pr[j]);
+    float r = gate_fn(gate_act, pr[H + j]);
+    AT* gt = gates + b * 3 * H;
+    stf<AT>(gt + j, z); stf<AT>(gt + H + j, r);
+    stf<AT>(rh + e, r * ldf<AT>(h_prev + e));
+  }
+}
+
+template <typename AT>
+__global__ void gru_out_kernel(int mix, int n, int H, const float* __restrict__ pre, const AT* __restrict__ h_prev, AT* __restrict__ gates,
+                               AT* __restrict__ h_new) {
+  long total = (long)n * H;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int j = (int)(e % H);
+    long b = e / H;
+    float hh = tanhf(pre[b * 3 * H + 2 * H + j]);
+    AT* gt = gates + b * 3 * H;
+    float z = ldf<AT>(gt + j), h = ldf<AT>(h_prev + e);
+    stf<AT>(gt + 2 * H + j, hh);
+    stf<AT>(h_new + e, mix == 0 ? z * h + (1.f - z) * hh : (1.f - z) * h + z * hh);
+  }
+}
+
+// reverse step, part 1: dh = dh_run + dh_ext + dh_last;  dG[:, 2H:3H] = da_h = dhh (1 - hh^2);  dG[:, 0:H] = da_z;  dh_run = the direct path to h_{t-1}
+template <typename AT, typename LT>
+__global__ void gru_bwd1_kernel(int gate_act, int mix, int n, int H, float* __restrict__ dh_run, const AT* __restrict__ dh_ext,
+                                const LT* __restrict__ dh_last, int ld_last, const AT* __restrict__ gates, const AT* __restrict__ h_prev,
+                                AT* __restrict__ dG) {
+  long total = (long)n * H;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int j = (int)(e % H);
+    long b = e / H;
+    float dh = dh_run[e];
+    if (dh_ext) dh += ldf<AT>(dh_ext + e);
+    if (dh_last) dh += ldf<LT>(dh_last + b * ld_last + j);
+    const AT* gt = gates + b * 3 * H;
+    float z = ldf<AT>(gt + j), hh = ldf<AT>(gt + 2 * H + j), h = ldf<AT>(h_prev + e);
+    float dz, dhh, direct;
+    if (mix == 0) { dz = dh * (h - hh); dhh = dh * (1.f - z); direct = dh * z; }
+    else { dz = dh * (hh - h); dhh = dh * z; direct = dh * (1.f - z); }
+    AT* dgp = dG + b * 3 * H;
+    stf<AT>(dgp + j, dz * gate_grad(gate_act, z));
+    stf<AT>(dgp + 2 * H + j, dhh * (1.f - hh * hh));
+    dh_run[e] = direct;
+  }
+}
+
+// reverse step, part 2: drh = da_h U_h^T (fp32);  da_r = drh h_{t-1} act'(r) -> dG[:, H:2H];  dh_run += drh r
+template <typename AT>
+__global__ void gru_bwd2_kernel(int gate_act, int n, int H, const float* __restrict__ drh, const AT* __restrict__ gates, const AT* __restrict__ h_prev,
+                                float* __restrict__ dh_run, AT* __restrict__ dG) {
+  long total = (long)n * H;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int j = (int)(e % H);
+    long b = e / H;
+    float r = ldf<AT>(gates + b * 3 * H + H + j), h = ldf<AT>(h_prev + e), d = drh[e];
+    stf<AT>(dG + b * 3 * H + H + j, d * h * gate_grad(gate_act, r));
+    dh_run[e] += d * r;
+  }
+}
+
 template <typename AT>
 __global__ void concat3_kernel(int n, int H, const AT* a, const AT* b, const AT* c, AT* u) {
   long total = (long)n * 3 * H;
@@ -283,7 +358,7 @@ __global__ void softmax_ce_kernel(int steps, int n, int D, float* logits, int ld
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
     if (labels) {
-      int y = labels[(long)b * steps + t];
+      int y = min((int)labels[(long)b * steps + t], 63);      // device-pointer callers are not range-checked on the host: stay inside the 64-wide row
       float py = __shfl_sync(0xffffffffu, y < 32 ? p0 : p1, y & 31);
       float wt = w ? w[(long)b * steps + t] : 1.f;
       if (lane == 0) {
@@ -540,6 +615,28 @@ void k_cell_bwd(DT act, CellCfg cc, int n, int H, const float* dh_run, const voi
                                                                    (const AT*)gates_t, (const AT*)cseq_t, (const AT*)cseq_t1, (AT*)dG_t);
     LAUNCH_CHECK();
   });
+}
+
+void k_gru_gates(DT act, int gate_act, int n, int H, const float* pre, const void* h_prev, void* gates_t, void* rh_t, cudaStream_t st) {
+  DISPATCH_ACT(act, { gru_gates_kernel<AT><<<nblk((long)n * H), TPB, 0, st>>>(gate_act, n, H, pre, (const AT*)h_prev, (AT*)gates_t, (AT*)rh_t); LAUNCH_CHECK(); });
+}
+void k_gru_out(DT act, int mix, int n, int H, const float* pre, const void* h_prev, void* gates_t, void* h_new, cudaStream_t st) {
+  DISPATCH_ACT(act, { gru_out_kernel<AT><<<nblk((long)n * H), TPB, 0, st>>>(mix, n, H, pre, (const AT*)h_prev, (AT*)gates_t, (AT*)h_new); LAUNCH_CHECK(); });
+}
+void k_gru_bwd1(DT act, int gate_act, int mix, int n, int H, float* dh_run, const void* dh_ext_t, const void* dh_last, int ld_last, DT last_t,
+                const void* gates_t, const void* h_prev, void* dG_t, cudaStream_t st) {
+  DISPATCH_ACT(act, {
+    if (last_t == DT_F32)
+      gru_bwd1_kernel<AT, float><<<nblk((long)n * H), TPB, 0, st>>>(gate_act, mix, n, H, dh_run, (const AT*)dh_ext_t, (const float*)dh_last, ld_last,
+                                                                    (const AT*)gates_t, (const AT*)h_prev, (AT*)dG_t);
+    else
+      gru_bwd1_kernel<AT, bf16><<<nblk((long)n * H), TPB, 0, st>>>(gate_act, mix, n, H, dh_run, (const AT*)dh_ext_t, (const bf16*)dh_last, ld_last,
+                                                                   (const AT*)gates_t, (const AT*)h_prev, (AT*)dG_t);
+    LAUNCH_CHECK();
+  });
+}
+void k_gru_bwd2(DT act, int gate_act, int n, int H, const float* drh, const void* gates_t, const void* h_prev, float* dh_run, void* dG_t, cudaStream_t st) {
+  DISPATCH_ACT(act, { gru_bwd2_kernel<AT><<<nblk((long)n * H), TPB, 0, st>>>(gate_act, n, H, drh, (const AT*)gates_t, (const AT*)h_prev, dh_run, (AT*)dG_t); LAUNCH_CHECK(); });
 }
 
 void k_concat3(DT act, int n, int H, const void* a, const void* b, const void* c, void* u, cudaStream_t st) {

@@ -19,6 +19,12 @@ void k_copy2d(DT src_t, DT dst_t, int rows, int cols, const void* src, int lds, 
 void k_cell_fwd(DT act, CellCfg cc, int n, int H, const float* pre, float* c_run, void* gates_t, void* cseq_t1, void* hseq_t1, cudaStream_t st);
 void k_cell_bwd(DT act, CellCfg cc, int n, int H, const float* dh_run, const void* dh_ext_t, const void* dh_last, int ld_last, DT last_t,
                 float* dc_run, const void* gates_t, const void* cseq_t, const void* cseq_t1, void* dG_t, cudaStream_t st);
+// GRU cell (blocks [z|r|h]; mix 0 = Keras GRU, 1 = recurrentshop GRUCell as recalled): two pointwise launches per step in each direction
+void k_gru_gates(DT act, int gate_act, int n, int H, const float* pre, const void* h_prev, void* gates_t, void* rh_t, cudaStream_t st);
+void k_gru_out(DT act, int mix, int n, int H, const float* pre, const void* h_prev, void* gates_t, void* h_new, cudaStream_t st);
+void k_gru_bwd1(DT act, int gate_act, int mix, int n, int H, float* dh_run, const void* dh_ext_t, const void* dh_last, int ld_last, DT last_t,
+                const void* gates_t, const void* h_prev, void* dG_t, cudaStream_t st);
+void k_gru_bwd2(DT act, int gate_act, int n, int H, const float* drh, const void* gates_t, const void* h_prev, float* dh_run, void* dG_t, cudaStream_t st);
 void k_concat3(DT act, int n, int H, const void* a, const void* b, const void* c, void* u, cudaStream_t st);
 void k_latent_fwd(DT act, int n, int L, int ldl, const float* mu, const float* lv, const float* eps, const float* hist, int has_hist,
                   float* z, void* q, int ldq, float beta, float m0, float s0, double* acc, cudaStream_t st);

@@ -595,7 +595,7 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
           } else if (p.x_mode == 1) {
             // one-hot input: x W + b is row `class` of the (64, 4H) table (row 63 = bias only = zero input)
             int cls = 63;
-            if (p.x_idx && t >= p.x_shift) cls = (int)__ldg(p.x_idx + (size_t)m * p.x_ld + (t - p.x_shift));
+            if (p.x_idx && t >= p.x_shift) cls = min(63, (int)__ldg(p.x_idx + (size_t)m * p.x_ld + (t - p.x_shift)));   // an index past the table = zero input, as in the dense expansion
             const bf16* xr = p.xtab + (size_t)cls * G + u0;
             xq[0] = __ldg(reinterpret_cast<const uint4*>(xr + bi * H));
             xq[1] = __ldg(reinterpret_cast<const uint4*>(xr + bfk * H));

@@ -54,22 +54,24 @@ void Model::build_params() {
     else { r.ib = add_param(nm + "/bias", 1, G); r.iU = add_param(nm + "/recurrent_kernel", H, G); }
   };
   enc_pitch.resize(ne);
-  for (int k = 0; k < ne; ++k) add_rec(enc_pitch[k], "lstm_" + std::to_string(k + 1), T, k == 0 ? Dp : H, k == 0 ? PD : H, MVAE_CELL_STANDARD, true);
-  add_rec(enc_instr, "lstm_meta_instrument", Ti, Di, ID, MVAE_CELL_STANDARD, true);
-  add_rec(enc_vel, "lstm_meta_velocity", T, 1, VD, MVAE_CELL_STANDARD, true);
+  const std::string pre = gru ? "gru_" : "lstm_";     // Keras layer names of the two branches (vae_definition.py:457-472)
+  for (int k = 0; k < ne; ++k) add_rec(enc_pitch[k], pre + std::to_string(k + 1), T, k == 0 ? Dp : H, k == 0 ? PD : H, MVAE_CELL_STANDARD, true);
+  add_rec(enc_instr, pre + "meta_instrument", Ti, Di, ID, MVAE_CELL_STANDARD, true);
+  add_rec(enc_vel, pre + "meta_velocity", T, 1, VD, MVAE_CELL_STANDARD, true);
   iWa = add_param("extra_instrument_after_concat_layer/kernel", 3 * H, H);
   iba = add_param("extra_instrument_after_concat_layer/bias", 1, H);
   if (cfg.extra_layer) { iWe = add_param("extra_layer/kernel", H, H); ibe = add_param("extra_layer/bias", 1, H); }
   iWmu = add_param("z_mean/kernel", half, L); ibmu = add_param("z_mean/bias", 1, L);
   iWlv = add_param("z_log_var/kernel", H - half, L); iblv = add_param("z_log_var/bias", 1, L);
   iWinit = add_param("dec_init/kernel", Q, nS * H); ibinit = add_param("dec_init/bias", 1, nS * H);
+  const int dvar = gru ? 1 : cfg.dec_cell_variant;      // GRU: mix 1 = recurrentshop GRUCell (encoders use mix 0 = Keras GRU)
   dec_notes.resize(nd);
   for (int k = 0; k < nd; ++k)
-    add_rec(dec_notes[k], "notes/cell_" + std::to_string(k + 1), T, k == 0 ? Dp : H, k == 0 ? PD : H, cfg.dec_cell_variant, false);
+    add_rec(dec_notes[k], "notes/cell_" + std::to_string(k + 1), T, k == 0 ? Dp : H, k == 0 ? PD : H, dvar, false);
   iWy = add_param("notes/out/kernel", H, Dp); iby = add_param("notes/out/bias", 1, Dp);
-  add_rec(dec_instr, "meta_instrument/cell", Ti, Di, ID, cfg.dec_cell_variant, false);
+  add_rec(dec_instr, "meta_instrument/cell", Ti, Di, ID, dvar, false);
   iWio = add_param("meta_instrument/out/kernel", H, Di); ibio = add_param("meta_instrument/out/bias", 1, Di);
-  add_rec(dec_vel, "meta_velocity/cell", T, 1, VD, cfg.dec_cell_variant, false);
+  add_rec(dec_vel, "meta_velocity/cell", T, 1, VD, dvar, false);
   // (H,1) stored as the row vector (1,H): same dense bytes, and the N = 1 head is a row-dot, not a GEMM
   iWvo = add_param("meta_velocity/out/kernel", 1, H); ibvo = add_param("meta_velocity/out/bias", 1, 1);
   ld_pn = ptab[iWy].ld; ld_pi = ptab[iWio].ld; ld_pv = 8;
@@ -133,6 +135,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   MVAE_REQUIRE(c.num_layers_encoder > 0 && c.num_layers_decoder > 0, "num_layers must be > 0 (vae_definition.py:177-178)");
   MVAE_REQUIRE(c.beta > 0, "beta must be > 0 (vae_definition.py:183)");
   MVAE_REQUIRE(c.max_batch > 0, "max_batch must be > 0");
+  MVAE_REQUIRE(c.meta_instrument_length > 0, "meta_instrument_length must be > 0 (settings.py:182 uses 4; the instrument loss divides by it)");
   MVAE_REQUIRE(c.input_dim > 0 && c.input_dim <= 64, "input_dim must be in 1..64");
   MVAE_REQUIRE(c.meta_instrument_dim > 0 && c.meta_instrument_dim <= 64, "meta_instrument_dim must be in 1..64");
   MVAE_REQUIRE(c.num_composers >= 1 && c.num_composers <= c.latent_rep_size, "num_composers must be in 1..latent_rep_size");
@@ -156,12 +159,14 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   MVAE_CUDA(cudaEventCreateWithFlags(&ev_bjoin, cudaEventDisableTiming));
   act = c.precision == MVAE_PREC_FP32 ? DT_F32 : DT_BF16;
   T = c.input_length; H = c.lstm_size; L = c.latent_rep_size; Dp = c.input_dim; Di = c.meta_instrument_dim; Ti = c.meta_instrument_length;
-  C = c.num_composers; ne = c.num_layers_encoder; nd = c.num_layers_decoder; G = 4 * H; NB = c.max_batch;
+  MVAE_REQUIRE(c.cell_type == MVAE_CELLTYPE_LSTM || c.cell_type == MVAE_CELLTYPE_GRU, "cell_type must be LSTM or GRU (vae_definition.py:457-472)");
+  gru = c.cell_type == MVAE_CELLTYPE_GRU; spc = gru ? 1 : 2;
+  C = c.num_composers; ne = c.num_layers_encoder; nd = c.num_layers_decoder; G = (gru ? 3 : 4) * H; NB = c.max_batch;
   PD = round_up(Dp, 8); ID = round_up(Di, 8); VD = 8;
-  ldl = round_up(L, 8); Q = c.history ? 2 * L : L; ldq = round_up(Q, 8); nS = 2 * (nd + 2); half = H / 2;
-  use_persist = act == DT_BF16 && cfg.rnn_mode != MVAE_RNN_STREAMED && rec_persist_supported(H, sm_count);
+  ldl = round_up(L, 8); Q = c.history ? 2 * L : L; ldq = round_up(Q, 8); nS = spc * (nd + 2); half = H / 2;
+  use_persist = !gru && act == DT_BF16 && cfg.rnn_mode != MVAE_RNN_STREAMED && rec_persist_supported(H, sm_count);
   if (cfg.rnn_mode == MVAE_RNN_PERSISTENT)
-    MVAE_REQUIRE(use_persist, "rnn_mode=persistent needs bf16 precision and lstm_size % 64 == 0 with a weight slice that fits in shared memory");
+    MVAE_REQUIRE(use_persist, "rnn_mode=persistent needs the LSTM cell, bf16 precision and lstm_size % 64 == 0 with a weight slice that fits in shared memory");
   use_cluster_fwd = use_persist && rec_cluster_supported(H);
   use_cluster_bwd = use_persist && rec_cluster_bwd_supported(H);
   // the cluster recurrences occupy 16 SMs per 64..128 batch rows and leave the rest of the chip idle: the batched weight-gradient
@@ -388,7 +393,7 @@ void Model::rec_forward_prepare(const FwdJob& j, int n) {
   prof_begin(PC_REC_FWD);
   if (j.h0) {
     k_copy2d(act, act, n, H, j.h0, j.ld0, r.hseq, H, st);
-    if (!use_persist) k_copy2d(act, act, n, H, j.c0, j.ld0, r.cseq, H, st);
+    if (!use_persist && !gru) k_copy2d(act, act, n, H, j.c0, j.ld0, r.cseq, H, st);
   } else {
     MVAE_CUDA(cudaMemsetAsync(r.hseq, 0, (size_t)n * H * asz(), st));
     if (!use_persist) MVAE_CUDA(cudaMemsetAsync(r.cseq, 0, (size_t)n * H * asz(), st));
@@ -452,7 +457,7 @@ void Model::rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n) {
   } else {
     for (const FwdJob* j : {ja, jb}) {
       if (!j) continue;
-      if (j->c0) k_copy2d(act, DT_F32, n, H, j->c0, j->ld0, c_run, H, st);
+      if (j->c0 && !gru) k_copy2d(act, DT_F32, n, H, j->c0, j->ld0, c_run, H, st);
       else MVAE_CUDA(cudaMemsetAsync(c_run, 0, (size_t)n * H * 4, st));
       rec_steps_forward(*j->r, n, 0, j->r->steps);
     }
@@ -462,6 +467,7 @@ void Model::rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n) {
 
 // steps [t0, t1): pre = h_{t-1} U + xw_t ; gate math  (step-streamed form)
 void Model::rec_steps_forward(Rec& r, int n, int t0, int t1) {
+  if (gru) { gru_steps_forward(r, n, t0, t1); return; }
   for (int t = t0; t < t1; ++t) {
     GemmArgs g; g.M = n; g.N = G; g.K = H; g.A = slab(r.hseq, t, (long)n * H); g.lda = H; g.B = W(r.iU); g.ldb = ld(r.iU);
     g.C = pre; g.ldc = G; g.c_type = DT_F32; g.addend = slab(r.xw, t, (long)n * G); g.ldadd = G; g.add_type = act;
@@ -469,6 +475,46 @@ void Model::rec_steps_forward(Rec& r, int n, int t0, int t1) {
     k_cell_fwd(act, cc(r.variant), n, H, pre, c_run, slab(r.gates, t, (long)n * G), slab(r.cseq, t + 1, (long)n * H),
                slab(r.hseq, t + 1, (long)n * H), st);
   }
+}
+
+// GRU, steps [t0, t1): two dependent products per step; the reset gate is applied BEFORE the candidate's recurrent product
+// (Keras 2.0.8 GRU / recurrentshop GRUCell).  Stash: gates_t = [z|r|hh], r.cseq slab t = r * h_{t-1} (a GRU has no cell state: the buffer is free).
+void Model::gru_steps_forward(Rec& r, int n, int t0, int t1) {
+  const size_t a = asz();
+  for (int t = t0; t < t1; ++t) {
+    const void* hp = slab(r.hseq, t, (long)n * H);
+    const void* xw_t = slab(r.xw, t, (long)n * G);
+    void* rh_t = slab(r.cseq, t, (long)n * H);
+    { GemmArgs g; g.M = n; g.N = 2 * H; g.K = H; g.A = hp; g.lda = H; g.B = W(r.iU); g.ldb = ld(r.iU);
+      g.C = pre; g.ldc = G; g.c_type = DT_F32; g.addend = xw_t; g.ldadd = G; g.add_type = act; gemm(g); }
+    k_gru_gates(act, cfg.gate_act, n, H, pre, hp, slab(r.gates, t, (long)n * G), rh_t, st);
+    { GemmArgs g; g.M = n; g.N = H; g.K = H; g.A = rh_t; g.lda = H; g.B = (const char*)W(r.iU) + (size_t)2 * H * a; g.ldb = ld(r.iU);
+      g.C = pre + 2 * H; g.ldc = G; g.c_type = DT_F32; g.addend = (const char*)xw_t + (size_t)2 * H * a; g.ldadd = G; g.add_type = act; gemm(g); }
+    k_gru_out(act, r.variant, n, H, pre, hp, slab(r.gates, t, (long)n * G), slab(r.hseq, t + 1, (long)n * H), st);
+  }
+}
+
+// GRU reverse-time sweep (hand-derived in oracle/manual_bptt.py, checked against autograd): per step
+//   [da_z | . | da_h], direct path  ->  drh = da_h U_h^T  ->  da_r, dh += drh r  ->  dh += [da_z | da_r] U_zr^T
+void Model::gru_backward_sweep(const BwdJob& j, int n) {
+  Rec& r = *j.r;
+  const size_t a = asz();
+  void* dG = r.xw;
+  float* drh = c_run;       // (n, H) fp32 scratch: a GRU has no running cell state
+  MVAE_CUDA(cudaMemsetAsync(dh_run, 0, (size_t)n * H * 4, st));
+  for (int t = r.steps - 1; t >= 0; --t) {
+    const void* hp = slab(r.hseq, t, (long)n * H);
+    const void* gt = slab(r.gates, t, (long)n * G);
+    void* dG_t = slab(dG, t, (long)n * G);
+    k_gru_bwd1(act, cfg.gate_act, r.variant, n, H, dh_run, j.use_dhext ? slab(r.dhext, t, (long)n * H) : nullptr, t == r.steps - 1 ? j.dh_last : nullptr,
+               j.ld_last, act, gt, hp, dG_t, st);
+    { GemmArgs g; g.M = n; g.N = H; g.K = H; g.A = (const char*)dG_t + (size_t)2 * H * a; g.lda = G; g.B = (const char*)W(r.iU) + (size_t)2 * H * a;
+      g.ldb = ld(r.iU); g.transB = true; g.C = drh; g.ldc = H; g.c_type = DT_F32; gemm(g); }
+    k_gru_bwd2(act, cfg.gate_act, n, H, drh, gt, hp, dh_run, dG_t, st);
+    { GemmArgs g; g.M = n; g.N = H; g.K = 2 * H; g.A = dG_t; g.lda = G; g.B = W(r.iU); g.ldb = ld(r.iU); g.transB = true;
+      g.C = dh_run; g.ldc = H; g.c_type = DT_F32; g.accumulate = true; gemm(g); }
+  }
+  if (j.dS_h) k_copy2d(DT_F32, act, n, H, dh_run, H, j.dS_h, j.ldS, st);
 }
 
 // --------------------------------------------------------------------------------------------- one recurrence, backward
@@ -523,6 +569,7 @@ void Model::rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n) {
   } else {
     for (const BwdJob* j : {ja, jb}) {
       if (!j) continue;
+      if (gru) { gru_backward_sweep(*j, n); continue; }
       Rec& r = *j->r;
       void* dG = r.xw;
       MVAE_CUDA(cudaMemsetAsync(dh_run, 0, (size_t)n * H * 4, st));
@@ -574,7 +621,14 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms,
   const void* dG = slab(r.xw, t0, (long)n * G);
   const void* Xc = j.X ? (const char*)j.X + (size_t)t0 * n * (j.kind == IN_RANK1 ? VD : r.ldin) * asz() : nullptr;
   prof_begin(PC_GEMM, s);
-  {  // dU += Hprev^T dG
+  if (gru) {  // dU_zr += Hprev^T [da_z | da_r];  dU_h += (r * Hprev)^T da_h   (the r * h sequence sits in the cseq buffer)
+    GemmArgs g; g.M = H; g.N = 2 * H; g.K = (int)rows; g.A = slab(r.hseq, t0, (long)n * H); g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
+    g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
+    gemm_on(g, s, sms);
+    GemmArgs h; h.M = H; h.N = H; h.K = (int)rows; h.A = slab(r.cseq, t0, (long)n * H); h.lda = H; h.transA = true;
+    h.B = (const char*)dG + (size_t)2 * H * asz(); h.ldb = G; h.C = Gp(r.iU) + 2 * H; h.ldc = ld(r.iU); h.c_type = DT_F32; h.accumulate = true;
+    gemm_on(h, s, sms);
+  } else {  // dU += Hprev^T dG
     GemmArgs g; g.M = H; g.N = G; g.K = (int)rows; g.A = slab(r.hseq, t0, (long)n * H); g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
     gemm_on(g, s, sms);
@@ -917,8 +971,8 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
   prof_end();
   if (feedback == MVAE_FB_FREE_RUNNING) { decoder_stepwise(n); return; }
   const bool tf = feedback == MVAE_FB_TEACHER_FORCED;
-  auto st1 = [&](int r) { return (const char*)S + (size_t)(2 * r) * H * asz(); };
-  auto st2 = [&](int r) { return (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
+  auto st1 = [&](int r) { return (const char*)S + (size_t)(spc * r) * H * asz(); };
+  auto st2 = [&](int r) { return gru ? (const char*)nullptr : (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
   FwdJob jv; jv.r = &dec_vel; jv.kind = tf ? IN_RANK1 : IN_NONE; jv.X = tf ? Xv_ext : nullptr; jv.h0 = st1(nd + 1); jv.c0 = st2(nd + 1); jv.ld0 = nS * H;
   const bool chunked = nd >= 2 && !inference_pass && chunked_ok(T, chunks);
   if (chunked) {
@@ -973,11 +1027,11 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
 
 // free-running decode (inference only): x_t = previous prediction, one step at a time
 void Model::decoder_stepwise(int n) {
-  auto st1 = [&](int r) { return (const char*)S + (size_t)(2 * r) * H * asz(); };
-  auto st2 = [&](int r) { return (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
+  auto st1 = [&](int r) { return (const char*)S + (size_t)(spc * r) * H * asz(); };
+  auto st2 = [&](int r) { return gru ? (const char*)nullptr : (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
   auto init = [&](Rec& r, int sidx) {
     k_copy2d(act, act, n, H, st1(sidx), nS * H, r.hseq, H, st);
-    k_copy2d(act, act, n, H, st2(sidx), nS * H, r.cseq, H, st);
+    if (!gru) k_copy2d(act, act, n, H, st2(sidx), nS * H, r.cseq, H, st);
   };
   auto step = [&](Rec& r, int t, int kind, const void* x, int ldx) {  // one cell step with input x (n rows) or none (t == 0 start vector = 0)
     void* xw_t = slab(r.xw, t, (long)n * G);
@@ -989,7 +1043,7 @@ void Model::decoder_stepwise(int n) {
     } else {
       k_fill_rows(act, xw_t, n, G, Wf(r.ib), st);
     }
-    k_copy2d(act, DT_F32, n, H, slab(r.cseq, t, (long)n * H), H, c_run, H, st);
+    if (!gru) k_copy2d(act, DT_F32, n, H, slab(r.cseq, t, (long)n * H), H, c_run, H, st);
     rec_steps_forward(r, n, t, t + 1);
   };
   prof_begin(PC_REC_FWD);
@@ -1092,8 +1146,8 @@ void Model::backward(const mvae_batch& b) {
   k_rank1_rows(act, dec_vel.dhext, (long)T * n, H, dlog_v, ld_pv, Wf(iWvo), nullptr, st);              // dh[r,:] = dlog[r] * Wv
   prof_end();
   // ---- decoder recurrences (top layer first)
-  auto dS1 = [&](int r) { return (char*)dS + (size_t)(2 * r) * H * asz(); };
-  auto dS2 = [&](int r) { return (char*)dS + (size_t)(2 * r + 1) * H * asz(); };
+  auto dS1 = [&](int r) { return (char*)dS + (size_t)(spc * r) * H * asz(); };
+  auto dS2 = [&](int r) { return gru ? (char*)nullptr : (char*)dS + (size_t)(2 * r + 1) * H * asz(); };
   {
     std::vector<BwdJob> stack, side;
     for (int k = nd - 1; k >= 0; --k) {

@@ -81,6 +81,8 @@ struct Model {
   DT act = DT_F32;
   // dimensions
   int T = 0, H = 0, L = 0, Dp = 0, Di = 0, Ti = 0, C = 0, ne = 0, nd = 0, G = 0, NB = 0;
+  bool gru = false;                    // cell_type GRU: G = 3H (blocks [z|r|h]), one state per cell, step-streamed recurrences only
+  int spc = 2;                         // states per decoder cell (LSTM: h, c; GRU: h)
   int PD = 64, ID = 16, VD = 8;        // padded widths of the dense pitch / instrument / velocity rows
   int ldl = 0, Q = 0, ldq = 0, nS = 0, half = 0;
   int ld_pn = 64, ld_pi = 16, ld_pv = 8;
@@ -227,6 +229,8 @@ struct Model {
   void prepare_inputs(const mvae_batch& b, bool need_target);
   void rec_forward(Rec& r, int n, int kind, const void* X, const void* h0, const void* c0, int ld0);
   void rec_steps_forward(Rec& r, int n, int t0, int t1);
+  void gru_steps_forward(Rec& r, int n, int t0, int t1);
+  void gru_backward_sweep(const BwdJob& j, int n);
   void rec_forward_prepare(const FwdJob& j, int n);
   RecPersistArgs fwd_args(const FwdJob& j, int n, int slot, int hs, bool pack = true);
   void rec_forward_jobs(const FwdJob* ja, const FwdJob* jb, int n);

@@ -37,7 +37,7 @@ class EngineConfig:
     extra_layer: bool = True
     split_lstm_vector: bool = True
     gate_act: str = "hard_sigmoid"
-    dec_cell_variant: str = "standard"
+    dec_cell_variant: str = "recurrentshop_recalled"   # what the reference decoder computes (recurrentshop LSTMCell); "standard" = Keras equations, an extension
     decoder_feedback: str = "as_wired"
     precision: str = "fp32"
     rnn_mode: str = "auto"
@@ -53,6 +53,7 @@ class EngineConfig:
     adam_beta_1: float = 0.9
     adam_beta_2: float = 0.999
     adam_epsilon: float = 1e-8
+    cell_type: str = "LSTM"        # 'LSTM' (north_star; cluster kernels) | 'GRU' (the reference's shipped default, settings.py:155)
 
     def to_c(self) -> MvaeConfig:
         c = MvaeConfig()
@@ -62,6 +63,7 @@ class EngineConfig:
             elif k == "decoder_feedback": v = _lib.FEEDBACK[v]
             elif k == "precision": v = _lib.PRECISION[v]
             elif k == "rnn_mode": v = _lib.RNN_MODE[v]
+            elif k == "cell_type": v = _lib.CELL_TYPE[v]
             setattr(c, k, int(v) if isinstance(v, bool) else v)
         return c
 
@@ -70,16 +72,18 @@ def reference_param_specs(cfg: EngineConfig) -> List[Tuple[str, Tuple[int, ...]]
     """(name, shape) in the reference checkpoint order: encoder layers, then the decoder's
     initial-state Denses (notes L1.., instrument, velocity), notes cells + Dense, instrument cell + Dense,
     velocity cell + Dense.  Per recurrentshop cell: kernel, bias, recurrent_kernel."""
-    H, L, G = cfg.lstm_size, cfg.latent_rep_size, 4 * cfg.lstm_size
+    gru = cfg.cell_type == "GRU"
+    H, L, G = cfg.lstm_size, cfg.latent_rep_size, (3 if gru else 4) * cfg.lstm_size
     Dp, Di = cfg.input_dim, cfg.meta_instrument_dim
+    pre = "gru" if gru else "lstm"
     s: List[Tuple[str, Tuple[int, ...]]] = []
 
     def keras_lstm(name, D):
         s.extend([(f"{name}/kernel", (D, G)), (f"{name}/recurrent_kernel", (H, G)), (f"{name}/bias", (G,))])
     for k in range(1, cfg.num_layers_encoder + 1):
-        keras_lstm(f"lstm_{k}", Dp if k == 1 else H)
-    keras_lstm("lstm_meta_instrument", Di)
-    keras_lstm("lstm_meta_velocity", 1)
+        keras_lstm(f"{pre}_{k}", Dp if k == 1 else H)
+    keras_lstm(f"{pre}_meta_instrument", Di)
+    keras_lstm(f"{pre}_meta_velocity", 1)
     s.extend([("extra_instrument_after_concat_layer/kernel", (3 * H, H)), ("extra_instrument_after_concat_layer/bias", (H,))])
     if cfg.extra_layer:
         s.extend([("extra_layer/kernel", (H, H)), ("extra_layer/bias", (H,))])
@@ -87,11 +91,15 @@ def reference_param_specs(cfg: EngineConfig) -> List[Tuple[str, Tuple[int, ...]]
     s.extend([("z_mean/kernel", (half, L)), ("z_mean/bias", (L,)), ("z_log_var/kernel", (H - half, L)), ("z_log_var/bias", (L,))])
     Q = 2 * L if cfg.history else L
     for nm in [f"notes_l{k}" for k in range(1, cfg.num_layers_decoder + 1)] + ["instr", "vel"]:
-        for j in (1, 2):
+        for j in ((1,) if gru else (1, 2)):          # one initial-state Dense per cell state (vae_definition.py:563-568)
             s.extend([(f"dec_init/{nm}_s{j}/kernel", (Q, H)), (f"dec_init/{nm}_s{j}/bias", (H,))])
 
     def rs_cell(name, D):
-        s.extend([(f"{name}/kernel", (D, G)), (f"{name}/bias", (G,)), (f"{name}/recurrent_kernel", (H, G))])
+        s.extend([(f"{name}/kernel", (D, G)), (f"{name}/bias", (G,))])
+        if gru:      # recurrentshop GRUCell: Dense(2H) on h for z, r and Dense(H) on r*h (the shipped checkpoints' dense_k+1, dense_k+2)
+            s.extend([(f"{name}/recurrent_kernel_1", (H, 2 * H)), (f"{name}/recurrent_kernel_2", (H, H))])
+        else:
+            s.extend([(f"{name}/recurrent_kernel", (H, G))])
     for k in range(1, cfg.num_layers_decoder + 1):
         rs_cell(f"notes/cell_{k}", Dp if k == 1 else H)
     s.extend([("notes/out/kernel", (H, Dp)), ("notes/out/bias", (Dp,))])
@@ -181,21 +189,31 @@ class Engine:
     def _init_names(self):
         return [f"notes_l{k}" for k in range(1, self.cfg.num_layers_decoder + 1)] + ["instr", "vel"]
 
+    def _init_cols(self):
+        """dec_init/<cell>_s<j> -> first column of that Dense inside the column-fused dec_init tensors."""
+        H = self.cfg.lstm_size
+        spc = 1 if self.cfg.cell_type == "GRU" else 2           # states per cell
+        return {f"dec_init/{nm}_s{j}": (spc * r + (j - 1)) * H for r, nm in enumerate(self._init_names()) for j in range(1, spc + 1)}
+
     def get_weights(self, grad: bool = False) -> Dict[str, np.ndarray]:
         """Reference-named tensors (or their gradients from the last forward_backward)."""
         H = self.cfg.lstm_size
         out: Dict[str, np.ndarray] = {}
         fused_k = self._get_internal("dec_init/kernel", grad)
         fused_b = self._get_internal("dec_init/bias", grad)
-        col = {}
-        for r, nm in enumerate(self._init_names()):
-            for j in (1, 2):
-                col[f"dec_init/{nm}_s{j}"] = (2 * r + (j - 1)) * H
+        col = self._init_cols()
+        cache: Dict[str, np.ndarray] = {}
         for name, shape in reference_param_specs(self.cfg):
             if name.startswith("dec_init/"):
                 base, kind = name.rsplit("/", 1)
                 c0 = col[base]
                 out[name] = (fused_k[:, c0:c0 + H] if kind == "kernel" else fused_b[0, c0:c0 + H]).copy()
+            elif name.endswith(("/recurrent_kernel_1", "/recurrent_kernel_2")):
+                # recurrentshop GRUCell: the (H,2H) z,r kernel and the (H,H) candidate kernel are one (H,3H) tensor [z|r|h] in the arena
+                base = name.rsplit("/", 1)[0] + "/recurrent_kernel"
+                if base not in cache:
+                    cache[base] = self._get_internal(base, grad)
+                out[name] = (cache[base][:, :2 * H] if name.endswith("_1") else cache[base][:, 2 * H:]).copy()
             else:
                 out[name] = self._get_internal(name, grad).reshape(shape).copy()
         return out
@@ -207,13 +225,11 @@ class Engine:
         if missing:
             raise KeyError(f"missing weight tensors: {missing[:4]}...")
         Q = 2 * self.cfg.latent_rep_size if self.cfg.history else self.cfg.latent_rep_size
-        nS = 2 * (self.cfg.num_layers_decoder + 2)
+        col = self._init_cols()
+        nS = len(col)
         fused_k = np.zeros((Q, nS * H), np.float32)
         fused_b = np.zeros((1, nS * H), np.float32)
-        col = {}
-        for r, nm in enumerate(self._init_names()):
-            for j in (1, 2):
-                col[f"dec_init/{nm}_s{j}"] = (2 * r + (j - 1)) * H
+        fused_u: Dict[str, np.ndarray] = {}
         for name, shape in specs:
             w = np.asarray(weights[name], np.float32)
             if w.shape != tuple(shape):
@@ -225,8 +241,16 @@ class Engine:
                     fused_k[:, c0:c0 + H] = w
                 else:
                     fused_b[0, c0:c0 + H] = w
+            elif name.endswith(("/recurrent_kernel_1", "/recurrent_kernel_2")):
+                u = fused_u.setdefault(name.rsplit("/", 1)[0] + "/recurrent_kernel", np.zeros((H, 3 * H), np.float32))
+                if name.endswith("_1"):
+                    u[:, :2 * H] = w
+                else:
+                    u[:, 2 * H:] = w
             else:
                 self._set_internal(name, w)
+        for name, u in fused_u.items():
+            self._set_internal(name, u)
         self._set_internal("dec_init/kernel", fused_k)
         self._set_internal("dec_init/bias", fused_b)
         check(self.lib.mvae_commit_params(self._h), self._h)

@@ -19,7 +19,7 @@ Extension keywords (not in the reference): ``precision`` ('fp32' | 'bf16'), ``ga
 """
 from __future__ import annotations
 
-import pickle
+import warnings
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -91,35 +91,58 @@ class _Base:
             cur[n] = np.asarray(w, np.float32)
         self._vae.engine.set_weights(cur)
 
+    def _keras_layout(self):
+        from . import keras_names
+        return keras_names.layout(self._vae.engine.cfg, self._part)
+
     def save_weights(self, path: str) -> None:
-        """Weights only (optimizer state is not saved, like the reference; vae_training.py:966-978).
-        Container: a pickled {name: ndarray} dict in reference order (the reference writes Keras HDF5 under
-        the same '.pickle' suffix; midi_vae_b200.hdf5 reads that layout)."""
+        """Weights only (optimizer state is not saved, like the reference; vae_training.py:966-978), written as the Keras-2.0.8 HDF5 layout of the
+        reference's own checkpoints (one group per layer in model order, ``layer_names`` / ``weight_names`` attributes, float32 datasets) -- the
+        reference writes exactly this under its '.pickle' suffix, so files are interchangeable in both directions.  Data only: nothing is pickled."""
+        from . import hdf5
         w = self._vae.engine.get_weights()
-        with open(path, "wb") as f:
-            pickle.dump({"format": "midi_vae_b200/weights/1", "part": self._part,
-                         "weights": [(n, w[n]) for n, _ in self._specs()]}, f, protocol=4)
+        hdf5.write_weights(path, [(layer, [(kn, w[en]) for kn, en in ws]) for layer, ws in self._keras_layout()])
 
     def load_weights(self, path: str, by_name: bool = False) -> None:
+        """Keras HDF5 weight files (the reference's shipped ``models/*/*.pickle`` and anything ``save_weights`` wrote).  ``by_name=False`` (what the
+        reference calls, vae_evaluation.py:553-559) assigns positionally over the layers that have weights, as Keras 2.0.8 does; ``by_name=True``
+        matches layer names.  The file is parsed as data (midi_vae_b200.hdf5); nothing is ever unpickled."""
+        from . import hdf5
         with open(path, "rb") as f:
             head = f.read(8)
-        if head == b"\x89HDF\r\n\x1a\n":
-            from . import hdf5
-            hdf5.load_keras_weights(self, path)
-            return
-        with open(path, "rb") as f:
-            blob = pickle.load(f)
-        if not isinstance(blob, dict) or blob.get("format") != "midi_vae_b200/weights/1":
-            raise ValueError(f"{path}: not a midi_vae_b200 weight file")
-        items = blob["weights"]
+        if head != hdf5.SIGNATURE:
+            raise ValueError(f"{path}: not an HDF5 weight file (the reference writes Keras HDF5 under the '.pickle' suffix; pickled containers are "
+                             "not read: unpickling executes code)")
+        t = hdf5.read_weights(path)
+        mine = [(layer, ws) for layer, ws in self._keras_layout() if ws]
+        theirs = [(layer, t["layers"][layer]) for layer in t["layer_names"] if t["layers"][layer]]
+        cur = self._vae.engine.get_weights()
         if by_name:
-            cur = self._vae.engine.get_weights()
-            for n, w in items:
-                if n in cur:
-                    cur[n] = w
-            self._vae.engine.set_weights(cur)
+            have = dict(theirs)
+            for layer, ws in mine:
+                if layer not in have:
+                    continue
+                if len(have[layer]) != len(ws):
+                    raise ValueError(f"{path}: layer {layer} holds {len(have[layer])} weights, this model {len(ws)}")
+                for (_, en), (_, arr) in zip(ws, have[layer]):
+                    cur[en] = self._fit(en, arr, cur[en], path)
         else:
-            self.set_weights([w for _, w in items])
+            if len(theirs) != len(mine):
+                raise ValueError(f"{path}: {len(theirs)} layers with weights, this {self._part} has {len(mine)} "
+                                 f"(cell_type={self._vae.engine.cfg.cell_type}; the shipped checkpoints are GRU models, settings.py:155)")
+            for (layer, ws), (tl, tensors) in zip(mine, theirs):
+                if len(ws) != len(tensors):
+                    raise ValueError(f"{path}: layer {tl} holds {len(tensors)} weights, layer {layer} of this model {len(ws)}")
+                for (_, en), (_, arr) in zip(ws, tensors):
+                    cur[en] = self._fit(en, arr, cur[en], path)
+        self._vae.engine.set_weights(cur)
+
+    @staticmethod
+    def _fit(name, arr, like, path):
+        arr = np.asarray(arr, np.float32)
+        if arr.shape != like.shape:
+            raise ValueError(f"{path}: tensor for {name} has shape {arr.shape}, this model needs {like.shape}")
+        return arr
 
 
 class EncoderModel(_Base):
@@ -244,8 +267,14 @@ class AutoencoderModel(_Base):
         m = vae.engine.evaluate_batch(P, Ii, Vv, style, H, e, w, tgt)
         return [m[k] for k in _HISTORY_KEYS]
 
-    def _loop(self, fn, x, y, batch_size, sample_weight, eps):
+    def _loop(self, fn, x, y, batch_size, sample_weight, eps, training=False):
         vae = self._vae
+        if batch_size > vae.max_batch:
+            # smaller mini-batches than asked for would move the Adam steps (fit) / the temporal-weight normaliser (evaluate): never silently
+            msg = (f"batch_size={batch_size} exceeds max_batch={vae.max_batch} of this model: create it with VAE().create(..., max_batch>={batch_size})")
+            if training:
+                raise ValueError(msg)
+            warnings.warn(msg + "; evaluating in mini-batches of max_batch instead")
         P, Ii, Vv, H = self._unpack_inputs(x)
         tgt, style = self._unpack_targets(y, P, Ii, Vv)
         w = self._sample_weight(sample_weight, *P.shape)
@@ -265,7 +294,7 @@ class AutoencoderModel(_Base):
             raise NotImplementedError("the reference always calls fit(shuffle=False) (vae_training.py:807)")
         h = History()
         for ep in range(epochs):
-            vals = self._loop(self._vae.engine.train_on_batch, x, y, batch_size, sample_weight, eps)
+            vals = self._loop(self._vae.engine.train_on_batch, x, y, batch_size, sample_weight, eps, training=True)
             for k, v in zip(_HISTORY_KEYS, vals):
                 h.history[k].append(float(v))
             h.epoch.append(ep)
@@ -305,7 +334,7 @@ class VAE(object):
                meta_next_notes_output_length=16, meta_next_notes_weight=1.0, meta_next_notes_teacher_force=False,
                activation_before_splitting='tanh',
                # ---- extensions (not in the reference) ----
-               precision='fp32', gate_act='hard_sigmoid', dec_cell_variant='standard', decoder_feedback='as_wired',
+               precision='fp32', gate_act='hard_sigmoid', dec_cell_variant='recurrentshop_recalled', decoder_feedback='as_wired',
                predict_feedback=None, max_batch=256, device=0, seed=0, rnn_mode='auto'):
         # the reference's own asserts (vae_definition.py:177-208)
         assert num_layers_encoder > 0 and num_layers_decoder > 0
@@ -316,7 +345,11 @@ class VAE(object):
                 raise NotImplementedError(f"{what} is outside the B200 hot path (disabled in the reference defaults, {where})")
         unsupported(use_embedding, "use_embedding=True", "settings.py:167")
         unsupported(bidirectional, "bidirectional=True", "settings.py:118")
-        unsupported(cell_type != 'LSTM', f"cell_type={cell_type!r} (GRU is the next row, SURVEY.md 8(f-1))", "settings.py:155")
+        if cell_type not in ('LSTM', 'GRU'):
+            raise NotImplementedError(f"cell_type={cell_type!r}: the B200 path implements the reference's 'GRU' (its shipped default, settings.py:155; "
+                                      "step-streamed kernels) and 'LSTM' (north_star's cell; cluster-resident kernels) branches, not SimpleRNN")
+        if meta_instrument_length <= 0:
+            raise ValueError("meta_instrument_length must be > 0 when meta_instrument=True (settings.py:182 uses 4)")
         unsupported(not meta_instrument or not meta_velocity, "a model without the instrument / velocity streams", "settings.py:180,211")
         unsupported(not include_composer_decoder, "include_composer_decoder=False", "settings.py:133")
         unsupported(meta_held_notes, "meta_held_notes=True", "settings.py:217")
@@ -347,7 +380,7 @@ class VAE(object):
             meta_instrument_dim=meta_instrument_dim, meta_instrument_length=meta_instrument_length, num_composers=num_composers,
             num_layers_encoder=num_layers_encoder, num_layers_decoder=num_layers_decoder, history=bool(history),
             extra_layer=bool(extra_layer), split_lstm_vector=True, gate_act=gate_act, dec_cell_variant=dec_cell_variant,
-            decoder_feedback=decoder_feedback, precision=precision, rnn_mode=rnn_mode, max_batch=max_batch, beta=beta,
+            decoder_feedback=decoder_feedback, precision=precision, rnn_mode=rnn_mode, max_batch=max_batch, beta=beta, cell_type=cell_type,
             prior_mean=prior_mean, prior_std=prior_std, notes_weight=1.0, meta_instrument_weight=meta_instrument_weight,
             meta_velocity_weight=meta_velocity_weight, composer_weight=composer_weight, learning_rate=learning_rate)
         self.engine = Engine(cfg, device)
@@ -376,10 +409,10 @@ def initial_weights(cfg: EngineConfig, seed: int = 42) -> Dict[str, np.ndarray]:
     H = cfg.lstm_size
     out: Dict[str, np.ndarray] = {}
     for name, shape in reference_param_specs(cfg):
-        keras_lstm = name.startswith("lstm_")
+        keras_lstm = name.startswith(("lstm_", "gru_"))        # Keras recurrent layers: orthogonal recurrent kernels
         if name.endswith("/bias"):
             w = np.zeros(shape)
-            if keras_lstm:
+            if name.startswith("lstm_"):                       # unit_forget_bias=True (Keras 2.0.8 LSTM); a GRU has none
                 w[H:2 * H] = 1.0
         elif name.endswith("/recurrent_kernel") and keras_lstm:
             a = rng.standard_normal(shape[::-1] if shape[0] < shape[1] else shape)

@@ -69,7 +69,7 @@ class OracleConfig:
     split_lstm_vector: bool = True  # settings.py:139
     # switches that resolve the north_star / reference differences
     gate_act: str = "hard_sigmoid"            # Keras 2.0.8 default; "sigmoid" = north_star wording
-    dec_cell_variant: str = "standard"        # or "recurrentshop_recalled"
+    dec_cell_variant: str = "recurrentshop_recalled"   # the reference decoder cell (recurrentshop LSTMCell as recalled); "standard" = Keras LSTM equations
     decoder_feedback: str = "as_wired"        # "as_wired" | "teacher_forced" | "free_running"
     # the reference's shipped default (settings.py:155) is GRU; the CUDA build implements the LSTM branch, the oracle restates both
     # (GRU = groundwork for SURVEY.md 8(f-1); GRUCell conventions as recalled: blocks [z|r|h], h' = (1 - z) h + z hh)

@@ -22,15 +22,15 @@ from tests import util  # noqa: E402
 
 
 def main():
-    feedback = "teacher_forced"
-    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, feedback=feedback, max_batch=8)
+    feedback, variant = "teacher_forced", "recurrentshop_recalled"      # the reference decoder cell (recurrentshop LSTMCell as recalled)
+    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, feedback=feedback, variant=variant, max_batch=8)
     w = util.make_weights(ecfg, seed=42, jitter=0.1)
     r, hist, eps, _ = util.make_batch(ecfg, 8, seed=1235)
     p = util.to_torch(w)
     X, I, V, C, th, te, _ = util.oracle_inputs(ocfg, r, hist, eps, None)
     m, g, _ = O.loss_and_grads(ocfg, p, X, I, V, C, th, te)
     st = O.style_transfer(ocfg, p, X, I, V, 0, 1, None, "as_wired")
-    out = dict(feedback=np.array(feedback), pitch=r.pitch, instr=r.instr, velocity=r.velocity, style=r.style, hist=hist, eps=eps,
+    out = dict(feedback=np.array(feedback), variant=np.array(variant), pitch=r.pitch, instr=r.instr, velocity=r.velocity, style=r.style, hist=hist, eps=eps,
                metrics=np.array([m[k] for k in METRIC_KEYS]), st_pitch=st["pitch"].numpy().astype(np.uint8),
                st_instr=st["instr"].numpy().astype(np.uint8), st_margin=O.top2_margin(st["Yh"]).numpy(),
                st_vel=st["Vh"].numpy()[..., 0].astype(np.float32))

@@ -87,3 +87,89 @@ def test_hdf5_reader_reproduces_the_fixture():
     k = dict(t["layers"]["notes"])["gru_cell_1/dense_1/kernel"]
     # the first decoder cell's input kernel still sits at its Glorot bound sqrt(6/(61+768))
     assert abs(abs(k).max() - (6.0 / (61 + 768)) ** 0.5) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------- round 2: GRU branch + writer
+def _gru_cfg():
+    return EngineConfig(input_length=64, lstm_size=H, latent_rep_size=256, cell_type="GRU")      # settings.py:108-112,155
+
+
+@pytest.mark.parametrize("part", ["encoder", "decoder", "autoencoder"])
+def test_gru_keras_names_equal_the_shipped_checkpoints(part):
+    """keras_names.layout at the reference's default GRU settings reproduces layer names, weight names, shapes and order of the shipped files
+    EXACTLY (no gru -> lstm mapping): what save_weights writes is what the reference's load_weights(by_name=False) expects."""
+    from midi_vae_b200 import keras_names
+    cfg = _gru_cfg()
+    shapes = dict(reference_param_specs(cfg))
+    ours = [[layer, kn, list(shapes[en])] for layer, ws in keras_names.layout(cfg, part) for kn, en in ws]
+    assert ours == FIX[f"JvP/{part}"]["layout"]
+    # every engine tensor of the part is written exactly once
+    names = [en for _, ws in keras_names.layout(cfg, part) for _, en in ws]
+    assert len(names) == len(set(names))
+    if part == "autoencoder":
+        assert sorted(names) == sorted(shapes)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/JvP/encoderEpoch440.pickle"), reason="reference checkout not present")
+@pytest.mark.parametrize("part", ["encoder", "decoder", "autoencoder"])
+def test_gru_layer_names_including_weightless_layers(part):
+    import glob
+    from midi_vae_b200 import keras_names
+    t = hdf5.read_weights(glob.glob(f"/root/reference/models/JvP/{part}Epoch*.pickle")[0])
+    assert [l for l, _ in keras_names.layout(_gru_cfg(), part)] == t["layer_names"]
+
+
+def test_lstm_keras_names_follow_the_same_construction_order():
+    from midi_vae_b200 import keras_names
+    cfg = EngineConfig(input_length=64, lstm_size=H, latent_rep_size=256)
+    lay = dict(keras_names.layout(cfg, "decoder"))
+    assert [k for k, _ in lay["notes"]] == ["lstm_cell_1/dense_1/kernel", "lstm_cell_1/dense_1/bias", "lstm_cell_1/dense_2/kernel",
+                                           "lstm_cell_2/dense_3/kernel", "lstm_cell_2/dense_3/bias", "lstm_cell_2/dense_4/kernel", "dense_5/kernel", "dense_5/bias"]
+    assert [l for l in lay if l.startswith("dense_")] == ["dense_6", "dense_7", "dense_8", "dense_9", "dense_13", "dense_14", "dense_18", "dense_19"]
+    assert [k for k, _ in lay["meta_velocity"]] == ["lstm_cell_4/dense_15/kernel", "lstm_cell_4/dense_15/bias", "lstm_cell_4/dense_16/kernel", "dense_17/kernel", "dense_17/bias"]
+    names = [en for _, ws in keras_names.layout(cfg, "autoencoder") for _, en in ws]
+    assert sorted(names) == sorted(n for n, _ in reference_param_specs(cfg))
+
+
+@pytest.mark.parametrize("cell_type", ["LSTM", "GRU"])
+def test_engine_and_oracle_inventories_agree(cell_type):
+    from oracle import midivae_oracle as O
+    e = reference_param_specs(EngineConfig(input_length=16, lstm_size=64, latent_rep_size=16, cell_type=cell_type))
+    o = [(n, tuple(s)) for n, s, _ in O.param_specs(O.OracleConfig(input_length=16, lstm_size=64, latent_rep_size=16, cell_type=cell_type))]
+    assert [(n, tuple(s)) for n, s in e] == o
+
+
+def test_hdf5_writer_round_trip(tmp_path):
+    """write_weights -> read_weights: names, order, nesting, shapes and bytes survive; the file starts with the same superblock fields as the shipped ones."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    layers = [("notes_input", []), ("gru_1", [("gru_1/kernel", rng.standard_normal((61, 24)).astype(np.float32)), ("gru_1/bias", rng.standard_normal(24).astype(np.float32))]),
+              ("lambda_1", [])] + [(f"dense_{i}", [(f"dense_{i}/kernel", rng.standard_normal((3, i + 1)).astype(np.float32))]) for i in range(1, 12)] + \
+             [("decoder", [("gru_cell_1/dense_1/kernel", rng.standard_normal((5, 7)).astype(np.float32)), ("gru_cell_1/dense_2/kernel", rng.standard_normal((2, 2)).astype(np.float32)),
+                           ("dense_7/bias", rng.standard_normal(1).astype(np.float32))])]
+    path = str(tmp_path / "w.pickle")
+    hdf5.write_weights(path, layers)
+    raw = open(path, "rb").read()
+    assert raw[:8] == hdf5.SIGNATURE and raw[8] == 0 and raw[13] == 8 and raw[14] == 8 and raw[16:20] == bytes([4, 0, 16, 0])      # superblock v0, leaf K 4, internal K 16
+    t = hdf5.read_weights(path)
+    assert t["layer_names"] == [l for l, _ in layers]
+    for layer, tensors in layers:
+        got = t["layers"][layer]
+        assert [n for n, _ in got] == [n for n, _ in tensors]
+        for (_, a), (_, b) in zip(tensors, got):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/JvP/autoencoderEpoch440.pickle"), reason="reference checkout not present")
+def test_hdf5_writer_reproduces_a_shipped_file_structure(tmp_path):
+    """Re-writing a shipped checkpoint yields a file the reader parses to the identical tree (all 50 tensors bit-equal, 23 layer names)."""
+    import numpy as np
+    src = "/root/reference/models/JvP/autoencoderEpoch440.pickle"
+    t = hdf5.read_weights(src)
+    path = str(tmp_path / "copy.pickle")
+    hdf5.write_weights(path, [(l, t["layers"][l]) for l in t["layer_names"]])
+    t2 = hdf5.read_weights(path)
+    assert t2["layer_names"] == t["layer_names"] and hdf5.layout(path) == hdf5.layout(src)
+    for l in t["layer_names"]:
+        for (_, a), (_, b) in zip(t["layers"][l], t2["layers"][l]):
+            assert np.array_equal(a, b)

@@ -144,7 +144,7 @@ def test_golden_fixture_cfg1():
     """Committed oracle-derived golden vectors (tests/golden/make_golden.py) for BASELINE config[0] shapes."""
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_step.npz"))
-    ecfg, _ = util.make_cfgs(T=16, H=64, L=16, feedback=str(g["feedback"]), max_batch=8)
+    ecfg, _ = util.make_cfgs(T=16, H=64, L=16, feedback=str(g["feedback"]), variant=str(g["variant"]), max_batch=8)
     w = {k[2:]: g[k] for k in g.files if k.startswith("w/")}
     eng = _engine(ecfg, w)
     P, Ii, Vv = eng.style_transfer(g["pitch"], g["instr"], g["velocity"], 0, 1, None, "as_wired")   # before the weights move

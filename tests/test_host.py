@@ -76,7 +76,7 @@ def _kwargs(**over):
     return kw
 
 
-@pytest.mark.parametrize("over", [dict(cell_type='GRU'), dict(bidirectional=True), dict(use_embedding=True), dict(meta_held_notes=True),
+@pytest.mark.parametrize("over", [dict(cell_type='SimpleRNN'), dict(bidirectional=True), dict(use_embedding=True), dict(meta_held_notes=True),
                                   dict(meta_next_notes=True), dict(signature_decoder=True), dict(optimizer='RMSprop'), dict(activation='sigmoid'),
                                   dict(meta_velocity=False), dict(include_composer_decoder=False), dict(split_lstm_vector=False)])
 def test_out_of_scope_branches_fail_loudly(over):

@@ -113,7 +113,7 @@ def test_history_shift_and_style_swap():
 def test_golden_vectors_reproduce():
     """tests/golden/cfg1_step.npz is what tests/golden/make_golden.py writes (oracle-derived, fp64)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_step.npz"))
-    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, feedback=str(g["feedback"]), max_batch=8)
+    ecfg, ocfg = util.make_cfgs(T=16, H=64, L=16, feedback=str(g["feedback"]), variant=str(g["variant"]), max_batch=8)
     p = {k[2:]: torch.tensor(g[k], dtype=torch.float64) for k in g.files if k.startswith("w/")}
     r = synth.Rolls(g["pitch"], g["instr"], g["velocity"], g["style"])
     X, I, V, C, th, te, _ = util.oracle_inputs(ocfg, r, g["hist"], g["eps"], None)

@@ -8,13 +8,13 @@ from midi_vae_b200 import EngineConfig, initial_weights, synth
 from oracle import midivae_oracle as O
 
 
-def make_cfgs(T=16, H=64, L=16, ne=2, nd=2, feedback="as_wired", gate="hard_sigmoid", variant="standard", precision="fp32", max_batch=8,
-              rnn_mode="auto", lr=2e-4):
+def make_cfgs(T=16, H=64, L=16, ne=2, nd=2, feedback="as_wired", gate="hard_sigmoid", variant="recurrentshop_recalled", precision="fp32", max_batch=8,
+              rnn_mode="auto", lr=2e-4, cell_type="LSTM"):
     ecfg = EngineConfig(input_length=T, lstm_size=H, latent_rep_size=L, num_layers_encoder=ne, num_layers_decoder=nd, gate_act=gate,
                         dec_cell_variant=variant, decoder_feedback=feedback, precision=precision, max_batch=max_batch, rnn_mode=rnn_mode,
-                        learning_rate=lr)
+                        learning_rate=lr, cell_type=cell_type)
     ocfg = O.OracleConfig(input_length=T, lstm_size=H, latent_rep_size=L, num_layers_encoder=ne, num_layers_decoder=nd, gate_act=gate,
-                          dec_cell_variant=variant, decoder_feedback=feedback, learning_rate=lr)
+                          dec_cell_variant=variant, decoder_feedback=feedback, learning_rate=lr, cell_type=cell_type)
     return ecfg, ocfg
 
 
