@@ -48,14 +48,6 @@ constexpr uint32_t CL_SLICE = 4 * CL_HALF * 16;   // one pushed piece: 4 k-granu
 constexpr uint32_t CL_STAGE = 2 * CL_SLICE;       // staging tile: both row halves of the CTA's h slice
 constexpr uint32_t CL_SCR = CL_ROWS * CL_GC * 4;  // fp32 scratch tile [64 rows][128 gate columns]
 
-struct ClusterP {
-  int n, H, G, steps, gate_act, variant, nswap, push_mode, ts;
-  const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates; const bf16* c0; int ldc0;
-  long long* trace;
-  const bf16* upack;   // ts: packed U read straight into tensor memory
-  uint8_t* hx;      // push_mode 2: global exchange buffer [clusters][2][CS][2 row halves][2 KB]
-};
-
 #define CL_TRACE(step, point)                                                                                              \
   do {                                                                                                                     \
     if (p.trace && blockIdx.x < 2 && (step) >= 16 && (step) < 24) p.trace[(blockIdx.x * 8 + (step) - 16) * 16 + (point)] = clock64(); \
@@ -89,292 +81,7 @@ __device__ __forceinline__ size_t gran_off(int slab, int ngran, int gran, int n,
 __device__ __forceinline__ void named_barrier(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Forward.  Buffers in dynamic shared memory (offsets identical in every CTA, as cta_group::2 and mapa require):
-//   U      [H/64 k-blocks][128 gate columns][64 k] bf16, SWIZZLE_128B (TMA), resident          A operand
-//   hbuf b [H/8 k-granules][32 rows][8 k] bf16 (no swizzle: 8 x 16 B core matrices), b = 0, 1     B operand (this CTA's half)
-//   stage b: the CTA's own new h slice as two 2 KB pieces (row half 0 / 1) in hbuf order         source of the pushes
-//   scratch [64 rows][128 gate columns] fp32, 16-byte chunks XOR-swizzled by (row & 7)            TMEM -> row ownership
-// h_t lives in hbuf[t & 1]; MMA t reads hbuf[(t+1) & 1] = h_{t-1} (the initial state is loaded into hbuf[1]).
-// At H = 512 the scratch tile aliases hbuf[(t+1) & 1] during epilogue t: MMA t has finished reading it, and the next
-// writers (pushes of h_{t+1}) cannot start before every CTA of the cluster has received this CTA's h_t, which it
-// pushes only after its scratch reads.
-template <int CS, bool HARD, bool STD>
-__global__ void __launch_bounds__(CL_THREADS, 1)
-rec_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tma_u, const ClusterP p) {
-  constexpr int H = CS * CL_HS, G = 4 * H, KB = H / 64;
-  constexpr uint32_t U_BYTES = (uint32_t)KB * CL_GC * 64 * 2;
-  constexpr uint32_t HBUF = (uint32_t)CL_HALF * H * 2;
-  constexpr bool ALIAS = (H >= 512);
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t u_full, h_full[2], peer_ready[2], tmem_full;
-  __shared__ uint32_t tmem_base_slot;
-
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_u = smem_base;
-  const uint32_t smem_h0 = smem_base + U_BYTES;                    // hbuf[b] = smem_h0 + b * HBUF
-  const uint32_t smem_st0 = smem_h0 + 2 * HBUF;                    // stage[b] = smem_st0 + b * CL_STAGE
-  const uint32_t smem_scr = smem_st0 + 2 * CL_STAGE;               // only when !ALIAS
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = ptx::cluster_ctarank();
-  const int cl = (int)blockIdx.x / CS;
-  const int e = (int)(rank & 1);
-  const int rh = e ^ p.nswap;                                      // which 32 rows of the group this CTA's operand tile holds
-  const int j = (int)rank;                                         // hidden units [32 j, 32 j + 32)
-  const int row0 = cl * CL_ROWS;
-  const int T = p.steps, n = p.n;
-
-  if (threadIdx.x == 0) {
-    ptx::prefetch_tmap(&tma_u);
-    ptx::mbar_init(ptx::smem_u32(&u_full), 1);
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(ptx::smem_u32(&h_full[b]), 1); ptx::mbar_init(ptx::smem_u32(&peer_ready[b]), 1); }
-    ptx::mbar_init(ptx::smem_u32(&tmem_full), 1);
-    ptx::fence_barrier_init();
-    if (!p.ts) {
-      const uint32_t ub = ptx::smem_u32(&u_full);
-      ptx::mbar_arrive_expect_tx(ub, U_BYTES);
-      for (int kb = 0; kb < KB; ++kb) ptx::tma_load_2d(smem_u + kb * (CL_GC * 128), &tma_u, ub, kb * 64, j * CL_GC);
-    }
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc2(ptx::smem_u32(&tmem_base_slot), 512);   // D: columns 0..63; U (ts): columns 64..64+H/2
-    ptx::tmem_relinquish2();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-  if (p.ts && warp >= 2 && warp < 6) {
-    // U slice -> tensor memory: lane = gate column, 32-bit column c = k pair (2c, 2c+1); each thread streams its own row
-    const int mrow = (warp & 3) * 32 + lane;
-    const uint4* src = reinterpret_cast<const uint4*>(p.upack + ((size_t)j * CL_GC + mrow) * H);
-    for (int c32 = 0; c32 < H / 64; ++c32) {
-      uint32_t r[32];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 v = __ldg(src + c32 * 8 + i);
-        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-      }
-      ptx::tmem_st_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 64u + (uint32_t)c32 * 32u, r);
-    }
-    ptx::tmem_st_wait();
-  }
-
-  // epilogue ownership (phase B): batch row rr of the group, units [8 q, 8 q + 8) of the CTA's 32
-  const int etid = (int)threadIdx.x - 64;
-  const int rr = etid & 63, q = (etid >> 6) & 3;
-  const int m = row0 + rr;
-  const bool row_ok = warp >= 2 && m < n;
-  const int u0 = j * CL_HS + q * 8, gu = u0 >> 3;
-  constexpr int bi = STD ? 0 : 1, bfk = 1 - bi;   // column block of the i and f gates
-  float cst[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) cst[u] = 0.f;
-
-  if (warp >= 2) {
-    // initial hidden state (hseq slab 0, row-major) -> hbuf[1] in operand order
-    for (int idx = etid; idx < CL_HALF * (H / 8); idx += 32 * CL_EPI_WARPS) {
-      const int r = idx / (H / 8), gk = idx % (H / 8);
-      const int mm = row0 + rh * CL_HALF + r;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (mm < n) v = *reinterpret_cast<const uint4*>(p.hseq + (size_t)mm * H + gk * 8);
-      ptx::st_shared_u4(smem_h0 + HBUF + gk * (CL_HALF * 16) + r * 16, v);
-    }
-    ptx::fence_proxy_async();
-    if (row_ok) {
-      uint4 cv = make_uint4(0u, 0u, 0u, 0u);
-      if (p.c0) cv = *reinterpret_cast<const uint4*>(p.c0 + (size_t)m * p.ldc0 + u0);
-      unpack8(cv, cst);
-      *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m)) = cv;   // stash slab 0 = c0
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  // barriers initialised, initial tiles written and TMEM allocated in EVERY CTA before anyone pushes or issues a pair MMA
-  ptx::cluster_arrive();
-  ptx::cluster_wait();
-  ptx::tc_fence_after();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      if (e == 0) {
-        // ===================== MMA issuer (even CTA of the pair) =====================
-        constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, CL_ROWS, false, false);
-        const uint16_t pair_mask = (uint16_t)(3u << rank);
-        if (!p.ts) ptx::mbar_wait(ptx::smem_u32(&u_full), 0);
-        for (int t = 0; t < T; ++t) {
-          // arm the barrier that the pushes of h_t will complete (its previous phase, h_{t-2}, completed before MMA t-1)
-          if (t + 1 < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&h_full[t & 1]), HBUF);
-          const int b = (t + 1) & 1;
-          // plain CTA-scope waits: an acquire at cluster scope makes ptxas emit CCTL.IVALL (L1 invalidate, ~1.5 k cycles in
-          // front of the next memory instruction); the payload is shared memory written and read through the async proxy
-          if (t > 0) ptx::mbar_wait(ptx::smem_u32(&h_full[b]), (uint32_t)(((t - 1) >> 1) & 1));
-          CL_TRACE(t, 7);
-          ptx::mbar_wait(ptx::smem_u32(&peer_ready[b]), (uint32_t)((t >> 1) & 1));   // the odd CTA's half of h_{t-1} (and its U) landed
-          if (p.push_mode == 1) ptx::fence_proxy_async();   // st.async data (observed through the barriers) -> tensor-core reads
-          ptx::tc_fence_after();
-          CL_TRACE(t, 0);
-          const uint32_t sb = smem_h0 + b * HBUF;
-#pragma unroll 1
-          for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // A: 128 gate columns x 16 k of the swizzled U block; B: 32 rows x 16 k = 2 k-granules, 512 B apart (LBO), 8-row groups 128 B apart (SBO)
-              const uint64_t bdesc = ptx::umma_desc_noswz(sb + (kb * 8 + k * 2) * (CL_HALF * 16), CL_HALF * 16, 128);
-              if (p.ts) ptx::umma_bf16_2cta_ts(tmem_base, tmem_base + 64u + (uint32_t)(kb * 4 + k) * 8u, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              else ptx::umma_bf16_2cta(tmem_base, ptx::umma_desc_sw128(smem_u + kb * (CL_GC * 128) + k * 32, 16, 1024), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-          }
-          ptx::umma_commit_2cta(ptx::smem_u32(&tmem_full), pair_mask);
-          CL_TRACE(t, 1);
-        }
-      } else {
-        // ===================== relay (odd CTA): tell the pair's MMA issuer when THIS CTA's operands are in place =====================
-        const uint32_t leader = rank - 1;
-        if (!p.ts) ptx::mbar_wait(ptx::smem_u32(&u_full), 0);
-        ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&peer_ready[1]), leader));   // U slice + initial h tile (hbuf[1])
-        for (int t = 0; t + 1 < T; ++t) {
-          const uint32_t hb = ptx::smem_u32(&h_full[t & 1]);
-          ptx::mbar_arrive_expect_tx(hb, HBUF);
-          ptx::mbar_wait(hb, (uint32_t)((t >> 1) & 1));
-          CL_TRACE(t + 1, 7);
-          if (p.push_mode == 1) ptx::fence_proxy_async();
-          ptx::mbar_arrive_remote_relaxed(ptx::mapa(ptx::smem_u32(&peer_ready[t & 1]), leader));
-          CL_TRACE(t + 1, 8);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== push warp: lane d sends this CTA's new h slice to CTA d of the cluster =====================
-    for (int t = 0; t + 1 < T && p.push_mode != 1; ++t) {
-      named_barrier(2, 32 * (CL_EPI_WARPS + 1));                    // staging tile of step t written (and fenced) by the epilogue warps
-      if (p.push_mode == 2) {
-        // the slice went to global memory; one multicast bulk load per row half brings it back into every CTA that holds that half
-        if (lane < 2) {
-          const uint8_t* src = p.hx + ((size_t)((cl * 2 + (t & 1)) * CS + j)) * CL_STAGE + (size_t)lane * CL_SLICE;
-          const uint16_t mask = (uint16_t)((((lane ^ p.nswap) & 1) ? 0xAAAAu : 0x5555u) & ((1u << CS) - 1u));
-          ptx::bulk_load_multicast(smem_h0 + (t & 1) * HBUF + (uint32_t)j * CL_SLICE, src, CL_SLICE, ptx::smem_u32(&h_full[t & 1]), mask);
-        }
-      } else if (lane < CS) {
-        const uint32_t d = (uint32_t)lane;
-        const uint32_t src = smem_st0 + (t & 1) * CL_STAGE + (((d & 1) ^ (uint32_t)p.nswap) * CL_SLICE);
-        const uint32_t dst = ptx::mapa(smem_h0 + (t & 1) * HBUF + (uint32_t)j * CL_SLICE, d);
-        ptx::bulk_copy_dsmem(dst, src, CL_SLICE, ptx::mapa(ptx::smem_u32(&h_full[t & 1]), d));
-      }
-      if (lane == 0) CL_TRACE(t, 6);
-    }
-  } else {
-    // ===================== epilogue warps 2..9 =====================
-    // phase A ownership: TMEM lane = gate column c = gate * 32 + unit of this CTA, 32 batch rows (column half ch)
-    const int wq = warp & 3, ch = (warp - 2) >> 2;
-    const int c = wq * 32 + lane;
-    const bool tracer = (etid == 0);
-    const uint32_t swB = (uint32_t)(rr & 7) << 4;
-    // push_mode 1: this thread's 16 bytes of h_t go straight into the operand tiles of the CS/2 CTAs that hold its row half
-    uint32_t rem_h[CS / 2], rem_bar[CS / 2];
-#pragma unroll
-    for (int i = 0; i < CS / 2; ++i) {
-      const uint32_t d = (uint32_t)(2 * i + ((rr >> 5) ^ p.nswap));
-      rem_h[i] = ptx::mapa(smem_h0 + (uint32_t)j * CL_SLICE + (uint32_t)q * (CL_HALF * 16) + (uint32_t)(rr & 31) * 16, d);
-      rem_bar[i] = ptx::mapa(ptx::smem_u32(&h_full[0]), d);
-    }
-    const uint32_t bar_step = ptx::smem_u32(&h_full[1]) - ptx::smem_u32(&h_full[0]);
-    for (int t = 0; t < T; ++t) {
-      // the input projection of this step does not depend on the recurrence: fetch it while the MMAs run
-      uint4 xq[4];
-      if (row_ok) {
-        const bf16* xr = p.xw + ((size_t)t * n + m) * G + u0;
-        xq[0] = __ldg(reinterpret_cast<const uint4*>(xr + bi * H));
-        xq[1] = __ldg(reinterpret_cast<const uint4*>(xr + bfk * H));
-        xq[2] = __ldg(reinterpret_cast<const uint4*>(xr + 2 * H));
-        xq[3] = __ldg(reinterpret_cast<const uint4*>(xr + 3 * H));
-      }
-      ptx::mbar_wait(ptx::smem_u32(&tmem_full), (uint32_t)(t & 1));
-      ptx::tc_fence_after();
-      if (tracer) CL_TRACE(t, 2);
-      const uint32_t scr = ALIAS ? (smem_h0 + ((t + 1) & 1) * HBUF) : smem_scr;
-      {
-        float v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ch * 32), v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int ra = ch * 32 + i;
-          ptx::st_shared_f32(scr + ra * (CL_GC * 4) + (((uint32_t)c * 4) ^ ((uint32_t)(ra & 7) << 4)), v[i]);
-        }
-      }
-      ptx::tc_fence_before();
-      named_barrier(1, 32 * CL_EPI_WARPS);
-      if (tracer) CL_TRACE(t, 3);
-      // phase B: the four gates of this thread's 8 units for its batch row
-      float pre[4][8];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t off = (uint32_t)(g * 32 + q * 8) * 4;
-        const float4 a0 = ptx::ld_shared_f32x4(scr + rr * (CL_GC * 4) + (off ^ swB));
-        const float4 a1 = ptx::ld_shared_f32x4(scr + rr * (CL_GC * 4) + ((off + 16) ^ swB));
-        pre[g][0] = a0.x; pre[g][1] = a0.y; pre[g][2] = a0.z; pre[g][3] = a0.w;
-        pre[g][4] = a1.x; pre[g][5] = a1.y; pre[g][6] = a1.z; pre[g][7] = a1.w;
-      }
-      float xi[8], xf[8], xg[8], xo[8], gi[8], gf[8], gg[8], go[8], cn[8], hn[8];
-      if (row_ok) { unpack8(xq[0], xi); unpack8(xq[1], xf); unpack8(xq[2], xg); unpack8(xq[3], xo); }
-      else {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { xi[u] = 0.f; xf[u] = 0.f; xg[u] = 0.f; xo[u] = 0.f; }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        gi[u] = gate_fwd<HARD>(pre[0][u] + xi[u]);
-        gf[u] = gate_fwd<HARD>(pre[1][u] + xf[u]);
-        gg[u] = tanh_fast(pre[2][u] + xg[u]);
-        go[u] = gate_fwd<HARD>(pre[3][u] + xo[u]);
-        const float s = gf[u] * cst[u] + gi[u] * gg[u];
-        if (STD) { cn[u] = s; hn[u] = go[u] * tanh_fast(s); }
-        else { cn[u] = tanh_fast(s); hn[u] = go[u] * cn[u]; }
-        cst[u] = cn[u];
-      }
-      uint4 st_h = pack8(hn);
-      if (!row_ok) st_h = make_uint4(0u, 0u, 0u, 0u);
-      if (t + 1 < T && p.push_mode == 1) {
-#pragma unroll
-        for (int i = 0; i < CS / 2; ++i) ptx::st_async_u4(rem_h[i] + (t & 1) * HBUF, st_h, rem_bar[i] + (t & 1) * bar_step);
-        if (tracer) CL_TRACE(t, 4);
-        if (etid == 255) CL_TRACE(t, 9);
-      } else if (t + 1 < T && p.push_mode == 2) {
-        uint8_t* dst = p.hx + ((size_t)((cl * 2 + (t & 1)) * CS + j)) * CL_STAGE + (size_t)(rr >> 5) * CL_SLICE + (size_t)q * (CL_HALF * 16) + (size_t)(rr & 31) * 16;
-        *reinterpret_cast<uint4*>(dst) = st_h;
-        ptx::fence_proxy_async_global();
-        if (tracer) CL_TRACE(t, 4);
-        named_barrier(2, 32 * (CL_EPI_WARPS + 1));
-        if (tracer) CL_TRACE(t, 5);
-      } else if (t + 1 < T) {
-        // stage[t & 1] was last read by the pushes of step t-2; they landed before any CTA could finish MMA t-1
-        ptx::st_shared_u4(smem_st0 + (t & 1) * CL_STAGE + (uint32_t)(rr >> 5) * CL_SLICE + (uint32_t)q * (CL_HALF * 16) + (uint32_t)(rr & 31) * 16, st_h);
-        ptx::fence_proxy_async();
-        if (tracer) CL_TRACE(t, 4);
-        named_barrier(2, 32 * (CL_EPI_WARPS + 1));
-        if (tracer) CL_TRACE(t, 5);
-      }
-      // the stash (read by the backward pass and the batched GEMMs) is written after the push: off the critical path
-      if (row_ok) {
-        *reinterpret_cast<uint4*>(p.hseq + ((size_t)(t + 1) * n + m) * H + u0) = st_h;
-        *reinterpret_cast<uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)) = pack8(cn);
-        *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)) = pack8(gi);
-        *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)) = pack8(gf);
-        *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)) = pack8(gg);
-        *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)) = pack8(go);
-      }
-    }
-  }
-
-  // nobody may leave (and release its shared memory / TMEM) while a peer can still read or write it
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::cluster_arrive();
-  ptx::cluster_wait();
-  if (warp == 1) ptx::tmem_dealloc2(tmem_base, 512);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Forward, second form: what the first form taught (profiles/r1/README.md):
+// Forward.  What the first form of this kernel (round 1, U in shared memory, DSMEM pushes; deleted) taught (profiles/r1/README.md):
 //   * an SS-mode MMA with N = 64 is paced by the fetch of its 4 KB A tile, so U lives in TENSOR MEMORY (A operand from
 //     TMEM, 32 x (M256 N64 K16) per step) and shared memory is free for operand tiles;
 //   * the DSMEM all-to-all is the slow path (6-13 B/clk/SM measured for st.async / bulk copies); the exchange goes
@@ -1396,76 +1103,10 @@ __global__ void pack_u_cluster_kernel(const float* __restrict__ U, int ldu, bf16
   }
 }
 
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeFn get_encode() {
-  static EncodeFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    MVAE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
-    MVAE_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-    fn = (EncodeFn)p;
-  }
-  return fn;
-}
-CUtensorMap make_map_sw128(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
-  CUtensorMap m;
-  cuuint64_t gdim[2] = {inner, outer};
-  cuuint64_t gstr[1] = {ld * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (rec_cluster)");
-  return m;
-}
-
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-
-template <int CS, bool HARD, bool STD>
-void launch_fwd(const RecPersistArgs& a, cudaStream_t st) {
-  constexpr int H = CS * CL_HS, KB = H / 64;
-  constexpr size_t smem = 1024 + (size_t)KB * CL_GC * 128 + 2 * (size_t)CL_HALF * H * 2 + 2 * CL_STAGE + (H >= 512 ? 0 : CL_SCR);
-  auto kern = rec_cluster_fwd_kernel<CS, HARD, STD>;
-  static bool configured = false;
-  if (!configured) {
-    MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (CS > 8) MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured = true;
-  }
-  const int clusters = (a.n + CL_ROWS - 1) / CL_ROWS;
-  ClusterP p{};
-  p.n = a.n; p.H = H; p.G = 4 * H; p.steps = a.steps; p.gate_act = a.gate_act; p.variant = a.variant;
-  p.nswap = env_int("MVAE_CL_NSWAP", 0);
-  p.push_mode = env_int("MVAE_CL_PUSH", 2);
-  p.ts = env_int("MVAE_CL_TS", 1);
-  p.upack = (const bf16*)a.upack;
-  p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates; p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0;
-  p.trace = (long long*)a.trace;
-  p.hx = (uint8_t*)a.hx;
-  if (p.push_mode == 2) MVAE_REQUIRE(p.hx != nullptr, "cluster forward: exchange buffer missing");
-  const CUtensorMap mu = make_map_sw128(a.upack, H, (uint64_t)CS * CL_GC, H, 64, CL_GC);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  static bool reported = false;
-  if (!reported && env_int("MVAE_CL_VERBOSE", 0)) {
-    int nc = -1;
-    cudaError_t err = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
-    fprintf(stderr, "rec_cluster_fwd<%d>: smem %zu B, max co-resident clusters %d (%s), launching %d\n", CS, smem, nc, cudaGetErrorString(err), clusters);
-    reported = true;
-  }
-  MVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, mu, p));
-  count_launch();
-}
-
 
 template <int CS, bool HARD, bool STD>
 void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
@@ -1713,7 +1354,6 @@ void rec_cluster_backward(const RecPersistArgs& a, cudaStream_t st) {
 void rec_cluster_forward(const RecPersistArgs& a, cudaStream_t st) {
   const bool hard = a.gate_act == MVAE_GATE_HARD_SIGMOID, stdc = a.variant == MVAE_CELL_STANDARD;
   MVAE_REQUIRE(a.H == 512 || a.H == 256, "cluster recurrence unsupported for this hidden size");
-  if (env_int("MVAE_CL_V", 2) == 2) {
 #define MVAE_CL_FWD2(CS)                                                       \
   do {                                                                         \
     if (hard && stdc) launch_fwd2<CS, true, true>(a, st);                      \
@@ -1721,21 +1361,9 @@ void rec_cluster_forward(const RecPersistArgs& a, cudaStream_t st) {
     else if (stdc) launch_fwd2<CS, false, true>(a, st);                        \
     else launch_fwd2<CS, false, false>(a, st);                                 \
   } while (0)
-    if (a.H == 512) MVAE_CL_FWD2(16);
-    else MVAE_CL_FWD2(8);
+  if (a.H == 512) MVAE_CL_FWD2(16);
+  else MVAE_CL_FWD2(8);
 #undef MVAE_CL_FWD2
-    return;
-  }
-#define MVAE_CL_FWD(CS)                                                        \
-  do {                                                                         \
-    if (hard && stdc) launch_fwd<CS, true, true>(a, st);                       \
-    else if (hard) launch_fwd<CS, true, false>(a, st);                         \
-    else if (stdc) launch_fwd<CS, false, true>(a, st);                         \
-    else launch_fwd<CS, false, false>(a, st);                                  \
-  } while (0)
-  if (a.H == 512) MVAE_CL_FWD(16);
-  else MVAE_CL_FWD(8);
-#undef MVAE_CL_FWD
 }
 
 }  // namespace mvae

@@ -38,17 +38,18 @@ def _compare_step(ecfg, ocfg, n, weights=False, tol=TOL32, grad_tol=None, seed=7
         ref = g_ref[k].numpy()
         scale = max(np.abs(ref).max(), 1e-6)
         assert np.abs(g[k] - ref).max() <= gt * scale + 1e-9, (k, float(np.abs(g[k] - ref).max()), float(scale), "worst", worst)
-    # one Keras-Adam step on the same gradients
+    # one Keras-Adam step.  The optimiser is checked on the gradients the device itself produced (fp32 arena), so that the tolerance can
+    # be tight on EVERY element -- including the tiny-gradient ones where Keras' epsilon placement (outside the bias-corrected sqrt,
+    # i.e. an effective eps / sqrt(1 - beta_2) on the first step) differs visibly from the textbook form -- independent of the precision mode
+    import torch as _t
     opt = O.KerasAdam(p, lr=ocfg.learning_rate)
-    opt.step(p, g_ref)
+    opt.step(p, {k: _t.tensor(np.asarray(g[k], np.float64)) for k in g_ref})
     w_new = eng.get_weights()
     for k in p:
-        # the first Adam step moves every weight by ~lr*sign(g); compare the UPDATE, not the weight
         d_ref = p[k].numpy() - w[k]
         d = w_new[k] - w[k]
-        live = np.abs(g_ref[k].numpy()) > 1e-4   # |g| >> eps/sqrt(1-beta_2): the update is ~lr*sign(g)
-        if live.any():
-            assert np.abs(d - d_ref)[live].max() <= 0.05 * ocfg.learning_rate, k
+        ulp = np.spacing(np.abs(w[k]).astype(np.float32)).astype(np.float64)
+        assert (np.abs(d - d_ref) <= 2e-3 * ocfg.learning_rate + 2 * ulp).all(), (k, float(np.abs(d - d_ref).max()))
     eng.close()
     return m, m_ref
 
