@@ -142,6 +142,17 @@ int mvae_style_transfer_host(mvae_handle h, const mvae_batch* host_batch, const 
                              int c_from, int c_to, int feedback,
                              uint8_t* pitch_out, uint8_t* instr_out, float* velocity_out);
 
+/* ---- output post-processing on the device: process_decoder_outputs (vae_definition.py:1131-1225, sample_method 'argmax') on the packed
+ *      outputs -- silent steps get velocity 0, override_sampled_pitches_based_on_velocity_info per voice (:1161-1190), held-note roll
+ *      D = 0 where the final velocity is above the played-note threshold (:1214-1221).
+ *      scope: 0 off (default), 1 the per-voice memory restarts at every chunk (the style-switch loop calls the reference function once per
+ *      chunk, vae_evaluation.py:2483), 2 at every song start (its whole-song call sites, vae_evaluation.py:799,814).
+ *      Once set, mvae_style_transfer[_host] applies it before the velocities leave the device. ---- */
+int mvae_set_postprocess(mvae_handle h, int scope, float velocity_threshold /* settings.py:30: 0.5 */, int override_by_velocity, int max_voices);
+/* the same rules on caller-supplied packed rolls (host): pitch u8 [n,T] (input_dim-1 = silent), velocity f32 [n,T] in place, held u8 [n,T] or NULL */
+int mvae_postprocess_host(mvae_handle h, int n, const uint8_t* pitch, const uint8_t* song_start /* [n] or NULL */, int scope,
+                          float* velocity_inout, uint8_t* held_out);
+
 /* ---- multi-GPU data parallelism: ONE ncclAllReduce(sum) over the gradient arena per step ---- */
 int mvae_nccl_unique_id(void* id_out_128_bytes);
 int mvae_nccl_init(mvae_handle h, const void* id_128_bytes, int world_size, int rank);

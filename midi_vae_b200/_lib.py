@@ -74,6 +74,8 @@ SYMBOLS = {
     "mvae_autoencode_host": (C.c_int, [_H, _P(MvaeBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvae_style_transfer": (C.c_int, [_H, _P(MvaeBatch), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvae_style_transfer_host": (C.c_int, [_H, _P(MvaeBatch), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mvae_set_postprocess": (C.c_int, [_H, C.c_int, C.c_float, C.c_int, C.c_int]),
+    "mvae_postprocess_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mvae_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mvae_nccl_init": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
     "mvae_world_size": (C.c_int, [_H, _P(C.c_int)]),

@@ -25,11 +25,20 @@ void Model::forward_backward(const mvae_batch& b, float* dev_metrics, cudaStream
   backward(b);
 }
 
+// Data parallelism: sum of the gradient arena over the ranks.  Every NCCL call of a handle goes to ONE stream (st_comm), in the
+// same order on every rank.  If backward() already sent the decoder bucket, only the encoder's tensors (arena head) remain; the step's stream
+// waits for the communication stream before the optimizer reads Gr.
 void Model::allreduce_grads() {
   if (world <= 1 || !nccl_comm) return;
-  prof_begin(PC_ALLREDUCE);
-  nccl_allreduce_sum_f32(nccl_comm, Gr, arena_n, st);
-  prof_end();
+  const size_t head = dec_bucket_issued ? ptab[iWinit].off : arena_n;
+  dec_bucket_issued = false;
+  MVAE_CUDA(cudaEventRecord(ev_pre_comm, st));          // every gradient is final on the step's stream here (backward() joined its streams)
+  MVAE_CUDA(cudaStreamWaitEvent(st_comm, ev_pre_comm, 0));
+  prof_begin(PC_ALLREDUCE, st_comm);
+  nccl_allreduce_sum_f32(nccl_comm, Gr, head, st_comm);
+  prof_end(st_comm);
+  MVAE_CUDA(cudaEventRecord(ev_comm, st_comm));
+  MVAE_CUDA(cudaStreamWaitEvent(st, ev_comm, 0));
 }
 
 // keras.optimizers.Adam (vae_definition.py:174-175; Keras 2.0.8 update rule)
@@ -88,6 +97,10 @@ void Model::style_transfer(const mvae_batch& b, const uint8_t* song_start, int c
   k_argmax_seq(T, b.n, Dp, Pn, ld_pn, pitch_out, st);
   k_argmax_seq(Ti, b.n, Di, Pi, ld_pi, instr_out, st);
   k_export_seq(T, b.n, 1, Pv, ld_pv, vel_out, st);
+  if (post_scope) {   // the reference's process_decoder_outputs rules on the packed outputs, before anything leaves the device
+    MVAE_REQUIRE(T % post_voices == 0, "post-processing: input_length must be a multiple of max_voices (import_midi.py:249)");
+    k_postprocess_voices(b.n, T, post_voices, Dp - 1, post_threshold, post_scope, post_override, pitch_out, song_start, vel_out, o_held, st);
+  }
   prof_end();
 }
 
@@ -278,6 +291,8 @@ int mvae_apply_update(mvae_handle h, float grad_scale, void* stream) {
 int mvae_train_step(mvae_handle h, const mvae_batch* b, float* dev_metrics, void* stream) {
   API_BEGIN(h)
   MVAE_REQUIRE(b != nullptr, "batch is null");
+  M.overlap_allreduce = true;
+  struct Reset { bool& f; ~Reset() { f = false; } } reset{M.overlap_allreduce};
   M.forward_backward(*b, dev_metrics, (cudaStream_t)stream);
   M.allreduce_grads();
   M.apply_update(1.0f / (float)M.world, (cudaStream_t)stream);
@@ -297,6 +312,8 @@ int mvae_train_step_host(mvae_handle h, const mvae_batch* hb, mvae_metrics* out)
   M.st = M.stream;
   M.check_batch(*hb, true);
   mvae_batch d = M.upload(*hb);
+  M.overlap_allreduce = true;
+  struct Reset { bool& f; ~Reset() { f = false; } } reset{M.overlap_allreduce};
   M.forward_backward(d, nullptr, nullptr);
   M.allreduce_grads();
   M.apply_update(1.0f / (float)M.world, nullptr);
@@ -430,6 +447,34 @@ int mvae_style_transfer_host(mvae_handle h, const mvae_batch* hb, const uint8_t*
   API_END()
 }
 
+int mvae_set_postprocess(mvae_handle h, int scope, float velocity_threshold, int override_by_velocity, int max_voices) {
+  API_BEGIN(h)
+  MVAE_REQUIRE(scope >= 0 && scope <= 2, "postprocess scope: 0 off, 1 per chunk, 2 per song");
+  MVAE_REQUIRE(max_voices >= 1 && M.T % max_voices == 0, "max_voices must divide input_length");
+  M.post_scope = scope; M.post_threshold = velocity_threshold; M.post_override = override_by_velocity != 0; M.post_voices = max_voices;
+  API_END()
+}
+
+int mvae_postprocess_host(mvae_handle h, int n, const uint8_t* pitch, const uint8_t* song_start, int scope, float* velocity_inout, uint8_t* held_out) {
+  API_BEGIN(h)
+  MVAE_REQUIRE(pitch && velocity_inout, "null argument");
+  MVAE_REQUIRE(n >= 1 && n <= M.NB, "number of chunks must be in 1..max_batch");
+  MVAE_REQUIRE(scope == 1 || scope == 2, "postprocess scope: 1 per chunk, 2 per song");
+  M.st = M.stream;
+  const size_t nt = (size_t)n * M.T;
+  MVAE_CUDA(cudaMemcpyAsync(M.o_pitch, pitch, nt, cudaMemcpyHostToDevice, M.st));
+  MVAE_CUDA(cudaMemcpyAsync(M.o_v, velocity_inout, nt * 4, cudaMemcpyHostToDevice, M.st));
+  if (song_start) MVAE_CUDA(cudaMemcpyAsync(M.d_song_start, song_start, (size_t)n, cudaMemcpyHostToDevice, M.st));
+  M.h2d_bytes += nt * 5 + (song_start ? n : 0);
+  mvae::k_postprocess_voices(n, M.T, M.post_voices, M.Dp - 1, M.post_threshold, scope, M.post_override, M.o_pitch, song_start ? M.d_song_start : nullptr,
+                             M.o_v, M.o_held, M.st);
+  MVAE_CUDA(cudaMemcpyAsync(velocity_inout, M.o_v, nt * 4, cudaMemcpyDeviceToHost, M.st));
+  if (held_out) MVAE_CUDA(cudaMemcpyAsync(held_out, M.o_held, nt, cudaMemcpyDeviceToHost, M.st));
+  MVAE_CUDA(cudaStreamSynchronize(M.st));
+  M.d2h_bytes += nt * 4 + (held_out ? nt : 0);
+  API_END()
+}
+
 int mvae_grad_arena(mvae_handle h, float** dev_ptr, size_t* n) { API_BEGIN(h) *dev_ptr = M.Gr; *n = M.arena_n; API_END() }
 int mvae_param_arena(mvae_handle h, float** dev_ptr, size_t* n) { API_BEGIN(h) *dev_ptr = M.P; *n = M.arena_n; API_END() }
 
@@ -440,7 +485,17 @@ int mvae_nccl_unique_id(void* id_out) {
 int mvae_nccl_init(mvae_handle h, const void* id, int world_size, int rank) {
   API_BEGIN(h)
   MVAE_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad world_size / rank");
-  if (world_size > 1) M.nccl_comm = mvae::nccl_comm_init(id, world_size, rank);
+  if (world_size > 1) {
+    M.nccl_comm = mvae::nccl_comm_init(id, world_size, rank);
+    if (!M.st_comm) {
+      int lo = 0, hi = 0;
+      MVAE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      MVAE_CUDA(cudaStreamCreateWithPriority(&M.st_comm, cudaStreamNonBlocking, hi));
+      MVAE_CUDA(cudaEventCreateWithFlags(&M.ev_dec_grads, cudaEventDisableTiming));
+      MVAE_CUDA(cudaEventCreateWithFlags(&M.ev_comm, cudaEventDisableTiming));
+      MVAE_CUDA(cudaEventCreateWithFlags(&M.ev_pre_comm, cudaEventDisableTiming));
+    }
+  }
   M.world = world_size; M.rank = rank;
   API_END()
 }

@@ -734,6 +734,46 @@ void k_finalize_metrics(const double* acc, int n, int T, int Ti, float w_notes, 
   LAUNCH_CHECK();
 }
 
+// Output post-processing of the decoder (vae_definition.py:1156-1190, 1214-1221) on the packed device outputs:
+// silent steps get velocity 0; override_sampled_pitches_based_on_velocity_info walks every voice (flattened step s belongs to voice
+// s % max_voices) through time with a (previous pitch, previous struck velocity) memory; the held-note roll is 1 unless the final
+// velocity says "struck".  One thread per (scan unit, voice): scope 1 = the memory restarts at every chunk (the reference's style-switch
+// loop post-processes chunk by chunk, vae_evaluation.py:2483), scope 2 = at every song start (its whole-song call sites, :799, :814).
+__global__ void postprocess_voices_kernel(int n, int T, int voices, int silent, float thr, int scope, int do_override, const uint8_t* __restrict__ pitch,
+                                          const uint8_t* __restrict__ song_start, float* __restrict__ vel, uint8_t* __restrict__ held) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n * voices) return;
+  const int chunk = x / voices, voice = x % voices;
+  int last = chunk;                                      // scan chunks [chunk, last]
+  if (scope == 2) {
+    if (chunk > 0 && !(song_start && song_start[chunk])) return;       // not the first chunk of a song: scanned by the thread of its song start
+    while (last + 1 < n && !(song_start && song_start[last + 1])) ++last;
+  }
+  int prev_pitch = -1;
+  float prev_vel = 0.f;
+  for (int c = chunk; c <= last; ++c) {
+    for (int i = voice; i < T; i += voices) {
+      const size_t s = (size_t)c * T + i;
+      const int pc = pitch[s];
+      const int p = pc == silent ? -1 : pc;
+      float v = p < 0 ? 0.f : vel[s];                    // a silent step has velocity 0
+      float out = v;
+      if (do_override) {
+        const bool vel_silent = v < thr;
+        if (vel_silent) {
+          if (p >= 0 && prev_pitch > 0 && prev_pitch != p) out = prev_vel;   // a new pitch without a struck velocity: as loud as the previous note
+        } else if (p < 0) {
+          out = 0.f;
+        }
+        prev_pitch = p;
+        if (!vel_silent) prev_vel = v;
+      }
+      vel[s] = out;
+      if (held) held[s] = out > thr ? 0 : 1;
+    }
+  }
+}
+
 void k_export_seq(int steps, int n, int D, const float* probs, int ld, float* out, cudaStream_t st) {
   export_seq_kernel<<<nblk((long)steps * n * D), TPB, 0, st>>>(steps, n, D, probs, ld, out);
   LAUNCH_CHECK();
@@ -741,6 +781,12 @@ void k_export_seq(int steps, int n, int D, const float* probs, int ld, float* ou
 
 void k_argmax_seq(int steps, int n, int D, const float* probs, int ld, uint8_t* out, cudaStream_t st) {
   argmax_seq_kernel<<<nblk((long)steps * n), TPB, 0, st>>>(steps, n, D, probs, ld, out);
+  LAUNCH_CHECK();
+}
+
+void k_postprocess_voices(int n, int T, int voices, int silent, float thr, int scope, int do_override, const uint8_t* pitch, const uint8_t* song_start,
+                          float* vel, uint8_t* held, cudaStream_t st) {
+  postprocess_voices_kernel<<<nblk((long)n * voices), TPB, 0, st>>>(n, T, voices, silent, thr, scope, do_override, pitch, song_start, vel, held);
   LAUNCH_CHECK();
 }
 

@@ -51,6 +51,9 @@ void k_finalize_metrics(const double* acc, int n, int T, int Ti, float w_notes, 
                         cudaStream_t st);
 void k_export_seq(int steps, int n, int D, const float* probs, int ld, float* out, cudaStream_t st);
 void k_argmax_seq(int steps, int n, int D, const float* probs, int ld, uint8_t* out, cudaStream_t st);
+// in place on the packed outputs: velocity override rules of process_decoder_outputs + held-note roll (held may be null)
+void k_postprocess_voices(int n, int T, int voices, int silent, float thr, int scope, int do_override, const uint8_t* pitch, const uint8_t* song_start,
+                          float* vel, uint8_t* held, cudaStream_t st);
 void k_swap_shift(DT act, int n, int L, int ldl, const float* mu, const uint8_t* song_start, int c_from, int c_to, int has_hist, void* q,
                   int ldq, float* z_sw, cudaStream_t st);
 void k_build_q(DT act, int n, int L, const float* z, const float* hist, int has_hist, void* q, int ldq, cudaStream_t st);

@@ -123,7 +123,7 @@ void Model::build_workspace() {
   dlog_n = alloc((size_t)T * n * ld_pn * a); dlog_i = alloc((size_t)Ti * n * ld_pi * a); dlog_v = alloc((size_t)T * n * ld_pv * a);
   acc = (double*)alloc(ACC_COUNT * 8); d_metrics = (float*)alloc(MVAE_NUM_METRICS * 4);
   o_y = (float*)alloc((size_t)n * T * Dp * 4); o_i = (float*)alloc((size_t)n * Ti * Di * 4); o_v = (float*)alloc((size_t)n * T * 4);
-  o_z = (float*)alloc((size_t)n * L * 4 * 3); o_pitch = (uint8_t*)alloc(n * T); o_instr = (uint8_t*)alloc(n * Ti);
+  o_z = (float*)alloc((size_t)n * L * 4 * 3); o_pitch = (uint8_t*)alloc(n * T); o_instr = (uint8_t*)alloc(n * Ti); o_held = (uint8_t*)alloc(n * T);
   // pinned staging: inputs + the largest output set
   pin_bytes = n * T * 2 + n * Ti + n * 2 + (size_t)n * T * 4 * 2 + (size_t)n * L * 4 * 3 + (size_t)n * T * Dp * 4 + (size_t)n * Ti * Di * 4 +
               (size_t)n * T * 4 + (size_t)n * C * 4 + 4096;
@@ -182,6 +182,8 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_XW_OVERLAP"); xw_overlap = (use_cluster_fwd && e) ? std::max(0, std::min(16, atoi(e))) : 0; }
   { const char* e = getenv("MVAE_WGRAD_CHUNKS"); wgrad_per_chunk = e ? atoi(e) != 0 : false; }
   { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
+  { const char* e = getenv("MVAE_AR_BUCKETS"); ar_buckets = e ? std::max(1, atoi(e)) : 2; }
+  { const char* e = getenv("MVAE_BRANCH_BWD_NCL"); branch_bwd_ncl = e ? std::max(0, atoi(e)) : 0; }
   if (chunks > 1 || chunks_bwd > 1 || xw_overlap > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
@@ -198,6 +200,8 @@ Model::~Model() {
   if (stream) cudaStreamSynchronize(stream);
   for (auto& ev : evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   if (nccl_comm) nccl_comm_destroy(nccl_comm);
+  if (st_comm) cudaStreamDestroy(st_comm);
+  for (cudaEvent_t e : {ev_dec_grads, ev_comm, ev_pre_comm}) if (e) cudaEventDestroy(e);
   for (void* p : allocs_) cudaFree(p);
   if (pin) cudaFreeHost(pin);
   if (stream) cudaStreamDestroy(stream);
@@ -547,7 +551,14 @@ void Model::rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n) {
       if (!j) continue;
       RecPersistArgs a = bwd_args(*j, n, cur_slot, 0);
       fork_if_pending();
-      rec_cluster_backward(a, st);
+      if (cur_slot == 1 && branch_bwd_ncl > 0 && a.steps > 16) {
+        // a branch recurrence never gets more than the cluster slots the main chain leaves (3 of 7): its fourth cluster runs as a second wave
+        // anyway, so launch it as waves of `branch_bwd_ncl` clusters and leave the other SMs to the weight-gradient GEMMs of the side stream
+        const int clusters = ((n + 63) / 64 + 1) / 2;
+        for (int c0 = 0; c0 < clusters; c0 += branch_bwd_ncl) { a.cl0 = c0; a.ncl = branch_bwd_ncl; rec_cluster_backward(a, st); }
+      } else {
+        rec_cluster_backward(a, st);
+      }
       dump_trace("bwd(cluster)", *j->r, 2);
     }
   } else if (use_persist) {
@@ -1178,6 +1189,17 @@ void Model::backward(const mvae_batch& b) {
   { GemmArgs g; g.M = n; g.N = Q; g.K = nS * H; g.A = dSpre; g.lda = nS * H; g.B = W(iWinit); g.ldb = ld(iWinit); g.transB = true;
     g.C = dq; g.ldc = ldq; g.c_type = act; gemm(g); }
   prof_end();
+  // every decoder-side weight gradient (arena tail from dec_init on) has been enqueued: its bucket of the data-parallel all-reduce
+  // goes to the communication stream now and overlaps the encoder's reverse sweeps
+  if (overlap_allreduce && world > 1 && nccl_comm && ar_buckets > 1) {
+    MVAE_CUDA(cudaEventRecord(ev_dec_grads, ws));
+    MVAE_CUDA(cudaStreamWaitEvent(st_comm, ev_dec_grads, 0));
+    const size_t off = ptab[iWinit].off;
+    prof_begin(PC_ALLREDUCE, st_comm);
+    nccl_allreduce_sum_f32(nccl_comm, Gr + off, arena_n - off, st_comm);
+    prof_end(st_comm);
+    dec_bucket_issued = true;
+  }
   // ---- style head + reparameterisation + KL
   prof_begin(PC_POINTWISE);
   k_latent_bwd(act, n, L, ldl, C, dq, ldq, mu, lv, b.eps, style_probs, b.style, cfg.beta, cfg.prior_mean, cfg.prior_std, cfg.composer_weight, dmu,

@@ -125,6 +125,13 @@ struct Model {
   // data parallel
   void* nccl_comm = nullptr;
   int world = 1, rank = 0;
+  // data parallel: the gradient arena is all-reduced in two buckets on a communication stream -- the decoder's tensors (the tail of the
+  // arena; final ~4 ms before the step ends) while the encoder's reverse sweeps still run, the encoder's at the join (api.cu)
+  cudaStream_t st_comm = nullptr;
+  cudaEvent_t ev_dec_grads = nullptr, ev_comm = nullptr, ev_pre_comm = nullptr;
+  bool overlap_allreduce = false;     // set by the fused train step only: the split API (forward_backward + apply_update) leaves Gr untouched
+  bool dec_bucket_issued = false;
+  int ar_buckets = 2;                 // MVAE_AR_BUCKETS=1: one all-reduce after the join (round-1 behaviour)
   // profiling
   bool profiling = false;
   struct Ev { int cls; cudaEvent_t a, b; };
@@ -144,6 +151,7 @@ struct Model {
   cudaStream_t st_branch = nullptr, st_saved = nullptr;
   cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
   bool use_branch = false;
+  int branch_bwd_ncl = 0;             // > 0: branch-stream reverse sweeps run as waves of this many clusters (MVAE_BRANCH_BWD_NCL)
   int cur_slot = 0;                   // which set of exchange buffers the recurrence being issued uses
   bool fork_pending = false;          // the fork point is the launch of the next main-stream recurrence (it must win the cluster slots)
   void fork_if_pending();
@@ -182,6 +190,9 @@ struct Model {
   const void* Y_ext_cur = nullptr;   // teacher-forcing source: Yp_ext or (target == pitch) Xp_ext
   const void* e_cur = nullptr;       // output of the last tanh Dense before the split
   bool stepwise_done = false;
+  // output post-processing on the device (vae_definition.py:1156-1190): 0 = off, 1 = voice memory restarts per chunk, 2 = per song
+  int post_scope = 0; float post_threshold = 0.5f; int post_override = 1; int post_voices = 4;
+  uint8_t* o_held = nullptr;
   bool use_persist = false;          // persistent-RNN kernels (bf16 precision, supported hidden size)
   bool use_cluster_fwd = false;      // cluster forward recurrence kernel (lstm_cluster.cu)
   bool use_cluster_bwd = false;      // cluster backward recurrence kernel (lstm_cluster.cu)

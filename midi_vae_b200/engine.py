@@ -338,6 +338,24 @@ class Engine:
         check(self.lib.mvae_autoencode_host(self._h, C.byref(b), _ptr(Y), _ptr(I), _ptr(V), _ptr(S), _ptr(z)), self._h)
         return Y, I, V, S, z
 
+    _SCOPES = {None: 0, "off": 0, "chunk": 1, "song": 2}
+
+    def set_postprocess(self, scope=None, velocity_threshold: float = 0.5, override_by_velocity: bool = True, max_voices: int = 4):
+        """Device-side process_decoder_outputs rules (vae_definition.py:1156-1190) for every following style_transfer call: scope 'chunk'
+        (the voice memory restarts per chunk, as in the reference's style-switch loop), 'song' (per song) or None (raw argmax / velocities)."""
+        check(self.lib.mvae_set_postprocess(self._h, self._SCOPES[scope], velocity_threshold, int(override_by_velocity), max_voices), self._h)
+
+    def postprocess(self, pitch, velocity, song_start=None, scope: str = "chunk"):
+        """The same rules on packed rolls supplied by the caller: returns (velocity', held) with held = 1 where no note is struck."""
+        cfg = self.cfg
+        P = np.ascontiguousarray(np.asarray(pitch, dtype=np.uint8).reshape(-1, cfg.input_length))
+        n = P.shape[0]
+        V = np.ascontiguousarray(np.asarray(velocity, np.float32).reshape(n, cfg.input_length)).copy()
+        ss = None if song_start is None else _u8(np.asarray(song_start).astype(np.uint8), (n,))
+        D = np.empty((n, cfg.input_length), np.uint8)
+        check(self.lib.mvae_postprocess_host(self._h, n, _ptr(P), _ptr(ss), self._SCOPES[scope], _ptr(V), _ptr(D)), self._h)
+        return V, D
+
     def style_transfer(self, pitch, instr, velocity, c_from=0, c_to=1, song_start=None, feedback: str = "as_wired"):
         cfg = self.cfg
         b = self._batch(pitch, instr, velocity)

@@ -436,3 +436,47 @@ def test_per_song_training_driver_cfg1():
     ev = training.evaluate_songs(vae, songs[:5], batch_size=8)
     assert np.isfinite(list(ev.values())).all()
     vae.engine.close()
+
+
+@pytest.mark.parametrize("scope", ["chunk", "song"])
+def test_postprocess_on_device_matches_reference_rules(scope):
+    """the override rules of process_decoder_outputs (vae_definition.py:1156-1190) run on the device.  Checked against
+    midi_vae_b200.postprocess (host numpy, pinned to the output of the reference's own function by tests/test_reference_pin.py) on random packed
+    rolls that exercise every rule: silent steps with velocity, new pitches without a struck velocity, struck velocities without a pitch."""
+    from midi_vae_b200 import postprocess as PP
+    T, n = 16, 24
+    ecfg, _ = util.make_cfgs(T=T, H=64, L=16, max_batch=n)
+    eng = Engine(ecfg, 0)
+    rng = np.random.default_rng(11)
+    pitch = rng.integers(0, 61, size=(n, T)).astype(np.uint8)
+    pitch[rng.random((n, T)) < 0.25] = 60                       # silent
+    pitch[rng.random((n, T)) < 0.1] = 0                         # pitch 0: "previous_pitch > 0" is false for it
+    hold = rng.random((n, T)) < 0.4
+    for i in range(4, T):                                       # sustained notes per voice (same pitch as the voice's previous step)
+        pitch[:, i] = np.where(hold[:, i], pitch[:, i - 4], pitch[:, i])
+    vel = rng.random((n, T)).astype(np.float32)
+    vel[rng.random((n, T)) < 0.3] = 0.5                         # exactly on the threshold: "not silent"
+    song_start = np.zeros(n, np.uint8); song_start[[0, 5, 6, 17]] = 1
+    V, D = eng.postprocess(pitch, vel, song_start, scope)
+    eng.close()
+    bounds = [(i, i + 1) for i in range(n)] if scope == "chunk" else list(zip([0, 5, 6, 17], [5, 6, 17, n]))
+    for a, b in bounds:                                         # the host function's memory runs over whatever one call is given
+        _, _, Vr, Dr = PP.process_decoder_outputs(pitch[a:b], np.zeros((b - a, 4), np.uint8), vel[a:b])
+        assert np.array_equal(V[a:b].reshape(-1).astype(np.float64), Vr), (scope, a, b)
+        assert np.array_equal(D[a:b].reshape(-1), Dr.astype(np.uint8)), (scope, a, b)
+
+
+def test_style_transfer_with_device_postprocess():
+    """mvae_set_postprocess: style_transfer hands back velocities that already went through the override rules (per chunk, as the reference's loop)."""
+    from midi_vae_b200 import postprocess as PP
+    ecfg, _ = util.make_cfgs(T=16, H=64, L=16, max_batch=40)
+    eng = _engine(ecfg, util.make_weights(ecfg, jitter=0.2))
+    r = synth.concat(synth.make_songs(3, 16, seed=5, min_chunks=8, max_chunks=14))
+    P0, I0, V0 = eng.style_transfer(r.pitch, r.instr, r.velocity, 0, 1, r.song_start, "as_wired")
+    eng.set_postprocess("chunk")
+    P1, I1, V1 = eng.style_transfer(r.pitch, r.instr, r.velocity, 0, 1, r.song_start, "as_wired")
+    eng.close()
+    assert np.array_equal(P0, P1) and np.array_equal(I0, I1)
+    for i in range(len(P0)):
+        _, _, Vr, _ = PP.process_decoder_outputs(P0[i:i + 1], I0[i:i + 1], V0[i:i + 1])
+        assert np.array_equal(V1[i].astype(np.float64), Vr), i
