@@ -769,6 +769,7 @@ struct ClusterQP {
   const bf16* upack;      // [16][128 output units][512 k]
   uint8_t* xbuf;          // dG exchange slots [clusters][ng][2][16 CTAs][2 row halves][8 KB]
   long long* trace;
+  int stm;                // partial-dh messages staged with fragment reads + stmatrix.trans instead of per-element stores
 };
 
 template <bool HARD, bool STD>
@@ -922,19 +923,28 @@ rec_cluster_bwd4_kernel(const ClusterQP p) {
       for (int u = 0; u < 8; ++u) dc[u] = 0.f;
       if (p.dc_last && row_ok) unpack8(__ldg(reinterpret_cast<const uint4*>(p.dc_last + (size_t)m * p.ld_last + u0)), dc);
 
+      // BPTT stash of a step (4 gate granules, c_t, dh_ext): loaded ONE STEP AHEAD -- issued right after the exchange barrier of the previous
+      // iteration, in flight during its TMEM drain and the wait for the partial messages -- so that the gate-gradient math never waits for L2
+      // (round 1 loaded at the top of the iteration: long_scoreboard was 45 % of the epilogue warps' stalls).  c_{t+1} of step t is c_t of t+1.
+      uint4 sg[4], sc0, sc1, sex;
+      sex = make_uint4(0u, 0u, 0u, 0u);
+      sc0 = sc1 = sg[0] = sg[1] = sg[2] = sg[3] = make_uint4(0u, 0u, 0u, 0u);
+      auto load_stash = [&](int ts) {
+        sg[0] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(ts, G / 8, bi * (H / 8) + gu, n, m)));
+        sg[1] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(ts, G / 8, bfk * (H / 8) + gu, n, m)));
+        sg[2] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(ts, G / 8, 2 * (H / 8) + gu, n, m)));
+        sg[3] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(ts, G / 8, 3 * (H / 8) + gu, n, m)));
+        sc0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(ts, H / 8, gu, n, m)));
+        if (p.dhext) sex = __ldg(reinterpret_cast<const uint4*>(p.dhext + ((size_t)ts * n + m) * H + u0));
+      };
+      if (row_ok && T > 0) {
+        sc0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(T, H / 8, gu, n, m)));   // becomes c_{t+1} of the first step below
+        sc1 = sc0;
+        load_stash(T - 1);
+      }
+
       for (int it = 0; it <= T; ++it) {
         const int t = T - 1 - it;
-        uint4 sg[4], sc0, sc1, sex;
-        sex = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0 && row_ok) {
-          sg[0] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bi * (H / 8) + gu, n, m)));
-          sg[1] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, bfk * (H / 8) + gu, n, m)));
-          sg[2] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)));
-          sg[3] = __ldg(reinterpret_cast<const uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)));
-          sc0 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t, H / 8, gu, n, m)));
-          sc1 = __ldg(reinterpret_cast<const uint4*>(p.cseq + gran_off(t + 1, H / 8, gu, n, m)));
-          if (p.dhext) sex = __ldg(reinterpret_cast<const uint4*>(p.dhext + ((size_t)t * n + m) * H + u0));
-        }
         if (p.l2_prefetch && t >= p.l2_prefetch && row_ok) {
           const int tp = t - p.l2_prefetch;
           prefetch_l2(p.gates + gran_off(tp, G / 8, bi * (H / 8) + gu, n, m));
@@ -1016,6 +1026,8 @@ rec_cluster_bwd4_kernel(const ClusterQP p) {
         ptx::fence_proxy_async_global();       // generic stores -> the multicast copy (async proxy); nothing else of this thread is in flight but old dG rows
         named_barrier(1 + g, 32 * (CL_EPI_WARPS + 1));
         if (tracer && g == 0) CL_TRACE(it, 3);
+        // next step's stash (after the fence above, so that the fence never waits for these loads)
+        if (row_ok && t > 0) { sc1 = sc0; load_stash(t - 1); }
         // ---- off the critical path: dG_t for the batched weight-gradient GEMMs
         if (row_ok) {
           bf16* dgp = p.dG + ((size_t)t * n + m) * G + u0;
@@ -1030,7 +1042,30 @@ rec_cluster_bwd4_kernel(const ClusterQP p) {
         if (tracer && g == 0) CL_TRACE(it, 4);
         if (it > 0) ptx::mbar_wait(ptx::smem_u32(&ack[g]), (uint32_t)((it - 1) & 1));   // every receiver has read message it-1
         if (tracer && g == 0) CL_TRACE(it, 5);
-        {
+        if (p.stm) {
+          // accumulator-fragment reads + transposing matrix stores: 2 x tcgen05.ld (16 lanes x 32 columns), 16 packed conversions, 4 x stmatrix.x4
+          // (each 8 units x 8 rows block lands as eight conflict-free 16-byte rows) instead of 32 two-byte stores per thread
+          const uint32_t mbase = gb + 2 * CLQ_BT + (uint32_t)wq * CLQ_MSG + (uint32_t)(ch * 32 + (lane & 7)) * 16;
+          const int mi = lane >> 3;                                   // which of the 4 matrices of an instruction this lane addresses
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl) {
+            float v[16];
+            ptx::tmem_ld_16x256b_x4(tmem_base + ((uint32_t)(wq * 32 + hl * 16) << 16) + (uint32_t)(g * 64 + ch * 32), v);
+#pragma unroll
+            for (int cbh = 0; cbh < 2; ++cbh) {
+              // matrix mi: unit granule 2 hl + (mi & 1), rows 32 ch + 8 (2 cbh + (mi >> 1)) + j
+              const uint32_t addr = mbase + (uint32_t)(2 * hl + (mi & 1)) * CLQ_MGS + (uint32_t)(8 * (2 * cbh + (mi >> 1))) * 16;
+              uint32_t r[4];
+#pragma unroll
+              for (int x = 0; x < 4; ++x) {
+                const int cb = 2 * cbh + (x >> 1), s2 = x & 1;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4 * cb + 2 * s2], v[4 * cb + 2 * s2 + 1]);
+                r[x] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              ptx::stmatrix_x4_trans(addr, r[0], r[1], r[2], r[3]);
+            }
+          }
+        } else {
           float v[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(g * 64 + ch * 32), v);
           const uint32_t base = gb + 2 * CLQ_BT + (uint32_t)wq * CLQ_MSG + (uint32_t)(lane >> 3) * CLQ_MGS + (uint32_t)(ch * 32) * 16 + (uint32_t)(lane & 7) * 2;
@@ -1254,6 +1289,7 @@ void launch_bwd4(const RecPersistArgs& a, cudaStream_t st) {
     p.dG = (bf16*)a.dG + t0 * nn * 4 * Hh; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
   }
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace; p.xbuf = (uint8_t*)a.partial;
+  p.stm = env_int("MVAE_CLB_STM", 0);
   MVAE_REQUIRE(p.upack != nullptr && p.xbuf != nullptr, "cluster backward: packed weights / exchange buffer missing");
   MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * 2 * CLQ_PIECE <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};

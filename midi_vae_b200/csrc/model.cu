@@ -114,6 +114,7 @@ void Model::build_workspace() {
   Xi_ext = alloc((size_t)(Ti + 1) * n * ID * a); Xv_ext = alloc((size_t)(T + 1) * n * VD * a);
   pre = (float*)alloc(n * G * 4); c_run = (float*)alloc(n * H * 4); dh_run = (float*)alloc(n * H * 4); dc_run = (float*)alloc(n * H * 4);
   xstep = alloc(n * 64 * a);
+  pre_b = (float*)alloc(n * G * 4); c_run_b = (float*)alloc(n * H * 4); xstep_b = alloc(n * 64 * a);
   u = alloc(n * 3 * H * a); a1 = alloc(n * H * a); e = alloc(n * H * a); q = alloc(n * ldq * a);
   S = alloc(n * nS * H * a); dS = alloc(n * nS * H * a); dSpre = alloc(n * nS * H * a); dq = alloc(n * ldq * a);
   dmu = alloc(n * ldl * a); dlv = alloc(n * ldl * a); de = alloc(n * H * a); dpre_e = alloc(n * H * a); da1 = alloc(n * H * a);
@@ -182,6 +183,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_XW_OVERLAP"); xw_overlap = (use_cluster_fwd && e) ? std::max(0, std::min(16, atoi(e))) : 0; }
   { const char* e = getenv("MVAE_WGRAD_CHUNKS"); wgrad_per_chunk = e ? atoi(e) != 0 : false; }
   { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
+  { const char* e = getenv("MVAE_STEPWISE_GRAPH"); stepwise_graph_on = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_AR_BUCKETS"); ar_buckets = e ? std::max(1, atoi(e)) : 2; }
   { const char* e = getenv("MVAE_BRANCH_BWD_NCL"); branch_bwd_ncl = e ? std::max(0, atoi(e)) : 0; }
   if (chunks > 1 || chunks_bwd > 1 || xw_overlap > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
@@ -199,6 +201,7 @@ Model::~Model() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
   for (auto& ev : evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  for (auto& kv : stepwise_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (nccl_comm) nccl_comm_destroy(nccl_comm);
   if (st_comm) cudaStreamDestroy(st_comm);
   for (cudaEvent_t e : {ev_dec_grads, ev_comm, ev_pre_comm}) if (e) cudaEventDestroy(e);
@@ -1038,6 +1041,39 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
 
 // free-running decode (inference only): x_t = previous prediction, one step at a time
 void Model::decoder_stepwise(int n) {
+  prof_begin(PC_REC_FWD);
+  StepwiseGraph& sg = stepwise_graphs[n];
+  if (!stepwise_graph_on) {
+    decoder_stepwise_body(n);
+  } else if (sg.state == 0) {
+    decoder_stepwise_body(n);          // first call for this batch size: eager (kernel attributes get set outside any capture)
+    sg.state = 1;
+  } else if (sg.state == 1) {
+    cudaGraph_t graph = nullptr;
+    const long long l0 = g_launches;
+    MVAE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    try {
+      decoder_stepwise_body(n);
+    } catch (...) {
+      cudaStreamEndCapture(st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    MVAE_CUDA(cudaStreamEndCapture(st, &graph));
+    sg.launches = g_launches - l0;
+    MVAE_CUDA(cudaGraphInstantiate(&sg.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    sg.state = 2;
+    MVAE_CUDA(cudaGraphLaunch(sg.exec, st));
+  } else {
+    MVAE_CUDA(cudaGraphLaunch(sg.exec, st));
+    count_launch((int)sg.launches);
+  }
+  prof_end();
+  stepwise_done = true;
+}
+
+void Model::decoder_stepwise_body(int n) {
   auto st1 = [&](int r) { return (const char*)S + (size_t)(spc * r) * H * asz(); };
   auto st2 = [&](int r) { return gru ? (const char*)nullptr : (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
   auto init = [&](Rec& r, int sidx) {
@@ -1057,7 +1093,8 @@ void Model::decoder_stepwise(int n) {
     if (!gru) k_copy2d(act, DT_F32, n, H, slab(r.cseq, t, (long)n * H), H, c_run, H, st);
     rec_steps_forward(r, n, t, t + 1);
   };
-  prof_begin(PC_REC_FWD);
+  // the velocity and instrument chains are independent of the notes chain: branch stream, own scratch (host code stays sequential)
+  MVAE_CUDA(cudaEventRecord(ev_bfork, st));
   // notes
   for (int k = 0; k < nd; ++k) init(dec_notes[k], k);
   for (int t = 0; t < T; ++t) {
@@ -1072,6 +1109,11 @@ void Model::decoder_stepwise(int n) {
     g.C = Pt; g.ldc = ld_pn; g.c_type = DT_F32; g.bias = Wf(iby); gemm(g);
     k_softmax_ce(act, 1, n, Dp, Pt, ld_pn, nullptr, nullptr, nullptr, 0.f, nullptr, ld_pn, acc, ACC_CE_NOTES, ACC_ACC_NOTES, st);
   }
+  MVAE_CUDA(cudaStreamWaitEvent(st_branch, ev_bfork, 0));
+  cudaStream_t st_main = st;
+  st = st_branch;
+  std::swap(pre, pre_b); std::swap(c_run, c_run_b); std::swap(xstep, xstep_b);
+  struct Restore { Model& m; cudaStream_t s; ~Restore() { m.st = s; std::swap(m.pre, m.pre_b); std::swap(m.c_run, m.c_run_b); std::swap(m.xstep, m.xstep_b); } } restore{*this, st_main};
   // instrument
   init(dec_instr, nd);
   for (int t = 0; t < Ti; ++t) {
@@ -1097,8 +1139,8 @@ void Model::decoder_stepwise(int n) {
     k_rowdot(act, n, H, slab(dec_vel.hseq, t + 1, (long)n * H), Wf(iWvo), Wf(ibvo), Pt, ld_pv, st);
     k_sigmoid_mse(act, 1, n, Pt, ld_pv, nullptr, 0.f, nullptr, ld_pv, acc, st);
   }
-  prof_end();
-  stepwise_done = true;
+  MVAE_CUDA(cudaEventRecord(ev_bjoin, st_branch));
+  MVAE_CUDA(cudaStreamWaitEvent(st_main, ev_bjoin, 0));
 }
 
 // softmax / sigmoid heads + Keras losses; train => also the gradients wrt the logits

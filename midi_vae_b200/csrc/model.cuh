@@ -1,6 +1,7 @@
 // model.cuh -- the MIDI-VAE model handle: parameter arena, workspace, and the orchestration of one
 // train / eval / predict / style-transfer call as a fixed sequence of kernel launches on one stream.
 #pragma once
+#include <map>
 #include <string>
 #include <vector>
 
@@ -253,6 +254,13 @@ struct Model {
   void head_forward(const mvae_batch& b, bool with_style_loss);
   void decoder_forward(const mvae_batch& b, int feedback);
   void decoder_stepwise(int n);
+  void decoder_stepwise_body(int n);
+  // free-running decode = thousands of tiny dependent launches: captured once per batch size into a CUDA graph (notes chain on the step's
+  // stream, velocity + instrument chains on the branch stream with their own scratch) and replayed; MVAE_STEPWISE_GRAPH=0 launches eagerly
+  struct StepwiseGraph { int state = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
+  std::map<int, StepwiseGraph> stepwise_graphs;
+  bool stepwise_graph_on = true;
+  float *pre_b = nullptr, *c_run_b = nullptr; void* xstep_b = nullptr;   // scratch of the branch chain
   void losses(const mvae_batch& b, bool train);
   void backward(const mvae_batch& b);
   void forward_backward(const mvae_batch& b, float* dev_metrics, cudaStream_t st);

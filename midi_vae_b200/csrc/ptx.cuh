@@ -107,6 +107,28 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// TMEM -> registers in the accumulator-fragment shape: 16 lanes x (4 x 8) fp32 columns.  Register 4 j + k of thread i: column block j (8 columns),
+// k = 0, 1: lane base + i / 4, columns 8 j + 2 (i % 4) + {0, 1};  k = 2, 3: lane base + 8 + i / 4, same columns  (the mma C-fragment layout, so a
+// converted pair is exactly one stmatrix register).  The lane field of taddr is the warp's quadrant base, + 16 for the upper half.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// four 8x8 b16 matrices, transposed on the way: register m of thread i holds F_m[i / 4][2 (i % 4) + {0, 1}]; the 16-byte shared-memory row whose
+// address thread 8 m + j supplies receives { F_m[0..7][j] }
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t row_addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(row_addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
 // ---------------------------------------------------------------- thread-block clusters / DSMEM / CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

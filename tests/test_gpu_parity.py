@@ -480,3 +480,32 @@ def test_style_transfer_with_device_postprocess():
     for i in range(len(P0)):
         _, _, Vr, _ = PP.process_decoder_outputs(P0[i:i + 1], I0[i:i + 1], V0[i:i + 1])
         assert np.array_equal(V1[i].astype(np.float64), Vr), i
+
+
+@pytest.mark.parametrize("precision,shape", [("fp32", (16, 64, 16)), ("bf16", (16, 256, 32))])
+def test_free_running_graph_replay_is_exact(precision, shape):
+    """The free-running decoder is captured into a CUDA graph on its second call for a batch size and replayed from the third on
+    (Model::decoder_stepwise): eager, capturing and replaying calls must return identical outputs, on new inputs too."""
+    T, H, L = shape
+    ecfg, ocfg = util.make_cfgs(T=T, H=H, L=L, precision=precision, max_batch=24)
+    w = util.make_weights(ecfg)
+    eng = _engine(ecfg, w)
+    ra = synth.concat(synth.make_songs(2, T, seed=5, min_chunks=12, max_chunks=12))
+    rb = synth.concat(synth.make_songs(2, T, seed=6, min_chunks=12, max_chunks=12))
+    outs_a = [eng.style_transfer(ra.pitch, ra.instr, ra.velocity, 0, 1, ra.song_start, "free_running") for _ in range(3)]   # eager, capture, replay
+    n0 = eng.launch_count()
+    out_b = eng.style_transfer(rb.pitch, rb.instr, rb.velocity, 0, 1, rb.song_start, "free_running")                         # replay, other inputs
+    n1 = eng.launch_count()
+    out_a4 = eng.style_transfer(ra.pitch, ra.instr, ra.velocity, 0, 1, ra.song_start, "free_running")
+    for o in outs_a[1:] + [out_a4]:
+        for x, y in zip(outs_a[0], o):
+            assert np.array_equal(x, y)
+    assert n1 - n0 > 4 * T            # replayed launches are counted
+    if precision == "fp32":
+        p = util.to_torch(w)
+        X, I, V, C = [torch.tensor(a) for a in rb.dense(np.float64)]
+        ref = O.style_transfer(ocfg, p, X, I, V, 0, 1, rb.song_start, "free_running")
+        safe = O.top2_margin(ref["Yh"]).numpy() > 1e-4
+        assert np.array_equal(out_b[0][safe], ref["pitch"].numpy()[safe])
+        assert np.abs(out_b[2] - ref["Vh"].numpy()[..., 0]).max() <= 2e-4
+    eng.close()
