@@ -509,3 +509,36 @@ def test_free_running_graph_replay_is_exact(precision, shape):
         assert np.array_equal(out_b[0][safe], ref["pitch"].numpy()[safe])
         assert np.abs(out_b[2] - ref["Vh"].numpy()[..., 0]).max() <= 2e-4
     eng.close()
+
+
+def test_packed_training_epoch_matches_oracle_on_the_same_packs():
+    """SURVEY 8(f-3) opt-in packing: several whole songs per mini-batch, histories from ONE batched encoder pass per pack, shifted inside each song.
+    The oracle runs the same packs (same history rule): epoch 1 (history in use) must agree, and later packed epochs must keep improving."""
+    from midi_vae_b200 import VAE, training
+    from midi_vae_b200.marshal import shift_history
+    T, H, L, B = 16, 64, 16, 32
+    vae = VAE().create(input_dim=61, output_dim=61, input_length=T, output_length=T, latent_rep_size=L, lstm_size=H, activation='softmax',
+                       include_composer_decoder=True, num_composers=2, composer_weight=0.1, num_layers_encoder=2, num_layers_decoder=2,
+                       learning_rate=2e-3, beta=0.1, extra_layer=True, meta_instrument=True, meta_instrument_dim=16, meta_instrument_length=4,
+                       meta_instrument_activation='softmax', meta_instrument_weight=0.1, meta_velocity=True, meta_velocity_length=T,
+                       meta_velocity_weight=1.0, epsilon_std=0.0, max_batch=B, decoder_feedback="teacher_forced")
+    songs = synth.make_songs(12, T, seed=77, min_chunks=5, max_chunks=14)
+    _, ocfg = util.make_cfgs(T=T, H=H, L=L, feedback="teacher_forced", max_batch=B, lr=2e-3)
+    p = util.to_torch(vae.engine.get_weights())
+    opt = O.KerasAdam(p, lr=2e-3)
+    tot, seen = 0.0, 0
+    for pack in training.pack_songs(songs, B):
+        X, I, V, C = [torch.tensor(a) for a in pack.dense(np.float64)]
+        n = len(pack)
+        zeros = torch.zeros(n, L, dtype=torch.float64)
+        z = O.encode(ocfg, p, X, I, V, zeros)[0].numpy()
+        Hh = torch.tensor(shift_history(z, pack.song_start))
+        for a in range(0, n, B):
+            b = min(n, a + B)
+            m, _ = O.train_on_batch(ocfg, p, opt, X[a:b], I[a:b], V[a:b], C[a:b], Hh[a:b], zeros[a:b])
+            tot += m["loss"] * (b - a); seen += b - a
+    m1 = training.train_epoch_packed(vae, songs, epoch=1, batch_size=B)
+    assert abs(m1["loss"] - tot / seen) <= 2e-3 * tot / seen, (m1["loss"], tot / seen)
+    losses = [training.train_epoch_packed(vae, songs, epoch=e, batch_size=B)["loss"] for e in range(2, 5)]
+    assert losses[-1] < losses[0] < m1["loss"] * 1.05, (m1["loss"], losses)
+    vae.engine.close()

@@ -155,3 +155,44 @@ def test_postprocess_matches_the_reference_loop():
         Y2, V2, D2 = _reference_postprocess_loop(pit, vel)
         assert np.array_equal(Y, Y2) and np.allclose(V, V2) and np.array_equal(D, D2)
         assert I.shape == (3, 4, 16) and np.all(I.sum(-1) == 1)
+
+
+def test_packed_training_epoch_host_logic():
+    """SURVEY 8(f-3) opt-in packing (training.train_epoch_packed): whole songs share mini-batches, every chunk is trained exactly once, in order,
+    and the history shift restarts at each song start.  A recording stand-in replaces the engine: this is host logic only."""
+    from types import SimpleNamespace
+    from midi_vae_b200 import training
+    songs = synth.make_songs(7, 16, seed=3, min_chunks=3, max_chunks=9)
+    L = 4
+
+    class FakeEngine:
+        cfg = SimpleNamespace(latent_rep_size=L, input_dim=61, notes_weight=1.0, composer_weight=0.1, meta_instrument_weight=0.1,
+                              meta_velocity_weight=1.0, beta=0.1)
+
+        def __init__(self):
+            self.trained, self.hist, self.batches = [], [], []
+
+        def encode(self, P, I, V, eps):
+            z = np.repeat(P[:, :1].astype(np.float32) + 1.0, L, axis=1)      # z of a chunk = its first pitch + 1: recognisable in the history
+            return z, z, z
+
+        def train_on_batch(self, P, I, V, style, H, eps, w=None):
+            self.trained.append(P.copy()); self.hist.append(H.copy()); self.batches.append(len(P))
+            return {k: 1.0 for k in training.METRIC_KEYS}
+
+    eng = FakeEngine()
+    vae = SimpleNamespace(engine=eng, max_batch=16, _eps=lambda n: np.zeros((n, L), np.float32))
+    out = training.train_epoch_packed(vae, songs, epoch=1, batch_size=16)
+    allp = np.concatenate([s.pitch for s in songs])
+    assert np.array_equal(np.concatenate(eng.trained), allp)                       # every chunk once, in song order
+    assert max(eng.batches) == 16 and sum(eng.batches) == len(allp)
+    H = np.concatenate(eng.hist)
+    starts = np.cumsum([0] + [len(s) for s in songs[:-1]])
+    assert np.all(H[starts] == 0)                                                    # H = 0 on the first chunk of every song
+    inner = np.setdiff1d(np.arange(len(allp)), starts)
+    assert np.array_equal(H[inner, 0], allp[inner - 1, 0].astype(np.float32) + 1.0)  # H[i] = z[i-1] inside a song
+    assert out["loss"] == 1.0 and "kl_loss" in out
+    # fewer optimiser steps than the per-song loop, which is the point
+    assert len(eng.batches) < sum(-(-len(s) // 16) for s in songs)
+    packs = training.pack_songs(songs, 16)
+    assert all(len(p) >= 16 for p in packs[:-1]) and all(p.song_start[0] == 1 for p in packs)
