@@ -78,7 +78,12 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 __device__ __forceinline__ size_t gran_off(int slab, int ngran, int gran, int n, int m) {
   return (((size_t)slab * ngran + gran) * n + m) * 8;
 }
-__device__ __forceinline__ void named_barrier(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// bar.sync is the ALIGNED barrier: every lane of an arriving warp must execute it together.  Warps get here out of spin loops and lane-predicated
+// blocks, so convergence is made explicit first (compute-sanitizer synccheck reported divergent arrivals without it).
+__device__ __forceinline__ void named_barrier(int id, int count) {
+  __syncwarp();
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // Forward.  What the first form of this kernel (round 1, U in shared memory, DSMEM pushes; deleted) taught (profiles/r1/README.md):
@@ -410,6 +415,17 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
   if (warp == 1) ptx::tmem_dealloc2(tmem_base, 512);
 }
 
+// A message whose destination is the sending CTA itself: the whole warp copies it with ordinary shared-memory accesses and completes the
+// receiver barrier's transaction bytes by hand.  (cp.async.bulk.shared::cluster with the CTA's own address as destination works on the
+// hardware, but compute-sanitizer memcheck rejects it -- "not located in remote CTA", reproduced by scripts/sanitizer_probe bulkx .. 0 --
+// and then blocks the copy, which hangs the kernel under the tool.)
+__device__ __forceinline__ void self_message(uint32_t dst, uint32_t src, uint32_t bytes, uint32_t bar, int lane) {
+  for (uint32_t o = (uint32_t)lane * 16u; o < bytes; o += 32u * 16u) ptx::st_shared_u4(dst + o, ptx::ld_shared_u4(src + o));
+  __threadfence_block();
+  __syncwarp();
+  if (lane == 0) ptx::mbar_complete_tx(bar, bytes);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Backward.  dh_{t-1} = dG_t U^T contracts over ALL 4H gate columns, so the weight-stationary split is over K:
 //   * pair q of the cluster owns hidden units [64 q, 64 q + 64) = 256 gate columns.  Within the pair, CTA e does the
@@ -557,6 +573,10 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
       const uint32_t dest = (uint32_t)(2 * (4 * mt + 2 * e + hp) + (ep ^ p.nswap));
       const uint32_t dst = ptx::mapa(gb + CLB_BT + (ND + q) * CLB_MSG, dest), dbar = ptx::mapa(ptx::smem_u32(&recv_full[g]), dest);
       const uint32_t src = gb + CLB_BT + (uint32_t)xl * CLB_MSG;
+      // which of my ND messages (if any) is addressed to this CTA itself: warp-uniform
+      int self_x = -1;
+      for (int x = 0; x < ND; ++x)
+        if ((uint32_t)(2 * (4 * (x >> 2) + 2 * e + ((x >> 1) & 1)) + ((x & 1) ^ p.nswap)) == rank) self_x = x;
       // via_l2: my staging tile goes to slot (cluster, g, rank) of the global exchange buffer in one bulk store; once it is complete the
       // ND destinations are told (relaxed remote arrives), and when my NP sources have told me I fetch my message out of each one's slot
       const size_t slot_bytes = (size_t)ND * CLB_MSG;
@@ -568,7 +588,8 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
         named_barrier(1 + g, 32 * (CL_EPI_WARPS + 1));
         ptx::fence_proxy_async();            // staging was written with generic stores by the epilogue warps (ordered by the barrier)
         if (!p.via_l2) {
-          if (lane < ND) ptx::bulk_copy_dsmem(dst, src, CLB_MSG, dbar);
+          if (lane < ND && dest != rank) ptx::bulk_copy_dsmem(dst, src, CLB_MSG, dbar);
+          if (self_x >= 0) self_message(gb + CLB_BT + (ND + q) * CLB_MSG, gb + CLB_BT + (uint32_t)self_x * CLB_MSG, CLB_MSG, ptx::smem_u32(&recv_full[g]), lane);
           if (lane == 0 && g == 0) CL_TRACE(it, 6);
         } else {
           if (lane == 0) {
@@ -900,7 +921,8 @@ rec_cluster_bwd4_kernel(const ClusterQP p) {
         if (lane == 0 && g == 0) CL_TRACE(it, 8);
         named_barrier(3 + g, 32 * (CL_EPI_WARPS + 1));                      // partial messages staged
         ptx::fence_proxy_async();
-        if (lane < 4) ptx::bulk_copy_dsmem(pdst, psrc, CLQ_MSG, pbar);
+        if (lane < 4 && dest != rank) ptx::bulk_copy_dsmem(pdst, psrc, CLQ_MSG, pbar);
+        if (c == kq) self_message(gb + 2 * CLQ_BT + (4 + kq) * CLQ_MSG, gb + 2 * CLQ_BT + (uint32_t)c * CLQ_MSG, CLQ_MSG, ptx::smem_u32(&recv_full[g]), lane);   // message c of CTA (kq = c, c) stays here
         if (lane == 0 && g == 0) CL_TRACE(it, 6);
       }
     }

@@ -183,6 +183,8 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_XW_OVERLAP"); xw_overlap = (use_cluster_fwd && e) ? std::max(0, std::min(16, atoi(e))) : 0; }
   { const char* e = getenv("MVAE_WGRAD_CHUNKS"); wgrad_per_chunk = e ? atoi(e) != 0 : false; }
   { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
+  { const char* e = getenv("MVAE_WGRAD_ROWS"); fuse_wgrad_rows = e ? atoi(e) != 0 : true; }
+  { const char* e = getenv("MVAE_TIMELINE"); prof_detail = e && atoi(e) >= 2; }
   { const char* e = getenv("MVAE_STEPWISE_GRAPH"); stepwise_graph_on = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_AR_BUCKETS"); ar_buckets = e ? std::max(1, atoi(e)) : 2; }
   { const char* e = getenv("MVAE_BRANCH_BWD_NCL"); branch_bwd_ncl = e ? std::max(0, atoi(e)) : 0; }
@@ -223,9 +225,9 @@ void Model::commit_params() {
 }
 
 // --------------------------------------------------------------------------------------------- profiling
-void Model::prof_begin(int cls, cudaStream_t s) {
+void Model::prof_begin(int cls, cudaStream_t s, const char* tag) {
   if (!profiling) return;
-  Ev ev; ev.cls = cls;
+  Ev ev; ev.cls = cls; ev.tag = tag;
   MVAE_CUDA(cudaEventCreate(&ev.a)); MVAE_CUDA(cudaEventCreate(&ev.b));
   MVAE_CUDA(cudaEventRecord(ev.a, s ? s : st));
   evs.push_back(ev);
@@ -245,7 +247,7 @@ void Model::prof_collect() {
     if (timeline) {
       float t0 = 0;
       MVAE_CUDA(cudaEventElapsedTime(&t0, evs[0].a, ev.a));
-      fprintf(stderr, "timeline %-9s start %8.3f ms  dur %7.3f ms\n", cls_name[ev.cls], t0, ms);
+      fprintf(stderr, "timeline %-9s start %8.3f ms  dur %7.3f ms  %s\n", cls_name[ev.cls], t0, ms, ev.tag ? ev.tag : "");
     }
     prof_ms[ev.cls] += ms; prof_n[ev.cls] += 1;
   }
@@ -634,7 +636,9 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms,
   const long rows = (long)nsteps * n;
   const void* dG = slab(r.xw, t0, (long)n * G);
   const void* Xc = j.X ? (const char*)j.X + (size_t)t0 * n * (j.kind == IN_RANK1 ? VD : r.ldin) * asz() : nullptr;
-  prof_begin(PC_GEMM, s);
+  const bool det = prof_detail;
+  auto seg = [&](const char* tag) { if (det) { prof_end(s); prof_begin(PC_GEMM, s, tag); } };
+  prof_begin(PC_GEMM, s, det ? "wgrad dU" : r.name.c_str());
   if (gru) {  // dU_zr += Hprev^T [da_z | da_r];  dU_h += (r * Hprev)^T da_h   (the r * h sequence sits in the cseq buffer)
     GemmArgs g; g.M = H; g.N = 2 * H; g.K = (int)rows; g.A = slab(r.hseq, t0, (long)n * H); g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
@@ -647,13 +651,29 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms,
     g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
     gemm_on(g, s, sms);
   }
+  const bool rows_ok = fuse_wgrad_rows && act == DT_BF16 && !gru && G % 8 == 0;
+  if (rows_ok && j.kind == IN_DENSE && j.idx) {         // one-hot input: dW (class table) and db in ONE pass over dG
+    seg("wgrad dW(one-hot)+db rows");
+    k_wgrad_rows(rows, n, G, G, dG, nullptr, 0, j.idx, j.idx_ld, j.idx_shift - t0, r.Din, Gp(r.iW), ld(r.iW), Gp(r.ib), s);
+    prof_end(s);
+    return;
+  }
+  if (rows_ok && j.kind == IN_RANK1) {                  // scalar input: dW (weighted column sum) and db in ONE pass
+    seg("wgrad dW(rank1)+db rows");
+    k_wgrad_rows(rows, n, G, G, dG, Xc, VD, nullptr, 0, 0, 0, Gp(r.iW), ld(r.iW), Gp(r.ib), s);
+    prof_end(s);
+    return;
+  }
   if (j.kind == IN_DENSE) {  // dW += X^T dG
+    seg("wgrad dW");
     GemmArgs g; g.M = r.Din; g.N = G; g.K = (int)rows; g.A = Xc; g.lda = r.ldin; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iW); g.ldc = ld(r.iW); g.c_type = DT_F32; g.accumulate = true;
     gemm_on(g, s, sms);
   } else if (j.kind == IN_RANK1) {
+    seg("wgrad dW rank1 colsum");
     k_colsum(act, rows, G, G, dG, Xc, VD, Gp(r.iW), s);
   }
+  seg("wgrad db colsum");
   k_colsum(act, rows, G, G, dG, nullptr, 0, Gp(r.ib), s);
   prof_end(s);
 }
@@ -1208,6 +1228,7 @@ void Model::backward(const mvae_batch& b) {
       j.X = k == 0 ? (tf ? Y_ext_cur : nullptr) : slab(dec_notes[k - 1].hseq, 1, (long)n * H);
       j.kind = k == 0 ? (tf ? IN_DENSE : IN_NONE) : IN_DENSE;
       j.use_dhext = true; j.need_dx = k > 0; j.dx_out = k > 0 ? dec_notes[k - 1].dhext : nullptr;
+      if (k == 0 && tf) { j.idx = cur_target; j.idx_ld = T; j.idx_shift = 1; }   // x_t = y_{t-1}, x_0 = 0
       j.dS_h = dS1(k); j.dS_c = dS2(k); j.ldS = nS * H;
       stack.push_back(j);
     }
@@ -1304,6 +1325,7 @@ void Model::backward(const mvae_batch& b) {
       j.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
       j.use_dhext = !is_top; j.dh_last = is_top ? du : nullptr; j.ld_last = 3 * H;
       j.need_dx = k > 0; j.dx_out = k > 0 ? enc_pitch[k - 1].dhext : nullptr;
+      if (k == 0) { j.idx = cur_pitch; j.idx_ld = T; j.idx_shift = 0; }
       stack.push_back(j);
     }
     { BwdJob j; j.r = &enc_vel; j.kind = IN_RANK1; j.X = slab(Xv_ext, 1, (long)n * VD); j.dh_last = (const char*)du + (size_t)2 * H * asz(); j.ld_last = 3 * H;

@@ -69,6 +69,10 @@ struct BwdJob {
   void* dS_h = nullptr;
   void* dS_c = nullptr;
   int ldS = 0;
+  // kind == IN_DENSE with a one-hot X: its class indices (u8 [n][idx_ld], step t reads column t - idx_shift); the weight gradient is then a
+  // single pass over dG (k_wgrad_rows) instead of a GEMM padded from 61 to 128 rows plus a separate bias column sum
+  const unsigned char* idx = nullptr;
+  int idx_ld = 0, idx_shift = 0;
 };
 
 enum ProfClass { PC_REC_FWD = 0, PC_REC_BWD, PC_GEMM, PC_POINTWISE, PC_ADAM, PC_ALLREDUCE, PC_COUNT };
@@ -135,7 +139,9 @@ struct Model {
   int ar_buckets = 2;                 // MVAE_AR_BUCKETS=1: one all-reduce after the join (round-1 behaviour)
   // profiling
   bool profiling = false;
-  struct Ev { int cls; cudaEvent_t a, b; };
+  struct Ev { int cls; cudaEvent_t a, b; const char* tag; };
+  bool fuse_wgrad_rows = true;        // MVAE_WGRAD_ROWS=0: round-1 weight gradients (padded one-hot GEMM, one column-sum pass per output)
+  bool prof_detail = false;           // MVAE_TIMELINE=2: every weight-gradient launch gets its own event pair and a tag
   std::vector<Ev> evs;
   float prof_ms[PC_COUNT] = {0};
   long long prof_n[PC_COUNT] = {0};
@@ -227,7 +233,7 @@ struct Model {
   void commit_params();
   void gemm(GemmArgs g);
   void gemm_on(GemmArgs g, cudaStream_t s, int sms);
-  void prof_begin(int cls, cudaStream_t s = nullptr);
+  void prof_begin(int cls, cudaStream_t s = nullptr, const char* tag = nullptr);
   void prof_end(cudaStream_t s = nullptr);
   void rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms, int t0 = 0, int nsteps = -1);
   void prof_collect();

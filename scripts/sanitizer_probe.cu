@@ -25,11 +25,34 @@ __global__ void bar_probe(int iters, int* out) {
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) bulk_probe(uint32_t dst_off, int* bad) {
+__global__ void barreg_probe(int iters, int* out) {
+  // two independent warp sets (warps 0-1 and 2-3), each meeting at its own named barrier; id and count come from registers, as in the kernels
+  __shared__ int acc[4];
+  const int warp = threadIdx.x >> 5, set = warp >> 1;
+  const int id = 1 + 2 * set, count = 64;
+  for (int i = 0; i < iters; ++i) {
+    if ((threadIdx.x & 31) == 0) acc[warp] = i;
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+    if ((threadIdx.x & 63) == 0) out[set] = acc[2 * set] + acc[2 * set + 1];
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+  }
+}
+
+template <bool STATIC>
+__device__ __forceinline__ void bulk_body(uint32_t dst_off, int hop, int* bad);
+
+__global__ void __cluster_dims__(2, 1, 1) bulk_probe(uint32_t dst_off, int* bad) { bulk_body<true>(dst_off, 1, bad); }
+// same body, cluster shape given by a launch attribute (cudaLaunchKernelEx), any size; hop = destination rank offset (0 = the CTA itself)
+__global__ void bulkx_probe(uint32_t dst_off, int hop, int* bad) { bulk_body<false>(dst_off, hop, bad); }
+
+template <bool STATIC>
+__device__ __forceinline__ void bulk_body(uint32_t dst_off, int hop, int* bad) {
   extern __shared__ __align__(128) uint8_t dyn[];
   __shared__ __align__(8) uint64_t bar;
-  uint32_t rank;
+  uint32_t rank, csize;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  const uint32_t dest = (rank + (uint32_t)hop) % csize, src_rank = (rank + csize - (uint32_t)hop % csize) % csize;
   const uint32_t base = (smem_u32(dyn) + 127u) & ~127u;
   constexpr uint32_t BYTES = 4160;
   for (uint32_t i = threadIdx.x; i < BYTES / 4; i += blockDim.x)
@@ -44,8 +67,8 @@ __global__ void __cluster_dims__(2, 1, 1) bulk_probe(uint32_t dst_off, int* bad)
   if (threadIdx.x == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     uint32_t rdst, rbar;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(base + dst_off), "r"(rank ^ 1u));
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&bar)), "r"(rank ^ 1u));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(base + dst_off), "r"(dest));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&bar)), "r"(dest));
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rdst), "r"(base), "r"(BYTES), "r"(rbar)
                  : "memory");
     uint32_t done = 0;
@@ -56,7 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) bulk_probe(uint32_t dst_off, int* bad)
   for (uint32_t i = threadIdx.x; i < BYTES / 4; i += blockDim.x) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + dst_off + i * 4) : "memory");
-    if (v != (rank ^ 1u) * 100000u + i) atomicAdd(bad, 1);
+    if (v != src_rank * 100000u + i) atomicAdd(bad, 1);
   }
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -68,6 +91,23 @@ int main(int argc, char** argv) {
   cudaMemset(d, 0, 4);
   if (!strcmp(which, "bar")) {
     bar_probe<<<1, 128>>>(4, d);
+  } else if (!strcmp(which, "barreg")) {
+    barreg_probe<<<1, 128>>>(4, d);
+  } else if (!strcmp(which, "bulkx")) {
+    // argv: bulkx <dst offset> <cluster size> <hop>
+    const uint32_t off = argc > 2 ? (uint32_t)atoi(argv[2]) : 8192u;
+    const int cs = argc > 3 ? atoi(argv[3]) : 2, hop = argc > 4 ? atoi(argv[4]) : 1;
+    const size_t smem = (size_t)off + 4160 + 256;
+    cudaFuncSetAttribute(bulkx_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cs > 8) cudaFuncSetAttribute(bulkx_probe, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, bulkx_probe, off, hop, d);
+    if (le != cudaSuccess) printf("launch: %s\n", cudaGetErrorString(le));
   } else {
     const uint32_t off = argc > 2 ? (uint32_t)atoi(argv[2]) : 8192u;
     const size_t smem = (size_t)off + 4160 + 256;
