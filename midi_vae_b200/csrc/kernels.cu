@@ -445,70 +445,42 @@ __global__ void colsum_kernel(long rows, int cols, int ld, const AT* __restrict_
   }
 }
 
-// One pass over a tall dG (rows = T n, time-major) for a recurrence whose input is a scalar (velocity) or a one-hot class (pitch roll):
-//   bias gradient        db[c]        += sum_r dG[r, c]
-//   scalar input         dW[0, c]     += sum_r x[r] dG[r, c]                              (x act-typed with stride ldx)
-//   one-hot input        dW[cls, c]   += sum_{r : class(r) = cls} dG[r, c]                (class(r) = idx[m * ld_idx + t - shift], r = t n + m; t < shift: no input)
-// The round-1 path read dG once per output (column sum, weighted column sum) and ran the one-hot product as a GEMM padded from 61 to 128 rows.
-// Block (32, 8): a thread owns 8 consecutive columns (one 16-byte load per row) for the rows of its lane; the class table lives in shared memory
-// ([classes][256] fp32, native shared-memory float adds), db / scalar sums in registers.
-template <typename AT, int MODE>   // MODE 0: db only, 1: + scalar dW, 2: + one-hot dW
-__global__ void wgrad_rows_kernel(long rows, int n, int cols, int ld, const AT* __restrict__ src, const AT* __restrict__ x, int ldx,
-                                  const uint8_t* __restrict__ idx, int ld_idx, int shift, int classes, float* __restrict__ dW, int ldw,
+// One pass over a tall dG (rows = T n, time-major) for a recurrence whose input is a scalar (velocity): bias gradient db[c] += sum_r dG[r, c]
+// and dW[0, c] += sum_r x[r] dG[r, c] (x act-typed with stride ldx) together -- round 1 read dG once per output.  Block (32, 8): a thread owns 8
+// consecutive columns (one 16-byte load per row) for the rows of its lane.  (A one-hot variant that scattered dG rows into a shared-memory class
+// table was measured 4x SLOWER than the padded tensor-core GEMM it replaced: shared-memory float adds are CAS loops (ATOMS.CAST.SPIN); dropped.)
+template <typename AT>
+__global__ void wgrad_rows_kernel(long rows, int cols, int ld, const AT* __restrict__ src, const AT* __restrict__ x, int ldx, float* __restrict__ dW,
                                   float* __restrict__ db) {
-  extern __shared__ float tab[];                    // MODE 2: [classes][256]
   __shared__ float sh[2][8][256 + 8];
   const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
   float s[8], sx[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; sx[i] = 0.f; }
-  if (MODE == 2) {
-    for (int i = threadIdx.y * 32 + threadIdx.x; i < classes * 256; i += 256) tab[i] = 0.f;
-    __syncthreads();
-  }
   if (c0 < cols) {
     for (long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long)gridDim.y * 8) {
       const uint4 u = *reinterpret_cast<const uint4*>(src + r * ld + c0);
+      const float xv = ldf<AT>(x + r * ldx);
       const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-      float f[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const float2 t2 = __bfloat1622float2(h2[i]); f[2 * i] = t2.x; f[2 * i + 1] = t2.y; }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s[i] += f[i];
-      if (MODE == 1) {
-        const float xv = ldf<AT>(x + r * ldx);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sx[i] += xv * f[i];
-      }
-      if (MODE == 2) {
-        const long t = r / n;
-        if (t >= shift) {
-          const int cls = idx[(r - t * n) * ld_idx + (t - shift)];
-          if (cls < classes) {
-            float* row = tab + cls * 256 + threadIdx.x * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(row + i, f[i]);
-          }
-        }
+      for (int i = 0; i < 4; ++i) {
+        const float2 t2 = __bfloat1622float2(h2[i]);
+        s[2 * i] += t2.x; s[2 * i + 1] += t2.y;
+        sx[2 * i] += xv * t2.x; sx[2 * i + 1] += xv * t2.y;
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sh[0][threadIdx.y][threadIdx.x * 8 + i] = s[i]; if (MODE == 1) sh[1][threadIdx.y][threadIdx.x * 8 + i] = sx[i]; }
+  for (int i = 0; i < 8; ++i) { sh[0][threadIdx.y][threadIdx.x * 8 + i] = s[i]; sh[1][threadIdx.y][threadIdx.x * 8 + i] = sx[i]; }
   __syncthreads();
   const int t = threadIdx.y * 32 + threadIdx.x;   // 0..255: one column each
   const int c = blockIdx.x * 256 + t;
   if (c < cols) {
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a += sh[0][i][t]; if (MODE == 1) b += sh[1][i][t]; }
+    for (int i = 0; i < 8; ++i) { a += sh[0][i][t]; b += sh[1][i][t]; }
     atomicAdd(db + c, a);
-    if (MODE == 1) atomicAdd(dW + c, b);
-    if (MODE == 2)
-      for (int k = 0; k < classes; ++k) {
-        const float v = tab[k * 256 + t];
-        if (v != 0.f) atomicAdd(dW + (size_t)k * ldw + c, v);
-      }
+    atomicAdd(dW + c, b);
   }
 }
 
@@ -784,24 +756,14 @@ void k_colsum(DT act, long rows, int cols, int ld, const void* src, const void* 
   DISPATCH_ACT(act, { colsum_kernel<AT><<<grid, block, 0, st>>>(rows, cols, ld, (const AT*)src, (const AT*)weight, ldw, dst); LAUNCH_CHECK(); });
 }
 
-void k_wgrad_rows(long rows, int n, int cols, int ld, const void* src, const void* x, int ldx, const uint8_t* idx, int ld_idx, int shift, int classes,
-                  float* dW, int ldw, float* db, cudaStream_t st) {
+void k_wgrad_rows(long rows, int cols, int ld, const void* src, const void* x, int ldx, float* dW, float* db, cudaStream_t st) {
   using AT = __nv_bfloat16;   // bf16 activations only (16-byte row pieces); callers keep the generic column sums for fp32
   long chunks = (rows + 127) / 128;
   const unsigned gx = (cols + 255) / 256;
-  const long cap = (148 * (idx ? 3 : 8) + gx - 1) / gx;
+  const long cap = (148 * 8 + gx - 1) / gx;
   dim3 grid(gx, (unsigned)(chunks < 1 ? 1 : (chunks > cap ? cap : chunks)));
   dim3 block(32, 8);
-  if (idx) {
-    const size_t smem = (size_t)classes * 256 * sizeof(float);
-    static bool configured = false;
-    if (!configured) { MVAE_CUDA(cudaFuncSetAttribute(wgrad_rows_kernel<AT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 256 * 4)); configured = true; }
-    wgrad_rows_kernel<AT, 2><<<grid, block, smem, st>>>(rows, n, cols, ld, (const AT*)src, nullptr, 0, idx, ld_idx, shift, classes, dW, ldw, db);
-  } else if (x) {
-    wgrad_rows_kernel<AT, 1><<<grid, block, 0, st>>>(rows, n, cols, ld, (const AT*)src, (const AT*)x, ldx, nullptr, 0, 0, 0, dW, ldw, db);
-  } else {
-    wgrad_rows_kernel<AT, 0><<<grid, block, 0, st>>>(rows, n, cols, ld, (const AT*)src, nullptr, 0, nullptr, 0, 0, 0, nullptr, 0, db);
-  }
+  wgrad_rows_kernel<AT><<<grid, block, 0, st>>>(rows, cols, ld, (const AT*)src, (const AT*)x, ldx, dW, db);
   LAUNCH_CHECK();
 }
 

@@ -40,10 +40,8 @@ void k_sigmoid_mse(DT act, int steps, int n, float* logits, int ld, const float*
 void k_tanh_bwd(DT act, long count, const void* dout, const void* out, void* dpre, cudaStream_t st);
 // dst[c] += sum_r weight[r] * src[r,c]   (weight == nullptr: plain column sum); weight is act-typed with stride ldw
 void k_colsum(DT act, long rows, int cols, int ld, const void* src, const void* weight, int ldw, float* dst, cudaStream_t st);
-// bf16 dG (rows = T n, time-major), ONE pass: db += column sums; x != null: dW[0,:] += sum_r x[r] dG[r,:]; idx != null: dW[class(r),:] += dG[r,:]
-// with class(r = t n + m) = idx[m * ld_idx + t - shift] (t < shift or class >= classes: no input).  Requires cols % 8 == 0, ld % 8 == 0.
-void k_wgrad_rows(long rows, int n, int cols, int ld, const void* src, const void* x, int ldx, const uint8_t* idx, int ld_idx, int shift, int classes,
-                  float* dW, int ldw, float* db, cudaStream_t st);
+// bf16 dG (rows = T n, time-major), ONE pass: db += column sums and dW[0,:] += sum_r x[r] dG[r,:] (scalar-input recurrences).  cols % 8 == 0, ld % 8 == 0.
+void k_wgrad_rows(long rows, int cols, int ld, const void* src, const void* x, int ldx, float* dW, float* db, cudaStream_t st);
 // out[r,c] = x[r] * w[c] + bias[c]   (x act-typed with stride ldx; w, bias fp32; bias may be null)
 void k_rank1_rows(DT act, void* out, long rows, int cols, const void* x, int ldx, const float* w, const float* bias, cudaStream_t st);
 // out[r*ldo] = dot(h[r,:H], w) + b[0]

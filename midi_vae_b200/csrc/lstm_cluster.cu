@@ -1311,7 +1311,7 @@ void launch_bwd4(const RecPersistArgs& a, cudaStream_t st) {
     p.dG = (bf16*)a.dG + t0 * nn * 4 * Hh; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
   }
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace; p.xbuf = (uint8_t*)a.partial;
-  p.stm = env_int("MVAE_CLB_STM", 0);
+  p.stm = env_int("MVAE_CLB_STM", 1);
   MVAE_REQUIRE(p.upack != nullptr && p.xbuf != nullptr, "cluster backward: packed weights / exchange buffer missing");
   MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * 2 * CLQ_PIECE <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};

@@ -652,15 +652,9 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms,
     gemm_on(g, s, sms);
   }
   const bool rows_ok = fuse_wgrad_rows && act == DT_BF16 && !gru && G % 8 == 0;
-  if (rows_ok && j.kind == IN_DENSE && j.idx) {         // one-hot input: dW (class table) and db in ONE pass over dG
-    seg("wgrad dW(one-hot)+db rows");
-    k_wgrad_rows(rows, n, G, G, dG, nullptr, 0, j.idx, j.idx_ld, j.idx_shift - t0, r.Din, Gp(r.iW), ld(r.iW), Gp(r.ib), s);
-    prof_end(s);
-    return;
-  }
   if (rows_ok && j.kind == IN_RANK1) {                  // scalar input: dW (weighted column sum) and db in ONE pass
     seg("wgrad dW(rank1)+db rows");
-    k_wgrad_rows(rows, n, G, G, dG, Xc, VD, nullptr, 0, 0, 0, Gp(r.iW), ld(r.iW), Gp(r.ib), s);
+    k_wgrad_rows(rows, G, G, dG, Xc, VD, Gp(r.iW), Gp(r.ib), s);
     prof_end(s);
     return;
   }
@@ -1228,7 +1222,6 @@ void Model::backward(const mvae_batch& b) {
       j.X = k == 0 ? (tf ? Y_ext_cur : nullptr) : slab(dec_notes[k - 1].hseq, 1, (long)n * H);
       j.kind = k == 0 ? (tf ? IN_DENSE : IN_NONE) : IN_DENSE;
       j.use_dhext = true; j.need_dx = k > 0; j.dx_out = k > 0 ? dec_notes[k - 1].dhext : nullptr;
-      if (k == 0 && tf) { j.idx = cur_target; j.idx_ld = T; j.idx_shift = 1; }   // x_t = y_{t-1}, x_0 = 0
       j.dS_h = dS1(k); j.dS_c = dS2(k); j.ldS = nS * H;
       stack.push_back(j);
     }
@@ -1325,7 +1318,6 @@ void Model::backward(const mvae_batch& b) {
       j.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
       j.use_dhext = !is_top; j.dh_last = is_top ? du : nullptr; j.ld_last = 3 * H;
       j.need_dx = k > 0; j.dx_out = k > 0 ? enc_pitch[k - 1].dhext : nullptr;
-      if (k == 0) { j.idx = cur_pitch; j.idx_ld = T; j.idx_shift = 0; }
       stack.push_back(j);
     }
     { BwdJob j; j.r = &enc_vel; j.kind = IN_RANK1; j.X = slab(Xv_ext, 1, (long)n * VD); j.dh_last = (const char*)du + (size_t)2 * H * asz(); j.ld_last = 3 * H;

@@ -69,10 +69,6 @@ struct BwdJob {
   void* dS_h = nullptr;
   void* dS_c = nullptr;
   int ldS = 0;
-  // kind == IN_DENSE with a one-hot X: its class indices (u8 [n][idx_ld], step t reads column t - idx_shift); the weight gradient is then a
-  // single pass over dG (k_wgrad_rows) instead of a GEMM padded from 61 to 128 rows plus a separate bias column sum
-  const unsigned char* idx = nullptr;
-  int idx_ld = 0, idx_shift = 0;
 };
 
 enum ProfClass { PC_REC_FWD = 0, PC_REC_BWD, PC_GEMM, PC_POINTWISE, PC_ADAM, PC_ALLREDUCE, PC_COUNT };
@@ -140,7 +136,7 @@ struct Model {
   // profiling
   bool profiling = false;
   struct Ev { int cls; cudaEvent_t a, b; const char* tag; };
-  bool fuse_wgrad_rows = true;        // MVAE_WGRAD_ROWS=0: round-1 weight gradients (padded one-hot GEMM, one column-sum pass per output)
+  bool fuse_wgrad_rows = true;        // MVAE_WGRAD_ROWS=0: scalar-input recurrences take one column-sum pass per output (round 1) instead of one pass
   bool prof_detail = false;           // MVAE_TIMELINE=2: every weight-gradient launch gets its own event pair and a tag
   std::vector<Ev> evs;
   float prof_ms[PC_COUNT] = {0};

@@ -25,6 +25,22 @@ __global__ void bar_probe(int iters, int* out) {
   }
 }
 
+__global__ void barwait_probe(int iters, int* out) {
+  // as bar_probe, but the fourth warp does not exit: it waits at the block-wide barrier at the end (as the idle lanes of the MMA / relay warp
+  // do in the recurrence kernels) while the other three keep meeting at the named barrier
+  __shared__ int acc[3];
+  const int warp = threadIdx.x >> 5;
+  if (warp < 3) {
+    for (int i = 0; i < iters; ++i) {
+      if ((threadIdx.x & 31) == 0) acc[warp] = i;
+      asm volatile("bar.sync 1, 96;" ::: "memory");
+      if (threadIdx.x == 0) out[0] = acc[0] + acc[1] + acc[2];
+      asm volatile("bar.sync 1, 96;" ::: "memory");
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void barreg_probe(int iters, int* out) {
   // two independent warp sets (warps 0-1 and 2-3), each meeting at its own named barrier; id and count come from registers, as in the kernels
   __shared__ int acc[4];
@@ -91,6 +107,8 @@ int main(int argc, char** argv) {
   cudaMemset(d, 0, 4);
   if (!strcmp(which, "bar")) {
     bar_probe<<<1, 128>>>(4, d);
+  } else if (!strcmp(which, "barwait")) {
+    barwait_probe<<<1, 128>>>(4, d);
   } else if (!strcmp(which, "barreg")) {
     barreg_probe<<<1, 128>>>(4, d);
   } else if (!strcmp(which, "bulkx")) {
