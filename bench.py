@@ -35,14 +35,16 @@ WORKLOADS = {   # BASELINE.json configs
     "cfg3": dict(T=256, H=512, L=256, B=512, kind="train"),
     "cfg4": dict(T=256, H=512, L=256, B=1024, kind="infer"),      # --cfg4-shape cfg2 runs it at T64 / H256 / L100
     "cfg5": dict(T=1024, H=1024, L=256, B=128, kind="train"),
+    # not a BASELINE config: the reference's own defaults (settings.py:108-112,155: GRU cells, T64 H256 L256, batch_size 256, decoder as wired)
+    "refdefault": dict(T=64, H=256, L=256, B=256, kind="train", cell="GRU", feedback="as_wired"),
 }
 METRIC_TRAIN = "MIDI sequences/sec (train step)"
 METRIC_INFER = "MIDI sequences/sec (style-transfer inference)"
 
 
-def flops_per_seq(T, H, L, feedback="teacher_forced", ne=2, nd=2, Dp=61, Di=16, Ti=4, Dv=1):
-    """Algorithmic GEMM FLOPs per sequence, forward (SURVEY.md 8(d) formula).  Returns (total_fwd, recurrent_fwd)."""
-    G = 4 * H
+def flops_per_seq(T, H, L, feedback="teacher_forced", ne=2, nd=2, Dp=61, Di=16, Ti=4, Dv=1, cell="LSTM"):
+    """Algorithmic GEMM FLOPs per sequence, forward (SURVEY.md 8(d) formula; 3 gate blocks for GRU).  Returns (total_fwd, recurrent_fwd)."""
+    G = (3 if cell == "GRU" else 4) * H
     enc = 2 * G * (T * (Dp + H) + (ne - 1) * T * 2 * H + Ti * (Di + H) + T * (Dv + H))
     head = 2 * (3 * H * H + H * H + 2 * (H // 2) * L)
     init = (nd + 2) * 2 * 2 * (2 * L) * H
@@ -66,10 +68,10 @@ def workload_string(name, wl, feedback, world=1):
     """The SAME string in the GPU arm and the reference arm: it names the workload, not how much of it an arm sampled."""
     if wl["kind"] == "infer":
         return (f"{name}: style-transfer inference (encode -> swap style dims -> history shift -> decode -> argmax), batch={wl['B']}/GPU = 16 synthetic songs x 64 chunks, "
-                f"seq_len={wl['T']} hidden={wl['H']} latent={wl['L']}, decoder_feedback={feedback}, LSTM, 2+2 layers, hard_sigmoid gates "
+                f"seq_len={wl['T']} hidden={wl['H']} latent={wl['L']}, decoder_feedback={feedback}, {wl.get('cell', 'LSTM')}, 2+2 layers, hard_sigmoid gates "
                 "(CPU arms time a bounded sample of this batch: see cpu_baseline.sample)")
     return (f"{name}: train step, seq_len={wl['T']} hidden={wl['H']} latent={wl['L']} batch={wl['B']}/GPU, decoder_feedback={feedback}, "
-            "LSTM, 2+2 layers, hard_sigmoid gates (CPU arms time a bounded sample of this batch: see cpu_baseline.sample)")
+            f"{wl.get('cell', 'LSTM')}, 2+2 layers, hard_sigmoid gates (CPU arms time a bounded sample of this batch: see cpu_baseline.sample)")
 
 
 class ClockSampler:
@@ -120,8 +122,8 @@ def cpu_oracle_train_rate(wl, feedback, sample_batch, steps, warmup):
     from midi_vae_b200 import EngineConfig, initial_weights, synth
     from oracle import midivae_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    ocfg = O.OracleConfig(input_length=wl["T"], lstm_size=wl["H"], latent_rep_size=wl["L"], decoder_feedback=feedback)
-    ecfg = EngineConfig(input_length=wl["T"], lstm_size=wl["H"], latent_rep_size=wl["L"])
+    ocfg = O.OracleConfig(input_length=wl["T"], lstm_size=wl["H"], latent_rep_size=wl["L"], decoder_feedback=feedback, cell_type=wl.get("cell", "LSTM"))
+    ecfg = EngineConfig(input_length=wl["T"], lstm_size=wl["H"], latent_rep_size=wl["L"], cell_type=wl.get("cell", "LSTM"))
     p = {k: torch.tensor(v, dtype=torch.float32) for k, v in initial_weights(ecfg, 42).items()}
     opt = O.KerasAdam(p, lr=2e-4)
     r = synth.make_batch(sample_batch, wl["T"], seed=1234)
@@ -217,9 +219,9 @@ class Dist:
             self.dist.destroy_process_group()
 
 
-def make_engine(D, T, H, L, B, feedback, precision, rnn_mode):
+def make_engine(D, T, H, L, B, feedback, precision, rnn_mode, cell="LSTM"):
     from midi_vae_b200 import Engine, EngineConfig, initial_weights, nccl_unique_id
-    cfg = EngineConfig(input_length=T, lstm_size=H, latent_rep_size=L, decoder_feedback=feedback, precision=precision, rnn_mode=rnn_mode, max_batch=B)
+    cfg = EngineConfig(input_length=T, lstm_size=H, latent_rep_size=L, decoder_feedback=feedback, precision=precision, rnn_mode=rnn_mode, max_batch=B, cell_type=cell)
     eng = Engine(cfg, D.local)
     eng.set_weights(initial_weights(cfg, 42))
     if D.world > 1:
@@ -255,7 +257,10 @@ def run_train(args, name, wl, D):
     from midi_vae_b200 import synth
     rank, world = D.rank, D.world
     T, H, L, B = wl["T"], wl["H"], wl["L"], wl["B"]
-    eng = make_engine(D, T, H, L, B, args.feedback, args.precision, args.rnn_mode)
+    if "feedback" in wl:
+        args.feedback = wl["feedback"]
+    cell = wl.get("cell", "LSTM")
+    eng = make_engine(D, T, H, L, B, args.feedback, args.precision, args.rnn_mode, cell)
 
     # synthetic rolls: NB distinct batches per rank, resident in HBM (weak scaling: B sequences per GPU)
     NB = 4
@@ -326,9 +331,9 @@ def run_train(args, name, wl, D):
     eng.set_profiling(False)
     if rank == 0:
         pk = peaks()
-        fwd, rec_fwd = flops_per_seq(T, H, L, args.feedback)
+        fwd, rec_fwd = flops_per_seq(T, H, L, args.feedback, cell=cell)
         train = 3 * fwd
-        fast = args.rnn_mode != "streamed" and args.precision == "bf16"
+        fast = args.rnn_mode != "streamed" and args.precision == "bf16" and cell == "LSTM"
         gen = "cluster-resident" if H in (256, 512) else "persistent"
         classes = {
             "rec_bwd": ((("rec_cluster_bwd4_kernel" if H == 512 else "rec_cluster_bwd_kernel" if H == 256 else "rec_persist_kernel<bwd>") + f": {gen} backward recurrence "
@@ -516,6 +521,8 @@ def main():
         wl.update(T=64, H=256, L=100)
     if args.workload == "cfg5" and args.steps > 5 and "--steps" not in " ".join(sys.argv):
         args.steps, args.warmup = 3, 3          # a cfg5 step is ~0.25 s
+    if "feedback" in wl:
+        args.feedback = wl["feedback"]
     if args.impl == "reference":
         run_reference(args, args.workload, wl, args.infer_feedback if wl["kind"] == "infer" else args.feedback)
         return

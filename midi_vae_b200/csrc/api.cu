@@ -15,6 +15,43 @@ void Model::forward_backward(const mvae_batch& b, float* dev_metrics, cudaStream
   st = s ? s : stream;
   check_batch(b, true);
   MVAE_REQUIRE(cfg.decoder_feedback != MVAE_FB_FREE_RUNNING, "training needs decoder_feedback as_wired or teacher_forced");
+  // the cluster / persistent paths are ~120 launches on three streams: nothing to gain from a graph.  Profiling needs its events un-captured.
+  if (!step_graph_on || use_persist || profiling || (overlap_allreduce && world > 1)) { forward_backward_body(b, dev_metrics); return; }
+  const std::vector<size_t> key = {(size_t)b.n, (size_t)b.pitch, (size_t)b.target, (size_t)b.instr, (size_t)b.velocity, (size_t)b.style,
+                                   (size_t)b.history, (size_t)b.eps, (size_t)b.w_notes, (size_t)dev_metrics};
+  if (step_graphs.size() > 64) {   // callers that keep passing fresh buffers would grow the cache without bound
+    for (auto& kv : step_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    step_graphs.clear();
+  }
+  StepGraph& sg = step_graphs[key];
+  if (sg.state == 0) {
+    forward_backward_body(b, dev_metrics);      // first time: eager (kernel attributes, lazily allocated scheduler words)
+    sg.state = 1;
+  } else if (sg.state == 1) {
+    cudaGraph_t graph = nullptr;
+    const long long l0 = g_launches;
+    MVAE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    try {
+      forward_backward_body(b, dev_metrics);
+    } catch (...) {
+      cudaStreamEndCapture(st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    MVAE_CUDA(cudaStreamEndCapture(st, &graph));
+    sg.launches = g_launches - l0;
+    MVAE_CUDA(cudaGraphInstantiate(&sg.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    sg.state = 2;
+    MVAE_CUDA(cudaGraphLaunch(sg.exec, st));
+  } else {
+    MVAE_CUDA(cudaGraphLaunch(sg.exec, st));
+    count_launch((int)sg.launches);
+  }
+}
+
+// One mini-batch of autoencoder.fit (vae_training.py:804-809): forward + loss + backward; grads stay in Gr.
+void Model::forward_backward_body(const mvae_batch& b, float* dev_metrics) {
   MVAE_CUDA(cudaMemsetAsync(acc, 0, ACC_COUNT * sizeof(double), st));
   prepare_inputs(b, cfg.decoder_feedback == MVAE_FB_TEACHER_FORCED);
   encoder_forward(b.n);

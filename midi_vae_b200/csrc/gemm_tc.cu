@@ -48,28 +48,22 @@ struct TcParams {
 // SOUT: bf16 outputs leave through a shared-memory staging tile so that every warp store covers whole 256 / 128-byte row segments (a thread
 // owns one output ROW in TMEM; written directly, each of its 16-byte stores lands in a different 4 KB-strided row: half-filled sectors, and the
 // L2 slices -- not the tensor pipe -- bound the K = 512 input-projection GEMMs).  One pipeline stage is traded for the staging tile.
-// BMT = 256: one CTA computes a 256 x 256 tile as two M = 128 MMAs per k-slice that share the B tile in shared memory (131 instead of 87 FLOP per
-// operand byte: the K = T n weight-gradient GEMMs are bound by the L2 -> SM operand stream, not by the tensor pipe).  Both accumulators fill the
-// 512 TMEM columns, so the epilogue of a tile does not overlap the next tile's MMAs -- irrelevant when a tile runs ~200 k-blocks (split-K).
-template <int BN, bool SOUT, int BMT = 128>
+template <int BN, bool SOUT>
 struct SmemLayout {
-  static constexpr int A_BYTES = BMT * BK * 2;   // 16 KB per 128 rows
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BMT == 256) ? 3 : ((BN == 256) ? (SOUT ? 3 : 4) : 5);
+  static constexpr int STAGES = (BN == 256) ? (SOUT ? 3 : 4) : 5;
   static constexpr int OUT_ROW = (BN / 2) * 2 + 16;            // one epilogue warp owns 32 rows x BN/2 columns; + 16 B against bank conflicts
   static constexpr int OUT_WARP = 32 * OUT_ROW;
   static constexpr int OUT_BYTES = SOUT ? kEpiWarps * OUT_WARP : 0;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + 1024;   // + alignment slack
 };
 
-template <bool A_MN, bool B_MN, int BN, bool SOUT, int BMT = 128>
+template <bool A_MN, bool B_MN, int BN, bool SOUT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
-  using L = SmemLayout<BN, SOUT, BMT>;
-  constexpr int MH = BMT / 128;                      // M halves (accumulators) per tile
-  constexpr uint32_t TMEM_COLS = MH == 2 ? 512 : 2 * BN;
-  static_assert(MH == 1 || (BN == 256 && !SOUT), "the 256-row tile exists for the split-K accumulate GEMMs only");
+  using L = SmemLayout<BN, SOUT>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
@@ -93,7 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), TMEM_COLS);
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), 2 * BN);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -113,7 +107,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         ptx::mbar_arrive(ptx::smem_u32(&sched_full[rs]));
         if (tile >= num_tiles) break;
         const int ks = tile % p.k_splits, mn = tile / p.k_splits;
-        const int m0 = (mn % p.m_tiles) * BMT, n0 = (mn / p.m_tiles) * BN;
+        const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -122,11 +116,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
           const int k0 = kb * BK;
           if (!A_MN) {
-#pragma unroll
-            for (int h = 0; h < MH; ++h) ptx::tma_load_2d(sa + h * 16384, &tma_a, fb, k0, m0 + h * 128);       // box {64 K, 128 M}
+            ptx::tma_load_2d(sa, &tma_a, fb, k0, m0);                       // box {64 K, 128 M}
           } else {
 #pragma unroll
-            for (int j = 0; j < BMT / 64; ++j) ptx::tma_load_2d(sa + j * 8192, &tma_a, fb, m0 + j * 64, k0);   // box {64 M, 64 K}
+            for (int j = 0; j < BM / 64; ++j) ptx::tma_load_2d(sa + j * 8192, &tma_a, fb, m0 + j * 64, k0);   // box {64 M, 64 K}
           }
           if (!B_MN) {
             ptx::tma_load_2d(sb, &tma_b, fb, k0, n0);                       // box {64 K, BN N}
@@ -141,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
       for (int it = 0;; ++it) {
         const int rs = it % RS;
@@ -151,7 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (tile >= num_tiles) break;
         const int ks = tile % p.k_splits;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const int acc = MH == 2 ? 0 : (it & 1); const uint32_t acc_phase = MH == 2 ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
+        const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -163,12 +156,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: 8-row groups 1024 B apart (SBO), advance 32 B per K=16 slice inside the 128 B swizzle row.
             // MN-major: 64-element atoms along M/N 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO), 2048 B per K=16 slice.
+            const uint64_t da = A_MN ? ptx::umma_desc_sw128(sa + k * 2048, 8192, 1024) : ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? ptx::umma_desc_sw128(sb + k * 2048, 8192, 1024) : ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
-#pragma unroll
-            for (int h = 0; h < MH; ++h) {     // M halves: 128 rows each, 16 KB apart in the A stage, accumulators BN columns apart
-              const uint64_t da = A_MN ? ptx::umma_desc_sw128(sa + h * 16384 + k * 2048, 8192, 1024) : ptx::umma_desc_sw128(sa + h * 16384 + k * 32, 16, 1024);
-              ptx::umma_bf16(d_tmem + (uint32_t)(h * BN), da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
+            ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));     // frees the smem stage once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -191,15 +181,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       tile = __shfl_sync(0xffffffffu, tile, 0);
       if (tile >= num_tiles) break;
       const int mn = tile / p.k_splits;
-      const int m0 = (mn % p.m_tiles) * BMT, n0 = (mn / p.m_tiles) * BN;
-      const int acc = MH == 2 ? 0 : (it & 1); const uint32_t acc_phase = MH == 2 ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
+      const int m0 = (mn % p.m_tiles) * BM, n0 = (mn / p.m_tiles) * BN;
+      const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int mh = 0; mh < MH; ++mh) {
-      const int m = m0 + mh * 128 + quad * 32 + lane;
+      const int m = m0 + quad * 32 + lane;
       const bool row_ok = m < p.M;
-      const uint32_t acc_col = (uint32_t)(MH == 2 ? mh * BN : acc * BN);
       // SOUT: warp (quad, ehalf) owns the contiguous column half ehalf of its 32 rows; otherwise the 32-column chunks alternate between the two warps
       constexpr int NCH = BN / 64;
 #pragma unroll 1
@@ -208,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int nb = n0 + c * 32;
         if (nb >= p.N) break;                                   // warp-uniform
         float v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc_col + (uint32_t)(c * 32), v);
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
         if (!SOUT && !row_ok) continue;
         const int nvalid = min(32, p.N - nb);
         if (p.bias) {
@@ -288,7 +275,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
       }
-      }   // M halves
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
@@ -319,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
   if (threadIdx.x == 0) {   // the last CTA to leave re-arms the scheduler for the next launch that uses it (launches sharing it are stream-ordered)
     __threadfence();
     if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; __threadfence(); }
@@ -360,13 +346,13 @@ CUtensorMap make_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t l
   return m;
 }
 
-template <bool A_MN, bool B_MN, int BN, bool SOUT, int BMT = 128>
+template <bool A_MN, bool B_MN, int BN, bool SOUT>
 void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
-  using L = SmemLayout<BN, SOUT, BMT>;
+  using L = SmemLayout<BN, SOUT>;
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_type == DT_BF16;
   p.bias = g.bias; p.addend = g.addend; p.ldadd = g.ldadd; p.add_bf16 = g.add_type == DT_BF16; p.act = g.act;
-  p.m_tiles = (g.M + BMT - 1) / BMT; p.n_tiles = (g.N + BN - 1) / BN; p.kb_total = (g.K + BK - 1) / BK;
+  p.m_tiles = (g.M + BM - 1) / BM; p.n_tiles = (g.N + BN - 1) / BN; p.kb_total = (g.K + BK - 1) / BK;
   int splits = 1;
   if (g.accumulate) {   // split K until the grid fills the chip, keeping >= 8 k-blocks per split
     const int tiles = p.m_tiles * p.n_tiles;
@@ -376,9 +362,9 @@ void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
   p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.atomic_acc = g.accumulate ? 1 : 0;
   p.sched = sched;
-  const CUtensorMap ma = A_MN ? make_map(g.A, g.M, g.K, g.lda, 64, 64) : make_map(g.A, g.K, g.M, g.lda, 64, 128);
+  const CUtensorMap ma = A_MN ? make_map(g.A, g.M, g.K, g.lda, 64, 64) : make_map(g.A, g.K, g.M, g.lda, 64, BM);
   const CUtensorMap mb = B_MN ? make_map(g.B, g.N, g.K, g.ldb, 64, 64) : make_map(g.B, g.K, g.N, g.ldb, 64, BN);
-  auto kern = gemm_tc_kernel<A_MN, B_MN, BN, SOUT, BMT>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, BN, SOUT>;
   static bool attr_set = false;
   if (!attr_set) {
     MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -437,16 +423,6 @@ void gemm_tc(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
       else launch<true, true, BN_, false>(g, st, sm_count, sched);                             \
     }                                                                                          \
   } while (0)
-  // 256 x 256 tiles for the long-K accumulate GEMMs (weight gradients)
-  static int big = -1;
-  if (big < 0) { const char* e = getenv("MVAE_GEMM_BM256"); big = e ? atoi(e) : 1; }
-  if (big && bn256 && g.accumulate && g.M >= 256 && g.K >= 4096) {
-    if (!a_mn && !b_mn) launch<false, false, 256, false, 256>(g, st, sm_count, sched);
-    else if (!a_mn && b_mn) launch<false, true, 256, false, 256>(g, st, sm_count, sched);
-    else if (a_mn && !b_mn) launch<true, false, 256, false, 256>(g, st, sm_count, sched);
-    else launch<true, true, 256, false, 256>(g, st, sm_count, sched);
-    return;
-  }
   if (bn256) MVAE_GEMM_LAUNCH(256);
   else MVAE_GEMM_LAUNCH(128);
 #undef MVAE_GEMM_LAUNCH
@@ -462,7 +438,7 @@ int gemm_tc_selftest(int device, int verbose) {
   MVAE_CUDA(cudaStreamCreate(&st));
   struct Case { int M, N, K; bool ta, tb; int epi; };   // epi: 0 plain f32, 1 bias+tanh bf16 out, 2 addend(bf16) f32 out, 3 accumulate (split-K)
   std::vector<Case> cases;
-  const int shapes[][3] = {{128, 128, 64}, {128, 128, 256}, {256, 384, 512}, {200, 61, 96}, {77, 130, 72}, {512, 2048, 512}, {61, 256, 4096}, {8, 256, 64}, {300, 16, 128}, {384, 1024, 128}, {200, 1096, 64}, {384, 256, 4352}, {512, 256, 4096}};
+  const int shapes[][3] = {{128, 128, 64}, {128, 128, 256}, {256, 384, 512}, {200, 61, 96}, {77, 130, 72}, {512, 2048, 512}, {61, 256, 4096}, {8, 256, 64}, {300, 16, 128}, {384, 1024, 128}, {200, 1096, 64}};
   for (auto& s : shapes)
     for (int ta = 0; ta < 2; ++ta)
       for (int tb = 0; tb < 2; ++tb)

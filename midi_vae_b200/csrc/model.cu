@@ -185,6 +185,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
   { const char* e = getenv("MVAE_WGRAD_ROWS"); fuse_wgrad_rows = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_TIMELINE"); prof_detail = e && atoi(e) >= 2; }
+  { const char* e = getenv("MVAE_STEP_GRAPH"); step_graph_on = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_STEPWISE_GRAPH"); stepwise_graph_on = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_AR_BUCKETS"); ar_buckets = e ? std::max(1, atoi(e)) : 2; }
   { const char* e = getenv("MVAE_BRANCH_BWD_NCL"); branch_bwd_ncl = e ? std::max(0, atoi(e)) : 0; }
@@ -204,6 +205,7 @@ Model::~Model() {
   if (stream) cudaStreamSynchronize(stream);
   for (auto& ev : evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto& kv : stepwise_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : step_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (nccl_comm) nccl_comm_destroy(nccl_comm);
   if (st_comm) cudaStreamDestroy(st_comm);
   for (cudaEvent_t e : {ev_dec_grads, ev_comm, ev_pre_comm}) if (e) cudaEventDestroy(e);

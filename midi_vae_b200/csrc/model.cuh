@@ -259,6 +259,12 @@ struct Model {
   void decoder_stepwise_body(int n);
   // free-running decode = thousands of tiny dependent launches: captured once per batch size into a CUDA graph (notes chain on the step's
   // stream, velocity + instrument chains on the branch stream with their own scratch) and replayed; MVAE_STEPWISE_GRAPH=0 launches eagerly
+  // step-streamed train steps (GRU cells, fp32 precision, rnn_mode=streamed) are thousands of small dependent launches on ONE stream: the whole
+  // forward + backward of a mini-batch is captured once per (batch size, buffer addresses) and replayed; MVAE_STEP_GRAPH=0 launches eagerly
+  struct StepGraph { int state = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
+  std::map<std::vector<size_t>, StepGraph> step_graphs;
+  bool step_graph_on = true;
+  void forward_backward_body(const mvae_batch& b, float* dev_metrics);
   struct StepwiseGraph { int state = 0; cudaGraphExec_t exec = nullptr; long long launches = 0; };
   std::map<int, StepwiseGraph> stepwise_graphs;
   bool stepwise_graph_on = true;
