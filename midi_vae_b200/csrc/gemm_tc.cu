@@ -45,25 +45,19 @@ struct TcParams {
   int* sched;   // [0] next tile, [1] finished CTAs (both zero between launches that share them): dynamic tile scheduler
 };
 
-// SOUT: bf16 outputs leave through a shared-memory staging tile so that every warp store covers whole 256 / 128-byte row segments (a thread
-// owns one output ROW in TMEM; written directly, each of its 16-byte stores lands in a different 4 KB-strided row: half-filled sectors, and the
-// L2 slices -- not the tensor pipe -- bound the K = 512 input-projection GEMMs).  One pipeline stage is traded for the staging tile.
-template <int BN, bool SOUT>
+template <int BN>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? (SOUT ? 3 : 4) : 5;
-  static constexpr int OUT_ROW = (BN / 2) * 2 + 16;            // one epilogue warp owns 32 rows x BN/2 columns; + 16 B against bank conflicts
-  static constexpr int OUT_WARP = 32 * OUT_ROW;
-  static constexpr int OUT_BYTES = SOUT ? kEpiWarps * OUT_WARP : 0;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + 1024;   // + alignment slack
+  static constexpr int STAGES = (BN == 256) ? 4 : 5;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;   // + alignment slack
 };
 
-template <bool A_MN, bool B_MN, int BN, bool SOUT>
+template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
-  using L = SmemLayout<BN, SOUT>;
+  using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
@@ -169,7 +163,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else {
     // ===================== epilogue: warps 2..9, TMEM lane quadrant = warp % 4, 32-column chunks c with c % 2 == ehalf =====================
     const int quad = warp & 3, ehalf = (warp - 2) >> 2;
-    const uint32_t out_stage = smem_base + STAGES * L::STAGE_BYTES + (uint32_t)(warp - 2) * L::OUT_WARP;   // SOUT only
     for (int it = 0;; ++it) {
       const int rs = it % RS;
       int tile = 0;
@@ -187,16 +180,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       ptx::tc_fence_after();
       const int m = m0 + quad * 32 + lane;
       const bool row_ok = m < p.M;
-      // SOUT: warp (quad, ehalf) owns the contiguous column half ehalf of its 32 rows; otherwise the 32-column chunks alternate between the two warps
-      constexpr int NCH = BN / 64;
 #pragma unroll 1
-      for (int ci = 0; ci < NCH; ++ci) {
-        const int c = SOUT ? ehalf * NCH + ci : ehalf + 2 * ci;
+      for (int c = ehalf; c < BN / 32; c += 2) {
         const int nb = n0 + c * 32;
         if (nb >= p.N) break;                                   // warp-uniform
         float v[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-        if (!SOUT && !row_ok) continue;
+        if (!row_ok) continue;
         const int nvalid = min(32, p.N - nb);
         if (p.bias) {
           if (nvalid == 32 && (reinterpret_cast<uintptr_t>(p.bias + nb) & 15) == 0) {
@@ -210,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
           }
         }
-        if (p.addend && row_ok) {
+        if (p.addend) {
           if (p.add_bf16) {
             const bf16* ad = (const bf16*)p.addend + (size_t)m * p.ldadd + nb;
             if (nvalid == 32 && (reinterpret_cast<uintptr_t>(ad) & 15) == 0) {
@@ -235,17 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
         }
-        if (SOUT) {
-          // this thread's 32 columns of its row -> the warp's staging tile (row = lane)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(v[j * 8 + 2 * t], v[j * 8 + 2 * t + 1]);
-            ptx::st_shared_u4(out_stage + (uint32_t)lane * L::OUT_ROW + (uint32_t)(ci * 64 + j * 16), u);
-          }
-        } else if (p.atomic_acc) {
+        if (p.atomic_acc) {
           float* cp = (float*)p.C + (size_t)m * p.ldc + nb;
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j < nvalid) atomicAdd(cp + j, v[j]);
@@ -278,28 +258,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
-      if (SOUT) {
-        // staging tile -> global: one warp instruction = RPI rows x (BN/2 columns = LPR lanes x 16 B), whole row segments
-        constexpr int LPR = (BN / 2) / 8, RPI = 32 / LPR;
-        const int nbase = n0 + ehalf * (BN / 2);
-        const int cl = (lane % LPR) * 8;                      // first column (within the half) of this lane's 16 bytes
-#pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += RPI) {
-          const int r = r0 + lane / LPR;
-          const int mm = m0 + quad * 32 + r;
-          const uint4 u = ptx::ld_shared_u4(out_stage + (uint32_t)r * L::OUT_ROW + (uint32_t)cl * 2);
-          if (mm < p.M && nbase + cl < p.N) {
-            bf16* cp = (bf16*)p.C + (size_t)mm * p.ldc + nbase + cl;
-            if (nbase + cl + 8 <= p.N) {
-              *reinterpret_cast<uint4*>(cp) = u;
-            } else {
-              const bf16* e = reinterpret_cast<const bf16*>(&u);
-              for (int t = 0; t < 8 && nbase + cl + t < p.N; ++t) cp[t] = e[t];
-            }
-          }
-        }
-        __syncwarp();                                           // the staging tile is rewritten by the next tile's chunks
-      }
     }
   }
 
@@ -346,9 +304,9 @@ CUtensorMap make_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t l
   return m;
 }
 
-template <bool A_MN, bool B_MN, int BN, bool SOUT>
+template <bool A_MN, bool B_MN, int BN>
 void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
-  using L = SmemLayout<BN, SOUT>;
+  using L = SmemLayout<BN>;
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_type == DT_BF16;
   p.bias = g.bias; p.addend = g.addend; p.ldadd = g.ldadd; p.add_bf16 = g.add_type == DT_BF16; p.act = g.act;
@@ -364,7 +322,7 @@ void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
   p.sched = sched;
   const CUtensorMap ma = A_MN ? make_map(g.A, g.M, g.K, g.lda, 64, 64) : make_map(g.A, g.K, g.M, g.lda, 64, BM);
   const CUtensorMap mb = B_MN ? make_map(g.B, g.N, g.K, g.ldb, 64, 64) : make_map(g.B, g.K, g.N, g.ldb, 64, BN);
-  auto kern = gemm_tc_kernel<A_MN, B_MN, BN, SOUT>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, BN>;
   static bool attr_set = false;
   if (!attr_set) {
     MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -405,27 +363,17 @@ void gemm_tc(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
   static int wide = -1;
   if (wide < 0) { const char* e = getenv("MVAE_GEMM_BN256"); wide = e ? atoi(e) : 1; }
   const bool bn256 = wide && g.N >= 256 && (g.N % 256 == 0 || g.N >= 1024);
-  // bf16 outputs with 16-byte aligned rows go through the staged (coalesced) epilogue
-  static int staged = -1;
-  if (staged < 0) { const char* e = getenv("MVAE_GEMM_STAGED_OUT"); staged = e ? atoi(e) : 1; }
-  const bool sout = staged && g.c_type == DT_BF16 && !g.accumulate && (g.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0;
-#define MVAE_GEMM_LAUNCH(BN_)                                                                  \
-  do {                                                                                         \
-    if (sout) {                                                                                \
-      if (!a_mn && !b_mn) launch<false, false, BN_, true>(g, st, sm_count, sched);             \
-      else if (!a_mn && b_mn) launch<false, true, BN_, true>(g, st, sm_count, sched);          \
-      else if (a_mn && !b_mn) launch<true, false, BN_, true>(g, st, sm_count, sched);          \
-      else launch<true, true, BN_, true>(g, st, sm_count, sched);                              \
-    } else {                                                                                   \
-      if (!a_mn && !b_mn) launch<false, false, BN_, false>(g, st, sm_count, sched);            \
-      else if (!a_mn && b_mn) launch<false, true, BN_, false>(g, st, sm_count, sched);         \
-      else if (a_mn && !b_mn) launch<true, false, BN_, false>(g, st, sm_count, sched);         \
-      else launch<true, true, BN_, false>(g, st, sm_count, sched);                             \
-    }                                                                                          \
-  } while (0)
-  if (bn256) MVAE_GEMM_LAUNCH(256);
-  else MVAE_GEMM_LAUNCH(128);
-#undef MVAE_GEMM_LAUNCH
+  if (bn256) {
+    if (!a_mn && !b_mn) launch<false, false, 256>(g, st, sm_count, sched);
+    else if (!a_mn && b_mn) launch<false, true, 256>(g, st, sm_count, sched);
+    else if (a_mn && !b_mn) launch<true, false, 256>(g, st, sm_count, sched);
+    else launch<true, true, 256>(g, st, sm_count, sched);
+    return;
+  }
+  if (!a_mn && !b_mn) launch<false, false, 128>(g, st, sm_count, sched);
+  else if (!a_mn && b_mn) launch<false, true, 128>(g, st, sm_count, sched);
+  else if (a_mn && !b_mn) launch<true, false, 128>(g, st, sm_count, sched);
+  else launch<true, true, 128>(g, st, sm_count, sched);
 }
 
 // ------------------------------------------------------------------------------------------------ self test

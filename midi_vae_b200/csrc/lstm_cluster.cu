@@ -99,15 +99,11 @@ constexpr int CL2_MAXG = 3;
 constexpr uint32_t CL2_TM_U = 64 * CL2_MAXG;   // TMEM: accumulator of group g at columns 64 g, U from column 192
 
 struct Cluster2P {
-  int n, steps, nswap, ng, dbg;   // dbg: timing experiments only (bit 0: no gate/c stash stores, bit 1: no xw loads)
+  int n, steps, nswap, ng;
   const bf16* xw; bf16* hseq; bf16* cseq; bf16* gates; const bf16* c0; int ldc0;
   const bf16* upack;
   uint8_t* hx;        // exchange buffer [clusters][ng][2][CS][2 row halves][2 KB]
   int no_stash;       // inference: h only, no BPTT stash
-  int cl0;            // first cluster of this launch (a launch may cover a sub-range of the batch's clusters)
-  unsigned* progress; // != null: counter c is incremented once per (CTA, active row group) when the h rows of steps < (c + 1) * progress_every are in global memory
-  int progress_every;
-  int c0_stash;       // this launch continues a sequence: initial c = stash slab 0 (granule layout) of the (offset) cseq pointer, h = hseq slab 0
   int x_mode; const bf16* xtab; const unsigned char* x_idx; int x_ld, x_shift; const bf16* x_scalar; const float* x_w; const float* x_b;
   long long* trace;
 };
@@ -133,7 +129,7 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
   const uint32_t smem_h0 = smem_base + (ALIAS ? 0u : 2u * CL_SCR);   // hbuf(g, b) = smem_h0 + (2 g + b) * HBUF
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int cl = (int)blockIdx.x / CS + p.cl0;
+  const int cl = (int)blockIdx.x / CS;
   const int e = (int)(rank & 1);
   const int rh = e ^ p.nswap;
   const int j = (int)rank;
@@ -277,12 +273,8 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
       const int m = row0 + g * CL_ROWS + rr;
       uint4 cv = make_uint4(0u, 0u, 0u, 0u);
       if (g < nga && m < n) {
-        if (p.c0_stash) {
-          cv = *reinterpret_cast<const uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m));
-        } else {
-          if (p.c0) cv = *reinterpret_cast<const uint4*>(p.c0 + (size_t)m * p.ldc0 + u0);
-          *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m)) = cv;   // stash slab 0 = c0
-        }
+        if (p.c0) cv = *reinterpret_cast<const uint4*>(p.c0 + (size_t)m * p.ldc0 + u0);
+        *reinterpret_cast<uint4*>(p.cseq + gran_off(0, H / 8, gu, n, m)) = cv;   // stash slab 0 = c0
       }
       unpack8(cv, cst[k]);
     }
@@ -393,16 +385,6 @@ rec_cluster_fwd2_kernel(const Cluster2P p) {
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 2 * (H / 8) + gu, n, m)) = pack8(gg);
           *reinterpret_cast<uint4*>(p.gates + gran_off(t, G / 8, 3 * (H / 8) + gu, n, m)) = pack8(go);
         }
-        if (p.progress && (t + 1) % p.progress_every == 0) {
-          // time-chunk boundary: this (CTA, group)'s h rows up to step t are written; publish them (gpu scope) and count, so that a consumer
-          // gated by a stream wait on the counter (the next layer's input projection of this chunk) may start while the recurrence goes on
-          __threadfence();
-          named_barrier(7 + set, 32 * CL_EPI_WARPS);
-          if (ew == 0 && lane == 0) {
-            __threadfence();      // cumulative over the set's stores observed through the barrier: fence and counter update by the SAME thread
-            atomicAdd(p.progress + ((t + 1) / p.progress_every - 1), 1u);
-          }
-        }
         if (tracer && g == 0) CL_TRACE(t, 9);
       }
     }
@@ -449,13 +431,9 @@ constexpr uint32_t CLB_BT = 32 * CLB_GS;           // 16896 B: 32 k-granules (4 
 struct ClusterBP {
   int n, steps, nswap, ng;
   const bf16* gates; const bf16* cseq; const bf16* dhext; const bf16* dh_last; int ld_last;
-  int cl0;                // first cluster of this launch (a launch may cover a sub-range of the batch's clusters)
-  const bf16* dc_last;    // time-chunked sweeps: cell-state gradient carried in from the chunk after this one (same leading dimension as dh_last)
   bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
   const bf16* upack;      // [CS][MT][128 units][256 gate columns of the pair]
   int l2_prefetch;        // > 0: prefetch the stash of step t - l2_prefetch into L2
-  uint8_t* xbuf;          // via_l2: global exchange buffer [clusters][ng][CS][ND messages]
-  int via_l2;             // messages travel smem -> L2 -> smem (bulk store, remote arrive, bulk load) instead of DSMEM bulk copies
   long long* trace;
 };
 
@@ -479,13 +457,13 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
   constexpr uint32_t TM_U = CLB_MAXG * MT * 64;                     // TMEM: D(g, mt) at (g MT + mt) 64, U^T tile mt at TM_U + 128 mt
   constexpr uint32_t GRP = CLB_BT + (ND + NP) * CLB_MSG;            // per group: operand tile | staging (ND messages) | receive (NP messages)
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t b_ready[CLB_MAXG], tmem_full[CLB_MAXG], recv_full[CLB_MAXG], ack[CLB_MAXG], msg_ready[CLB_MAXG];
+  __shared__ __align__(8) uint64_t b_ready[CLB_MAXG], tmem_full[CLB_MAXG], recv_full[CLB_MAXG], ack[CLB_MAXG];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int cl = (int)blockIdx.x / CS + p.cl0;
+  const int cl = (int)blockIdx.x / CS;
   const int e = (int)(rank & 1), q = (int)(rank >> 1);
   const int rhs = e ^ p.nswap;                                      // which 32 rows of a group this CTA does the cell math for
   const int T = p.steps, n = p.n, ng = p.ng;
@@ -498,7 +476,6 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
       ptx::mbar_init(ptx::smem_u32(&tmem_full[g]), 1);
       ptx::mbar_init(ptx::smem_u32(&recv_full[g]), 1);
       ptx::mbar_init(ptx::smem_u32(&ack[g]), ND * CL_EPI_WARPS);
-      ptx::mbar_init(ptx::smem_u32(&msg_ready[g]), NP);
     }
     ptx::fence_barrier_init();
     for (int g = 0; g < CLB_MAXG; ++g) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&recv_full[g]), NP * CLB_MSG);   // messages of iteration 0
@@ -577,33 +554,12 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
       int self_x = -1;
       for (int x = 0; x < ND; ++x)
         if ((uint32_t)(2 * (4 * (x >> 2) + 2 * e + ((x >> 1) & 1)) + ((x & 1) ^ p.nswap)) == rank) self_x = x;
-      // via_l2: my staging tile goes to slot (cluster, g, rank) of the global exchange buffer in one bulk store; once it is complete the
-      // ND destinations are told (relaxed remote arrives), and when my NP sources have told me I fetch my message out of each one's slot
-      const size_t slot_bytes = (size_t)ND * CLB_MSG;
-      uint8_t* my_slot = p.xbuf + ((size_t)(cl * ng + g) * CS + rank) * slot_bytes;
-      const uint32_t ready_remote = ptx::mapa(ptx::smem_u32(&msg_ready[g]), dest);
-      const int my_msg = (q >> 2) * 4 + (q & 1) * 2 + (e ^ p.nswap);                 // index of the message for me in a source's staging tile
-      const uint8_t* fetch_src = p.xbuf + ((size_t)(cl * ng + g) * CS + (size_t)(2 * (lane % NP) + ((q & 3) >> 1))) * slot_bytes + (size_t)my_msg * CLB_MSG;
       for (int it = 0; it < T; ++it) {
         named_barrier(1 + g, 32 * (CL_EPI_WARPS + 1));
         ptx::fence_proxy_async();            // staging was written with generic stores by the epilogue warps (ordered by the barrier)
-        if (!p.via_l2) {
-          if (lane < ND && dest != rank) ptx::bulk_copy_dsmem(dst, src, CLB_MSG, dbar);
-          if (self_x >= 0) self_message(gb + CLB_BT + (ND + q) * CLB_MSG, gb + CLB_BT + (uint32_t)self_x * CLB_MSG, CLB_MSG, ptx::smem_u32(&recv_full[g]), lane);
-          if (lane == 0 && g == 0) CL_TRACE(it, 6);
-        } else {
-          if (lane == 0) {
-            ptx::bulk_store(my_slot, gb + CLB_BT, (uint32_t)slot_bytes);
-            ptx::bulk_commit();
-            ptx::bulk_wait_all();
-          }
-          __syncwarp();
-          if (lane < ND) ptx::mbar_arrive_remote_relaxed(ready_remote);
-          if (lane == 0 && g == 0) CL_TRACE(it, 6);
-          ptx::mbar_wait(ptx::smem_u32(&msg_ready[g]), (uint32_t)(it & 1));
-          if (lane < NP) ptx::bulk_load(gb + CLB_BT + (ND + lane) * CLB_MSG, fetch_src, CLB_MSG, ptx::smem_u32(&recv_full[g]));
-          if (lane == 0 && g == 0) CL_TRACE(it, 8);
-        }
+        if (lane < ND && dest != rank) ptx::bulk_copy_dsmem(dst, src, CLB_MSG, dbar);
+        if (self_x >= 0) self_message(gb + CLB_BT + (ND + q) * CLB_MSG, gb + CLB_BT + (uint32_t)self_x * CLB_MSG, CLB_MSG, ptx::smem_u32(&recv_full[g]), lane);
+        if (lane == 0 && g == 0) CL_TRACE(it, 6);
       }
     }
   } else {
@@ -624,7 +580,6 @@ rec_cluster_bwd_kernel(const ClusterBP p) {
       float dc[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) dc[u] = 0.f;
-      if (p.dc_last && row_ok) unpack8(__ldg(reinterpret_cast<const uint4*>(p.dc_last + (size_t)m * p.ld_last + u0)), dc);
 
       for (int it = 0; it <= T; ++it) {
         const int t = T - 1 - it;
@@ -784,8 +739,6 @@ constexpr uint32_t CLQ_GRP = 2 * CLQ_BT + 8 * CLQ_MSG; // per group: 2 B tiles |
 struct ClusterQP {
   int n, steps, nswap, ng, l2_prefetch;
   const bf16* gates; const bf16* cseq; const bf16* dhext; const bf16* dh_last; int ld_last;
-  int cl0;                // first cluster of this launch (a launch may cover a sub-range of the batch's clusters)
-  const bf16* dc_last;    // time-chunked sweeps: cell-state gradient carried in from the chunk after this one (same leading dimension as dh_last)
   bf16* dG; bf16* dS_h; bf16* dS_c; int ldS;
   const bf16* upack;      // [16][128 output units][512 k]
   uint8_t* xbuf;          // dG exchange slots [clusters][ng][2][16 CTAs][2 row halves][8 KB]
@@ -805,7 +758,7 @@ rec_cluster_bwd4_kernel(const ClusterQP p) {
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int cl = (int)blockIdx.x / CS + p.cl0;
+  const int cl = (int)blockIdx.x / CS;
   const int e = (int)(rank & 1), kq = (int)(rank >> 2), c = (int)(rank & 3);
   const int T = p.steps, n = p.n, ng = p.ng;
   const int row0 = cl * CL_ROWS * ng;
@@ -943,7 +896,6 @@ rec_cluster_bwd4_kernel(const ClusterQP p) {
       float dc[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) dc[u] = 0.f;
-      if (p.dc_last && row_ok) unpack8(__ldg(reinterpret_cast<const uint4*>(p.dc_last + (size_t)m * p.ld_last + u0)), dc);
 
       // BPTT stash of a step (4 gate granules, c_t, dh_ext): loaded ONE STEP AHEAD -- issued right after the exchange barrier of the previous
       // iteration, in flight during its TMEM drain and the wait for the partial messages -- so that the gate-gradient math never waits for L2
@@ -1186,29 +1138,22 @@ void launch_fwd2(const RecPersistArgs& a, cudaStream_t st) {
     if (CS == 16 && (groups + 1) / 2 > 7 && (groups + 2) / 3 <= 7) ng = 3;
     if (CS == 8 && groups <= env_int("MVAE_CL_NG1_MAX", 8)) ng = 1;   // 8-CTA clusters are plentiful: one group each has the shortest chain
   }
-  if (a.ng > 0) ng = a.ng;
   ng = std::max(1, std::min(std::min(ng, CL2_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
-  const int cl0 = std::min(std::max(a.cl0, 0), clusters), ncl = a.ncl > 0 ? std::min(a.ncl, clusters - cl0) : clusters - cl0;
-  if (ncl <= 0) return;
   const size_t smem = 1024 + scr_bytes + (size_t)ng * 2 * hbuf;
   Cluster2P p{};
-  p.cl0 = cl0;
-  p.progress = a.progress_every > 0 ? a.progress : nullptr; p.progress_every = a.progress_every;
-  p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.dbg = env_int("MVAE_CL_DBG", 0);
-  // a.t0 > 0: this launch continues the sequence at step t0 (time-chunked recurrences): every time-indexed buffer is simply offset
-  const size_t t0 = (size_t)a.t0, nn = (size_t)a.n;
-  p.xw = a.xw ? (const bf16*)a.xw + t0 * nn * 4 * H : nullptr;
-  p.hseq = (bf16*)a.hseq + t0 * nn * H; p.cseq = (bf16*)a.cseq + t0 * nn * H; p.gates = (bf16*)a.gates + t0 * nn * 4 * H;
-  p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0; p.c0_stash = a.t0 > 0; p.no_stash = a.no_stash;
+  p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng;
+  p.xw = (const bf16*)a.xw;
+  p.hseq = (bf16*)a.hseq; p.cseq = (bf16*)a.cseq; p.gates = (bf16*)a.gates;
+  p.c0 = (const bf16*)a.c0; p.ldc0 = a.ldc0; p.no_stash = a.no_stash;
   p.upack = (const bf16*)a.upack; p.hx = (uint8_t*)a.hx; p.trace = (long long*)a.trace;
-  p.x_mode = a.x_mode; p.xtab = (const bf16*)a.xtab; p.x_idx = a.x_idx; p.x_ld = a.x_ld; p.x_shift = a.x_shift - a.t0;
-  p.x_scalar = a.x_scalar ? (const bf16*)a.x_scalar + t0 * nn * a.x_ld : nullptr; p.x_w = a.x_w; p.x_b = a.x_b;
+  p.x_mode = a.x_mode; p.xtab = (const bf16*)a.xtab; p.x_idx = a.x_idx; p.x_ld = a.x_ld; p.x_shift = a.x_shift;
+  p.x_scalar = (const bf16*)a.x_scalar; p.x_w = a.x_w; p.x_b = a.x_b;
   MVAE_REQUIRE(p.x_mode == 0 ? p.xw != nullptr : (p.x_mode == 1 ? p.xtab != nullptr : (p.x_scalar && p.x_w && p.x_b)), "cluster forward: input projection source missing");
   MVAE_REQUIRE(p.hx != nullptr, "cluster forward: exchange buffer missing");
   MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * CL_STAGE <= rec_cluster_hx_bytes(a.n, H), "cluster forward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(ncl * CS)); cfg.blockDim = dim3(CLF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1242,28 +1187,17 @@ void launch_bwd(const RecPersistArgs& a, cudaStream_t st) {
   if (ng <= 0) ng = (CS == 8 && groups <= env_int("MVAE_CL_NG1_MAX", 8)) ? 1 : CLB_MAXG;
   ng = std::max(1, std::min(std::min(ng, CLB_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
-  const int cl0 = std::min(std::max(a.cl0, 0), clusters), ncl = a.ncl > 0 ? std::min(a.ncl, clusters - cl0) : clusters - cl0;
-  if (ncl <= 0) return;
   const size_t smem = 1024 + (size_t)ng * grp;
   ClusterBP p{};
-  p.cl0 = cl0;
   p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng;
-  {
-    // a.t0 > 0: this launch sweeps steps [t0, t0 + steps) of the sequence in reverse (time-chunked sweeps): every time-indexed buffer is offset,
-    // the carry from the later chunk arrives through dh_last / dc_last and leaves through dS_h / dS_c
-    const size_t t0 = (size_t)a.t0, nn = (size_t)a.n, Hh = (size_t)a.H;
-    p.gates = (const bf16*)a.gates + t0 * nn * 4 * Hh; p.cseq = (const bf16*)a.cseq + t0 * nn * Hh;
-    p.dhext = a.dhext ? (const bf16*)a.dhext + t0 * nn * Hh : nullptr; p.dh_last = (const bf16*)a.dh_last; p.dc_last = (const bf16*)a.dc_last; p.ld_last = a.ld_last;
-    p.dG = (bf16*)a.dG + t0 * nn * 4 * Hh; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
-  }
+  p.gates = (const bf16*)a.gates; p.cseq = (const bf16*)a.cseq; p.dhext = (const bf16*)a.dhext;
+  p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last;
+  p.dG = (bf16*)a.dG; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace;
   MVAE_REQUIRE(p.upack != nullptr, "cluster backward: packed weights missing");
   p.l2_prefetch = env_int("MVAE_CLB_PREFETCH", 2);
-  p.xbuf = (uint8_t*)a.partial;
-  p.via_l2 = env_int("MVAE_CLB_L2", 0) && p.xbuf != nullptr;
-  if (p.via_l2) MVAE_REQUIRE((size_t)clusters * ng * CS * ND * CLB_MSG <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(ncl * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1296,26 +1230,18 @@ void launch_bwd4(const RecPersistArgs& a, cudaStream_t st) {
   if (ng <= 0) ng = CLB_MAXG;
   ng = std::max(1, std::min(std::min(ng, CLB_MAXG), groups));
   const int clusters = (groups + ng - 1) / ng;
-  const int cl0 = std::min(std::max(a.cl0, 0), clusters), ncl = a.ncl > 0 ? std::min(a.ncl, clusters - cl0) : clusters - cl0;
-  if (ncl <= 0) return;
   const size_t smem = 1024 + (size_t)ng * CLQ_GRP;
   ClusterQP p{};
-  p.cl0 = cl0;
   p.n = a.n; p.steps = a.steps; p.nswap = env_int("MVAE_CL_NSWAP", 0); p.ng = ng; p.l2_prefetch = env_int("MVAE_CLB_PREFETCH", 2);
-  {
-    // a.t0 > 0: this launch sweeps steps [t0, t0 + steps) of the sequence in reverse (time-chunked sweeps): every time-indexed buffer is offset,
-    // the carry from the later chunk arrives through dh_last / dc_last and leaves through dS_h / dS_c
-    const size_t t0 = (size_t)a.t0, nn = (size_t)a.n, Hh = (size_t)a.H;
-    p.gates = (const bf16*)a.gates + t0 * nn * 4 * Hh; p.cseq = (const bf16*)a.cseq + t0 * nn * Hh;
-    p.dhext = a.dhext ? (const bf16*)a.dhext + t0 * nn * Hh : nullptr; p.dh_last = (const bf16*)a.dh_last; p.dc_last = (const bf16*)a.dc_last; p.ld_last = a.ld_last;
-    p.dG = (bf16*)a.dG + t0 * nn * 4 * Hh; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
-  }
+  p.gates = (const bf16*)a.gates; p.cseq = (const bf16*)a.cseq; p.dhext = (const bf16*)a.dhext;
+  p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last;
+  p.dG = (bf16*)a.dG; p.dS_h = (bf16*)a.dS_h; p.dS_c = (bf16*)a.dS_c; p.ldS = a.ldS;
   p.upack = (const bf16*)a.upack_bwd; p.trace = (long long*)a.trace; p.xbuf = (uint8_t*)a.partial;
   p.stm = env_int("MVAE_CLB_STM", 1);
   MVAE_REQUIRE(p.upack != nullptr && p.xbuf != nullptr, "cluster backward: packed weights / exchange buffer missing");
   MVAE_REQUIRE((size_t)clusters * ng * 2 * CS * 2 * CLQ_PIECE <= rec_cluster_xbuf_bytes(a.n, H), "cluster backward: exchange buffer too small");
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(ncl * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(clusters * CS)); cfg.blockDim = dim3(CLW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1333,10 +1259,10 @@ bool rec_cluster_supported(int H) {
   return enabled && (H == 256 || H == 512);
 }
 
-// global exchange buffer of the backward kernel (via_l2): [64-row groups rounded up to whole clusters][H/32 CTAs][H/64 messages of 4224 B]
+// global dG exchange slots of the quad-form backward kernel: [64-row groups rounded up to whole clusters][2][H/32 CTAs][2 row halves][8 KB]
 size_t rec_cluster_xbuf_bytes(int n, int H) {
   const size_t groups = (size_t)((n + CL_ROWS - 1) / CL_ROWS + CLB_MAXG), ctas = (size_t)(H / CL_HS);
-  return std::max(groups * ctas * (size_t)(H / 64) * CLB_MSG, groups * 2 * ctas * 2 * (size_t)CLQ_PIECE);
+  return groups * 2 * ctas * 2 * (size_t)CLQ_PIECE;
 }
 
 // global exchange buffer of the forward kernel: [64-row groups, rounded up to whole clusters][2][H/32 CTAs][4 KB]

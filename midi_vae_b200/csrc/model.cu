@@ -100,8 +100,6 @@ void Model::build_workspace() {
     rec_hx = alloc(hxb); rec_hx2 = alloc(hxb);
   }
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
-  if (chunks_bwd > 1) for (int i = 0; i < 4; ++i) rec_carry[i] = alloc(n * H * a);
-  if (xw_overlap > 1) rec_progress = (unsigned*)alloc(2 * 16 * sizeof(unsigned));
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
   for (int k = 0; k < nd; ++k) rec_bufs(dec_notes[k], true);
@@ -177,19 +175,11 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_FUSE_XPROJ"); fuse_xproj = use_cluster_fwd && (e ? atoi(e) != 0 : true); }
   { const char* e = getenv("MVAE_BRANCH"); use_branch = use_cluster_fwd && use_cluster_bwd && (e ? atoi(e) != 0 : true); }
   if (side_sms <= 0) side_sms = std::max(16, sm_count - 16 * ((NB + 127) / 128));
-  { const char* e = getenv("MVAE_CHUNKS"); chunks = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
-  { const char* e = getenv("MVAE_CHUNKS_BWD"); chunks_bwd = (use_branch && e) ? std::max(1, std::min(8, atoi(e))) : 1; }
-  { const char* e = getenv("MVAE_PIPE_SMS"); pipe_sms = e ? atoi(e) : 0; }
-  { const char* e = getenv("MVAE_XW_OVERLAP"); xw_overlap = (use_cluster_fwd && e) ? std::max(0, std::min(16, atoi(e))) : 0; }
-  { const char* e = getenv("MVAE_WGRAD_CHUNKS"); wgrad_per_chunk = e ? atoi(e) != 0 : false; }
-  { const char* e = getenv("MVAE_BRANCH_AT"); branch_at = e ? std::max(0, atoi(e)) : 0; }
   { const char* e = getenv("MVAE_WGRAD_ROWS"); fuse_wgrad_rows = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_TIMELINE"); prof_detail = e && atoi(e) >= 2; }
   { const char* e = getenv("MVAE_STEP_GRAPH"); step_graph_on = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_STEPWISE_GRAPH"); stepwise_graph_on = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_AR_BUCKETS"); ar_buckets = e ? std::max(1, atoi(e)) : 2; }
-  { const char* e = getenv("MVAE_BRANCH_BWD_NCL"); branch_bwd_ncl = e ? std::max(0, atoi(e)) : 0; }
-  if (chunks > 1 || chunks_bwd > 1 || xw_overlap > 1) MVAE_CUDA(cudaStreamCreateWithPriority(&st_pipe, cudaStreamNonBlocking, prio_greatest));
   build_params();
   P = (float*)alloc(arena_n * 4); Gr = (float*)alloc(arena_n * 4); M1 = (float*)alloc(arena_n * 4); V2 = (float*)alloc(arena_n * 4);
   if (act == DT_BF16) Pb = (__nv_bfloat16*)alloc(arena_n * 2);
@@ -214,8 +204,6 @@ Model::~Model() {
   if (stream) cudaStreamDestroy(stream);
   if (side) cudaStreamDestroy(side);
   if (st_branch) cudaStreamDestroy(st_branch);
-  if (st_pipe) cudaStreamDestroy(st_pipe);
-  for (auto& ev : ev_pool) cudaEventDestroy(ev);
   if (ev_bfork) cudaEventDestroy(ev_bfork);
   if (ev_bjoin) cudaEventDestroy(ev_bjoin);
   if (ev_fork) cudaEventDestroy(ev_fork);
@@ -327,7 +315,7 @@ void Model::gemm(GemmArgs g) { gemm_on(g, st, sm_count); }
 void Model::gemm_on(GemmArgs g, cudaStream_t s, int sms) {
   g.in_type = act;
   // one scheduler word pair per stream: launches that share a pair must be stream-ordered
-  int* sched = gemm_sched + (s == side ? 2 : (s == st_branch ? 4 : (s == st_pipe && st_pipe ? 6 : 0)));
+  int* sched = gemm_sched + (s == side ? 2 : (s == st_branch ? 4 : 0));
   if (act == DT_BF16 && gemm_tc_supported(g)) gemm_tc(g, s, sms, sched);
   else gemm_simt(g, s);
 }
@@ -386,9 +374,7 @@ void Model::rec_forward_prepare(const FwdJob& j, int n) {
   const long rows = (long)r.steps * n;
   const bool fused = fuse_xproj && r.steps > 8 && ((j.kind == IN_DENSE && j.onehot) || j.kind == IN_RANK1 || j.kind == IN_NONE);
   prof_begin(PC_GEMM);
-  if (j.xw_ready) {
-    // the input projection was (or is being) written chunk by chunk on the pipe stream; the caller has made this stream wait for it
-  } else if (fused) {
+  if (fused) {
     // the cluster kernel computes x W + b itself: a row gather for one-hot inputs (table built here), x w + b for the scalar stream
     if (j.kind != IN_RANK1) rec_cluster_build_xtab(W(r.iW), ld(r.iW), j.kind == IN_DENSE ? r.Din : 0, Wf(r.ib), r.xtab, H, st);
   } else if (j.kind == IN_DENSE) {
@@ -424,7 +410,6 @@ RecPersistArgs Model::fwd_args(const FwdJob& j, int n, int slot, int hs, bool pa
   a.hx = slot ? rec_hx2 : rec_hx;
   a.trace = slot ? nullptr : trace_buf;
   a.no_stash = inference_pass ? 1 : 0;
-  a.progress = j.progress; a.progress_every = j.progress_every;
   if (fuse_xproj && r.steps > 8) {
     if ((j.kind == IN_DENSE && j.onehot) || j.kind == IN_NONE) {
       a.x_mode = 1; a.xtab = r.xtab;
@@ -558,14 +543,7 @@ void Model::rec_backward_sweep(const BwdJob* ja, const BwdJob* jb, int n) {
       if (!j) continue;
       RecPersistArgs a = bwd_args(*j, n, cur_slot, 0);
       fork_if_pending();
-      if (cur_slot == 1 && branch_bwd_ncl > 0 && a.steps > 16) {
-        // a branch recurrence never gets more than the cluster slots the main chain leaves (3 of 7): its fourth cluster runs as a second wave
-        // anyway, so launch it as waves of `branch_bwd_ncl` clusters and leave the other SMs to the weight-gradient GEMMs of the side stream
-        const int clusters = ((n + 63) / 64 + 1) / 2;
-        for (int c0 = 0; c0 < clusters; c0 += branch_bwd_ncl) { a.cl0 = c0; a.ncl = branch_bwd_ncl; rec_cluster_backward(a, st); }
-      } else {
-        rec_cluster_backward(a, st);
-      }
+      rec_cluster_backward(a, st);
       dump_trace("bwd(cluster)", *j->r, 2);
     }
   } else if (use_persist) {
@@ -630,26 +608,24 @@ void Model::rec_backward_gemms(const BwdJob& j, int n, bool tail) {
   else rec_backward_wgrads(j, n, st, sm_count);
 }
 
-void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms, int t0, int nsteps) {
-  // steps [t0, t0 + nsteps) of the sequence (default: all): every product accumulates into the zeroed gradient arena, so a sequence may be
-  // covered by several calls (time-chunked sweeps hand their chunks over as soon as they are complete)
+void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms) {
+  // every product accumulates into the zeroed gradient arena
   Rec& r = *j.r;
-  if (nsteps < 0) nsteps = r.steps - t0;
-  const long rows = (long)nsteps * n;
-  const void* dG = slab(r.xw, t0, (long)n * G);
-  const void* Xc = j.X ? (const char*)j.X + (size_t)t0 * n * (j.kind == IN_RANK1 ? VD : r.ldin) * asz() : nullptr;
+  const long rows = (long)r.steps * n;
+  const void* dG = r.xw;
+  const void* Xc = j.X;
   const bool det = prof_detail;
   auto seg = [&](const char* tag) { if (det) { prof_end(s); prof_begin(PC_GEMM, s, tag); } };
   prof_begin(PC_GEMM, s, det ? "wgrad dU" : r.name.c_str());
   if (gru) {  // dU_zr += Hprev^T [da_z | da_r];  dU_h += (r * Hprev)^T da_h   (the r * h sequence sits in the cseq buffer)
-    GemmArgs g; g.M = H; g.N = 2 * H; g.K = (int)rows; g.A = slab(r.hseq, t0, (long)n * H); g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
+    GemmArgs g; g.M = H; g.N = 2 * H; g.K = (int)rows; g.A = r.hseq; g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
     gemm_on(g, s, sms);
-    GemmArgs h; h.M = H; h.N = H; h.K = (int)rows; h.A = slab(r.cseq, t0, (long)n * H); h.lda = H; h.transA = true;
+    GemmArgs h; h.M = H; h.N = H; h.K = (int)rows; h.A = r.cseq; h.lda = H; h.transA = true;
     h.B = (const char*)dG + (size_t)2 * H * asz(); h.ldb = G; h.C = Gp(r.iU) + 2 * H; h.ldc = ld(r.iU); h.c_type = DT_F32; h.accumulate = true;
     gemm_on(h, s, sms);
   } else {  // dU += Hprev^T dG
-    GemmArgs g; g.M = H; g.N = G; g.K = (int)rows; g.A = slab(r.hseq, t0, (long)n * H); g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
+    GemmArgs g; g.M = H; g.N = G; g.K = (int)rows; g.A = r.hseq; g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
     gemm_on(g, s, sms);
   }
@@ -676,7 +652,6 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms,
 
 // a stack of layers (top first) plus independent side recurrences: pair the i-th stack layer with the i-th side recurrence
 void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n, bool last_group) {
-  if (stack.size() >= 2 && chunked_ok(stack[0].r->steps, chunks_bwd)) { stack_backward_chunked(stack, side, n, last_group); return; }
   if (use_branch) {
     // the stack (top layer first) is the critical chain; the independent recurrences run next to it on the branch stream
     branch_fork();
@@ -705,248 +680,17 @@ void Model::rec_backward_group(std::vector<BwdJob>& stack, std::vector<BwdJob>& 
   }
 }
 
-// --------------------------------------------------------------------------------------------- projection overlap (stream-ordered memory waits)
-namespace {
-typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-WaitValueFn get_wait_value() {
-  static WaitValueFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    MVAE_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qres));
-    MVAE_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuStreamWaitValue32 not available from the driver");
-    fn = (WaitValueFn)p;
-  }
-  return fn;
-}
-}  // namespace
-
-// The producer's counters are zeroed on the main stream before its launch; the pipe stream picks up from there.
-void Model::overlap_arm(FwdJob& producer, int n) {
-  (void)n;
-  progress_flip ^= 1;
-  producer.progress = rec_progress + 16 * progress_flip;
-  producer.progress_every = producer.r->steps / xw_overlap;
-  MVAE_CUDA(cudaMemsetAsync(producer.progress, 0, 16 * sizeof(unsigned), st));
-  cudaEvent_t e = next_event();
-  MVAE_CUDA(cudaEventRecord(e, st));
-  MVAE_CUDA(cudaStreamWaitEvent(st_pipe, e, 0));
-}
-
-// Input projection of the consumer layer, one GEMM per time chunk on the pipe stream, each gated by a stream wait until every (CTA, row group)
-// of the producer has published that chunk.  The main stream then waits for the last GEMM only.
-void Model::overlap_project(const FwdJob& producer, Rec& rn, int n) {
-  const int NC = xw_overlap, Tc = producer.progress_every;
-  const unsigned expected = (unsigned)((H / 32) * ((n + 63) / 64));
-  const int psms = pipe_grid(n);
-  for (int c = 0; c < NC; ++c) {     // (not timed by the profiling events: the span would include the wait)
-    const CUresult r = get_wait_value()((CUstream)st_pipe, (CUdeviceptr)(uintptr_t)(producer.progress + c), expected, CU_STREAM_WAIT_VALUE_GEQ);
-    MVAE_REQUIRE(r == CUDA_SUCCESS, "cuStreamWaitValue32 failed");
-    GemmArgs g; g.M = Tc * n; g.N = G; g.K = rn.Din; g.A = slab(producer.r->hseq, (long)c * Tc + 1, (long)n * H); g.lda = rn.ldin;
-    g.B = W(rn.iW); g.ldb = ld(rn.iW); g.C = slab(rn.xw, (long)c * Tc, (long)n * G); g.ldc = G; g.c_type = act; g.bias = Wf(rn.ib);
-    gemm_on(g, st_pipe, c + 1 < NC ? psms : sm_count);     // the last chunk starts when the producer is done: the whole chip
-  }
-  cudaEvent_t d = next_event();
-  MVAE_CUDA(cudaEventRecord(d, st_pipe));
-  MVAE_CUDA(cudaStreamWaitEvent(st, d, 0));
-}
-
-// --------------------------------------------------------------------------------------------- time-chunked layer pipeline
-cudaEvent_t Model::next_event() {
-  if (ev_next == ev_pool.size()) {
-    cudaEvent_t e;
-    MVAE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ev_pool.push_back(e);
-  }
-  return ev_pool[ev_next++];
-}
-
-bool Model::chunked_ok(int steps, int nc) const {
-  return nc > 1 && use_branch && use_cluster_fwd && use_cluster_bwd && steps % nc == 0 && steps / nc >= 8;
-}
-
-// grid of a pipe-stream GEMM: only the SMs that stay free while the stack's and the branch's clusters are resident.  A larger grid would leave
-// CTAs pending; those take the SMs a finishing chunk releases and hold them until the GEMM runs out of tiles, so the next chunk's clusters
-// (16 free SMs in one GPC each) could not form
-int Model::pipe_grid(int n) const {
-  if (pipe_sms > 0) return std::min(pipe_sms, sm_count);
-  const int groups = (n + 63) / 64;
-  const int held = H == 512 ? 16 * 7 : 8 * 2 * std::min(groups, 8);
-  return std::max(16, sm_count - held);
-}
-
-// Forward over a stack of layers (jobs[0] = bottom).  Layer k runs as `chunks` launches of T / chunks steps (the cluster kernel continues from the
-// h slab / c stash the previous launch left); the moment chunk c of layer k is done, the input projection of chunk c of layer k + 1 starts on
-// the pipe stream, and layer k + 1 chunk c waits only for that.  The independent velocity / instrument recurrences go to the branch stream at
-// the first launch of layer `branch_at`, limited to the cluster slots the stack leaves free (a straggling branch cluster would otherwise take
-// a slot between two chunks of the stack and halve its width).
-void Model::stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel, FwdJob* binstr) {
-  const int L = (int)jobs.size(), NC = chunks, Tc = jobs[0].r->steps / NC, psms = pipe_grid(n);
-  const int bat = std::min(branch_at, L - 1);
-  ev_next = 0;
-  rec_forward_prepare(jobs[0], n);                      // one-hot table / whole projection of the bottom layer + its initial-state slab
-  prof_begin(PC_REC_FWD);
-  for (int k = 1; k < L; ++k) {
-    Rec& r = *jobs[k].r;
-    if (jobs[k].h0) k_copy2d(act, act, n, H, jobs[k].h0, jobs[k].ld0, r.hseq, H, st);
-    else MVAE_CUDA(cudaMemsetAsync(r.hseq, 0, (size_t)n * H * asz(), st));
-  }
-  std::vector<RecPersistArgs> base((size_t)L);
-  for (int k = 0; k < L; ++k) base[(size_t)k] = fwd_args(jobs[k], n, 0, 0, true);   // packs U (main stream, before the first launch)
-  prof_end();
-  // cluster slots the branch may hold while the stack runs: 16-CTA clusters: 7 co-resident, the stack uses ceil(groups / 2)
-  const int groups = (n + 63) / 64;
-  const int free_slots = H == 512 ? std::max(1, 7 - (groups + 1) / 2) : 0;
-  auto launch_branch = [&]() {
-    branch_begin();
-    for (FwdJob* j : {bvel, binstr}) {
-      if (!j) continue;
-      rec_forward_prepare(*j, n);
-      RecPersistArgs a = fwd_args(*j, n, cur_slot, 0, true);
-      if (free_slots > 0 && (groups + 1) / 2 > free_slots) a.ng = 3;     // fewer, wider clusters
-      const int ngb = a.ng > 0 ? a.ng : 2, ncl_all = (groups + ngb - 1) / ngb;
-      if (free_slots > 0 && ncl_all > free_slots) {
-        for (int c0 = 0; c0 < ncl_all; c0 += free_slots) { a.cl0 = c0; a.ncl = free_slots; rec_cluster_forward(a, st); }
-      } else {
-        rec_cluster_forward(a, st);
-      }
-    }
-    branch_end();
-  };
-  std::vector<cudaEvent_t> proj_done((size_t)NC), proj_next((size_t)NC);
-  for (int k = 0; k < L; ++k) {
-    for (int c = 0; c < NC; ++c) {
-      if (k > 0) MVAE_CUDA(cudaStreamWaitEvent(st, proj_done[(size_t)c], 0));
-      RecPersistArgs a = base[(size_t)k];
-      a.t0 = c * Tc; a.steps = Tc;
-      if (k == bat && c == 0) fork_if_pending();
-      prof_begin(PC_REC_FWD);               // (prof_begin / prof_end pairs do not nest: the branch work below opens its own)
-      rec_cluster_forward(a, st);
-      prof_end();
-      if (k == bat && c == 0 && (bvel || binstr)) launch_branch();
-      if (k + 1 < L) {
-        Rec& rn = *jobs[k + 1].r;
-        cudaEvent_t e = next_event();
-        MVAE_CUDA(cudaEventRecord(e, st));
-        MVAE_CUDA(cudaStreamWaitEvent(st_pipe, e, 0));
-        GemmArgs g; g.M = Tc * n; g.N = G; g.K = rn.Din; g.A = slab(jobs[k].r->hseq, (long)c * Tc + 1, (long)n * H); g.lda = rn.ldin;
-        g.B = W(rn.iW); g.ldb = ld(rn.iW); g.C = slab(rn.xw, (long)c * Tc, (long)n * G); g.ldc = G; g.c_type = act; g.bias = Wf(rn.ib);
-        gemm_on(g, st_pipe, psms);
-        cudaEvent_t d = next_event();
-        MVAE_CUDA(cudaEventRecord(d, st_pipe));
-        proj_next[(size_t)c] = d;
-      }
-    }
-    proj_done.swap(proj_next);
-  }
-}
-
-// Reverse sweeps over a stack of layers (stack[0] = top).  Chunks run latest-first; the (dh, dc) carry between two chunks of a layer goes
-// through rec_carry (bf16, ping-pong); dx = dG W^T of a chunk starts on the pipe stream as soon as the chunk's dG is complete, and the layer
-// below waits per chunk.  Weight gradients of a layer are whole-sequence GEMMs on the side stream after its last chunk.
-void Model::stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJob>& sidej, int n, bool last_group) {
-  const int L = (int)stack.size(), NC = chunks_bwd, Tc = stack[0].r->steps / NC, psms = pipe_grid(n);
-  ev_next = 0;
-  std::vector<RecPersistArgs> base((size_t)L);
-  for (int k = 0; k < L; ++k) base[(size_t)k] = bwd_args(stack[k], n, 0, 0, true);   // packs U^T (main stream)
-  const int groups = (n + 63) / 64;
-  const int free_slots = H == 512 ? std::max(1, 7 - (groups + 1) / 2) : 0;
-  auto launch_branch = [&]() {
-    branch_begin();
-    for (auto& j : sidej) {
-      prof_begin(PC_REC_BWD);
-      RecPersistArgs a = bwd_args(j, n, cur_slot, 0, true);
-      const int ncl_all = (groups + 1) / 2;
-      if (free_slots > 0 && ncl_all > free_slots) {
-        for (int c0 = 0; c0 < ncl_all; c0 += free_slots) { a.cl0 = c0; a.ncl = free_slots; rec_cluster_backward(a, st); }
-      } else {
-        rec_cluster_backward(a, st);
-      }
-      prof_end();
-      rec_backward_gemms(j, n);
-    }
-    branch_end();
-  };
-  branch_fork();
-  std::vector<cudaEvent_t> dx_done((size_t)NC), dx_next((size_t)NC);
-  for (int k = 0; k < L; ++k) {
-    BwdJob& j = stack[k];
-    Rec& r = *j.r;
-    prof_begin(PC_REC_BWD);
-    for (int i = 0; i < NC; ++i) {
-      const int c = NC - 1 - i;                         // chunk of steps [c Tc, (c + 1) Tc)
-      if (k > 0) MVAE_CUDA(cudaStreamWaitEvent(st, dx_done[(size_t)c], 0));
-      RecPersistArgs a = base[(size_t)k];
-      a.t0 = c * Tc; a.steps = Tc;
-      if (i > 0) { a.dh_last = rec_carry[(i - 1) & 1]; a.dc_last = rec_carry[2 + ((i - 1) & 1)]; a.ld_last = H; }
-      if (i + 1 < NC) { a.dS_h = rec_carry[i & 1]; a.dS_c = rec_carry[2 + (i & 1)]; a.ldS = H; }
-      if (k == 0 && i == 0) fork_if_pending();
-      rec_cluster_backward(a, st);
-      cudaEvent_t e = nullptr;
-      if (j.need_dx || (use_side && wgrad_per_chunk)) { e = next_event(); MVAE_CUDA(cudaEventRecord(e, st)); }
-      if (j.need_dx) {
-        MVAE_CUDA(cudaStreamWaitEvent(st_pipe, e, 0));
-        GemmArgs g; g.M = Tc * n; g.N = r.Din; g.K = G; g.A = slab(r.xw, (long)c * Tc, (long)n * G); g.lda = G; g.B = W(r.iW); g.ldb = ld(r.iW);
-        g.transB = true; g.C = slab(j.dx_out, (long)c * Tc, (long)n * H); g.ldc = H; g.c_type = act;
-        gemm_on(g, st_pipe, psms);
-        cudaEvent_t d = next_event();
-        MVAE_CUDA(cudaEventRecord(d, st_pipe));
-        dx_next[(size_t)c] = d;
-      }
-      if (use_side && wgrad_per_chunk) {   // the chunk's dG is final: its share of the weight gradients can start now
-        prof_end();
-        MVAE_CUDA(cudaStreamWaitEvent(side, e, 0));
-        rec_backward_wgrads(j, n, side, (last_group && k + 1 == L && i + 1 == NC) ? sm_count : side_sms, c * Tc, Tc);
-        prof_begin(PC_REC_BWD);
-      }
-    }
-    prof_end();
-    dx_done.swap(dx_next);
-    const bool tail = last_group && k + 1 == L;
-    if (use_side && wgrad_per_chunk) {
-      // already handed over chunk by chunk above
-    } else if (use_side) {
-      MVAE_CUDA(cudaEventRecord(ev_fork, st));          // dG of this layer is final here
-      MVAE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-      rec_backward_wgrads(j, n, side, tail ? sm_count : side_sms);
-    } else {
-      rec_backward_wgrads(j, n, st, sm_count);
-    }
-    if (k == 0 && !sidej.empty()) launch_branch();      // issued after the top layer's weight gradients so that those are first in the side stream
-  }
-  branch_join();
-}
-
 // --------------------------------------------------------------------------------------------- encoder (vae_definition.py:443-516)
 void Model::encoder_forward(int n) {
   // the first pitch layer and the velocity stream are independent and equally long: they share a launch
   FwdJob jv; jv.r = &enc_vel; jv.kind = IN_RANK1; jv.X = slab(Xv_ext, 1, (long)n * VD);
-  if (ne >= 2 && !inference_pass && chunked_ok(T, chunks)) {
-    std::vector<FwdJob> jobs((size_t)ne);
-    for (int k = 0; k < ne; ++k) {
-      FwdJob& jp = jobs[(size_t)k]; jp.r = &enc_pitch[k]; jp.kind = IN_DENSE;
-      jp.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
-      if (k == 0) { jp.onehot = true; jp.idx = cur_pitch; jp.idx_ld = T; jp.idx_shift = 0; }
-    }
-    FwdJob ji; ji.r = &enc_instr; ji.kind = IN_DENSE; ji.X = slab(Xi_ext, 1, (long)n * ID);
-    branch_fork();
-    stack_forward_chunked(jobs, n, &jv, &ji);
-    branch_join();
-    return;
-  }
   if (use_branch) {
     branch_fork();
-    ev_next = 0;
-    bool xw_ready = false;
     for (int k = 0; k < ne; ++k) {
       FwdJob jp; jp.r = &enc_pitch[k]; jp.kind = IN_DENSE;
       jp.X = k == 0 ? slab(Xp_ext, 1, (long)n * PD) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
       if (k == 0) { jp.onehot = true; jp.idx = cur_pitch; jp.idx_ld = T; jp.idx_shift = 0; }
-      jp.xw_ready = xw_ready; xw_ready = false;
-      const bool ov = k + 1 < ne && overlap_ok(T);
-      if (ov) overlap_arm(jp, n);
       rec_forward_jobs(&jp, nullptr, n);
-      if (ov) { overlap_project(jp, enc_pitch[k + 1], n); xw_ready = true; }
       if (k == 0) {   // velocity and instrument streams: next to the pitch stack
         branch_begin();
         rec_forward_jobs(&jv, nullptr, n);
@@ -1004,34 +748,14 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
   auto st1 = [&](int r) { return (const char*)S + (size_t)(spc * r) * H * asz(); };
   auto st2 = [&](int r) { return gru ? (const char*)nullptr : (const char*)S + (size_t)(2 * r + 1) * H * asz(); };
   FwdJob jv; jv.r = &dec_vel; jv.kind = tf ? IN_RANK1 : IN_NONE; jv.X = tf ? Xv_ext : nullptr; jv.h0 = st1(nd + 1); jv.c0 = st2(nd + 1); jv.ld0 = nS * H;
-  const bool chunked = nd >= 2 && !inference_pass && chunked_ok(T, chunks);
-  if (chunked) {
-    std::vector<FwdJob> jobs((size_t)nd);
-    for (int k = 0; k < nd; ++k) {
-      FwdJob& jp = jobs[(size_t)k]; jp.r = &dec_notes[k]; jp.h0 = st1(k); jp.c0 = st2(k); jp.ld0 = nS * H;
-      if (k == 0) { jp.kind = tf ? IN_DENSE : IN_NONE; jp.X = tf ? Y_ext_cur : nullptr; }
-      else { jp.kind = IN_DENSE; jp.X = slab(dec_notes[k - 1].hseq, 1, (long)n * H); }
-      if (k == 0 && tf) { jp.onehot = true; jp.idx = cur_target; jp.idx_ld = T; jp.idx_shift = 1; }
-    }
-    FwdJob ji; ji.r = &dec_instr; ji.kind = tf ? IN_DENSE : IN_NONE; ji.X = tf ? Xi_ext : nullptr; ji.h0 = st1(nd); ji.c0 = st2(nd); ji.ld0 = nS * H;
-    branch_fork();
-    stack_forward_chunked(jobs, n, &jv, &ji);
-    branch_join();
-  }
-  if (use_branch && !chunked) branch_fork();
-  bool dec_xw_ready = false;
-  if (!chunked) ev_next = 0;
-  for (int k = 0; k < nd && !chunked; ++k) {
+  if (use_branch) branch_fork();
+  for (int k = 0; k < nd; ++k) {
     FwdJob jp; jp.r = &dec_notes[k]; jp.h0 = st1(k); jp.c0 = st2(k); jp.ld0 = nS * H;
     if (k == 0) { jp.kind = tf ? IN_DENSE : IN_NONE; jp.X = tf ? Y_ext_cur : nullptr; }
     else { jp.kind = IN_DENSE; jp.X = slab(dec_notes[k - 1].hseq, 1, (long)n * H); }
     if (k == 0 && tf) { jp.onehot = true; jp.idx = cur_target; jp.idx_ld = T; jp.idx_shift = 1; }   // x_t = y_{t-1}, x_0 = 0
     if (use_branch) {
-      jp.xw_ready = dec_xw_ready; dec_xw_ready = false;
-      const bool ov = k + 1 < nd && overlap_ok(T);
-      if (ov) overlap_arm(jp, n);
       rec_forward_jobs(&jp, nullptr, n);
-      if (ov) { overlap_project(jp, dec_notes[k + 1], n); dec_xw_ready = true; }
       if (k == 0) {
         branch_begin();
         rec_forward_jobs(&jv, nullptr, n);
@@ -1042,10 +766,8 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
       rec_forward_jobs(&jp, k == 0 ? &jv : nullptr, n);
     }
   }
-  if (!chunked) {
-    if (use_branch) branch_join();
-    else rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
-  }
+  if (use_branch) branch_join();
+  else rec_forward(dec_instr, n, tf ? IN_DENSE : IN_NONE, tf ? Xi_ext : nullptr, st1(nd), st2(nd), nS * H);
   prof_begin(PC_GEMM);
   { GemmArgs g; g.M = T * n; g.N = Dp; g.K = H; g.A = slab(dec_notes[nd - 1].hseq, 1, (long)n * H); g.lda = H; g.B = W(iWy); g.ldb = ld(iWy);
     g.C = Pn; g.ldc = ld_pn; g.c_type = DT_F32; g.bias = Wf(iby); gemm(g); }

@@ -50,10 +50,6 @@ struct FwdJob {
   const unsigned char* idx = nullptr;
   int idx_ld = 0, idx_shift = 0;
   bool onehot = false;
-  // projection overlap (MVAE_XW_OVERLAP): this recurrence publishes per-time-chunk progress counters / its xw buffer is filled elsewhere
-  unsigned* progress = nullptr;
-  int progress_every = 0;
-  bool xw_ready = false;
 };
 
 // one backward recurrence: where its inputs / external gradients come from and where its outputs go
@@ -154,7 +150,6 @@ struct Model {
   cudaStream_t st_branch = nullptr, st_saved = nullptr;
   cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
   bool use_branch = false;
-  int branch_bwd_ncl = 0;             // > 0: branch-stream reverse sweeps run as waves of this many clusters (MVAE_BRANCH_BWD_NCL)
   int cur_slot = 0;                   // which set of exchange buffers the recurrence being issued uses
   bool fork_pending = false;          // the fork point is the launch of the next main-stream recurrence (it must win the cluster slots)
   void fork_if_pending();
@@ -162,30 +157,6 @@ struct Model {
   void branch_begin();
   void branch_end();
   void branch_join();
-  // time-chunked layer pipeline (MVAE_CHUNKS > 1): a stack of layers runs its recurrences in `chunks` launches of T / chunks steps each, so that
-  // the batched GEMM between two layers (input projection forward, dx backward) of chunk c runs on the pipe stream while the producing
-  // layer is already working on chunk c + 1: the GEMMs leave the critical chain
-  int chunks = 1, chunks_bwd = 1;     // forward / backward (MVAE_CHUNKS / MVAE_CHUNKS_BWD)
-  int pipe_sms = 0;                   // MVAE_PIPE_SMS: grid of a pipe-stream GEMM (0 = the SMs the resident clusters leave free)
-  int pipe_grid(int n) const;
-  // projection overlap: a layer's recurrence stays ONE launch but publishes a counter per time chunk; the next layer's input projection of that
-  // chunk is a GEMM on the pipe stream gated by a stream wait (cuStreamWaitValue32) on the counter: no relaunch, no slot churn, no carry
-  int xw_overlap = 0;                 // MVAE_XW_OVERLAP = number of chunks (0 = off)
-  unsigned* rec_progress = nullptr;   // 2 x 16 counters (ping-pong between consecutive producing layers)
-  int progress_flip = 0;
-  bool overlap_ok(int steps) const { return xw_overlap > 1 && use_cluster_fwd && st_pipe && steps % xw_overlap == 0 && steps / xw_overlap >= 8; }
-  void overlap_arm(FwdJob& producer, int n);                                  // before the producer is launched
-  void overlap_project(const FwdJob& producer, Rec& consumer, int n);         // after the producer is launched
-  bool wgrad_per_chunk = false;       // chunked reverse sweeps: MVAE_WGRAD_CHUNKS=1 hands the weight-gradient GEMMs over per chunk (measured slower)
-  int branch_at = 0;                  // the branch recurrences fork at the first launch of this layer of the stack (0 = first layer)
-  cudaStream_t st_pipe = nullptr;
-  std::vector<cudaEvent_t> ev_pool;   // disable-timing events, handed out round-robin within a step
-  size_t ev_next = 0;
-  cudaEvent_t next_event();
-  void* rec_carry[4] = {nullptr, nullptr, nullptr, nullptr};   // (n, H) act: dh / dc carried between the chunks of a reverse sweep (ping-pong)
-  bool chunked_ok(int steps, int nc) const;
-  void stack_forward_chunked(std::vector<FwdJob>& jobs, int n, FwdJob* bvel, FwdJob* binstr);
-  void stack_backward_chunked(std::vector<BwdJob>& stack, std::vector<BwdJob>& side, int n, bool last_group);
   const unsigned char* cur_pitch = nullptr;   // device u8 rolls of the batch in flight (class indices)
   const unsigned char* cur_target = nullptr;
   bool inference_pass = false;      // forward only (style transfer / predict): the recurrences skip the BPTT stash
@@ -231,7 +202,7 @@ struct Model {
   void gemm_on(GemmArgs g, cudaStream_t s, int sms);
   void prof_begin(int cls, cudaStream_t s = nullptr, const char* tag = nullptr);
   void prof_end(cudaStream_t s = nullptr);
-  void rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms, int t0 = 0, int nsteps = -1);
+  void rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms);
   void prof_collect();
   void dump_trace(const char* dir, const Rec& r, int nctas = 1);
 

@@ -23,7 +23,6 @@ struct RecPersistArgs {
   const void* dhext = nullptr;        // (steps, n, H) bf16 or null
   const void* dh_last = nullptr;      // (n, ld_last) bf16 or null: extra gradient into the last step's h
   int ld_last = 0;
-  const void* dc_last = nullptr;      // cluster kernels, time-chunked sweeps: (n, ld_last) bf16 cell-state gradient carried in (null = zeros)
   void* dG = nullptr;                 // (steps, n, 4H) bf16 written
   void* dS_h = nullptr;               // (n, ldS) bf16 gradient wrt h0 / c0 (or null)
   void* dS_c = nullptr;
@@ -33,11 +32,6 @@ struct RecPersistArgs {
   void* partial = nullptr;            // K-split backward: exchange buffer, rec_persist_partial_bytes
   void* trace = nullptr;              // optional: 8 steps x 16 clock64 stamps of CTA 0 (profiling aid)
   int no_stash = 0;                   // cluster forward: inference, do not write the gates / c stash
-  int t0 = 0;                         // cluster kernels: this launch covers steps [t0, t0 + steps) of the sequence (time-chunked recurrences); time-indexed buffers are passed un-offset
-  unsigned* progress = nullptr;       // cluster forward: per-time-chunk completion counters (see Cluster2P::progress); expected value = (H / 32) * ceil(n / 64)
-  int progress_every = 0;             //   steps per chunk (0 = no publishing)
-  int ng = 0;                         // cluster forward: row groups per cluster (0 = the launcher's choice)
-  int cl0 = 0, ncl = 0;               // cluster kernels: launch only clusters [cl0, cl0 + ncl) of the batch (ncl = 0: all from cl0)
   // cluster forward only: input projection computed inside the kernel instead of streamed from the (steps, n, 4H) xw buffer
   int x_mode = 0;                     // 0: xw buffer; 1: one-hot input = row gather from xtab; 2: scalar input (x w + b)
   const void* xtab = nullptr;         // x_mode 1: (64, 4H) bf16: row i = W[i] + b for the one-hot class i, row 63 = b (zero input)

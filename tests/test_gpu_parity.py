@@ -252,76 +252,6 @@ def test_persistent_rnn_matches_streamed(shape, feedback, variant):
         assert np.abs(gs[k] - gp[k]).max() <= 3e-2 * scale + 1e-9, (k, float(np.abs(gs[k] - gp[k]).max()), float(scale))
 
 
-@pytest.mark.parametrize("shape,chunks", [((64, 256, 32, 70), 4), ((32, 512, 48, 130), 2), ((64, 512, 48, 520), 4), ((48, 512, 24, 65), 3)])
-@pytest.mark.parametrize("feedback,variant", [("teacher_forced", "standard"), ("as_wired", "recurrentshop_recalled")])
-def test_time_chunked_layer_pipeline_matches_whole_sequence_launches(shape, chunks, feedback, variant, monkeypatch):
-    """MVAE_CHUNKS / MVAE_CHUNKS_BWD > 1: the layer stacks run their cluster recurrences as several launches of T / chunks steps (forward: continue from the h slab /
-    c stash; backward: (dh, dc) carried through a bf16 buffer), with the inter-layer GEMMs of a chunk on a pipe stream and the branch
-    recurrences limited to the free cluster slots (sub-range launches, 3 groups per cluster).  Same arithmetic as the whole-sequence
-    launches except for the bf16 rounding of c / dc at the chunk boundaries.  520 rows = 9 groups = 5 clusters (ragged last one)."""
-    T, H, L, n = shape
-    res = {}
-    for nc in (1, chunks):
-        monkeypatch.setenv("MVAE_CHUNKS", str(nc))
-        monkeypatch.setenv("MVAE_CHUNKS_BWD", str(nc))
-        monkeypatch.setenv("MVAE_WGRAD_CHUNKS", "1" if chunks == 4 else "0")      # per-chunk / per-layer weight-gradient GEMMs
-        ecfg, _ = util.make_cfgs(T=T, H=H, L=L, feedback=feedback, variant=variant, precision="bf16", max_batch=n, rnn_mode="persistent")
-        w = util.make_weights(ecfg)
-        eng = _engine(ecfg, w)
-        r, hist, eps, sw = util.make_batch(ecfg, n, weights=True)
-        m = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)
-        g = eng.get_grads()
-        m2 = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)      # a second step: buffers / events are reused
-        res[nc] = (m, g, m2)
-        eng.close()
-    monkeypatch.delenv("MVAE_CHUNKS")
-    monkeypatch.delenv("MVAE_CHUNKS_BWD")
-    monkeypatch.delenv("MVAE_WGRAD_CHUNKS")
-    (ma, ga, ma2), (mb, gb, mb2) = res[1], res[chunks]
-    for k in METRIC_KEYS:
-        tol_k = 0.05 if "acc" in k else 2e-3 * max(1.0, abs(ma[k]))
-        assert abs(ma[k] - mb[k]) <= tol_k, (k, ma[k], mb[k])
-        assert abs(ma2[k] - mb2[k]) <= (0.05 if "acc" in k else 5e-3 * max(1.0, abs(ma2[k]))), (k, ma2[k], mb2[k])
-    for k in ga:
-        scale = max(np.abs(ga[k]).max(), 1e-6)
-        assert np.abs(ga[k] - gb[k]).max() <= 1e-2 * scale + 1e-9, (k, float(np.abs(ga[k] - gb[k]).max()), float(scale))
-
-
-@pytest.mark.parametrize("shape,nc", [((64, 256, 32, 70), 4), ((32, 512, 48, 130), 2), ((64, 512, 48, 520), 8), ((48, 512, 24, 65), 3)])
-def test_projection_overlap_is_exact(shape, nc, monkeypatch):
-    """MVAE_XW_OVERLAP = nc: a layer's forward recurrence stays one launch but publishes a counter per time chunk; the next layer's input
-    projection runs per chunk on the pipe stream behind cuStreamWaitValue32 on that counter.  Same kernels, same arithmetic per element:
-    metrics and gradients must be identical to the un-overlapped schedule (train step, second train step, and the inference path)."""
-    T, H, L, n = shape
-    res = {}
-    for v in (0, nc):
-        monkeypatch.setenv("MVAE_XW_OVERLAP", str(v))
-        ecfg, _ = util.make_cfgs(T=T, H=H, L=L, feedback="teacher_forced", precision="bf16", max_batch=n, rnn_mode="persistent")
-        w = util.make_weights(ecfg)
-        eng = _engine(ecfg, w)
-        r, hist, eps, sw = util.make_batch(ecfg, n, weights=True)
-        P, Ii, Vv = eng.style_transfer(r.pitch, r.instr, r.velocity, 0, 1, None, "as_wired")      # inference pass (no stash)
-        m = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)
-        g = eng.get_grads()
-        m2 = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps, sw)
-        res[v] = (m, g, m2, P, Vv)
-        eng.close()
-    monkeypatch.delenv("MVAE_XW_OVERLAP")
-    (ma, ga, ma2, Pa, Va), (mb, gb, mb2, Pb, Vb) = res[0], res[nc]
-    # expected identical; the bound below still catches a chunk of the projection computed from stale rows (which would move whole time ranges)
-    assert (Pa != Pb).mean() <= 1e-3 and np.abs(Va - Vb).max() <= 1e-3, (float((Pa != Pb).mean()), float(np.abs(Va - Vb).max()))
-    for k in METRIC_KEYS:
-        assert ma[k] == mb[k] or abs(ma[k] - mb[k]) <= 1e-6 * max(1.0, abs(ma[k])), (k, ma[k], mb[k])
-        # the second step runs on weights updated from gradients that were accumulated with fp32 atomics (split-K; order differs from run to run, with
-        # or without the overlap): last-bit weight differences may flip a near-tied argmax, i.e. move an accuracy by a few 1 / (n T)
-        tol2 = 1e-3 if "acc" in k else 1e-4 * max(1.0, abs(ma2[k]))
-        assert abs(ma2[k] - mb2[k]) <= tol2, (k, ma2[k], mb2[k])
-    for k in ga:
-        # weight gradients accumulate with fp32 atomics (split-K): order-dependent in the last bits
-        scale = max(np.abs(ga[k]).max(), 1e-6)
-        assert np.abs(ga[k] - gb[k]).max() <= 1e-5 * scale + 1e-9, (k, float(np.abs(ga[k] - gb[k]).max()), float(scale))
-
-
 def test_cluster_rnn_sigmoid_gates():
     """The logistic-sigmoid gate variant (north_star's wording; the reference default is hard_sigmoid) through the cluster kernels."""
     T, H, L, n = 16, 256, 32, 70
