@@ -64,6 +64,13 @@ typedef struct mvae_config {
   int cell_type;               /* MVAE_CELLTYPE_*: LSTM (north_star; cluster / persistent kernels) or GRU (the reference's shipped default;
                                   step-streamed kernels).  GRU: Keras 2.0.8 GRU encoders (blocks [z|r|h], h' = z h + (1-z) hh) and recurrentshop
                                   GRUCell decoders (as recalled: h' = (1-z) h + z hh; dec_cell_variant applies to the LSTM cells only)      */
+  int model_kind;              /* 0: the three-stream VAE (everything above).  1: a STYLE CLASSIFIER (pitch_classifier.py:89-103,
+                                  velocity_classifier.py:110-118, instrument_classifier.py:93-103): num_layers_encoder stacked recurrent layers of
+                                  lstm_size units over a (input_length, D) sequence -> last state -> Dense(num_composers, softmax), categorical
+                                  cross-entropy, Adam.  Only the mvae_cls_* entry points and the parameter / optimizer calls apply to it.       */
+  int cls_scalar_input;        /* classifier: 0 = one-hot input of input_dim classes given as class indices (batch.pitch, u8 [n, input_length]:
+                                  the pitch roll, or the 4 x 16 instrument matrix with input_length = 4, input_dim = 16); 1 = scalar input
+                                  (batch.velocity, f32 [n, input_length]).  Labels: batch.style.                                              */
 } mvae_config;
 
 /* One mini-batch = a consecutive slice of <= batch_size chunks of a song
@@ -152,6 +159,19 @@ int mvae_set_postprocess(mvae_handle h, int scope, float velocity_threshold /* s
 /* the same rules on caller-supplied packed rolls (host): pitch u8 [n,T] (input_dim-1 = silent), velocity f32 [n,T] in place, held u8 [n,T] or NULL */
 int mvae_postprocess_host(mvae_handle h, int n, const uint8_t* pitch, const uint8_t* song_start /* [n] or NULL */, int scope,
                           float* velocity_inout, uint8_t* held_out);
+
+/* ---- history latents from the batch itself (opt-in): mode 1 makes train / eval steps build the decoder's history input from the
+ *      step's own z -- H[i] = z[i-1] inside a song, 0 on a song's first chunk (flags set with mvae_set_song_start_host for the NEXT call; none =
+ *      one song), row 0 continuing the previous call's last row -- instead of reading batch.history, which the reference fills from a separate
+ *      encoder.predict of the song (vae_training.py:788-798).  Saves that encoder pass; differs from the reference in that the history comes from
+ *      the same weights and the same epsilon draw as the step.  mode 0 (default) = batch.history. ---- */
+int mvae_set_history_mode(mvae_handle h, int mode);
+int mvae_set_song_start_host(mvae_handle h, const uint8_t* song_start /* [n] or NULL */, int n);
+
+/* ---- style classifiers (model_kind = 1; the evaluators of vae_evaluation.py:110-117): one mini-batch of model.fit / evaluate / predict.
+ *      metrics out: v[MVAE_M_LOSS] = v[MVAE_M_STYLE_LOSS] = mean categorical cross-entropy, v[MVAE_M_STYLE_ACC] = accuracy; probs [n, num_composers] ---- */
+int mvae_cls_train_step_host(mvae_handle h, const mvae_batch* host_batch, mvae_metrics* out);
+int mvae_cls_eval_step_host(mvae_handle h, const mvae_batch* host_batch, mvae_metrics* out, float* probs_out /* or NULL */);
 
 /* ---- multi-GPU data parallelism: ONE ncclAllReduce(sum) over the gradient arena per step ---- */
 int mvae_nccl_unique_id(void* id_out_128_bytes);

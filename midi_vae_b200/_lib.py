@@ -27,7 +27,7 @@ class MvaeConfig(C.Structure):
         "num_composers", "num_layers_encoder", "num_layers_decoder", "history", "extra_layer", "split_lstm_vector",
         "gate_act", "dec_cell_variant", "decoder_feedback", "precision", "rnn_mode", "max_batch")] + [(n, C.c_float) for n in (
         "beta", "prior_mean", "prior_std", "notes_weight", "meta_instrument_weight", "meta_velocity_weight", "composer_weight",
-        "learning_rate", "adam_beta_1", "adam_beta_2", "adam_epsilon")] + [("cell_type", C.c_int)]
+        "learning_rate", "adam_beta_1", "adam_beta_2", "adam_epsilon")] + [("cell_type", C.c_int), ("model_kind", C.c_int), ("cls_scalar_input", C.c_int)]
 
 
 class MvaeBatch(C.Structure):
@@ -76,6 +76,10 @@ SYMBOLS = {
     "mvae_style_transfer_host": (C.c_int, [_H, _P(MvaeBatch), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvae_set_postprocess": (C.c_int, [_H, C.c_int, C.c_float, C.c_int, C.c_int]),
     "mvae_postprocess_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mvae_set_history_mode": (C.c_int, [_H, C.c_int]),
+    "mvae_set_song_start_host": (C.c_int, [_H, C.c_void_p, C.c_int]),
+    "mvae_cls_train_step_host": (C.c_int, [_H, _P(MvaeBatch), _P(MvaeMetrics)]),
+    "mvae_cls_eval_step_host": (C.c_int, [_H, _P(MvaeBatch), _P(MvaeMetrics), C.c_void_p]),
     "mvae_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mvae_nccl_init": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
     "mvae_world_size": (C.c_int, [_H, _P(C.c_int)]),

@@ -18,7 +18,8 @@ void Model::forward_backward(const mvae_batch& b, float* dev_metrics, cudaStream
   // the cluster / persistent paths are ~120 launches on three streams: nothing to gain from a graph.  Profiling needs its events un-captured.
   if (!step_graph_on || use_persist || profiling || (overlap_allreduce && world > 1)) { forward_backward_body(b, dev_metrics); return; }
   const std::vector<size_t> key = {(size_t)b.n, (size_t)b.pitch, (size_t)b.target, (size_t)b.instr, (size_t)b.velocity, (size_t)b.style,
-                                   (size_t)b.history, (size_t)b.eps, (size_t)b.w_notes, (size_t)dev_metrics};
+                                   (size_t)b.history, (size_t)b.eps, (size_t)b.w_notes, (size_t)dev_metrics,
+                                   (size_t)history_mode, (size_t)song_start_set, (size_t)carry_valid};   // host-side switches baked into the launches
   if (step_graphs.size() > 64) {   // callers that keep passing fresh buffers would grow the cache without bound
     for (auto& kv : step_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     step_graphs.clear();
@@ -509,6 +510,62 @@ int mvae_postprocess_host(mvae_handle h, int n, const uint8_t* pitch, const uint
   if (held_out) MVAE_CUDA(cudaMemcpyAsync(held_out, M.o_held, nt, cudaMemcpyDeviceToHost, M.st));
   MVAE_CUDA(cudaStreamSynchronize(M.st));
   M.d2h_bytes += nt * 4 + (held_out ? nt : 0);
+  API_END()
+}
+
+int mvae_set_history_mode(mvae_handle h, int mode) {
+  API_BEGIN(h)
+  MVAE_REQUIRE(mode == 0 || mode == 1, "history mode: 0 = batch.history (the reference's separate encoder pass), 1 = from the batch's own z");
+  MVAE_REQUIRE(!M.cls, "not applicable to a classifier handle");
+  M.history_mode = mode; M.carry_valid = false; M.song_start_set = false;
+  API_END()
+}
+
+int mvae_set_song_start_host(mvae_handle h, const uint8_t* song_start, int n) {
+  API_BEGIN(h)
+  MVAE_REQUIRE(!M.cls, "not applicable to a classifier handle");
+  MVAE_REQUIRE(n >= 0 && n <= M.NB, "song_start: at most max_batch flags");
+  if (song_start && n > 0) {
+    MVAE_CUDA(cudaStreamSynchronize(M.stream));     // the staging below is a plain pageable copy: keep it out of a step in flight
+    MVAE_CUDA(cudaMemcpy(M.d_song_start, song_start, (size_t)n, cudaMemcpyHostToDevice));
+    M.h2d_bytes += (size_t)n;
+    M.song_start_set = true;
+  } else {
+    M.song_start_set = false;
+  }
+  API_END()
+}
+
+static mvae_batch cls_upload(Model& M, const mvae_batch& hb) {
+  MVAE_REQUIRE(M.cls, "this handle is not a style classifier (mvae_config::model_kind = 1)");
+  MVAE_REQUIRE(hb.n >= 1 && hb.n <= M.NB, "mini-batch size must be in 1..max_batch");
+  mvae_batch in{}; in.n = hb.n;
+  in.pitch = M.cls_scalar ? nullptr : hb.pitch; in.velocity = M.cls_scalar ? hb.velocity : nullptr; in.style = hb.style;
+  return M.upload(in);
+}
+
+int mvae_cls_train_step_host(mvae_handle h, const mvae_batch* hb, mvae_metrics* out) {
+  API_BEGIN(h)
+  MVAE_REQUIRE(hb != nullptr, "batch is null");
+  M.st = M.stream;
+  mvae_batch d = cls_upload(M, *hb);
+  M.cls_forward(d, true);
+  M.cls_backward(d);
+  M.apply_update(1.0f, nullptr);
+  fetch_metrics(M, out);
+  API_END()
+}
+
+int mvae_cls_eval_step_host(mvae_handle h, const mvae_batch* hb, mvae_metrics* out, float* probs_out) {
+  API_BEGIN(h)
+  MVAE_REQUIRE(hb != nullptr, "batch is null");
+  M.st = M.stream;
+  mvae_batch d = cls_upload(M, *hb);
+  M.inference_pass = true;
+  struct Reset { bool& f; ~Reset() { f = false; } } reset{M.inference_pass};
+  M.cls_forward(d, false);
+  fetch_metrics(M, out);
+  fetch_f32(M, M.Pn, d.n, M.C, M.ld_pn, probs_out);
   API_END()
 }
 

@@ -598,6 +598,22 @@ __global__ void swap_shift_kernel(int n, int L, int ldl, const float* mu, const 
   }
 }
 
+// history latents taken from the batch itself (opt-in; vae_training.py:791-798 takes them from a separate encoder.predict of the same song):
+// q[b, L + j] = z[b - 1, j] inside a song, 0 on a song's first chunk; row 0 continues the previous call's last row (carry) unless it starts a song.
+template <typename AT>
+__global__ void self_history_kernel(int n, int L, int ldl, const float* __restrict__ z, const uint8_t* __restrict__ song_start, const float* __restrict__ carry,
+                                    int carry_valid, AT* q, int ldq) {
+  long total = (long)n * L;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int j = (int)(e % L);
+    long b = e / L;
+    const bool first = song_start && song_start[b];
+    float h = 0.f;
+    if (!first) h = b > 0 ? z[(b - 1) * ldl + j] : (carry_valid ? carry[j] : 0.f);
+    stf<AT>(q + b * ldq + L + j, h);
+  }
+}
+
 template <typename AT>
 __global__ void build_q_kernel(int n, int L, const float* z, const float* hist, int has_hist, AT* q, int ldq) {
   long total = (long)n * L;
@@ -846,6 +862,11 @@ void k_swap_shift(DT act, int n, int L, int ldl, const float* mu, const uint8_t*
     swap_shift_kernel<AT><<<nblk((long)n * L), TPB, 0, st>>>(n, L, ldl, mu, song_start, c_from, c_to, has_hist, (AT*)q, ldq, z_sw);
     LAUNCH_CHECK();
   });
+}
+
+void k_self_history(DT act, int n, int L, int ldl, const float* z, const uint8_t* song_start, const float* carry, int carry_valid, void* q, int ldq,
+                    cudaStream_t st) {
+  DISPATCH_ACT(act, { self_history_kernel<AT><<<nblk((long)n * L), TPB, 0, st>>>(n, L, ldl, z, song_start, carry, carry_valid, (AT*)q, ldq); LAUNCH_CHECK(); });
 }
 
 void k_build_q(DT act, int n, int L, const float* z, const float* hist, int has_hist, void* q, int ldq, cudaStream_t st) {

@@ -58,6 +58,8 @@ void k_postprocess_voices(int n, int T, int voices, int silent, float thr, int s
                           float* vel, uint8_t* held, cudaStream_t st);
 void k_swap_shift(DT act, int n, int L, int ldl, const float* mu, const uint8_t* song_start, int c_from, int c_to, int has_hist, void* q,
                   int ldq, float* z_sw, cudaStream_t st);
+void k_self_history(DT act, int n, int L, int ldl, const float* z, const uint8_t* song_start, const float* carry, int carry_valid, void* q, int ldq,
+                    cudaStream_t st);
 void k_build_q(DT act, int n, int L, const float* z, const float* hist, int has_hist, void* q, int ldq, cudaStream_t st);
 
 }  // namespace mvae

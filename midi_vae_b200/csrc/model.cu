@@ -55,6 +55,13 @@ void Model::build_params() {
   };
   enc_pitch.resize(ne);
   const std::string pre = gru ? "gru_" : "lstm_";     // Keras layer names of the two branches (vae_definition.py:457-472)
+  if (cls) {   // pitch_classifier.py:89-103: GRU x num_layers -> Dense(num_classes, softmax); names as in the shipped classifier files
+    for (int k = 0; k < ne; ++k)
+      add_rec(enc_pitch[k], pre + std::to_string(k + 1), T, k == 0 ? (cls_scalar ? 1 : Dp) : H, k == 0 ? (cls_scalar ? VD : PD) : H, MVAE_CELL_STANDARD, true);
+    iWy = add_param("dense_1/kernel", H, C); iby = add_param("dense_1/bias", 1, C);
+    ld_pn = ptab[iWy].ld;
+    return;
+  }
   for (int k = 0; k < ne; ++k) add_rec(enc_pitch[k], pre + std::to_string(k + 1), T, k == 0 ? Dp : H, k == 0 ? PD : H, MVAE_CELL_STANDARD, true);
   add_rec(enc_instr, pre + "meta_instrument", Ti, Di, ID, MVAE_CELL_STANDARD, true);
   add_rec(enc_vel, pre + "meta_velocity", T, 1, VD, MVAE_CELL_STANDARD, true);
@@ -101,6 +108,17 @@ void Model::build_workspace() {
   }
   if (use_persist) rec_flags = (unsigned*)alloc(rec_persist_flag_count(NB, std::max(T, Ti)) * sizeof(unsigned));
   for (int k = 0; k < ne; ++k) rec_bufs(enc_pitch[k], k < ne - 1);
+  if (cls) {   // the classifier needs the stack, its input expansion, the logits and the head gradients only
+    d_pitch = (uint8_t*)alloc(n * T); d_style = (uint8_t*)alloc(n); d_vel = (float*)alloc(n * T * 4);
+    d_target = d_pitch; d_instr = d_pitch; d_hist = d_vel; d_eps = d_vel; d_w = d_vel; d_song_start = d_style;   // never uploaded in this mode
+    if (cls_scalar) Xv_ext = alloc((size_t)(T + 1) * n * VD * a); else Xp_ext = alloc((size_t)(T + 1) * n * PD * a);
+    pre = (float*)alloc(n * G * 4); c_run = (float*)alloc(n * H * 4); dh_run = (float*)alloc(n * H * 4); dc_run = (float*)alloc(n * H * 4);
+    Pn = (float*)alloc(n * ld_pn * 4); dlog_n = alloc(n * ld_pn * a); du = alloc(n * H * a);
+    acc = (double*)alloc(ACC_COUNT * 8); d_metrics = (float*)alloc(MVAE_NUM_METRICS * 4); o_y = (float*)alloc(n * C * 4);
+    pin_bytes = n * T * 5 + n + (size_t)n * C * 4 + 4096;
+    MVAE_CUDA(cudaMallocHost((void**)&pin, pin_bytes));
+    return;
+  }
   rec_bufs(enc_instr, false); rec_bufs(enc_vel, false);
   for (int k = 0; k < nd; ++k) rec_bufs(dec_notes[k], true);
   rec_bufs(dec_instr, true); rec_bufs(dec_vel, true);
@@ -118,6 +136,7 @@ void Model::build_workspace() {
   dmu = alloc(n * ldl * a); dlv = alloc(n * ldl * a); de = alloc(n * H * a); dpre_e = alloc(n * H * a); da1 = alloc(n * H * a);
   dpre_a = alloc(n * H * a); du = alloc(n * 3 * H * a);
   mu = (float*)alloc(n * ldl * 4); lv = (float*)alloc(n * ldl * 4); z = (float*)alloc(n * ldl * 4); style_probs = (float*)alloc(n * C * 4);
+  hist_carry = (float*)alloc(ldl * 4);
   Pn = (float*)alloc((size_t)T * n * ld_pn * 4); Pi = (float*)alloc((size_t)Ti * n * ld_pi * 4); Pv = (float*)alloc((size_t)T * n * ld_pv * 4);
   dlog_n = alloc((size_t)T * n * ld_pn * a); dlog_i = alloc((size_t)Ti * n * ld_pi * a); dlog_v = alloc((size_t)T * n * ld_pv * a);
   acc = (double*)alloc(ACC_COUNT * 8); d_metrics = (float*)alloc(MVAE_NUM_METRICS * 4);
@@ -160,6 +179,8 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   T = c.input_length; H = c.lstm_size; L = c.latent_rep_size; Dp = c.input_dim; Di = c.meta_instrument_dim; Ti = c.meta_instrument_length;
   MVAE_REQUIRE(c.cell_type == MVAE_CELLTYPE_LSTM || c.cell_type == MVAE_CELLTYPE_GRU, "cell_type must be LSTM or GRU (vae_definition.py:457-472)");
   gru = c.cell_type == MVAE_CELLTYPE_GRU; spc = gru ? 1 : 2;
+  cls = c.model_kind == 1; cls_scalar = cls && c.cls_scalar_input != 0;
+  MVAE_REQUIRE(c.model_kind == 0 || c.model_kind == 1, "model_kind: 0 (VAE) or 1 (style classifier)");
   C = c.num_composers; ne = c.num_layers_encoder; nd = c.num_layers_decoder; G = (gru ? 3 : 4) * H; NB = c.max_batch;
   PD = round_up(Dp, 8); ID = round_up(Di, 8); VD = 8;
   ldl = round_up(L, 8); Q = c.history ? 2 * L : L; ldq = round_up(Q, 8); nS = spc * (nd + 2); half = H / 2;
@@ -732,6 +753,11 @@ void Model::head_forward(const mvae_batch& b, bool with_style_loss) {
   prof_end();
   prof_begin(PC_POINTWISE);
   k_latent_fwd(act, n, L, ldl, mu, lv, b.eps, b.history, cfg.history, z, q, ldq, cfg.beta, cfg.prior_mean, cfg.prior_std, acc, st);
+  if (history_mode == 1 && cfg.history && with_style_loss) {   // train / evaluate only: the history is this batch's own z, a constant of the step
+    k_self_history(act, n, L, ldl, z, song_start_set ? d_song_start : nullptr, hist_carry, carry_valid ? 1 : 0, q, ldq, st);
+    MVAE_CUDA(cudaMemcpyAsync(hist_carry, z + (size_t)(n - 1) * ldl, (size_t)L * 4, cudaMemcpyDeviceToDevice, st));
+    carry_valid = true;
+  }
   k_style_head(n, C, z, ldl, with_style_loss ? b.style : nullptr, style_probs, acc, st);
   prof_end();
 }
@@ -775,6 +801,68 @@ void Model::decoder_forward(const mvae_batch& b, int feedback) {
     g.C = Pi; g.ldc = ld_pi; g.c_type = DT_F32; g.bias = Wf(ibio); gemm(g); }
   k_rowdot(act, (long)T * n, H, slab(dec_vel.hseq, 1, (long)n * H), Wf(iWvo), Wf(ibvo), Pv, ld_pv, st);
   prof_end();
+}
+
+// --------------------------------------------------------------------------------------------- style classifier (model_kind = 1)
+// pitch_classifier.py:89-103 / velocity_classifier.py:110-118 / instrument_classifier.py:93-103: stacked recurrent layers over the (T, D) input,
+// last state of the top layer -> Dense(C, softmax); loss = mean categorical cross-entropy, metric = accuracy (:100-101)
+void Model::cls_forward(const mvae_batch& b, bool train) {
+  const int n = b.n;
+  MVAE_REQUIRE(n >= 1 && n <= NB, "mini-batch size must be in 1..max_batch");
+  MVAE_REQUIRE(cls_scalar ? b.velocity != nullptr : b.pitch != nullptr, "classifier input roll is missing (pitch: class indices, or velocity: scalars)");
+  MVAE_REQUIRE(!train || b.style, "classifier labels (batch.style) are required for training");
+  MVAE_CUDA(cudaMemsetAsync(acc, 0, ACC_COUNT * sizeof(double), st));
+  prof_begin(PC_POINTWISE);
+  k_expand_inputs(act, n, T, Ti, PD, ID, VD, b.pitch, nullptr, nullptr, b.velocity, cls_scalar ? nullptr : Xp_ext, nullptr, nullptr, cls_scalar ? Xv_ext : nullptr, st);
+  cur_pitch = b.pitch;
+  prof_end();
+  for (int k = 0; k < ne; ++k) {
+    FwdJob jp; jp.r = &enc_pitch[k];
+    if (k == 0) {
+      jp.kind = cls_scalar ? IN_RANK1 : IN_DENSE;
+      jp.X = cls_scalar ? slab(Xv_ext, 1, (long)n * VD) : slab(Xp_ext, 1, (long)n * PD);
+      if (!cls_scalar) { jp.onehot = true; jp.idx = cur_pitch; jp.idx_ld = T; jp.idx_shift = 0; }
+    } else {
+      jp.kind = IN_DENSE; jp.X = slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
+    }
+    rec_forward_jobs(&jp, nullptr, n);
+  }
+  prof_begin(PC_GEMM);
+  { GemmArgs g; g.M = n; g.N = C; g.K = H; g.A = slab(enc_pitch[ne - 1].hseq, T, (long)n * H); g.lda = H; g.B = W(iWy); g.ldb = ld(iWy);
+    g.C = Pn; g.ldc = ld_pn; g.c_type = DT_F32; g.bias = Wf(iby); gemm(g); }
+  prof_end();
+  prof_begin(PC_POINTWISE);
+  k_softmax_ce(act, 1, n, C, Pn, ld_pn, b.style, nullptr, nullptr, 1.f, train ? dlog_n : nullptr, ld_pn, acc, ACC_CE_STYLE, ACC_ACC_STYLE, st);
+  k_finalize_metrics(acc, n, T, Ti, 0.f, 0.f, 0.f, 1.f, d_metrics, st);
+  prof_end();
+}
+
+void Model::cls_backward(const mvae_batch& b) {
+  const int n = b.n;
+  MVAE_CUDA(cudaMemsetAsync(Gr, 0, arena_n * 4, st));
+  const void* hT = slab(enc_pitch[ne - 1].hseq, T, (long)n * H);
+  prof_begin(PC_GEMM);
+  { GemmArgs g; g.M = H; g.N = C; g.K = n; g.A = hT; g.lda = H; g.transA = true; g.B = dlog_n; g.ldb = ld_pn; g.C = Gp(iWy); g.ldc = ld(iWy);
+    g.c_type = DT_F32; g.accumulate = true; gemm(g); }
+  k_colsum(act, n, C, ld_pn, dlog_n, nullptr, 0, Gp(iby), st);
+  { GemmArgs g; g.M = n; g.N = H; g.K = C; g.A = dlog_n; g.lda = ld_pn; g.B = W(iWy); g.ldb = ld(iWy); g.transB = true; g.C = du; g.ldc = H;
+    g.c_type = act; gemm(g); }
+  prof_end();
+  std::vector<BwdJob> stack, none;
+  for (int k = ne - 1; k >= 0; --k) {
+    const bool top = k == ne - 1;
+    BwdJob j; j.r = &enc_pitch[k];
+    j.kind = (k == 0 && cls_scalar) ? IN_RANK1 : IN_DENSE;
+    j.X = k == 0 ? (cls_scalar ? slab(Xv_ext, 1, (long)n * VD) : slab(Xp_ext, 1, (long)n * PD)) : slab(enc_pitch[k - 1].hseq, 1, (long)n * H);
+    j.use_dhext = !top; j.dh_last = top ? du : nullptr; j.ld_last = H;
+    j.need_dx = k > 0; j.dx_out = k > 0 ? enc_pitch[k - 1].dhext : nullptr;
+    stack.push_back(j);
+  }
+  rec_backward_group(stack, none, n, true);
+  if (use_side) {
+    MVAE_CUDA(cudaEventRecord(ev_join, this->side));
+    MVAE_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+  }
 }
 
 // free-running decode (inference only): x_t = previous prediction, one step at a time
@@ -916,15 +1004,20 @@ void Model::backward(const mvae_batch& b) {
   };
   // ---- output heads
   Rec& top = dec_notes[nd - 1];
-  prof_begin(PC_GEMM, ws);
+  auto hseg = [&](const char* tag) { if (prof_detail) { prof_end(ws); prof_begin(PC_GEMM, ws, tag); } };
+  prof_begin(PC_GEMM, ws, prof_detail ? "heads dWy gemm" : "heads wgrad");
   { GemmArgs g; g.M = H; g.N = Dp; g.K = T * n; g.A = slab(top.hseq, 1, (long)n * H); g.lda = H; g.transA = true; g.B = dlog_n; g.ldb = ld_pn;
     g.C = Gp(iWy); g.ldc = ld(iWy); g.c_type = DT_F32; g.accumulate = true; gemm_on(g, ws, wsms); }
+  hseg("heads dby colsum");
   k_colsum(act, (long)T * n, Dp, ld_pn, dlog_n, nullptr, 0, Gp(iby), ws);
+  hseg("heads instr gemm + colsum");
   { GemmArgs g; g.M = H; g.N = Di; g.K = Ti * n; g.A = slab(dec_instr.hseq, 1, (long)n * H); g.lda = H; g.transA = true; g.B = dlog_i; g.ldb = ld_pi;
     g.C = Gp(iWio); g.ldc = ld(iWio); g.c_type = DT_F32; g.accumulate = true; gemm_on(g, ws, wsms); }
   k_colsum(act, (long)Ti * n, Di, ld_pi, dlog_i, nullptr, 0, Gp(ibio), ws);
   // velocity head (N = 1): rank-1 forms instead of GEMMs
+  hseg("heads vel weighted colsum");
   k_colsum(act, (long)T * n, H, H, slab(dec_vel.hseq, 1, (long)n * H), dlog_v, ld_pv, Gp(iWvo), ws);   // dWv[j] = sum_r dlog[r] h[r,j]
+  hseg("heads vel bias colsum");
   k_colsum(act, (long)T * n, 1, ld_pv, dlog_v, nullptr, 0, Gp(ibvo), ws);
   prof_end(ws);
   prof_begin(PC_GEMM);

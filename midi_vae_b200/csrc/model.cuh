@@ -226,6 +226,13 @@ struct Model {
   void encoder_forward(int n);
   void head_forward(const mvae_batch& b, bool with_style_loss);
   void decoder_forward(const mvae_batch& b, int feedback);
+  // opt-in: the decoder's history input is built from THIS batch's own z (shifted inside each song) instead of a separate encoder pass
+  // (mvae_set_history_mode).  carry = z of the last row of the previous call, for a song that continues across two calls.
+  int history_mode = 0; bool song_start_set = false; bool carry_valid = false; float* hist_carry = nullptr;
+  // style-classifier mode (mvae_config::model_kind = 1): enc_pitch[] is the recurrent stack, (iWy, iby) the softmax Dense, Pn the logits
+  bool cls = false, cls_scalar = false;
+  void cls_forward(const mvae_batch& b, bool train);
+  void cls_backward(const mvae_batch& b);
   void decoder_stepwise(int n);
   void decoder_stepwise_body(int n);
   // free-running decode = thousands of tiny dependent launches: captured once per batch size into a CUDA graph (notes chain on the step's

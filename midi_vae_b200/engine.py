@@ -290,14 +290,30 @@ class Engine:
         return {k: float(m.v[i]) for i, k in enumerate(METRIC_KEYS)}
 
     # ------------------------------------------------------------------ hot path (host-pointer API)
-    def train_on_batch(self, pitch, instr, velocity, style, history=None, eps=None, w_notes=None, target=None) -> Dict[str, float]:
+    def set_history_mode(self, from_batch: bool):
+        """Opt-in: True = train / evaluate steps take the decoder's history latents from the step's own z (H[i] = z[i-1] inside a
+        song; pass ``song_start`` to the step) instead of the ``history`` argument the reference fills from a separate encoder pass."""
+        check(self.lib.mvae_set_history_mode(self._h, 1 if from_batch else 0), self._h)
+        self._history_from_batch = bool(from_batch)
+
+    def _song_start(self, song_start, n):
+        if not getattr(self, "_history_from_batch", False):
+            if song_start is not None:
+                raise ValueError("song_start is only used with set_history_mode(True)")
+            return
+        ss = None if song_start is None else _u8(np.asarray(song_start).astype(np.uint8), (n,))
+        check(self.lib.mvae_set_song_start_host(self._h, _ptr(ss), n if ss is not None else 0), self._h)
+
+    def train_on_batch(self, pitch, instr, velocity, style, history=None, eps=None, w_notes=None, target=None, song_start=None) -> Dict[str, float]:
         b = self._batch(pitch, instr, velocity, style, history, eps, w_notes, target)
+        self._song_start(song_start, b.n)
         m = MvaeMetrics()
         check(self.lib.mvae_train_step_host(self._h, C.byref(b), C.byref(m)), self._h)
         return self._metrics(m)
 
-    def evaluate_batch(self, pitch, instr, velocity, style, history=None, eps=None, w_notes=None, target=None) -> Dict[str, float]:
+    def evaluate_batch(self, pitch, instr, velocity, style, history=None, eps=None, w_notes=None, target=None, song_start=None) -> Dict[str, float]:
         b = self._batch(pitch, instr, velocity, style, history, eps, w_notes, target)
+        self._song_start(song_start, b.n)
         m = MvaeMetrics()
         check(self.lib.mvae_eval_step_host(self._h, C.byref(b), C.byref(m)), self._h)
         return self._metrics(m)

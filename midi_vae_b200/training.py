@@ -74,7 +74,8 @@ def pack_songs(songs: Sequence[Rolls], batch_size: int) -> List[Rolls]:
     return packs
 
 
-def train_epoch_packed(vae, songs: Sequence[Rolls], epoch: int, batch_size: int = 256, history: bool = True, silent_weight: float = 1.0) -> Dict[str, float]:
+def train_epoch_packed(vae, songs: Sequence[Rolls], epoch: int, batch_size: int = 256, history: bool = True, silent_weight: float = 1.0,
+                       fused_history: bool = False) -> Dict[str, float]:
     """OPT-IN variant of train_epoch for real data: songs are 10-40 chunks long, so the reference's one-fit-per-song loop runs
     the GPU at B = 10..40.  Here several whole songs share a mini-batch: per pack, ONE batched encoder pass builds every song's history latents
     (shifted inside each song), then consecutive mini-batches of ``batch_size`` chunks are trained.
@@ -82,7 +83,26 @@ def train_epoch_packed(vae, songs: Sequence[Rolls], epoch: int, batch_size: int 
     This is NOT the reference's arithmetic, on purpose, and it says so: (i) Adam takes one step per ``batch_size`` chunks instead of one per song
     remainder, (ii) the histories of all songs of a pack come from the weights at the start of the pack (the reference re-encodes before every
     song), (iii) the returned values are chunk-weighted means over the epoch, not means over songs of per-song means.  train_epoch() is the
-    reference-faithful loop."""
+    reference-faithful loop.  ``fused_history=True`` goes one step further: no encoder pass at all, each step takes its history from its own z
+    on the device (same weights and same epsilon draw as the step; a song that continues into the next mini-batch carries its last z over)."""
+    if fused_history and history and epoch > 0:
+        # no encoder pass at all: every step builds its history from its own z on the device (Engine.set_history_mode; song boundaries per step)
+        vae.engine.set_history_mode(True)
+        try:
+            tot, seen = np.zeros(len(_KEYS)), 0
+            step = min(batch_size, vae.max_batch)
+            for pack in pack_songs(songs, batch_size):
+                n = len(pack)
+                for a in range(0, n, step):
+                    b = min(n, a + step)
+                    ss = pack.song_start[a:b].copy()
+                    if a == 0:
+                        ss[0] = 1
+                    m = vae.engine.train_on_batch(pack.pitch[a:b], pack.instr[a:b], pack.velocity[a:b], pack.style[a:b], None, vae._eps(b - a), None, None, ss)
+                    tot += np.array([m[k] for k in _KEYS]) * (b - a); seen += b - a
+            return _summarise((tot / max(seen, 1))[None, :], vae)
+        finally:
+            vae.engine.set_history_mode(False)
     tot, seen = np.zeros(len(_KEYS)), 0
     for pack in pack_songs(songs, batch_size):
         n = len(pack)

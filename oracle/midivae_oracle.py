@@ -532,3 +532,29 @@ def top2_margin(prob: Tensor) -> Tensor:
     """top-1 minus top-2 probability: argmax parity is demanded only where this exceeds the tolerance."""
     t = prob.topk(2, dim=-1).values
     return t[..., 0] - t[..., 1]
+
+
+# --------------------------------------------------------------------------------------
+# style classifiers  (pitch_classifier.py:89-103, velocity_classifier.py:110-118, instrument_classifier.py:93-103)
+# --------------------------------------------------------------------------------------
+def classifier_forward(cfg: OracleConfig, p: Dict[str, Tensor], X: Tensor, num_layers: int = 2) -> Tensor:
+    """Input(None, D) -> GRU x (num_layers - 1, return_sequences) -> GRU -> Dense(C, softmax): class probabilities (B, C)."""
+    rnn, pre = (keras_gru, "gru") if cfg.cell_type == "GRU" else (keras_lstm, "lstm")
+    h = X
+    for k in range(1, num_layers):
+        h = rnn(cfg, p, f"{pre}_{k}", h, True)
+    h = rnn(cfg, p, f"{pre}_{num_layers}", h, False)
+    return torch.softmax(h @ p["dense_1/kernel"] + p["dense_1/bias"], dim=-1)
+
+
+def classifier_loss_and_grads(cfg: OracleConfig, p: Dict[str, Tensor], X: Tensor, Y: Tensor, num_layers: int = 2):
+    """Keras categorical_crossentropy (renormalise, clip to [1e-7, 1 - 1e-7], mean over the batch) + accuracy; autograd gradients."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    probs = classifier_forward(cfg, leaves, X, num_layers)
+    q = probs / probs.sum(-1, keepdim=True)
+    q = q.clamp(1e-7, 1 - 1e-7)
+    loss = -(Y * q.log()).sum(-1).mean()
+    acc = (probs.argmax(-1) == Y.argmax(-1)).double().mean()
+    names = list(leaves)
+    gl = torch.autograd.grad(loss, [leaves[k] for k in names])
+    return {"loss": float(loss.detach()), "acc": float(acc)}, dict(zip(names, gl)), probs.detach()

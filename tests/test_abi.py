@@ -44,7 +44,7 @@ def test_default_config_is_the_reference_settings(lib_path):
 
 def test_struct_layouts_match_header(lib_path):
     from midi_vae_b200 import _lib
-    assert C.sizeof(_lib.MvaeConfig) == 18 * 4 + 11 * 4 + 4      # + cell_type
+    assert C.sizeof(_lib.MvaeConfig) == 18 * 4 + 11 * 4 + 3 * 4      # + cell_type, model_kind, cls_scalar_input
     assert C.sizeof(_lib.MvaeMetrics) == 40
     assert C.sizeof(_lib.MvaeBatch) == 8 + 8 * 8
 

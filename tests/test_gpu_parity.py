@@ -472,3 +472,33 @@ def test_packed_training_epoch_matches_oracle_on_the_same_packs():
     losses = [training.train_epoch_packed(vae, songs, epoch=e, batch_size=B)["loss"] for e in range(2, 5)]
     assert losses[-1] < losses[0] < m1["loss"] * 1.05, (m1["loss"], losses)
     vae.engine.close()
+
+
+def test_history_from_the_batch_itself_equals_explicit_history():
+    """Opt-in fused history (mvae_set_history_mode 1): the step builds H[i] = z[i-1] (0 at song starts, row 0 carried over from the
+    previous call) from its own z on the device.  Same result as handing the step that history explicitly: z from an encoder pass with the same
+    weights and the same epsilon, shifted on the host."""
+    from midi_vae_b200.marshal import shift_history
+    ecfg, _ = util.make_cfgs(T=16, H=64, L=16, feedback="teacher_forced", max_batch=12, lr=1e-3)
+    w = util.make_weights(ecfg)
+    a, b = _engine(ecfg, w), _engine(ecfg, w)
+    b.set_history_mode(True)
+    carry = None
+    for step in range(3):
+        r, _, eps, _ = util.make_batch(ecfg, 12, seed=40 + step)
+        ss = np.zeros(12, np.uint8); ss[[4, 9]] = 1
+        if step == 0:
+            ss[0] = 1                                    # the first call starts a song; later calls continue the previous call's last song
+        z = a.encode(r.pitch, r.instr, r.velocity, eps)[0]
+        H = shift_history(z, ss)
+        if step > 0:
+            H[0] = carry
+        carry = z[-1].copy()
+        ma = a.train_on_batch(r.pitch, r.instr, r.velocity, r.style, H.astype(np.float32), eps)
+        mb = b.train_on_batch(r.pitch, r.instr, r.velocity, r.style, None, eps, song_start=ss)
+        for k in METRIC_KEYS:
+            assert abs(ma[k] - mb[k]) <= 2e-6 * max(1.0, abs(ma[k])), (step, k, ma[k], mb[k])
+        ga, gb = a.get_grads(), b.get_grads()
+        for k in ga:
+            assert np.abs(ga[k] - gb[k]).max() <= 1e-5 * max(np.abs(ga[k]).max(), 1e-6) + 1e-9, (step, k)
+    a.close(); b.close()
