@@ -42,11 +42,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
+// Bounded spin: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.  The bound is 2^28 failed
+// try_waits (each of which the hardware already suspends for a while: tens of seconds in total), far beyond any stall of a healthy run -- a cfg5
+// sweep of 1024 steps takes 20 ms.  Build with -DMVAE_NO_SPIN_TRAP to spin without bound (debuggers, time-sliced or preempted contexts).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef MVAE_NO_SPIN_TRAP
+  while (!mbar_try_wait(bar, parity)) {}
+  return;
+#endif
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 28)) {
       printf("mbar_wait timeout: block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
       __trap();
     }

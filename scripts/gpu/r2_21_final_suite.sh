@@ -27,3 +27,6 @@ for tool in memcheck synccheck racecheck; do
     echo "$tool $H rc=$?"; grep -E "SUMMARY|sanitize_case H" gpurun_out/r2_21_san_${tool}_${H}.log | tail -3
   done
 done
+for sms in 64 100 116; do
+  MVAE_SIDE_SMS=$sms python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('side_sms',$sms,round(d['ms_per_step'],3),round(d['value']))"
+done
