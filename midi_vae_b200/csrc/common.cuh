@@ -58,6 +58,9 @@ struct GemmArgs {
   const void* addend = nullptr; int ldadd = 0; DT add_type = DT_F32;
   int act = 0;               // 0 = identity, 1 = tanh
   bool accumulate = false;   // C += result (fp32 C only)
+  // optional second product sharing B and K (accumulate GEMMs on the tcgen05 path only): C2[M2,N] += op(A2) op(B), op(A2) laid out like op(A).
+  // One launch, K-split-major tile order: the two weight gradients of a layer (dU = Hprev^T dG, dW = X^T dG) read dG from DRAM once.
+  const void* A2 = nullptr; int lda2 = 0; int M2 = 0; void* C2 = nullptr; int ldc2 = 0;
 };
 
 // SIMT fp32-math GEMM (inputs fp32 or bf16).  Always available; exact fp32 accumulation.

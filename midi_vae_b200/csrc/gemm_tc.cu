@@ -42,6 +42,7 @@ struct TcParams {
   const void* addend; int ldadd; int add_bf16;
   int act; int atomic_acc;
   int m_tiles, n_tiles, k_splits, kb_total, kb_per_split, ks_major, n_fast;
+  int m_tiles1, M2; void* C2; int ldc2;   // m tiles >= m_tiles1 belong to the second product (A2 -> C2); m_tiles1 == m_tiles: none
   int* sched;   // [0] next tile, [1] finished CTAs (both zero between launches that share them): dynamic tile scheduler
 };
 
@@ -56,7 +57,7 @@ struct SmemLayout {
 
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_a2, const TcParams p) {
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -75,6 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
+    ptx::prefetch_tmap(&tma_a2);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1); ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), kEpiWarps); }
     for (int r = 0; r < RS; ++r) { ptx::mbar_init(ptx::smem_u32(&sched_full[r]), 1); ptx::mbar_init(ptx::smem_u32(&sched_empty[r]), 1 + kEpiWarps); }
@@ -104,7 +106,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // output tiles of the wave (MVAE_GEMM_RASTER=0: output-tile major, the round-1 order; measured 13.1-13.3 -> 12.7 ms per cfg3 step)
         const int mnt = p.m_tiles * p.n_tiles;
         const int ks = p.ks_major ? tile / mnt : tile % p.k_splits, mn = p.ks_major ? tile % mnt : tile / p.k_splits;
-        const int m0 = (p.n_fast ? mn / p.n_tiles : mn % p.m_tiles) * BM, n0 = (p.n_fast ? mn % p.n_tiles : mn / p.m_tiles) * BN;
+        const int mt = p.n_fast ? mn / p.n_tiles : mn % p.m_tiles;
+        const CUtensorMap* map_a = mt >= p.m_tiles1 ? &tma_a2 : &tma_a;
+        const int m0 = (mt >= p.m_tiles1 ? mt - p.m_tiles1 : mt) * BM, n0 = (p.n_fast ? mn % p.n_tiles : mn / p.m_tiles) * BN;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -113,10 +117,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
           const int k0 = kb * BK;
           if (!A_MN) {
-            ptx::tma_load_2d(sa, &tma_a, fb, k0, m0);                       // box {64 K, 128 M}
+            ptx::tma_load_2d(sa, map_a, fb, k0, m0);                        // box {64 K, 128 M}
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) ptx::tma_load_2d(sa + j * 8192, &tma_a, fb, m0 + j * 64, k0);   // box {64 M, 64 K}
+            for (int j = 0; j < BM / 64; ++j) ptx::tma_load_2d(sa + j * 8192, map_a, fb, m0 + j * 64, k0);    // box {64 M, 64 K}
           }
           if (!B_MN) {
             ptx::tma_load_2d(sb, &tma_b, fb, k0, n0);                       // box {64 K, BN N}
@@ -177,12 +181,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       tile = __shfl_sync(0xffffffffu, tile, 0);
       if (tile >= num_tiles) break;
       const int mn = p.ks_major ? tile % (p.m_tiles * p.n_tiles) : tile / p.k_splits;
-      const int m0 = (p.n_fast ? mn / p.n_tiles : mn % p.m_tiles) * BM, n0 = (p.n_fast ? mn % p.n_tiles : mn / p.m_tiles) * BN;
+      const int mt = p.n_fast ? mn / p.n_tiles : mn % p.m_tiles;
+      const bool second = mt >= p.m_tiles1;
+      const int m0 = (second ? mt - p.m_tiles1 : mt) * BM, n0 = (p.n_fast ? mn % p.n_tiles : mn / p.m_tiles) * BN;
+      const int Mlim = second ? p.M2 : p.M;
       const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
       ptx::tc_fence_after();
       const int m = m0 + quad * 32 + lane;
-      const bool row_ok = m < p.M;
+      const bool row_ok = m < Mlim;
 #pragma unroll 1
       for (int c = ehalf; c < BN / 32; c += 2) {
         const int nb = n0 + c * 32;
@@ -229,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
         }
         if (p.atomic_acc) {
-          float* cp = (float*)p.C + (size_t)m * p.ldc + nb;
+          float* cp = second ? (float*)p.C2 + (size_t)m * p.ldc2 + nb : (float*)p.C + (size_t)m * p.ldc + nb;
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j < nvalid) atomicAdd(cp + j, v[j]);
         } else if (p.c_bf16) {
@@ -313,7 +320,9 @@ void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_type == DT_BF16;
   p.bias = g.bias; p.addend = g.addend; p.ldadd = g.ldadd; p.add_bf16 = g.add_type == DT_BF16; p.act = g.act;
-  p.m_tiles = (g.M + BM - 1) / BM; p.n_tiles = (g.N + BN - 1) / BN; p.kb_total = (g.K + BK - 1) / BK;
+  p.m_tiles1 = (g.M + BM - 1) / BM; p.m_tiles = p.m_tiles1 + (g.A2 ? (g.M2 + BM - 1) / BM : 0);
+  p.M2 = g.M2; p.C2 = g.C2; p.ldc2 = g.ldc2;
+  p.n_tiles = (g.N + BN - 1) / BN; p.kb_total = (g.K + BK - 1) / BK;
   int splits = 1;
   if (g.accumulate) {   // split K until the grid fills the chip, keeping >= 8 k-blocks per split
     const int tiles = p.m_tiles * p.n_tiles;
@@ -328,6 +337,7 @@ void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
     p.n_fast = raster >= 2 && p.k_splits == 1; }
   p.sched = sched;
   const CUtensorMap ma = A_MN ? make_map(g.A, g.M, g.K, g.lda, 64, 64) : make_map(g.A, g.K, g.M, g.lda, 64, BM);
+  const CUtensorMap ma2 = !g.A2 ? ma : (A_MN ? make_map(g.A2, g.M2, g.K, g.lda2, 64, 64) : make_map(g.A2, g.K, g.M2, g.lda2, 64, BM));
   const CUtensorMap mb = B_MN ? make_map(g.B, g.N, g.K, g.ldb, 64, 64) : make_map(g.B, g.K, g.N, g.ldb, 64, BN);
   auto kern = gemm_tc_kernel<A_MN, B_MN, BN>;
   static bool attr_set = false;
@@ -337,7 +347,7 @@ void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
   }
   const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = std::min(tiles, sm_count);
-  kern<<<grid, kThreads, L::TOTAL, st>>>(ma, mb, p);
+  kern<<<grid, kThreads, L::TOTAL, st>>>(ma, mb, ma2, p);
   count_launch();
   MVAE_CUDA(cudaGetLastError());
 }
@@ -346,6 +356,7 @@ void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
 
 bool gemm_tc_supported(const GemmArgs& g) {
   if (g.in_type != DT_BF16) return false;
+  if (g.A2 && (!g.accumulate || g.M2 <= 0 || !g.C2 || (reinterpret_cast<uintptr_t>(g.A2) & 15) || (g.lda2 % 8))) return false;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
   if ((g.lda % 8) || (g.ldb % 8)) return false;

@@ -196,6 +196,7 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   { const char* e = getenv("MVAE_FUSE_XPROJ"); fuse_xproj = use_cluster_fwd && (e ? atoi(e) != 0 : true); }
   { const char* e = getenv("MVAE_BRANCH"); use_branch = use_cluster_fwd && use_cluster_bwd && (e ? atoi(e) != 0 : true); }
   if (side_sms <= 0) side_sms = std::max(16, sm_count - 16 * ((NB + 127) / 128));
+  { const char* e = getenv("MVAE_WGRAD_DUAL"); fuse_dual_wgrad = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_WGRAD_ROWS"); fuse_wgrad_rows = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_TIMELINE"); prof_detail = e && atoi(e) >= 2; }
   { const char* e = getenv("MVAE_STEP_GRAPH"); step_graph_on = e ? atoi(e) != 0 : true; }
@@ -636,6 +637,7 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms)
   const void* dG = r.xw;
   const void* Xc = j.X;
   const bool det = prof_detail;
+  bool dual_done = false;
   auto seg = [&](const char* tag) { if (det) { prof_end(s); prof_begin(PC_GEMM, s, tag); } };
   prof_begin(PC_GEMM, s, det ? "wgrad dU" : r.name.c_str());
   if (gru) {  // dU_zr += Hprev^T [da_z | da_r];  dU_h += (r * Hprev)^T da_h   (the r * h sequence sits in the cseq buffer)
@@ -648,6 +650,14 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms)
   } else {  // dU += Hprev^T dG
     GemmArgs g; g.M = H; g.N = G; g.K = (int)rows; g.A = r.hseq; g.lda = H; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iU); g.ldc = ld(r.iU); g.c_type = DT_F32; g.accumulate = true;
+    if (fuse_dual_wgrad && j.kind == IN_DENSE && act == DT_BF16) {
+      // ... and dW += X^T dG in the same launch: both products stream the same dG, which is then read from DRAM once (K-split-major tile order).
+      // (Letting the bias gradient ride along as a third, one-row product against a column of ones was measured too: the padded 128-row tile costs
+      // more GEMM time on the weight-gradient stream than the column-sum launch it removes.)
+      g.A2 = Xc; g.lda2 = r.ldin; g.M2 = r.Din; g.C2 = Gp(r.iW); g.ldc2 = ld(r.iW);
+      g.in_type = act;
+      if (!gemm_tc_supported(g)) { g.A2 = nullptr; g.M2 = 0; g.C2 = nullptr; } else dual_done = true;
+    }
     gemm_on(g, s, sms);
   }
   const bool rows_ok = fuse_wgrad_rows && act == DT_BF16 && !gru && G % 8 == 0;
@@ -657,7 +667,7 @@ void Model::rec_backward_wgrads(const BwdJob& j, int n, cudaStream_t s, int sms)
     prof_end(s);
     return;
   }
-  if (j.kind == IN_DENSE) {  // dW += X^T dG
+  if (j.kind == IN_DENSE && !dual_done) {  // dW += X^T dG
     seg("wgrad dW");
     GemmArgs g; g.M = r.Din; g.N = G; g.K = (int)rows; g.A = Xc; g.lda = r.ldin; g.transA = true; g.B = dG; g.ldb = G;
     g.C = Gp(r.iW); g.ldc = ld(r.iW); g.c_type = DT_F32; g.accumulate = true;

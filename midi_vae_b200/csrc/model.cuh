@@ -132,6 +132,7 @@ struct Model {
   // profiling
   bool profiling = false;
   struct Ev { int cls; cudaEvent_t a, b; const char* tag; };
+  bool fuse_dual_wgrad = true;        // MVAE_WGRAD_DUAL=0: dU and dW of a dense-input recurrence as two GEMM launches (each streams dG)
   bool fuse_wgrad_rows = true;        // MVAE_WGRAD_ROWS=0: scalar-input recurrences take one column-sum pass per output (round 1) instead of one pass
   bool prof_detail = false;           // MVAE_TIMELINE=2: every weight-gradient launch gets its own event pair and a tag
   std::vector<Ev> evs;
