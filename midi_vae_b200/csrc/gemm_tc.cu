@@ -16,6 +16,12 @@
 // CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2..9 epilogue
 // (TMEM -> registers -> global, one output row per thread, two warps per lane quadrant).  Two TMEM accumulators (2 x BN columns) let
 // the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// PAIR form (template parameter): the kernel runs as 2-CTA clusters and one `tcgen05.mma.cta_group::2` (M 256, N 256, K 16) works on a 256 x 256
+// output tile: each CTA stages ITS 128 rows of A and ITS 128 columns of B (32 KB per k-block instead of 48 KB for a 128 x 256 single-CTA tile:
+// 128 instead of 87 FLOP per operand byte), both CTAs' TMA loads complete transaction bytes on the LEADER's full barrier (`cp.async.bulk.tensor
+// ...cta_group::2`), the leader issues the MMAs and its commits arrive on both CTAs' barriers (multicast), each CTA drains the 128 accumulator rows
+// its own tensor memory holds.  The leader's producer draws the tile and hands it to the peer through distributed shared memory.
 #include <cuda.h>
 
 #include <stdlib.h>
@@ -43,27 +49,31 @@ struct TcParams {
   int act; int atomic_acc;
   int m_tiles, n_tiles, k_splits, kb_total, kb_per_split, ks_major, n_fast;
   int m_tiles1, M2; void* C2; int ldc2;   // m tiles >= m_tiles1 belong to the second product (A2 -> C2); m_tiles1 == m_tiles: none
+  int red_v4;   // split-K accumulation with 16-byte vector reductions (red.global.add.v4.f32)
   int* sched;   // [0] next tile, [1] finished CTAs (both zero between launches that share them): dynamic tile scheduler
 };
 
-template <int BN>
+// BN = columns of B one CTA stages (PAIR: half of the tile's 2 BN columns); A_BYTES / B_BYTES / STAGE_BYTES are per CTA
+template <int BN, bool PAIR>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 5;
+  static constexpr int STAGES = PAIR ? 6 : (BN == 256) ? 4 : 5;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;   // + alignment slack
 };
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_a2, const TcParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, PAIR>;
   constexpr int STAGES = L::STAGES;
+  constexpr int BMT = PAIR ? 2 * BM : BM, BNT = PAIR ? 2 * BN : BN;   // output tile of the CTA / the CTA pair; a CTA's accumulator = BM lanes x BNT columns
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   // tiles are handed out by an atomic counter (a CTA that becomes resident late -- other kernels may hold part of the chip -- simply finds
-  // nothing left); the producer warp draws the tile and passes it to the MMA and epilogue warps through this ring
+  // nothing left); the producer warp (PAIR: of the leader CTA) draws the tile and passes it to the MMA and epilogue warps (PAIR: and to the peer
+  // CTA's producer and epilogue warps, through distributed shared memory) through this ring
   constexpr int RS = 4;
   __shared__ __align__(8) uint64_t sched_full[RS], sched_empty[RS];
   __shared__ int sched_tile[RS];
@@ -72,83 +82,113 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const uint32_t crank = PAIR ? ptx::cluster_ctarank() : 0u;               // PAIR: CTA 0 of the cluster is the leader
+  const bool leader = crank == 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
     ptx::prefetch_tmap(&tma_a2);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1); ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), kEpiWarps); }
-    for (int r = 0; r < RS; ++r) { ptx::mbar_init(ptx::smem_u32(&sched_full[r]), 1); ptx::mbar_init(ptx::smem_u32(&sched_empty[r]), 1 + kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[a]), 1); ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[a]), (PAIR ? 2 : 1) * kEpiWarps); }
+    for (int r = 0; r < RS; ++r) { ptx::mbar_init(ptx::smem_u32(&sched_full[r]), 1); ptx::mbar_init(ptx::smem_u32(&sched_empty[r]), (PAIR ? 2 : 1) * (1 + kEpiWarps)); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), 2 * BN);
-    ptx::tmem_relinquish();
+    if (PAIR) { ptx::tmem_alloc2(ptx::smem_u32(&tmem_base_slot), 2 * BNT); ptx::tmem_relinquish2(); }
+    else { ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), 2 * BNT); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) { ptx::cluster_arrive(); ptx::cluster_wait(); }               // the peer's barriers exist before anything arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  // one consumer of the tile ring (a whole warp calls; lane 0 does the barrier work): returns the tile of ring position `it`
+  auto next_tile = [&](int it) -> int {
+    const int rs = it % RS;
+    int tile = 0;
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int sit = 0;; ++sit) {
-        const int rs = sit % RS;
-        ptx::mbar_wait(ptx::smem_u32(&sched_empty[rs]), (uint32_t)(((sit / RS) & 1) ^ 1));
-        const int tile = atomicAdd(p.sched, 1);
-        sched_tile[rs] = tile;
-        ptx::mbar_arrive(ptx::smem_u32(&sched_full[rs]));
-        if (tile >= num_tiles) break;
-        // K-split major: tiles that run at the same time share their K range, so an A / B k-block is fetched from DRAM once and hit in L2 by the other
-        // output tiles of the wave (MVAE_GEMM_RASTER=0: output-tile major, the round-1 order; measured 13.1-13.3 -> 12.7 ms per cfg3 step)
-        const int mnt = p.m_tiles * p.n_tiles;
-        const int ks = p.ks_major ? tile / mnt : tile % p.k_splits, mn = p.ks_major ? tile % mnt : tile / p.k_splits;
-        const int mt = p.n_fast ? mn / p.n_tiles : mn % p.m_tiles;
-        const CUtensorMap* map_a = mt >= p.m_tiles1 ? &tma_a2 : &tma_a;
-        const int m0 = (mt >= p.m_tiles1 ? mt - p.m_tiles1 : mt) * BM, n0 = (p.n_fast ? mn % p.n_tiles : mn / p.m_tiles) * BN;
-        const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
-          ptx::mbar_arrive_expect_tx(fb, L::STAGE_BYTES);
-          const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-          const int k0 = kb * BK;
-          if (!A_MN) {
-            ptx::tma_load_2d(sa, map_a, fb, k0, m0);                        // box {64 K, 128 M}
-          } else {
-#pragma unroll
-            for (int j = 0; j < BM / 64; ++j) ptx::tma_load_2d(sa + j * 8192, map_a, fb, m0 + j * 64, k0);    // box {64 M, 64 K}
+      if (PAIR && !leader) ptx::mbar_wait_cluster(ptx::smem_u32(&sched_full[rs]), (uint32_t)((it / RS) & 1));   // completed by the leader's remote arrive
+      else ptx::mbar_wait(ptx::smem_u32(&sched_full[rs]), (uint32_t)((it / RS) & 1));
+      tile = *reinterpret_cast<volatile int*>(&sched_tile[rs]);
+      if (PAIR) ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(&sched_empty[rs]), 0));
+      else ptx::mbar_arrive(ptx::smem_u32(&sched_empty[rs]));
+    }
+    return __shfl_sync(0xffffffffu, tile, 0);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (PAIR: one per CTA, each stages its own halves) =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int sit = 0;; ++sit) {
+      int tile = 0;
+      if (leader) {
+        if (lane == 0) {
+          const int rs = sit % RS;
+          if (PAIR) ptx::mbar_wait_cluster(ptx::smem_u32(&sched_empty[rs]), (uint32_t)(((sit / RS) & 1) ^ 1));
+          else ptx::mbar_wait(ptx::smem_u32(&sched_empty[rs]), (uint32_t)(((sit / RS) & 1) ^ 1));
+          tile = atomicAdd(p.sched, 1);
+          sched_tile[rs] = tile;
+          ptx::mbar_arrive(ptx::smem_u32(&sched_full[rs]));
+          if (PAIR) {
+            ptx::st_cluster_u32(ptx::mapa(ptx::smem_u32(&sched_tile[rs]), 1), (uint32_t)tile);
+            ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(&sched_full[rs]), 1));   // release at cluster scope: orders the store above
           }
-          if (!B_MN) {
-            ptx::tma_load_2d(sb, &tma_b, fb, k0, n0);                       // box {64 K, BN N}
-          } else {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * 8192, &tma_b, fb, n0 + j * 64, k0);   // box {64 N, 64 K}
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+      } else {
+        tile = next_tile(sit);
+      }
+      if (tile >= num_tiles) break;
+      if (lane != 0) continue;
+      // K-split major: tiles that run at the same time share their K range, so an A / B k-block is fetched from DRAM once and hit in L2 by the other
+      // output tiles of the wave (MVAE_GEMM_RASTER=0: output-tile major, the round-1 order; measured 13.1-13.3 -> 12.7 ms per cfg3 step)
+      const int mnt = p.m_tiles * p.n_tiles;
+      const int ks = p.ks_major ? tile / mnt : tile % p.k_splits, mn = p.ks_major ? tile % mnt : tile / p.k_splits;
+      const int mt = p.n_fast ? mn / p.n_tiles : mn % p.m_tiles;
+      const CUtensorMap* map_a = mt >= p.m_tiles1 ? &tma_a2 : &tma_a;
+      const int m0 = (mt >= p.m_tiles1 ? mt - p.m_tiles1 : mt) * BMT + (int)crank * BM;
+      const int n0 = (p.n_fast ? mn % p.n_tiles : mn / p.m_tiles) * BNT + (int)crank * BN;
+      const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+        // PAIR: both CTAs' loads complete their bytes on the LEADER's barrier, which expects the two stages' worth
+        const uint32_t fb = PAIR ? ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0) : ptx::smem_u32(&full_bar[stage]);
+        if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full_bar[stage]), (PAIR ? 2 : 1) * L::STAGE_BYTES);
+        const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+        const int k0 = kb * BK;
+        if (!A_MN) {
+          ptx::tma_load_2d_g<PAIR>(sa, map_a, fb, k0, m0);                        // box {64 K, 128 M}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) ptx::tma_load_2d_g<PAIR>(sa + j * 8192, map_a, fb, m0 + j * 64, k0);    // box {64 M, 64 K}
+        }
+        if (!B_MN) {
+          ptx::tma_load_2d_g<PAIR>(sb, &tma_b, fb, k0, n0);                       // box {64 K, BN N}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d_g<PAIR>(sb + j * 8192, &tma_b, fb, n0 + j * 64, k0);   // box {64 N, 64 K}
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    // ===================== MMA issuer (PAIR: the leader's, for both CTAs) =====================
+    if (leader) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BMT, BNT, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
       for (int it = 0;; ++it) {
-        const int rs = it % RS;
-        ptx::mbar_wait(ptx::smem_u32(&sched_full[rs]), (uint32_t)((it / RS) & 1));
-        const int tile = sched_tile[rs];
-        ptx::mbar_arrive(ptx::smem_u32(&sched_empty[rs]));
+        const int tile = next_tile(it);
         if (tile >= num_tiles) break;
+        if (lane != 0) continue;
         const int ks = p.ks_major ? tile / (p.m_tiles * p.n_tiles) : tile % p.k_splits;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-        ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+        if (PAIR) ptx::mbar_wait_cluster(ptx::smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);   // both CTAs' epilogues have drained this accumulator
+        else ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * BNT;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
           ptx::tc_fence_after();
@@ -157,33 +197,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: 8-row groups 1024 B apart (SBO), advance 32 B per K=16 slice inside the 128 B swizzle row.
             // MN-major: 64-element atoms along M/N 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO), 2048 B per K=16 slice.
+            // PAIR: the same descriptors address each CTA's own stage (its 128 rows of A, its BN columns of B)
             const uint64_t da = A_MN ? ptx::umma_desc_sw128(sa + k * 2048, 8192, 1024) : ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? ptx::umma_desc_sw128(sb + k * 2048, 8192, 1024) : ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
-            ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) ptx::umma_bf16_2cta(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else ptx::umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));     // frees the smem stage once these MMAs retire
+          // frees the smem stage (PAIR: of both CTAs) once these MMAs retire
+          if (PAIR) ptx::umma_commit_2cta(ptx::smem_u32(&empty_bar[stage]), (uint16_t)3);
+          else ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(ptx::smem_u32(&tmem_full_bar[acc]));     // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (PAIR: of both CTAs)
+        if (PAIR) ptx::umma_commit_2cta(ptx::smem_u32(&tmem_full_bar[acc]), (uint16_t)3);
+        else ptx::umma_commit(ptx::smem_u32(&tmem_full_bar[acc]));
       }
     }
   } else {
     // ===================== epilogue: warps 2..9, TMEM lane quadrant = warp % 4, 32-column chunks c with c % 2 == ehalf =====================
     const int quad = warp & 3, ehalf = (warp - 2) >> 2;
     for (int it = 0;; ++it) {
-      const int rs = it % RS;
-      int tile = 0;
-      if (lane == 0) {
-        ptx::mbar_wait(ptx::smem_u32(&sched_full[rs]), (uint32_t)((it / RS) & 1));
-        tile = sched_tile[rs];
-        ptx::mbar_arrive(ptx::smem_u32(&sched_empty[rs]));
-      }
-      tile = __shfl_sync(0xffffffffu, tile, 0);
+      const int tile = next_tile(it);
       if (tile >= num_tiles) break;
       const int mn = p.ks_major ? tile % (p.m_tiles * p.n_tiles) : tile / p.k_splits;
       const int mt = p.n_fast ? mn / p.n_tiles : mn % p.m_tiles;
       const bool second = mt >= p.m_tiles1;
-      const int m0 = (second ? mt - p.m_tiles1 : mt) * BM, n0 = (p.n_fast ? mn % p.n_tiles : mn / p.m_tiles) * BN;
+      const int m0 = (second ? mt - p.m_tiles1 : mt) * BMT + (int)crank * BM, n0 = (p.n_fast ? mn % p.n_tiles : mn / p.m_tiles) * BNT;
       const int Mlim = second ? p.M2 : p.M;
       const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase);
@@ -191,11 +230,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int m = m0 + quad * 32 + lane;
       const bool row_ok = m < Mlim;
 #pragma unroll 1
-      for (int c = ehalf; c < BN / 32; c += 2) {
+      for (int c = ehalf; c < BNT / 32; c += 2) {
         const int nb = n0 + c * 32;
         if (nb >= p.N) break;                                   // warp-uniform
         float v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BNT + c * 32), v);
         if (!row_ok) continue;
         const int nvalid = min(32, p.N - nb);
         if (p.bias) {
@@ -237,8 +276,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         if (p.atomic_acc) {
           float* cp = second ? (float*)p.C2 + (size_t)m * p.ldc2 + nb : (float*)p.C + (size_t)m * p.ldc + nb;
+          if (p.red_v4 && nvalid == 32 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < nvalid) atomicAdd(cp + j, v[j]);
+            for (int j = 0; j < 8; ++j) ptx::red_add_v4(cp + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);   // one L2 reduction per 16 bytes
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) atomicAdd(cp + j, v[j]);
+          }
         } else if (p.c_bf16) {
           bf16* cp = (bf16*)p.C + (size_t)m * p.ldc + nb;
           if (nvalid == 32 && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
@@ -267,13 +311,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's MMA issuer waits for both CTAs
+        else ptx::mbar_arrive(ptx::smem_u32(&tmem_empty_bar[acc]));
+      }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
+  if (PAIR) { ptx::cluster_arrive(); ptx::cluster_wait(); }   // no CTA leaves (or frees tensor memory) while the peer's MMAs / commits can still touch it
+  if (warp == 1) {
+    if (PAIR) ptx::tmem_dealloc2(tmem_base, 2 * BNT);
+    else ptx::tmem_dealloc(tmem_base, 2 * BNT);
+  }
   if (threadIdx.x == 0) {   // the last CTA to leave re-arms the scheduler for the next launch that uses it (launches sharing it are stream-ordered)
     __threadfence();
     if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; __threadfence(); }
@@ -314,19 +365,23 @@ CUtensorMap make_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t l
   return m;
 }
 
-template <bool A_MN, bool B_MN, int BN>
+int g_pair_mode = -1;   // -1: by shape (gemm_tc), 0: never, 1: always (self test)
+
+template <bool A_MN, bool B_MN, int BN, bool PAIR>
 void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, PAIR>;
+  constexpr int BMT = PAIR ? 2 * BM : BM, BNT = PAIR ? 2 * BN : BN;
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_type == DT_BF16;
   p.bias = g.bias; p.addend = g.addend; p.ldadd = g.ldadd; p.add_bf16 = g.add_type == DT_BF16; p.act = g.act;
-  p.m_tiles1 = (g.M + BM - 1) / BM; p.m_tiles = p.m_tiles1 + (g.A2 ? (g.M2 + BM - 1) / BM : 0);
+  p.m_tiles1 = (g.M + BMT - 1) / BMT; p.m_tiles = p.m_tiles1 + (g.A2 ? (g.M2 + BMT - 1) / BMT : 0);
   p.M2 = g.M2; p.C2 = g.C2; p.ldc2 = g.ldc2;
-  p.n_tiles = (g.N + BN - 1) / BN; p.kb_total = (g.K + BK - 1) / BK;
+  p.n_tiles = (g.N + BNT - 1) / BNT; p.kb_total = (g.K + BK - 1) / BK;
+  const int workers = PAIR ? std::max(1, sm_count / 2) : sm_count;   // CTAs / CTA pairs the launch may occupy
   int splits = 1;
   if (g.accumulate) {   // split K until the grid fills the chip, keeping >= 8 k-blocks per split
     const int tiles = p.m_tiles * p.n_tiles;
-    splits = std::max(1, std::min((2 * sm_count + tiles - 1) / tiles, p.kb_total / 8));
+    splits = std::max(1, std::min((2 * workers + tiles - 1) / tiles, p.kb_total / 8));
   }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
@@ -335,21 +390,41 @@ void launch(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
     // un-split GEMMs (tall activations x a small weight matrix): all N tiles of an M tile back to back, so the activation rows are read from DRAM once
     // (MVAE_GEMM_RASTER=1: M fastest; 12.7-12.9 -> 12.5-12.7 ms per cfg3 step)
     p.n_fast = raster >= 2 && p.k_splits == 1; }
+  { static int rv4 = -1; if (rv4 < 0) { const char* e = getenv("MVAE_GEMM_REDV4"); rv4 = e ? atoi(e) : 1; } p.red_v4 = rv4; }
   p.sched = sched;
   const CUtensorMap ma = A_MN ? make_map(g.A, g.M, g.K, g.lda, 64, 64) : make_map(g.A, g.K, g.M, g.lda, 64, BM);
   const CUtensorMap ma2 = !g.A2 ? ma : (A_MN ? make_map(g.A2, g.M2, g.K, g.lda2, 64, 64) : make_map(g.A2, g.K, g.M2, g.lda2, 64, BM));
   const CUtensorMap mb = B_MN ? make_map(g.B, g.N, g.K, g.ldb, 64, 64) : make_map(g.B, g.K, g.N, g.ldb, 64, BN);
-  auto kern = gemm_tc_kernel<A_MN, B_MN, BN>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
-  const int grid = std::min(tiles, sm_count);
-  kern<<<grid, kThreads, L::TOTAL, st>>>(ma, mb, ma2, p);
+  const int grid = std::min(tiles, workers) * (PAIR ? 2 : 1);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, ma2, p));
+  } else {
+    kern<<<grid, kThreads, L::TOTAL, st>>>(ma, mb, ma2, p);
+  }
   count_launch();
   MVAE_CUDA(cudaGetLastError());
+}
+
+template <int BN, bool PAIR>
+void launch_major(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
+  const bool a_mn = g.transA, b_mn = !g.transB;
+  if (!a_mn && !b_mn) launch<false, false, BN, PAIR>(g, st, sm_count, sched);
+  else if (!a_mn && b_mn) launch<false, true, BN, PAIR>(g, st, sm_count, sched);
+  else if (a_mn && !b_mn) launch<true, false, BN, PAIR>(g, st, sm_count, sched);
+  else launch<true, true, BN, PAIR>(g, st, sm_count, sched);
 }
 
 }  // namespace
@@ -376,22 +451,19 @@ static int* default_sched() {
 void gemm_tc(const GemmArgs& g, cudaStream_t st, int sm_count, int* sched) {
   MVAE_REQUIRE(gemm_tc_supported(g), "shape / alignment not supported by the tcgen05 GEMM");
   if (!sched) sched = default_sched();
-  const bool a_mn = g.transA, b_mn = !g.transB;
+  // 256 x 256 tiles on CTA pairs (128 FLOP per operand byte and SM) for the split-K weight gradients when both output dimensions fill them
+  // (MVAE_GEMM_PAIR=0: single-CTA tiles only; 2: un-split GEMMs too -- measured: the K = 512 projection is bound by its epilogue and gets 6 % slower)
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("MVAE_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
+  auto fills = [](int x) { return x >= 256 && (x % 256 == 0 || x >= 1024); };
+  const bool pair = g_pair_mode >= 0 ? g_pair_mode != 0 : (pair_env && (g.accumulate || pair_env >= 2) && sm_count >= 2 && fills(g.M) && fills(g.N) && (!g.A2 || fills(g.M2)));
+  if (pair) { launch_major<128, true>(g, st, sm_count, sched); return; }
   // 128x256 tiles (87 FLOP per operand byte instead of 64) when N is wide enough to fill them
   static int wide = -1;
   if (wide < 0) { const char* e = getenv("MVAE_GEMM_BN256"); wide = e ? atoi(e) : 1; }
   const bool bn256 = wide && g.N >= 256 && (g.N % 256 == 0 || g.N >= 1024);
-  if (bn256) {
-    if (!a_mn && !b_mn) launch<false, false, 256>(g, st, sm_count, sched);
-    else if (!a_mn && b_mn) launch<false, true, 256>(g, st, sm_count, sched);
-    else if (a_mn && !b_mn) launch<true, false, 256>(g, st, sm_count, sched);
-    else launch<true, true, 256>(g, st, sm_count, sched);
-    return;
-  }
-  if (!a_mn && !b_mn) launch<false, false, 128>(g, st, sm_count, sched);
-  else if (!a_mn && b_mn) launch<false, true, 128>(g, st, sm_count, sched);
-  else if (a_mn && !b_mn) launch<true, false, 128>(g, st, sm_count, sched);
-  else launch<true, true, 128>(g, st, sm_count, sched);
+  if (bn256) launch_major<256, false>(g, st, sm_count, sched);
+  else launch_major<128, false>(g, st, sm_count, sched);
 }
 
 // ------------------------------------------------------------------------------------------------ self test
@@ -412,7 +484,11 @@ int gemm_tc_selftest(int device, int verbose) {
   int failures = 0;
   uint32_t seed = 12345u;
   auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  // every case through the single-CTA tiles (pm = 0) and through the CTA-pair form (pm = 1; also on shapes gemm_tc would not pick it for:
+  // M <= 128 leaves the peer CTA entirely out of bounds)
+  for (int pm = 0; pm < 2; ++pm)
   for (const Case& c : cases) {
+    g_pair_mode = pm;
     const int lda = ((c.ta ? c.M : c.K) + 7) / 8 * 8, ldb = ((c.tb ? c.K : c.N) + 7) / 8 * 8, ldc = (c.N + 7) / 8 * 8;
     const size_t na = (size_t)(c.ta ? c.K : c.M) * lda, nb = (size_t)(c.tb ? c.N : c.K) * ldb, nc = (size_t)c.M * ldc;
     std::vector<bf16> ha(na), hb(nb), hadd(nc);
@@ -441,7 +517,7 @@ int gemm_tc_selftest(int device, int verbose) {
     gemm_tc(g1, st, sm);
     gemm_simt(g2, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { fprintf(stderr, "selftest: kernel failure %s on M%d N%d K%d ta%d tb%d epi%d\n", cudaGetErrorString(e), c.M, c.N, c.K, c.ta, c.tb, c.epi); return 100; }
+    if (e != cudaSuccess) { fprintf(stderr, "selftest: kernel failure %s on %s M%d N%d K%d ta%d tb%d epi%d\n", cudaGetErrorString(e), pm ? "pair" : "single", c.M, c.N, c.K, c.ta, c.tb, c.epi); g_pair_mode = -1; return 100; }
     std::vector<float> r1(nc), r2(nc);
     if (c.epi == 1) {
       std::vector<bf16> t1(nc), t2(nc);
@@ -459,7 +535,7 @@ int gemm_tc_selftest(int device, int verbose) {
     const double tol = (c.epi == 1 ? 1e-2 : 2e-3) * std::max(1.0, max_ref);
     // independent witness: the same product in float64 on the HOST from the bf16 operands (no kernel of this library involved)
     double max_err_host = 0;
-    if ((double)c.M * c.N * c.K <= 6e8) {
+    if ((double)c.M * c.N * c.K <= (pm ? 1e8 : 6e8)) {
       std::vector<float> fa(na), fb(nb);
       for (size_t i = 0; i < na; ++i) fa[i] = __bfloat162float(ha[i]);
       for (size_t i = 0; i < nb; ++i) fb[i] = __bfloat162float(hb[i]);
@@ -481,12 +557,13 @@ int gemm_tc_selftest(int device, int verbose) {
     if (verbose || !ok) printf("  host float64 witness: max_err=%.3e\n", max_err_host);
     if (!ok) ++failures;
     if (verbose || !ok)
-      printf("gemm_tc selftest M=%d N=%d K=%d transA=%d transB=%d epi=%d : max_err=%.3e (ref max %.3e) %s\n", c.M, c.N, c.K, (int)c.ta, (int)c.tb,
-             c.epi, max_err, max_ref, ok ? "ok" : "FAIL");
+      printf("gemm_tc selftest %s M=%d N=%d K=%d transA=%d transB=%d epi=%d : max_err=%.3e (ref max %.3e) %s\n", pm ? "pair" : "single", c.M, c.N, c.K,
+             (int)c.ta, (int)c.tb, c.epi, max_err, max_ref, ok ? "ok" : "FAIL");
     cudaFree(dA); cudaFree(dB); cudaFree(dAdd); cudaFree(dBias); cudaFree(dC1); cudaFree(dC2); cudaFree(dCb1); cudaFree(dCb2);
   }
+  g_pair_mode = -1;
   cudaStreamDestroy(st);
-  printf("gemm_tc selftest: %d cases, %d failures\n", (int)cases.size(), failures);
+  printf("gemm_tc selftest: %d cases, %d failures\n", 2 * (int)cases.size(), failures);
   return failures;
 }
 

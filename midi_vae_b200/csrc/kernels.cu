@@ -409,20 +409,49 @@ __global__ void tanh_bwd_kernel(long count, const AT* dout, const AT* out, AT* d
 }
 
 // column sums of a tall matrix (bias gradients, rank-1 weight gradients): each thread owns 8 consecutive columns
-// (one 16-byte load per row for bf16), a block covers 256 columns x 8 row lanes; grid (ceil(cols/256), row chunks)
+// (one 16-byte load per row for bf16), a block covers 256 columns x 8 row lanes; grid (ceil(cols/256), row chunks).
+// These passes run next to the cluster recurrences on the few SMs those leave free, so what bounds them is bytes in flight per SM, not
+// bandwidth: the vector path keeps CS_UNROLL independent 16-byte loads per thread in the air (round 2 had one: 134 MB took 0.66 ms).
+// wsum (weighted form only): also accumulates sum_r weight[r] -- the bias gradient of a one-column head -- instead of a second launch.
+constexpr int CS_UNROLL = 8;
 template <typename AT>
-__global__ void colsum_kernel(long rows, int cols, int ld, const AT* __restrict__ src, const AT* __restrict__ weight, int ldw, float* dst) {
+__global__ void colsum_kernel(long rows, int cols, int ld, const AT* __restrict__ src, const AT* __restrict__ weight, int ldw, float* dst,
+                              float* wsum) {
   __shared__ float sh[8][256 + 8];
+  __shared__ float shw[8];
   const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
   float s[8];
+  float wacc = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = 0.f;
   const bool vec = (c0 + 8 <= cols) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && sizeof(AT) == 2;
+  const bool wown = wsum && weight && blockIdx.x == 0 && threadIdx.x == 0;   // one thread per row lane sums the weights
   if (c0 < cols) {
-    for (long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long)gridDim.y * 8) {
+    const long stride = (long)gridDim.y * 8;
+    long r = blockIdx.y * 8 + threadIdx.y;
+    if (vec) {
+      for (; r + (CS_UNROLL - 1) * stride < rows; r += CS_UNROLL * stride) {
+        uint4 u[CS_UNROLL];
+        float w[CS_UNROLL];
+#pragma unroll
+        for (int k = 0; k < CS_UNROLL; ++k) {
+          u[k] = __ldg(reinterpret_cast<const uint4*>(src + (r + k * stride) * ld + c0));
+          w[k] = weight ? ldf<AT>(weight + (r + k * stride) * ldw) : 1.f;
+        }
+#pragma unroll
+        for (int k = 0; k < CS_UNROLL; ++k) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h2[i]); s[2 * i] += w[k] * f.x; s[2 * i + 1] += w[k] * f.y; }
+          wacc += w[k];
+        }
+      }
+    }
+    for (; r < rows; r += stride) {
       const float wgt = weight ? ldf<AT>(weight + r * ldw) : 1.f;
+      wacc += wgt;
       if (vec) {
-        uint4 u = *reinterpret_cast<const uint4*>(src + r * ld + c0);
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(src + r * ld + c0));
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h2[i]); s[2 * i] += wgt * f.x; s[2 * i + 1] += wgt * f.y; }
@@ -434,6 +463,7 @@ __global__ void colsum_kernel(long rows, int cols, int ld, const AT* __restrict_
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) sh[threadIdx.y][threadIdx.x * 8 + i] = s[i];
+  if (threadIdx.x == 0) shw[threadIdx.y] = wown ? wacc : 0.f;
   __syncthreads();
   const int t = threadIdx.y * 32 + threadIdx.x;   // 0..255: one column each
   const int c = blockIdx.x * 256 + t;
@@ -443,12 +473,20 @@ __global__ void colsum_kernel(long rows, int cols, int ld, const AT* __restrict_
     for (int i = 0; i < 8; ++i) tsum += sh[i][t];
     atomicAdd(dst + c, tsum);
   }
+  if (wsum && weight && blockIdx.x == 0 && t == 0) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tsum += shw[i];
+    atomicAdd(wsum, tsum);
+  }
 }
 
 // One pass over a tall dG (rows = T n, time-major) for a recurrence whose input is a scalar (velocity): bias gradient db[c] += sum_r dG[r, c]
 // and dW[0, c] += sum_r x[r] dG[r, c] (x act-typed with stride ldx) together -- round 1 read dG once per output.  Block (32, 8): a thread owns 8
-// consecutive columns (one 16-byte load per row) for the rows of its lane.  (A one-hot variant that scattered dG rows into a shared-memory class
-// table was measured 4x SLOWER than the padded tensor-core GEMM it replaced: shared-memory float adds are CAS loops (ATOMS.CAST.SPIN); dropped.)
+// consecutive columns (one 16-byte load per row) for the rows of its lane, WR_UNROLL rows in flight.  (A one-hot variant that scattered dG rows
+// into a shared-memory class table was measured 4x SLOWER than the padded tensor-core GEMM it replaced: shared-memory float adds are CAS loops
+// (ATOMS.CAST.SPIN); dropped.)
+constexpr int WR_UNROLL = 4;
 template <typename AT>
 __global__ void wgrad_rows_kernel(long rows, int cols, int ld, const AT* __restrict__ src, const AT* __restrict__ x, int ldx, float* __restrict__ dW,
                                   float* __restrict__ db) {
@@ -458,8 +496,29 @@ __global__ void wgrad_rows_kernel(long rows, int cols, int ld, const AT* __restr
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; sx[i] = 0.f; }
   if (c0 < cols) {
-    for (long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long)gridDim.y * 8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(src + r * ld + c0);
+    const long stride = (long)gridDim.y * 8;
+    long r = blockIdx.y * 8 + threadIdx.y;
+    for (; r + (WR_UNROLL - 1) * stride < rows; r += WR_UNROLL * stride) {
+      uint4 u[WR_UNROLL];
+      float xv[WR_UNROLL];
+#pragma unroll
+      for (int k = 0; k < WR_UNROLL; ++k) {
+        u[k] = __ldg(reinterpret_cast<const uint4*>(src + (r + k * stride) * ld + c0));
+        xv[k] = ldf<AT>(x + (r + k * stride) * ldx);
+      }
+#pragma unroll
+      for (int k = 0; k < WR_UNROLL; ++k) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 t2 = __bfloat1622float2(h2[i]);
+          s[2 * i] += t2.x; s[2 * i + 1] += t2.y;
+          sx[2 * i] += xv[k] * t2.x; sx[2 * i + 1] += xv[k] * t2.y;
+        }
+      }
+    }
+    for (; r < rows; r += stride) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + r * ld + c0));
       const float xv = ldf<AT>(x + r * ldx);
       const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -763,13 +822,13 @@ void k_rowdot(DT act, long rows, int H, const void* h, const float* w, const flo
   DISPATCH_ACT(act, { rowdot_kernel<AT><<<nblk(rows * 32), TPB, 0, st>>>(rows, H, (const AT*)h, w, b, out, ldo); LAUNCH_CHECK(); });
 }
 
-void k_colsum(DT act, long rows, int cols, int ld, const void* src, const void* weight, int ldw, float* dst, cudaStream_t st) {
+void k_colsum(DT act, long rows, int cols, int ld, const void* src, const void* weight, int ldw, float* dst, cudaStream_t st, float* wsum) {
   long chunks = (rows + 127) / 128;
   const unsigned gx = (cols + 255) / 256;
   const long cap = (148 * 8 + gx - 1) / gx;
   dim3 grid(gx, (unsigned)(chunks < 1 ? 1 : (chunks > cap ? cap : chunks)));
   dim3 block(32, 8);
-  DISPATCH_ACT(act, { colsum_kernel<AT><<<grid, block, 0, st>>>(rows, cols, ld, (const AT*)src, (const AT*)weight, ldw, dst); LAUNCH_CHECK(); });
+  DISPATCH_ACT(act, { colsum_kernel<AT><<<grid, block, 0, st>>>(rows, cols, ld, (const AT*)src, (const AT*)weight, ldw, dst, wsum); LAUNCH_CHECK(); });
 }
 
 void k_wgrad_rows(long rows, int cols, int ld, const void* src, const void* x, int ldx, float* dW, float* db, cudaStream_t st) {

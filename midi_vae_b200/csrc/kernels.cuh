@@ -39,7 +39,8 @@ void k_sigmoid_mse(DT act, int steps, int n, float* logits, int ld, const float*
                    cudaStream_t st);
 void k_tanh_bwd(DT act, long count, const void* dout, const void* out, void* dpre, cudaStream_t st);
 // dst[c] += sum_r weight[r] * src[r,c]   (weight == nullptr: plain column sum); weight is act-typed with stride ldw
-void k_colsum(DT act, long rows, int cols, int ld, const void* src, const void* weight, int ldw, float* dst, cudaStream_t st);
+// wsum (optional, with weight): += sum_r weight[r]
+void k_colsum(DT act, long rows, int cols, int ld, const void* src, const void* weight, int ldw, float* dst, cudaStream_t st, float* wsum = nullptr);
 // bf16 dG (rows = T n, time-major), ONE pass: db += column sums and dW[0,:] += sum_r x[r] dG[r,:] (scalar-input recurrences).  cols % 8 == 0, ld % 8 == 0.
 void k_wgrad_rows(long rows, int cols, int ld, const void* src, const void* x, int ldx, float* dW, float* db, cudaStream_t st);
 // out[r,c] = x[r] * w[c] + bias[c]   (x act-typed with stride ldx; w, bias fp32; bias may be null)

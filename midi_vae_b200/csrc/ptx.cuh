@@ -70,6 +70,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
                : "memory");
 }
 
+// the same issued by a CTA of a CTA pair: `bar` is a shared::cluster address and may name a barrier of the PEER CTA (cta_group::2 lifts the
+// "barrier in the destination CTA" rule), so both CTAs' loads of a pipeline stage complete their bytes on the leader's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+               : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void tma_load_2d_g(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  if (PAIR) tma_load_2d_pair(dst, m, bar, c0, c1);
+  else tma_load_2d(dst, m, bar, c0, c1);
+}
+
 // 1-D bulk copy global -> shared (contiguous `bytes`, multiple of 16), completion on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
@@ -265,6 +278,14 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
                : "memory");
+}
+// 32-bit store into the shared memory of a CTA of the cluster (address from mapa)
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// fire-and-forget fp32 reduction of four consecutive floats (16-byte aligned) in global memory
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ float4 ld_shared_f32x4(uint32_t addr) {
