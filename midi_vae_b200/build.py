@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libmidivae.so")
-SOURCES = ["gemm_simt.cu", "gemm_tc.cu", "lstm_persist.cu", "lstm_cluster.cu", "kernels.cu", "model.cu", "api.cu"]
+SOURCES = ["gemm_simt.cu", "gemm_tc.cu", "lstm_persist.cu", "lstm_cluster.cu", "gru_cluster.cu", "kernels.cu", "model.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

@@ -144,6 +144,7 @@ struct Model {
   cudaStream_t side = nullptr;        // weight-gradient GEMMs run here, next to the (SM-sparse) backward recurrences
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_side = false;
+  bool use_gru_cluster = false;       // GRU, bf16, H = 256: gru_cluster.cu (MVAE_GRU_CLUSTER=0 or rnn_mode=streamed: step-streamed kernels)
   int* gemm_sched = nullptr;          // dynamic tile scheduler words of the GEMM kernel, one pair per stream
   int side_sms = 0;
   // independent recurrences (velocity / instrument streams) run on a branch stream next to the pitch stack: a cluster recurrence

@@ -70,4 +70,23 @@ bool rec_cluster_bwd_supported(int H);
 void rec_cluster_pack_u_bwd(const float* U, int ldu, void* upack_bwd, int H, int variant, cudaStream_t st);
 void rec_cluster_backward(const RecPersistArgs& a, cudaStream_t st);
 
+
+// cluster-resident GRU recurrence (gru_cluster.cu): H = 256, bf16; buffers in the layouts of the step-streamed GRU path (row-major, act-typed)
+struct GruClusterArgs {
+  int n = 0, H = 0, t0 = 0, t1 = 0;   // steps [t0, t1)
+  int gate_act = 0, mix = 0;          // mix 0: h = z h' + (1 - z) hh (Keras GRU); 1: (1 - z) h' + z hh (recurrentshop GRUCell)
+  const void* U = nullptr; int ldu = 0;   // (H, 3H) bf16 recurrent kernel [z | r | h]
+  const void* xw = nullptr;           // (T, n, 3H) forward: x W + b
+  void* hseq = nullptr;               // (T + 1, n, H): slab t0 read, slabs t0 + 1 .. t1 written (reverse sweep: read)
+  void* gates = nullptr;              // (T, n, 3H) [z | r | hh]: written forward, read by the reverse sweep
+  void* rh = nullptr;                 // (T, n, H) r * h_{t-1}: written forward (operand of the dU_h weight gradient)
+  const void* dhext = nullptr;        // reverse sweep: (T, n, H) or null
+  const void* dh_last = nullptr; int ld_last = 0;   // (n, ld_last) or null
+  void* dG = nullptr;                 // (T, n, 3H) [da_z | da_r | da_h] written
+  void* dS_h = nullptr; int ldS = 0;  // (n, ldS) gradient wrt the initial state, or null
+};
+bool gru_cluster_supported(int H);
+void gru_cluster_forward(const GruClusterArgs& a, cudaStream_t st);
+void gru_cluster_backward(const GruClusterArgs& a, cudaStream_t st);
+
 }  // namespace mvae

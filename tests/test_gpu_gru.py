@@ -3,7 +3,8 @@
 Encoders are Keras 2.0.8 GRU layers (blocks [z|r|h], reset gate applied before the candidate's recurrent product, h' = z h + (1-z) hh),
 decoders recurrentshop GRUCells (Dense(3H)+b on x, Dense(2H) and Dense(H) on h; h' = (1-z) h + z hh as recalled) -- the oracle's GRU branch is
 pinned at 1e-9 to the reference's own graph code run at its default settings (tests/test_reference_pin.py).  The CUDA path runs them as
-step-streamed recurrences (two dependent GEMMs + two pointwise launches per step and direction)."""
+step-streamed recurrences (two dependent GEMMs + two pointwise launches per step and direction; the fp32 parity precision, any size) or, at the
+reference's default size H = 256 in bf16, as ONE cluster-resident launch per recurrence and direction (csrc/gru_cluster.cu)."""
 import os
 
 import numpy as np
@@ -37,6 +38,35 @@ def test_gru_reference_default_shape_bf16():
     """The reference's default shape (T64, H256, L256, settings.py:108-112) in the tensor-core precision: bf16 operands, fp32 accumulation."""
     ecfg, ocfg = util.make_cfgs(T=64, H=256, L=256, feedback="as_wired", precision="bf16", max_batch=16, cell_type="GRU")
     _compare_step(ecfg, ocfg, 16, tol=2e-2, grad_tol=6e-2)
+
+
+@pytest.mark.parametrize("feedback,n", [("teacher_forced", 40), ("as_wired", 5), ("teacher_forced", 33)])
+def test_gru_cluster_kernels_ragged_batches_bf16(feedback, n):
+    """Cluster-resident GRU kernels (H = 256, bf16) on batches that are not a multiple of the 32 rows a cluster owns, both decoder feedbacks
+    (teacher_forced exercises the dense / scalar input projections of the decoder cells), against the fp64 oracle."""
+    ecfg, ocfg = util.make_cfgs(T=24, H=256, L=64, feedback=feedback, precision="bf16", max_batch=48, cell_type="GRU")
+    _compare_step(ecfg, ocfg, n, tol=2e-2, grad_tol=6e-2)
+
+
+def test_gru_cluster_matches_streamed_bf16():
+    """The same bf16 step through the cluster-resident kernels (rnn_mode auto) and through the step-streamed kernels (rnn_mode streamed): metrics and
+    every gradient tensor agree to bf16 rounding (the two paths round the candidate at different points)."""
+    outs = []
+    for mode in ("auto", "streamed"):
+        ecfg, _ = util.make_cfgs(T=32, H=256, L=100, feedback="teacher_forced", precision="bf16", max_batch=72, cell_type="GRU", rnn_mode=mode)
+        w = util.make_weights(ecfg)
+        eng = Engine(ecfg, 0); eng.set_weights(w)
+        r, hist, eps, _ = util.make_batch(ecfg, 72, seed=11)
+        m = eng.train_on_batch(r.pitch, r.instr, r.velocity, r.style, hist, eps)
+        outs.append((m, eng.get_grads(), eng.launch_count()))
+        eng.close()
+    (ma, ga, la), (mb, gb, lb) = outs
+    assert la < lb / 4, (la, lb)          # the cluster path really ran: a fraction of the step-streamed launch count
+    for k in METRIC_KEYS:
+        assert abs(ma[k] - mb[k]) <= 1e-2 * max(1.0, abs(mb[k])), (k, ma[k], mb[k])
+    for k in ga:
+        scale = max(float(np.abs(gb[k]).max()), 1e-6)
+        assert np.abs(ga[k] - gb[k]).max() <= 4e-2 * scale + 1e-9, (k, float(np.abs(ga[k] - gb[k]).max()), scale)
 
 
 def test_gru_evaluate_predict_decode_fp32():
