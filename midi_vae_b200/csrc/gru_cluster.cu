@@ -4,7 +4,7 @@
 // A GRU step is TWO dependent products -- [z | r] = act(x W_zr + h U_zr), then hh = tanh(x W_h + (r * h) U_h) -- so the step-streamed form is
 // four tiny dependent launches per step (two GEMMs, two pointwise kernels: ~44 us per step, launch- and latency-bound).  Here one launch runs
 // the whole sequence:
-//   * a 4-CTA thread-block cluster owns 32 batch rows for all T steps; clusters never talk to each other;
+//   * a 4-CTA thread-block cluster owns 16 or 32 batch rows for all T steps; clusters never talk to each other;
 //   * CTA c owns 64 hidden units: its columns of U_zr and U_h (forward: transposed, [unit][k]) or its rows (reverse sweep: dh_{t-1} needs
 //     U^T, i.e. the natural rows) stay in shared memory for the whole sequence (96 KB of bf16);
 //   * the products are warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 in, fp32 accumulate): the tiles are 32 rows x 64..128 columns per
@@ -33,12 +33,11 @@ namespace {
 using bf16 = __nv_bfloat16;
 
 constexpr int GC_H = 256, GC_CS = 4, GC_HU = GC_H / GC_CS;      // hidden size, cluster size, units per CTA
-constexpr int GC_R = 32;                                        // batch rows per cluster (two m16 tiles)
+// batch rows per cluster: R = 16 MT (MT m16 tiles; template parameter): 16 while that fills at most one wave of 4-CTA clusters, else 32
 constexpr int GC_THREADS = 256;                                 // 8 warps x 8 units
-constexpr int GC_BLK_LD = GC_HU + 8;                            // operand-tile block: [32 rows][64 units + 8 pad] bf16 (144-byte rows: conflict-free ldmatrix)
-constexpr uint32_t GC_BLK = GC_R * GC_BLK_LD * 2;               // 4608 B, one bulk copy
-constexpr int GC_BLK2_LD = 2 * GC_HU + 8;                       // reverse sweep, second exchange: [32 rows][z 64 | r 64 | 8 pad]
-constexpr uint32_t GC_BLK2 = GC_R * GC_BLK2_LD * 2;             // 8704 B
+constexpr int GC_BLK_LD = GC_HU + 8;                            // operand-tile block: [R rows][64 units + 8 pad] bf16 (144-byte rows: conflict-free ldmatrix),
+                                                                // R x 144 B = one bulk copy
+constexpr int GC_BLK2_LD = 2 * GC_HU + 8;                       // reverse sweep, second exchange: [R rows][z 64 | r 64 | 8 pad]
 constexpr int GC_W_LD = GC_H + 8;                               // weight rows: [unit][256 k + 8 pad] (528-byte rows)
 constexpr int GC_W2_LD = 2 * GC_H + 8;                          // reverse sweep: U_zr rows [unit][512 k' + 8 pad]
 
@@ -78,12 +77,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 __device__ __forceinline__ float2 unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
-// acc[w][mt][4] += A(tile, 32 rows x K) * B_w^T(this warp's 8 units x K) for NW weight sets that share the A fragments, over NB k-blocks of 64
-// (one block = one source CTA's units).  tile: blocks of [32 rows][blk_ld] bf16 `blk_bytes` apart, of each block row the k sub-range
+// acc[w][mt][4] += A(tile, 16 MT rows x K) * B_w^T(this warp's 8 units x K) for NW weight sets that share the A fragments, over NB k-blocks of 64
+// (one block = one source CTA's units).  tile: blocks of [16 MT rows][blk_ld] bf16 `blk_bytes` apart, of each block row the k sub-range
 // [koff, koff + 64) is used; wrow[w]: address of this warp's first weight row of set w, rows w_ld elements apart; the k-block kb of the tile
 // meets weight elements [wk0 + kb * wkstride, + 64).
-template <int NB, int NW>
-__device__ __forceinline__ void mma_rows(float (&acc)[NW][2][4], uint32_t tile, uint32_t blk_bytes, int blk_ld, int koff, const uint32_t (&wrow)[NW],
+template <int NB, int NW, int MT>
+__device__ __forceinline__ void mma_rows(float (&acc)[NW][MT][4], uint32_t tile, uint32_t blk_bytes, int blk_ld, int koff, const uint32_t (&wrow)[NW],
                                          int w_ld, int wk0, int wkstride, int lane) {
   // ldmatrix row addresses: A (x4: rows 0-7 / 8-15 x k 0-7 / 8-15 of an m16 x k16 tile), B (x4: this warp's 8 units x k 0-7 / 8-15 / 16-23 / 24-31)
   const uint32_t a_lane = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * blk_ld + (lane >> 4) * 8) * 2u;
@@ -100,7 +99,7 @@ __device__ __forceinline__ void mma_rows(float (&acc)[NW][2][4], uint32_t tile, 
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
           uint32_t a0, a1, a2, a3;
           ldsm_x4(ab + (uint32_t)(mt * 16 * blk_ld + k2 * 32 + ks * 16) * 2u, a0, a1, a2, a3);
 #pragma unroll
@@ -122,11 +121,13 @@ __device__ __forceinline__ void push_block(uint32_t blk_addr, uint32_t bytes, ui
 
 // ------------------------------------------------------------------------------------------------------------------ forward
 // shared memory: W_zr^T [128][264] | W_h^T [64][264] | h tile [4 blocks] | r*h tile [4 blocks]
-constexpr uint32_t GF_WZR = 0, GF_WH = GF_WZR + 2 * GC_HU * GC_W_LD * 2, GF_HT = GF_WH + GC_HU * GC_W_LD * 2, GF_RHT = GF_HT + GC_CS * GC_BLK,
-                   GF_TOTAL = GF_RHT + GC_CS * GC_BLK;
+constexpr uint32_t GF_WZR = 0, GF_WH = GF_WZR + 2 * GC_HU * GC_W_LD * 2, GF_HT = GF_WH + GC_HU * GC_W_LD * 2;
+constexpr uint32_t gf_total(int mt) { return GF_HT + 2 * GC_CS * (uint32_t)(16 * mt * GC_BLK_LD * 2); }
 
+template <int MT>
 __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const GruP p) {
-  constexpr int H = GC_H, G = 3 * GC_H;
+  constexpr int H = GC_H, G = 3 * GC_H, GC_R = 16 * MT;
+  constexpr uint32_t GC_BLK = GC_R * GC_BLK_LD * 2, GF_RHT = GF_HT + GC_CS * GC_BLK;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_rh, bar_h;
   const uint32_t sm = (ptx::smem_u32(smem_raw) + 127u) & ~127u;
@@ -164,9 +165,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const Gr
   // this thread's 8 (row, unit pair) elements: m-tile mt, row half hf: row = 16 mt + 8 hf + g, units u0 + {0, 1}
   const int u0 = warp * 8 + 2 * q;                       // within the CTA
   const int gu0 = (int)rank * GC_HU + u0;                // global unit
-  float hprev[2][2][2];
+  float hprev[MT][2][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       const int m = row0 + 16 * mt + 8 * hf + g;
@@ -185,9 +186,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const Gr
       ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_h), (GC_CS - 1) * GC_BLK);
     }
     // input projections of this step (independent of the chain: in flight during the first product)
-    uint32_t xz[2][2], xr[2][2], xh[2][2];
+    uint32_t xz[MT][2], xr[MT][2], xh[MT][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int m = row0 + 16 * mt + 8 * hf + g;
@@ -200,19 +201,19 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const Gr
         }
       }
     // ---- [z | r] = act(xw + h_{t-1} U_zr)
-    float azr[2][2][4];
+    float azr[2][MT][4];
 #pragma unroll
     for (int w = 0; w < 2; ++w)
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) azr[w][mt][i] = 0.f;
-    mma_rows<GC_CS, 2>(azr, sm + GF_HT, GC_BLK, GC_BLK_LD, 0, wzr_rows, GC_W_LD, 0, GC_HU, lane);
-    const float (&az)[2][4] = azr[0];
-    const float (&ar)[2][4] = azr[1];
-    float zv[2][2][2];
+    mma_rows<GC_CS, 2, MT>(azr, sm + GF_HT, GC_BLK, GC_BLK_LD, 0, wzr_rows, GC_W_LD, 0, GC_HU, lane);
+    const float (&az)[MT][4] = azr[0];
+    const float (&ar)[MT][4] = azr[1];
+    float zv[MT][2][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int m = row0 + 16 * mt + 8 * hf + g;
@@ -237,15 +238,15 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const Gr
     if (threadIdx.x == 0) push_block(my_rh, GC_BLK, ptx::smem_u32(&bar_rh), rank);
     ptx::mbar_wait(ptx::smem_u32(&bar_rh), par);        // the three peers' blocks have landed
     // ---- hh = tanh(xw_h + (r * h_{t-1}) U_h);  h_t = mix(z, h_{t-1}, hh)
-    float ahh[1][2][4];
+    float ahh[1][MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) ahh[0][mt][i] = 0.f;
-    mma_rows<GC_CS, 1>(ahh, sm + GF_RHT, GC_BLK, GC_BLK_LD, 0, wh_rows, GC_W_LD, 0, GC_HU, lane);
-    const float (&ah)[2][4] = ahh[0];
+    mma_rows<GC_CS, 1, MT>(ahh, sm + GF_RHT, GC_BLK, GC_BLK_LD, 0, wh_rows, GC_W_LD, 0, GC_HU, lane);
+    const float (&ah)[MT][4] = ahh[0];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int m = row0 + 16 * mt + 8 * hf + g;
@@ -280,11 +281,13 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_fwd_kernel(const Gr
 
 // ------------------------------------------------------------------------------------------------------------------ reverse sweep
 // shared memory: U_h rows [64][264] | U_zr rows [64][520] (k' = 128 block + 64 gate + unit) | da_h tile [4 blocks] | [da_z | da_r] tile [4 blocks]
-constexpr uint32_t GB_WH = 0, GB_WZR = GB_WH + GC_HU * GC_W_LD * 2, GB_T1 = GB_WZR + GC_HU * GC_W2_LD * 2, GB_T2 = GB_T1 + GC_CS * GC_BLK,
-                   GB_TOTAL = GB_T2 + GC_CS * GC_BLK2;
+constexpr uint32_t GB_WH = 0, GB_WZR = GB_WH + GC_HU * GC_W_LD * 2, GB_T1 = GB_WZR + GC_HU * GC_W2_LD * 2;
+constexpr uint32_t gb_total(int mt) { return GB_T1 + GC_CS * (uint32_t)(16 * mt * (GC_BLK_LD + GC_BLK2_LD) * 2); }
 
+template <int MT>
 __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const GruP p) {
-  constexpr int H = GC_H, G = 3 * GC_H;
+  constexpr int H = GC_H, G = 3 * GC_H, GC_R = 16 * MT;
+  constexpr uint32_t GC_BLK = GC_R * GC_BLK_LD * 2, GC_BLK2 = GC_R * GC_BLK2_LD * 2, GB_T2 = GB_T1 + GC_CS * GC_BLK;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_1, bar_2;
   const uint32_t sm = (ptx::smem_u32(smem_raw) + 127u) & ~127u;
@@ -315,9 +318,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const Gr
   ptx::cluster_wait();
 
   const int u0 = warp * 8 + 2 * q, gu0 = (int)rank * GC_HU + u0;
-  float dh[2][2][2];
+  float dh[MT][2][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) dh[mt][hf][0] = dh[mt][hf][1] = 0.f;
   const uint32_t my_1 = sm + GB_T1 + rank * GC_BLK, my_2 = sm + GB_T2 + rank * GC_BLK2;
@@ -330,10 +333,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const Gr
       ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_2), (GC_CS - 1) * GC_BLK2);
     }
     // ---- part 1 (gru_bwd1): dh = carried + external;  da_z, da_h, direct path
-    float rv[2][2][2], hv[2][2][2], daz[2][2][2];
-    uint32_t dahp[2][2];
+    float rv[MT][2][2], hv[MT][2][2], daz[MT][2][2];
+    uint32_t dahp[MT][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int m = row0 + 16 * mt + 8 * hf + g;
@@ -370,15 +373,15 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const Gr
     if (threadIdx.x == 0) push_block(my_1, GC_BLK, ptx::smem_u32(&bar_1), rank);
     ptx::mbar_wait(ptx::smem_u32(&bar_1), par);
     // ---- drh = da_h U_h^T;  part 2 (gru_bwd2): da_r = drh h_{t-1} act'(r);  dh += drh r
-    float a1s[1][2][4];
+    float a1s[1][MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) a1s[0][mt][i] = 0.f;
-    mma_rows<GC_CS, 1>(a1s, sm + GB_T1, GC_BLK, GC_BLK_LD, 0, wh_rows, GC_W_LD, 0, GC_HU, lane);
-    const float (&a1)[2][4] = a1s[0];
+    mma_rows<GC_CS, 1, MT>(a1s, sm + GB_T1, GC_BLK, GC_BLK_LD, 0, wh_rows, GC_W_LD, 0, GC_HU, lane);
+    const float (&a1)[MT][4] = a1s[0];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int m = row0 + 16 * mt + 8 * hf + g;
@@ -405,22 +408,22 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const Gr
     if (threadIdx.x == 0) push_block(my_2, GC_BLK2, ptx::smem_u32(&bar_2), rank);
     ptx::mbar_wait(ptx::smem_u32(&bar_2), par);
     // ---- dh += [da_z | da_r] U_zr^T
-    float a2s[1][2][4];
+    float a2s[1][MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) a2s[0][mt][i] = 0.f;
-    mma_rows<GC_CS, 1>(a2s, sm + GB_T2, GC_BLK2, GC_BLK2_LD, 0, wzr_rows, GC_W2_LD, 0, 2 * GC_HU, lane);             // the z halves of the four blocks
-    mma_rows<GC_CS, 1>(a2s, sm + GB_T2, GC_BLK2, GC_BLK2_LD, GC_HU, wzr_rows, GC_W2_LD, GC_HU, 2 * GC_HU, lane);     // the r halves
-    const float (&a2)[2][4] = a2s[0];
+    mma_rows<GC_CS, 1, MT>(a2s, sm + GB_T2, GC_BLK2, GC_BLK2_LD, 0, wzr_rows, GC_W2_LD, 0, 2 * GC_HU, lane);             // the z halves of the four blocks
+    mma_rows<GC_CS, 1, MT>(a2s, sm + GB_T2, GC_BLK2, GC_BLK2_LD, GC_HU, wzr_rows, GC_W2_LD, GC_HU, 2 * GC_HU, lane);     // the r halves
+    const float (&a2)[MT][4] = a2s[0];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) { dh[mt][hf][0] += a2[mt][2 * hf]; dh[mt][hf][1] += a2[mt][2 * hf + 1]; }
   }
   if (p.dS_h) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int m = row0 + 16 * mt + 8 * hf + g;
@@ -433,12 +436,12 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gru_cluster_bwd_kernel(const Gr
 }
 
 template <typename K>
-void launch(K kern, bool& configured, const GruP& p, size_t smem, cudaStream_t st) {
+void launch(K kern, bool& configured, const GruP& p, int rows, size_t smem, cudaStream_t st) {
   if (!configured) {
     MVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int clusters = (p.n + GC_R - 1) / GC_R;
+  const int clusters = (p.n + rows - 1) / rows;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * GC_CS)); cfg.blockDim = dim3(GC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -447,6 +450,17 @@ void launch(K kern, bool& configured, const GruP& p, size_t smem, cudaStream_t s
   cfg.attrs = at; cfg.numAttrs = 1;
   MVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   count_launch();
+}
+
+// 16 rows per cluster while all clusters are co-resident in one wave (the step is a latency chain: more, thinner clusters shorten it), else 32
+int rows_per_cluster(int n) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MVAE_GRU_ROWS"); forced = e ? atoi(e) : 0; }
+  if (forced == 16 || forced == 32) return forced;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return ((n + 15) / 16) * GC_CS <= sms ? 16 : 32;
 }
 
 }  // namespace
@@ -462,8 +476,9 @@ void gru_cluster_forward(const GruClusterArgs& a, cudaStream_t st) {
   GruP p{};
   p.n = a.n; p.t0 = a.t0; p.t1 = a.t1; p.gate_act = a.gate_act; p.mix = a.mix;
   p.U = (const bf16*)a.U; p.ldu = a.ldu; p.xw = (const bf16*)a.xw; p.hseq = (bf16*)a.hseq; p.gates = (bf16*)a.gates; p.rh = (bf16*)a.rh;
-  static bool configured = false;
-  launch(gru_cluster_fwd_kernel, configured, p, GF_TOTAL + 128, st);
+  static bool configured1 = false, configured2 = false;
+  if (rows_per_cluster(a.n) == 16) launch(gru_cluster_fwd_kernel<1>, configured1, p, 16, gf_total(1) + 128, st);
+  else launch(gru_cluster_fwd_kernel<2>, configured2, p, 32, gf_total(2) + 128, st);
 }
 
 void gru_cluster_backward(const GruClusterArgs& a, cudaStream_t st) {
@@ -472,8 +487,9 @@ void gru_cluster_backward(const GruClusterArgs& a, cudaStream_t st) {
   p.n = a.n; p.t0 = a.t0; p.t1 = a.t1; p.gate_act = a.gate_act; p.mix = a.mix;
   p.U = (const bf16*)a.U; p.ldu = a.ldu; p.hseq = (bf16*)a.hseq; p.gates = (bf16*)a.gates;
   p.dhext = (const bf16*)a.dhext; p.dh_last = (const bf16*)a.dh_last; p.ld_last = a.ld_last; p.dG = (bf16*)a.dG; p.dS_h = (bf16*)a.dS_h; p.ldS = a.ldS;
-  static bool configured = false;
-  launch(gru_cluster_bwd_kernel, configured, p, GB_TOTAL + 128, st);
+  static bool configured1 = false, configured2 = false;
+  if (rows_per_cluster(a.n) == 16) launch(gru_cluster_bwd_kernel<1>, configured1, p, 16, gb_total(1) + 128, st);
+  else launch(gru_cluster_bwd_kernel<2>, configured2, p, 32, gb_total(2) + 128, st);
 }
 
 }  // namespace mvae

@@ -192,11 +192,11 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   // the cluster recurrences occupy 16 SMs per 64..128 batch rows and leave the rest of the chip idle: the batched weight-gradient
   // GEMMs (needed only by the optimizer) run next to them on a second stream, on a grid sized for the idle SMs
   { const char* e = getenv("MVAE_SIDE_STREAM"); use_side = use_cluster_bwd && (e ? atoi(e) != 0 : true); }
-  // the reference's default cell at its default size: one cluster-resident launch per recurrence instead of four launches per step
-  use_gru_cluster = gru && act == DT_BF16 && cfg.rnn_mode != MVAE_RNN_STREAMED && gru_cluster_supported(H);
   { const char* e = getenv("MVAE_SIDE_SMS"); side_sms = e ? atoi(e) : 0; }
   { const char* e = getenv("MVAE_FUSE_XPROJ"); fuse_xproj = use_cluster_fwd && (e ? atoi(e) != 0 : true); }
-  { const char* e = getenv("MVAE_BRANCH"); use_branch = use_cluster_fwd && use_cluster_bwd && (e ? atoi(e) != 0 : true); }
+  // the reference's default cell at its default size: one cluster-resident launch per recurrence instead of four launches per step
+  use_gru_cluster = gru && act == DT_BF16 && cfg.rnn_mode != MVAE_RNN_STREAMED && gru_cluster_supported(H);
+  { const char* e = getenv("MVAE_BRANCH"); use_branch = ((use_cluster_fwd && use_cluster_bwd) || use_gru_cluster) && (e ? atoi(e) != 0 : true); }
   if (side_sms <= 0) side_sms = std::max(16, sm_count - 16 * ((NB + 127) / 128));
   { const char* e = getenv("MVAE_WGRAD_DUAL"); fuse_dual_wgrad = e ? atoi(e) != 0 : true; }
   { const char* e = getenv("MVAE_WGRAD_ROWS"); fuse_wgrad_rows = e ? atoi(e) != 0 : true; }
@@ -504,6 +504,7 @@ void Model::gru_steps_forward(Rec& r, int n, int t0, int t1) {
   if (use_gru_cluster && t1 - t0 >= 2) {   // the whole range in ONE cluster-resident launch (single steps -- the free-running decoder -- stay streamed)
     GruClusterArgs g; g.n = n; g.H = H; g.t0 = t0; g.t1 = t1; g.gate_act = cfg.gate_act; g.mix = r.variant;
     g.U = W(r.iU); g.ldu = ld(r.iU); g.xw = r.xw; g.hseq = r.hseq; g.gates = r.gates; g.rh = r.cseq;
+    fork_if_pending();   // the independent (velocity / instrument) recurrences may start on the branch stream now
     gru_cluster_forward(g, st);
     return;
   }
@@ -530,6 +531,7 @@ void Model::gru_backward_sweep(const BwdJob& j, int n) {
     GruClusterArgs g; g.n = n; g.H = H; g.t0 = 0; g.t1 = r.steps; g.gate_act = cfg.gate_act; g.mix = r.variant;
     g.U = W(r.iU); g.ldu = ld(r.iU); g.hseq = r.hseq; g.gates = r.gates;
     g.dhext = j.use_dhext ? r.dhext : nullptr; g.dh_last = j.dh_last; g.ld_last = j.ld_last; g.dG = dG; g.dS_h = j.dS_h; g.ldS = j.ldS;
+    fork_if_pending();
     gru_cluster_backward(g, st);
     return;
   }
