@@ -234,8 +234,8 @@ def make_engine(D, T, H, L, B, feedback, precision, rnn_mode, cell="LSTM"):
 def ncu_traffic(dom, workload, T, B, H):
     """DRAM bytes per launch of the dominant recurrence kernel.  NOT measured in this run: read from the committed `ncu --set full` capture of the
     same kernel on the same workload (a run under ncu is never a bench value, so the two cannot be the same process)."""
-    for rel in (("profiles/r2/ncu_rec_bwd4_cfg3.json", "profiles/r1/ncu_rec_cluster_cfg3_r1h.json") if dom == "rec_bwd" else
-                ("profiles/r2/ncu_rec_fwd2_cfg3.json", "profiles/r1/ncu_rec_cluster_cfg3.json")):
+    for rel in (("profiles/r2/ncu_rec_cluster_cfg3.json", "profiles/r1/ncu_rec_cluster_cfg3_r1h.json") if dom == "rec_bwd" else
+                ("profiles/r2/ncu_rec_cluster_cfg3.json", "profiles/r1/ncu_rec_cluster_cfg3.json")):
         f = os.path.join(ROOT, rel)
         if workload != "cfg3" or not os.path.exists(f):
             continue
@@ -335,11 +335,15 @@ def run_train(args, name, wl, D):
         train = 3 * fwd
         fast = args.rnn_mode != "streamed" and args.precision == "bf16" and cell == "LSTM"
         gen = "cluster-resident" if H in (256, 512) else "persistent"
+        gru_fast = args.rnn_mode != "streamed" and args.precision == "bf16" and cell == "GRU" and H == 256
         classes = {
             "rec_bwd": ((("rec_cluster_bwd4_kernel" if H == 512 else "rec_cluster_bwd_kernel" if H == 256 else "rec_persist_kernel<bwd>") + f": {gen} backward recurrence "
-                         "(dG*U^T per step on tcgen05 + gate-gradient math)") if fast else "step-streamed backward recurrence", rec_fwd * B),
+                         "(dG*U^T per step on tcgen05 + gate-gradient math)") if fast else
+                        "gru_cluster_bwd_kernel: cluster-resident GRU reverse sweep (two dependent products per step, mma.sync tiles, DSMEM exchanges)" if gru_fast
+                        else "step-streamed backward recurrence", rec_fwd * B),
             "rec_fwd": ((("rec_cluster_fwd2_kernel" if H in (256, 512) else "rec_persist_kernel<fwd>") + f": {gen} forward recurrence (h*U per step on tcgen05 + gate math)")
-                        if fast else "step-streamed forward recurrence", rec_fwd * B),
+                        if fast else "gru_cluster_fwd_kernel: cluster-resident GRU recurrence (two dependent products per step, mma.sync tiles, DSMEM exchanges)"
+                        if gru_fast else "step-streamed forward recurrence", rec_fwd * B),
             "gemm": ("gemm_tc_kernel: batched tcgen05 GEMMs (input projections, heads, weight gradients)", (train - 2 * rec_fwd) * B),
         }
         dom = max(classes, key=lambda k: kms[k][0])
