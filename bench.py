@@ -281,8 +281,10 @@ def run_train(args, name, wl, D):
     # ---- device-resident timing
     for i in range(args.warmup):
         eng.train_step_device(dev[i % NB][1], metrics_dev.data_ptr())
-    D.barrier()
+    # the clock sampler (an nvidia-smi child process per rank) starts BEFORE the barrier: launched after it, its start-up time -- tens of milliseconds,
+    # different on every rank -- sat inside the timed region of whichever rank came out first (that rank then waits in its first all-reduce)
     sampler = ClockSampler(D.local); sampler.start(); time.sleep(0.25)
+    D.barrier()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -427,8 +429,8 @@ def run_infer(args, name, wl, D):
 
     for i in range(max(3, args.warmup)):
         call(i)
+    sampler = ClockSampler(D.local); sampler.start(); time.sleep(0.25)   # before the barrier: see run_train
     D.barrier()
-    sampler = ClockSampler(D.local); sampler.start(); time.sleep(0.25)
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
