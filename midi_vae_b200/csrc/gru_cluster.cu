@@ -119,6 +119,18 @@ __device__ __forceinline__ void push_block(uint32_t blk_addr, uint32_t bytes, ui
   }
 }
 
+// Hazard notes (why single-buffered operand tiles and two mbarriers per CTA are enough).  Every step has two exchanges, X1 then X2 (forward: r*h, h;
+// reverse: da_h, [da_z | da_r]); product P1 reads the X2 tile of the previous step, product P2 reads the X1 tile of this step.
+//   * A peer's X1 block of step t+1 can only be produced after that peer received MY X2 block of step t, which I push after all my warps finished
+//     P2 of step t (the __syncthreads in front of the push): nobody overwrites the X1 tile while I still read it.  Symmetrically a peer's X2
+//     block of step t needs my X1 block of step t, pushed after all my warps finished P1 of step t: the X2 tile is not overwritten under P1.
+//   * I re-write my OWN block of a tile one step after I pushed it; by then every peer has used it (its next message reached me, see above), i.e.
+//     the bulk copies that read it have completed (complete_tx is signalled after the data has been written at the destination).
+//   * An mbarrier phase cannot be completed early: thread 0 arms both barriers (arrive.expect_tx of the three peers' bytes) at the top of the step, and
+//     a peer's bytes for the NEXT phase cannot arrive before this CTA pushed its block of the current one, which happens after every thread passed the
+//     wait of the previous phase.  Bytes that land before the arming only make the transaction count transiently negative.
+//   * The final cluster barrier keeps every CTA (its shared memory, its barriers) alive until all peers have seen their last message.
+
 // ------------------------------------------------------------------------------------------------------------------ forward
 // shared memory: W_zr^T [128][264] | W_h^T [64][264] | h tile [4 blocks] | r*h tile [4 blocks]
 constexpr uint32_t GF_WZR = 0, GF_WH = GF_WZR + 2 * GC_HU * GC_W_LD * 2, GF_HT = GF_WH + GC_HU * GC_W_LD * 2;
