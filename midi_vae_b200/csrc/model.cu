@@ -191,11 +191,11 @@ Model::Model(const mvae_config& c, int dev) : cfg(c), device(dev) {
   use_cluster_bwd = use_persist && rec_cluster_bwd_supported(H);
   // the cluster recurrences occupy 16 SMs per 64..128 batch rows and leave the rest of the chip idle: the batched weight-gradient
   // GEMMs (needed only by the optimizer) run next to them on a second stream, on a grid sized for the idle SMs
-  { const char* e = getenv("MVAE_SIDE_STREAM"); use_side = use_cluster_bwd && (e ? atoi(e) != 0 : true); }
-  { const char* e = getenv("MVAE_SIDE_SMS"); side_sms = e ? atoi(e) : 0; }
-  { const char* e = getenv("MVAE_FUSE_XPROJ"); fuse_xproj = use_cluster_fwd && (e ? atoi(e) != 0 : true); }
   // the reference's default cell at its default size: one cluster-resident launch per recurrence instead of four launches per step
   use_gru_cluster = gru && act == DT_BF16 && cfg.rnn_mode != MVAE_RNN_STREAMED && gru_cluster_supported(H);
+  { const char* e = getenv("MVAE_SIDE_STREAM"); use_side = (use_cluster_bwd || use_gru_cluster) && (e ? atoi(e) != 0 : true); }
+  { const char* e = getenv("MVAE_SIDE_SMS"); side_sms = e ? atoi(e) : 0; }
+  { const char* e = getenv("MVAE_FUSE_XPROJ"); fuse_xproj = use_cluster_fwd && (e ? atoi(e) != 0 : true); }
   { const char* e = getenv("MVAE_BRANCH"); use_branch = ((use_cluster_fwd && use_cluster_bwd) || use_gru_cluster) && (e ? atoi(e) != 0 : true); }
   if (side_sms <= 0) side_sms = std::max(16, sm_count - 16 * ((NB + 127) / 128));
   { const char* e = getenv("MVAE_WGRAD_DUAL"); fuse_dual_wgrad = e ? atoi(e) != 0 : true; }
