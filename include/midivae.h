@@ -35,6 +35,9 @@ enum { MVAE_GATE_HARD_SIGMOID = 0, MVAE_GATE_SIGMOID = 1 };            /* Keras 
 enum { MVAE_CELL_STANDARD = 0, MVAE_CELL_RECURRENTSHOP_RECALLED = 1 };  /* SURVEY.md appendix A.3 */
 enum { MVAE_FB_AS_WIRED = 0, MVAE_FB_TEACHER_FORCED = 1, MVAE_FB_FREE_RUNNING = 2 };  /* SURVEY.md 8(a) row D-fb */
 enum { MVAE_PREC_FP32 = 0, MVAE_PREC_BF16 = 1 };   /* fp32 SIMT parity path / bf16 tcgen05 tensor-core path */
+/* sequence loop of a recurrence (bf16 only): STREAMED = one GEMM + gate-math launch per step; PERSISTENT = require the LSTM persistent / cluster
+   kernels (error if the cell / size has none); AUTO = the fastest available form: LSTM cluster kernels (H = 256 / 512), first-generation
+   persistent kernels (other H % 64 == 0), GRU cluster kernels (H = 256), else streamed */
 enum { MVAE_RNN_STREAMED = 0, MVAE_RNN_PERSISTENT = 1, MVAE_RNN_AUTO = 2 };
 enum { MVAE_CELLTYPE_LSTM = 0, MVAE_CELLTYPE_GRU = 1 };                 /* vae_definition.py:457-472,535,585,623; settings.py:155 ships GRU */
 
