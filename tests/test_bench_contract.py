@@ -14,7 +14,9 @@ def _line(name):
         return json.loads(f.read().strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("name,n_gpus", [("bench_cfg3_r1_final_default.json", 1), ("bench_cfg3_r1_final_dp1.json", 1), ("bench_cfg3_r1_final_dp2.json", 2)])
+@pytest.mark.parametrize("name,n_gpus", [("bench_cfg3_r1_final_default.json", 1), ("bench_cfg3_r1_final_dp1.json", 1), ("bench_cfg3_r1_final_dp2.json", 2),
+                                         ("../r2/bench_cfg3.json", 1), ("../r2/bench_cfg3_final_check.json", 1), ("../r2/bench_cfg3_n2.json", 2),
+                                         ("../r2/bench_cfg3_n4.json", 4), ("../r2/bench_cfg3_n8.json", 8)])
 def test_own_arm_line(name, n_gpus):
     d = _line(name)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
@@ -48,6 +50,16 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"].startswith("MIDI sequences/sec") and d["unit"] == "sequences/s"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_reference_default_gru_line():
+    """The reference's own default configuration (GRU, settings.py:108-115,155) through the cluster-resident GRU kernels."""
+    d = _line("../r2/bench_refdefault_gru.json")
+    assert "refdefault" in d["config"]["workload"] and "GRU" in d["config"]["workload"] and d["dtype"] == "bf16"
+    assert abs(d["value"] - 256 / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-6
+    assert d["roofline"]["kernel"].startswith("gru_cluster_") and d["e2e"]["h2d_bytes_per_step"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    s = _line("../r2/bench_refdefault_gru_streamed.json")
+    assert d["value"] > 8 * s["value"]                 # one launch per recurrence instead of four per step
 
 
 def test_flop_model_matches_the_survey():
